@@ -1,0 +1,231 @@
+/*
+ * llc.h — C ABI of libllc.so: the B200 (sm_100a) implementation of LifeLong-CLIP's online-step hot
+ * path (CLIP ViT image tower forward/backward with LoRA on the attention projections + the cosine
+ * logit / softmax / cross-entropy head).
+ *
+ * The reference (qcNPU/LifeLong-CLIP) is pure Python/PyTorch and has NO FFI layer; its operator
+ * API is a set of nn.Module classes. Each entry point below names the reference lines it replaces
+ * (paths relative to the reference root); the ctypes binding a maintainer would add is shown in
+ * INTEGRATION.md and implemented in lifelong-clip_b200/_capi.py.
+ *
+ * Conventions
+ *  - extern "C", plain pointers + sizes; every device pointer is owned by the caller (PyTorch's
+ *    caching allocator); the library retains nothing past the call.
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and never
+ *    synchronise the device; all are CUDA-graph capturable.
+ *  - return 0 on success; <0 = argument/shape error found before launch; >0 = cudaError_t.
+ *    Text via llc_last_error() (thread-local). No CPU fallback exists: a missing GPU or a
+ *    non-sm_100 device is an error.
+ *  - token layout: activations are row-major [T, ld] with T = N*L tokens; token (n, l) is row
+ *    n*tok_stride_n + l*tok_stride_l (sample-major [N,L,D]: (L,1); the reference's
+ *    sequence-first [L,N,D], models/clip/model.py:767: (1,N)).
+ */
+#ifndef LLC_H_
+#define LLC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLC_VERSION 100
+#define LLC_ERR_ARG (-1)
+#define LLC_ERR_ARCH (-2)
+#define LLC_LORA_PAD 16 /* rank-r LoRA columns are padded to one UMMA K step (16 bf16) */
+
+int llc_version(void);
+const char* llc_last_error(void);
+/* 0 when device `dev` is sm_100 (B200); LLC_ERR_ARCH otherwise. */
+int llc_check_device(int dev);
+/* number of kernels this process has launched through the library (bench.py: gpu_launches) */
+unsigned long long llc_launch_count(void);
+
+/* ---- dense contraction: out[M,N] = epi(A[M,K] . B[N,K]^T), bf16 operands, fp32 accumulate ----
+ * TMA-fed tcgen05/TMEM GEMM. Replaces every F.linear on the path: in-proj lora.py:837-839,
+ * out-proj lora.py:1072-1074, mlp model.py:219-222, and their activation-gradient transposes.
+ * A and B are K-major (row-major [rows, ld]); K % 16 == 0, ld % 8 == 0, N % 8 == 0. */
+typedef struct llc_gemm_epi {
+  const float* bias;  /* [N] fp32 or NULL */
+  const float* resid; /* fp32 [M, ld_resid] or NULL: added to the result (residual stream) */
+  int ld_resid;
+  int act;            /* 0 none | 1 QuickGELU: out=z (may be NULL), out2=z*sigmoid(1.702z)
+                         | 2 multiply by QuickGELU'(aux) (backward of model.py:203-206) */
+  const void* aux;    /* bf16 [M, ld_aux], pre-activation z for act==2 */
+  int ld_aux;
+  void* out;          /* [M, ld_out] */
+  int ld_out;
+  int out_fp32;       /* 0: bf16, 1: fp32 */
+  void* out2;         /* bf16 [M, ld_out2], only act==1 */
+  int ld_out2;
+} llc_gemm_epi;
+int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                     const llc_gemm_epi* epi, void* stream);
+
+/* ---- LayerNorm (model.py:194-200: fp32, eps 1e-5, affine) --------------------------------- */
+/* y = LN(x)*g+b -> bf16 [T, ld_y]; if lora_A != NULL also writes u = LN(x) . lora_A^T (r cols,
+ * bf16, zero padded to LLC_LORA_PAD) at column D of y: the K-augmentation that folds the rank-r
+ * update of lora.py:838-839 into the following GEMM. */
+int llc_ln_fwd(const float* x, int ld_x, const float* gamma, const float* beta, int T, int D,
+               void* y, int ld_y, const float* lora_A, int r, void* stream);
+/* dx_out = dx_in + LNbackward(dy) (gamma/beta frozen: no weight grads, methods/adapter_clip.py:
+ * 115-119). Writes fp32 dx_out [T, D] (may alias dx_in), and if dxb != NULL a bf16 copy
+ * [T, ld_dxb]; if lora_B != NULL appends du = scale * dx_out . lora_B (r cols) at column D of dxb. */
+int llc_ln_bwd(const float* x, int ld_x, const float* gamma, const void* dy, int ld_dy,
+               const float* dx_in, float* dx_out, int T, int D, void* dxb, int ld_dxb,
+               const float* lora_B, int r, float scale, void* stream);
+
+/* ---- attention core (lora.py:950,1002-1006,1043,1063-1071): softmax(q k^T / sqrt(hd)) v ------
+ * qkv bf16 [T, ld_qkv] holds q | k | v at columns [0,D) [D,2D) [2D,3D); head h of sample n uses
+ * columns h*hd..; no mask (vision tower) or causal (text tower). o bf16 [T, ld_o]; lse fp32
+ * [N*H*L] saved for backward. hd must be 64. */
+int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L, int H,
+                 int tok_stride_n, int tok_stride_l, int causal, void* stream);
+int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o, int ld_do,
+                 const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H, int tok_stride_n,
+                 int tok_stride_l, int causal, void* stream);
+
+/* ---- LoRA side reductions (lora.py:838-839,1072-1074 and their autograd) ---------------------
+ * One pass over X bf16 [T, ld_x] (C columns):
+ *   rowdot: if Mrd != NULL, w_out[t, j] = rd_scale * sum_c X[t,c] * Mrd[c*rd_sc + j*rd_sj], j<r,
+ *           written bf16 (zero padded to LLC_LORA_PAD) at X[t, C..C+16)   (u = x A^T, du = s g B)
+ *   colsum: if w != NULL (bf16 [T, ld_w], r cols), partial[c, j] += sum_t X[t,c] * w[t,j]
+ * followed by llc_lora_colsum_finish which reduces the per-CTA partials deterministically into
+ * out[c*o_sc + j*o_sj] = cs_scale * sum (dB = s g^T u, dA = du^T h). */
+int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float* Mrd, int rd_sc, int rd_sj,
+                  float rd_scale, const void* w, int ld_w, float* partial, int* n_partials,
+                  void* stream);
+int llc_lora_colsum_finish(const float* partial, int n_partials, int C, int r, float cs_scale,
+                           float* out, int o_sc, int o_sj, void* stream);
+int llc_lora_side_max_partials(void);
+
+/* ---- weight preparation (frozen backbone: done once; LoRA columns refreshed every step) ------ */
+/* dst bf16 [rows, ld_dst] <- src fp32 [rows, cols] (row-major) or its transpose */
+int llc_pack_weight(const float* src, int rows, int cols, int transpose, void* dst, int ld_dst,
+                    void* stream);
+/* dst[i, col0 + j] = scale * src[i*s_i + j*s_j], j < r; columns r..LLC_LORA_PAD zeroed */
+int llc_pack_lora_cols(const float* src, int rows, int r, int s_i, int s_j, float scale, void* dst,
+                       int ld_dst, int col0, void* stream);
+
+/* ---- patch embedding front end (model.py:756-767) -------------------------------------------- */
+/* NCHW fp32 image -> bf16 patch rows [N*G*G, ld_out] (im2col of the stride-P conv, no bias);
+ * columns >= 3*P*P are zero-filled (K padding to a multiple of 16) */
+int llc_patchify(const float* img, int N, int C, int HW, int P, void* out, int ld_out,
+                 void* stream);
+/* x0[n,0,:] = LN_pre(class_emb + pos[0]); x0[n,1+g,:] = LN_pre(patch_out[n*G*G+g] + pos[1+g]) */
+int llc_embed_ln_pre(const float* patch_out, int ld_p, const float* class_emb, const float* pos,
+                     const float* gamma, const float* beta, int N, int L, int D, float* x0,
+                     void* stream);
+
+/* ---- head (model.py:782-785, 966-973; models/adapter_clip.py:99; methods/adapter_clip.py:89-90;
+ *           mask variant methods/mvp_clip.py:113-118) ---------------------------------------- */
+typedef struct llc_head_args {
+  const float* x;        /* residual stream fp32; CLS token of sample n at row n*cls_stride */
+  int cls_stride, ld_x;
+  const float* ln_g;     /* ln_post */
+  const float* ln_b;
+  const float* proj;     /* [D, E] fp32 (visual.proj) */
+  const float* text;     /* [C_all, E] fp32, L2-normalised cached class text features */
+  const int64_t* cls_idx;/* [C] rows of `text` visible this step (gather-then-compute), or NULL */
+  const float* add_mask; /* [C] additive logit mask (0 / -inf), or NULL */
+  float logit_scale;     /* exp(logit_scale) */
+  int N, D, E, C;
+  const int64_t* labels; /* [N] local (remapped) labels, or NULL (inference) */
+  int double_softmax;    /* 1: CE applied to the probabilities (the reference's loss) */
+  float inv_batch;       /* 1 / global batch (mean reduction) */
+  /* outputs */
+  float* feat;           /* [N, E] image features before normalisation */
+  float* fnorm;          /* [N, E] normalised */
+  float* logits;         /* [N, C] */
+  float* probs;          /* [N, C] */
+  float* loss_rows;      /* [N] per-sample loss (already * inv_batch) */
+  int64_t* pred;         /* [N] argmax (lowest index among ties) */
+} llc_head_args;
+int llc_head_fwd(const llc_head_args* a, void* stream);
+/* d_probs (may be NULL: then the analytic gradient of the fused loss is used, scaled by
+ * loss_scale) -> d_x rows of the CLS tokens: fp32 [T, ld_dx] (other rows untouched) */
+int llc_head_bwd(const llc_head_args* a, const float* d_probs, float loss_scale, float* dx,
+                 int ld_dx, void* stream);
+/* y_local[i] = lut[y_global[i]] (methods/adapter_clip.py:75-76; -1 when the class is unseen) */
+int llc_label_remap(const int64_t* y_global, const int64_t* lut, int lut_size, int64_t* y_local,
+                    int n, void* stream);
+/* per-step scalars: out[0] = sum(loss_rows), out[1] = #(pred == labels) */
+int llc_loss_acc(const float* loss_rows, const int64_t* pred, const int64_t* labels, int n,
+                 float* out2, void* stream);
+
+/* ---- fused AdamW on the flat LoRA buffer (utils/train_utils.py:27-28, torch.optim.AdamW) ----- */
+int llc_adamw(float* p, const float* g, float* m, float* v, int n, float lr, float beta1,
+              float beta2, float eps, float wd, int step, float grad_scale, void* stream);
+
+/* ---- whole image tower (VisualTransformer.forward model.py:755-787 on LoRA blocks :400-415) - */
+typedef struct llc_vit_cfg {
+  int image_size, patch, width, layers, heads, mlp_dim, embed_dim;
+  int lora_r;
+  float lora_scale; /* alpha / r */
+} llc_vit_cfg;
+
+typedef struct llc_vit_layer {
+  /* frozen, prepared bf16 K-major (llc_pack_weight); *_aug carry LLC_LORA_PAD extra K columns */
+  void* wqkv_aug;  /* [3D, D+16]: W_in | s*B_in        */
+  void* wo_aug;    /* [D, D+16]:  W_o  | s*B_o         */
+  void* wfc;       /* [mlp, D]                          */
+  void* wproj;     /* [D, mlp]                          */
+  void* wqkvT_aug; /* [D, 3D+16]: W_in^T | A_in^T       */
+  void* woT_aug;   /* [D, D+16]:  W_o^T  | A_o^T        */
+  void* wfcT;      /* [D, mlp]                          */
+  void* wprojT;    /* [mlp, D]                          */
+  const float *bqkv, *bo, *bfc, *bproj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  /* live fp32 LoRA parameters and their gradient slots (views of the flat buffers) */
+  const float *in_A, *in_B, *out_A, *out_B; /* [r,D] [3D,r] [r,D] [D,r] */
+  float *g_in_A, *g_in_B, *g_out_A, *g_out_B;
+} llc_vit_layer;
+
+typedef struct llc_vit_weights {
+  void* wpatch;            /* [D, 3*P*P] bf16 (conv1.weight viewed 2-D) */
+  const float *class_emb, *pos_emb, *ln_pre_g, *ln_pre_b;
+  const llc_vit_layer* layers;
+} llc_vit_weights;
+
+/* activation arena: sizes from llc_vit_arena_bytes; saved-for-backward tensors live here */
+size_t llc_vit_arena_bytes(const llc_vit_cfg* cfg, int N, int training);
+/* images fp32 NCHW [N,3,S,S] -> x_final fp32 [N*L, D] (pointer returned inside the arena) */
+int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w, const float* images, int N,
+                    void* arena, int training, float** x_final, void* stream);
+/* dx_final fp32 [N*L, D] (the head's gradient; consumed/overwritten) -> LoRA grads in w->layers */
+int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N, void* arena,
+                     float* dx_final, void* stream);
+/* refresh the LoRA columns of the augmented weights from the live parameters */
+int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weights* w, void* stream);
+
+/* one transformer block on [T, D] fp32 (ResidualAttentionBlock.forward model.py:233-236) */
+typedef struct llc_block_bufs {
+  float* x_in;   /* [T, D] fp32 input (saved)                     */
+  void* h1;      /* [T, D+16] bf16  LN1 out | u_in (saved)        */
+  void* qkv;     /* [T, 3D+16] bf16 (saved; bwd reuses pad cols)  */
+  float* lse;    /* [N*H*L]                                        */
+  void* o;       /* [T, D+16] bf16 attn out | u_o (saved)         */
+  float* x_mid;  /* [T, D] fp32 (saved)                           */
+  void* h2;      /* [T, D] bf16 transient                         */
+  void* z;       /* [T, mlp] bf16 (saved)                         */
+  void* g;       /* [T, mlp] bf16 transient                       */
+  float* x_out;  /* [T, D] fp32                                    */
+} llc_block_bufs;
+int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
+                      int N, int L, int tok_stride_n, int tok_stride_l, int causal, void* stream);
+typedef struct llc_block_bwd_bufs {
+  float* dx;     /* [T, D] fp32 in: grad wrt x_out; out: grad wrt x_in (in place) */
+  void* dxb;     /* [T, D+16] bf16: in: bf16 copy of dx; out: copy of the new dx  */
+  void* dz;      /* [T, mlp] bf16 scratch                                          */
+  void* dh;      /* [T, D] bf16 scratch                                            */
+  void* d_o;     /* [T, D] bf16 scratch                                            */
+  void* dqkv;    /* [T, 3D+16] bf16 scratch                                        */
+  float* partial;/* llc_lora_side partials: max_partials * 3D * r floats           */
+} llc_block_bwd_bufs;
+int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
+                       const llc_block_bwd_bufs* s, int N, int L, int tok_stride_n,
+                       int tok_stride_l, int causal, int need_dx_in, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLC_H_ */

@@ -1,0 +1,330 @@
+// Image-text head of the online step, one CTA per sample:
+//   ln_post(CLS) @ proj                      reference models/clip/model.py:782-785
+//   f = z/|z|, logits = exp(logit_scale) f T^T                    model.py:966-973
+//   probs = softmax(logits)                              models/adapter_clip.py:99
+//   loss = CrossEntropy(probs, y)  (CE applied to probabilities)  methods/adapter_clip.py:89,
+//          criterion methods/_trainer.py:164;  pred = argmax      methods/adapter_clip.py:90
+//   class restriction: gather of the visible class rows (methods/adapter_clip.py:53-61,84) or the
+//   additive seen-class mask (methods/mvp_clip.py:113-118)
+// and the analytic backward down to the CLS rows of the residual stream (proj, ln_post frozen).
+// Also the integer label remap (methods/adapter_clip.py:75-76) and the per-step loss/acc scalars.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kLnEps = 1e-5f;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kThreads / 32; ++i) s += red[i];
+  return s;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kThreads / 32; ++i) s = fmaxf(s, red[i]);
+  return s;
+}
+
+struct HeadK {
+  const float* x; int cls_stride, ld_x;
+  const float *ln_g, *ln_b, *proj, *text;
+  const int64_t* cls_idx;
+  const float* add_mask;
+  float logit_scale;
+  int N, D, E, C;
+  const int64_t* labels;
+  int double_softmax;
+  float inv_batch;
+  float *feat, *fnorm, *logits, *probs, *loss_rows;
+  int64_t* pred;
+};
+
+// smem: y[D] | f[E] | p[C] | red[32]
+__global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadK a) {
+  extern __shared__ float sm[];
+  float* sy = sm;
+  float* sf = sy + a.D;
+  float* sp = sf + a.E;
+  float* red = sp + a.C;
+  __shared__ int s_arg;
+  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* xr = a.x + (size_t)n * a.cls_stride * a.ld_x;
+
+  // ln_post
+  float s = 0.f;
+  for (int k = tid; k < a.D; k += kThreads) { sy[k] = xr[k]; s += sy[k]; }
+  const float mean = block_sum(s, red) / a.D;
+  float q = 0.f;
+  for (int k = tid; k < a.D; k += kThreads) { const float d = sy[k] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q, red) / a.D + kLnEps);
+  for (int k = tid; k < a.D; k += kThreads)
+    sy[k] = (sy[k] - mean) * rstd * a.ln_g[k] + a.ln_b[k];
+  __syncthreads();
+
+  // z = y @ proj
+  float nrm = 0.f;
+  for (int e = tid; e < a.E; e += kThreads) {
+    float acc = 0.f;
+    for (int k = 0; k < a.D; ++k) acc += sy[k] * __ldg(a.proj + (size_t)k * a.E + e);
+    sf[e] = acc;
+    a.feat[(size_t)n * a.E + e] = acc;
+    nrm += acc * acc;
+  }
+  const float inv_norm = 1.0f / sqrtf(block_sum(nrm, red));
+  for (int e = tid; e < a.E; e += kThreads) {
+    sf[e] *= inv_norm;
+    a.fnorm[(size_t)n * a.E + e] = sf[e];
+  }
+  __syncthreads();
+
+  // logits: one warp per class, lanes stride the embedding
+  for (int c = warp; c < a.C; c += kThreads / 32) {
+    const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
+    const float* tr = a.text + (size_t)row * a.E;
+    float acc = 0.f;
+    for (int e = lane; e < a.E; e += 32) acc += sf[e] * __ldg(tr + e);
+    acc = warp_sum(acc) * a.logit_scale;
+    if (a.add_mask) acc += a.add_mask[c];
+    if (lane == 0) {
+      sp[c] = acc;
+      a.logits[(size_t)n * a.C + c] = acc;
+    }
+  }
+  __syncthreads();
+
+  // softmax
+  float m = -INFINITY;
+  for (int c = tid; c < a.C; c += kThreads) m = fmaxf(m, sp[c]);
+  m = block_max(m, red);
+  float z = 0.f;
+  for (int c = tid; c < a.C; c += kThreads) z += __expf(sp[c] - m);
+  z = block_sum(z, red);
+  const float logz = m + logf(z);
+  float pm = -1.f;
+  for (int c = tid; c < a.C; c += kThreads) {
+    const float p = __expf(sp[c] - m) / z;
+    const float lg = sp[c];
+    sp[c] = p;
+    a.probs[(size_t)n * a.C + c] = p;
+    pm = fmaxf(pm, p);
+    (void)lg;
+  }
+  pm = block_max(pm, red);
+  // argmax: lowest index among the maxima
+  if (tid == 0) s_arg = 0x7fffffff;
+  __syncthreads();
+  for (int c = tid; c < a.C; c += kThreads)
+    if (sp[c] == pm) atomicMin(&s_arg, c);
+  __syncthreads();
+  if (tid == 0 && a.pred) a.pred[n] = (int64_t)s_arg;
+
+  if (a.labels && a.loss_rows) {
+    const int64_t yv = a.labels[n];
+    float loss;
+    if (a.double_softmax) {
+      // CE on probabilities: -p_y + log sum_j exp(p_j)
+      float z2 = 0.f;
+      for (int c = tid; c < a.C; c += kThreads) z2 += __expf(sp[c]);
+      z2 = block_sum(z2, red);
+      const float py = (yv >= 0 && yv < a.C) ? sp[yv] : 0.f;
+      loss = -py + logf(z2);
+    } else {
+      const float ly = (yv >= 0 && yv < a.C) ? a.logits[(size_t)n * a.C + yv] : 0.f;
+      loss = -(ly - logz);
+    }
+    if (tid == 0) a.loss_rows[n] = loss * a.inv_batch;
+  }
+}
+
+// smem: g[C] | f[E] | z[E](df then dz) | dy[D] | xh[D] | red[32]
+__global__ void __launch_bounds__(kThreads)
+head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
+                float* __restrict__ dx, int ld_dx) {
+  extern __shared__ float sm[];
+  float* sg = sm;
+  float* sf = sg + a.C;
+  float* sz = sf + a.E;
+  float* sdy = sz + a.E;
+  float* sxh = sdy + a.D;
+  float* red = sxh + a.D;
+  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* pr = a.probs + (size_t)n * a.C;
+
+  // dL/dlogits
+  if (d_probs == nullptr && !a.double_softmax) {
+    const int64_t yv = a.labels[n];
+    for (int c = tid; c < a.C; c += kThreads)
+      sg[c] = (pr[c] - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
+  } else {
+    if (d_probs != nullptr) {
+      for (int c = tid; c < a.C; c += kThreads) sg[c] = d_probs[(size_t)n * a.C + c] * loss_scale;
+    } else {
+      const int64_t yv = a.labels[n];
+      float z2 = 0.f;
+      for (int c = tid; c < a.C; c += kThreads) z2 += __expf(pr[c]);
+      z2 = block_sum(z2, red);
+      for (int c = tid; c < a.C; c += kThreads)
+        sg[c] = (__expf(pr[c]) / z2 - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
+    }
+    __syncthreads();
+    float dot = 0.f;
+    for (int c = tid; c < a.C; c += kThreads) dot += sg[c] * pr[c];
+    dot = block_sum(dot, red);
+    for (int c = tid; c < a.C; c += kThreads) sg[c] = pr[c] * (sg[c] - dot);
+  }
+  for (int e = tid; e < a.E; e += kThreads) sf[e] = a.fnorm[(size_t)n * a.E + e];
+  __syncthreads();
+
+  // df = scale * dlogits @ T ; dz = (df - f (f.df)) / |z|
+  float fd = 0.f, zz = 0.f;
+  for (int e = tid; e < a.E; e += kThreads) {
+    float acc = 0.f;
+    for (int c = 0; c < a.C; ++c) {
+      const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
+      acc += sg[c] * __ldg(a.text + (size_t)row * a.E + e);
+    }
+    acc *= a.logit_scale;
+    sz[e] = acc;
+    fd += acc * sf[e];
+    const float zf = a.feat[(size_t)n * a.E + e];
+    zz += zf * zf;
+  }
+  fd = block_sum(fd, red);
+  zz = block_sum(zz, red);
+  const float inv_norm = 1.0f / sqrtf(zz);
+  for (int e = tid; e < a.E; e += kThreads) sz[e] = (sz[e] - sf[e] * fd) * inv_norm;
+  __syncthreads();
+
+  // dy = dz @ proj^T : one warp per k
+  for (int k = warp; k < a.D; k += kThreads / 32) {
+    const float* prow = a.proj + (size_t)k * a.E;
+    float acc = 0.f;
+    for (int e = lane; e < a.E; e += 32) acc += sz[e] * __ldg(prow + e);
+    acc = warp_sum(acc);
+    if (lane == 0) sdy[k] = acc;
+  }
+  // ln_post backward (input gradient only)
+  const float* xr = a.x + (size_t)n * a.cls_stride * a.ld_x;
+  float s = 0.f;
+  for (int k = tid; k < a.D; k += kThreads) { sxh[k] = xr[k]; s += sxh[k]; }
+  const float mean = block_sum(s, red) / a.D;
+  float q = 0.f;
+  for (int k = tid; k < a.D; k += kThreads) { const float d = sxh[k] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q, red) / a.D + kLnEps);
+  float c1 = 0.f, c2 = 0.f;
+  for (int k = tid; k < a.D; k += kThreads) {
+    const float xh = (sxh[k] - mean) * rstd;
+    const float g = sdy[k] * a.ln_g[k];
+    sxh[k] = xh;
+    sdy[k] = g;
+    c1 += g;
+    c2 += g * xh;
+  }
+  c1 = block_sum(c1, red) / a.D;
+  c2 = block_sum(c2, red) / a.D;
+  float* dr = dx + (size_t)n * a.cls_stride * ld_dx;
+  for (int k = tid; k < a.D; k += kThreads) dr[k] = rstd * (sdy[k] - c1 - sxh[k] * c2);
+}
+
+__global__ void label_remap_kernel(const int64_t* __restrict__ y, const int64_t* __restrict__ lut,
+                                   int lut_size, int64_t* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t v = y[i];
+  out[i] = (v >= 0 && v < lut_size) ? lut[v] : (int64_t)-1;
+}
+
+__global__ void loss_acc_kernel(const float* __restrict__ loss_rows,
+                                const int64_t* __restrict__ pred,
+                                const int64_t* __restrict__ labels, int n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float l = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < n; i += kThreads) {
+    l += loss_rows[i];
+    c += (pred[i] == labels[i]) ? 1.f : 0.f;
+  }
+  l = block_sum(l, red);
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) { out[0] = l; out[1] = c; }
+}
+
+int to_k(const llc_head_args* a, HeadK* k, const char* who) {
+  LLC_REQUIRE(a && a->x && a->ln_g && a->ln_b && a->proj && a->text, "%s: null input", who);
+  LLC_REQUIRE(a->N > 0 && a->D > 0 && a->E > 0 && a->C > 0, "%s: empty problem", who);
+  LLC_REQUIRE(a->feat && a->fnorm && a->logits && a->probs, "%s: null output", who);
+  k->x = a->x; k->cls_stride = a->cls_stride; k->ld_x = a->ld_x;
+  k->ln_g = a->ln_g; k->ln_b = a->ln_b; k->proj = a->proj; k->text = a->text;
+  k->cls_idx = a->cls_idx; k->add_mask = a->add_mask; k->logit_scale = a->logit_scale;
+  k->N = a->N; k->D = a->D; k->E = a->E; k->C = a->C; k->labels = a->labels;
+  k->double_softmax = a->double_softmax; k->inv_batch = a->inv_batch;
+  k->feat = a->feat; k->fnorm = a->fnorm; k->logits = a->logits; k->probs = a->probs;
+  k->loss_rows = a->loss_rows; k->pred = a->pred;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int llc_head_fwd(const llc_head_args* a, void* stream) {
+  HeadK k;
+  if (int rc = to_k(a, &k, "llc_head_fwd")) return rc;
+  const size_t smem = (size_t)(a->D + a->E + a->C + 32) * sizeof(float);
+  LLC_REQUIRE(smem <= 200 * 1024, "llc_head_fwd: D+E+C too large for one CTA");
+  if (smem > 48 * 1024)
+    LLC_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  head_fwd_kernel<<<a->N, kThreads, smem, (cudaStream_t)stream>>>(k);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("head_fwd_kernel");
+  return 0;
+}
+
+extern "C" int llc_head_bwd(const llc_head_args* a, const float* d_probs, float loss_scale,
+                            float* dx, int ld_dx, void* stream) {
+  HeadK k;
+  if (int rc = to_k(a, &k, "llc_head_bwd")) return rc;
+  LLC_REQUIRE(dx && ld_dx >= a->D, "llc_head_bwd: bad dx");
+  LLC_REQUIRE(d_probs || a->labels, "llc_head_bwd: need d_probs or labels");
+  const size_t smem = (size_t)(a->C + 2 * a->E + 2 * a->D + 32) * sizeof(float);
+  LLC_REQUIRE(smem <= 200 * 1024, "llc_head_bwd: sizes too large for one CTA");
+  if (smem > 48 * 1024)
+    LLC_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  head_bwd_kernel<<<a->N, kThreads, smem, (cudaStream_t)stream>>>(k, d_probs, loss_scale, dx,
+                                                                  ld_dx);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("head_bwd_kernel");
+  return 0;
+}
+
+extern "C" int llc_label_remap(const int64_t* y_global, const int64_t* lut, int lut_size,
+                               int64_t* y_local, int n, void* stream) {
+  LLC_REQUIRE(y_global && lut && y_local && n >= 0 && lut_size > 0, "llc_label_remap: bad args");
+  if (n == 0) return 0;
+  label_remap_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y_global, lut, lut_size,
+                                                                        y_local, n);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("label_remap_kernel");
+  return 0;
+}
+
+extern "C" int llc_loss_acc(const float* loss_rows, const int64_t* pred, const int64_t* labels,
+                            int n, float* out2, void* stream) {
+  LLC_REQUIRE(loss_rows && pred && labels && out2 && n > 0, "llc_loss_acc: bad args");
+  loss_acc_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(loss_rows, pred, labels, n, out2);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("loss_acc_kernel");
+  return 0;
+}

@@ -1,0 +1,599 @@
+// HBM-bound row-wise kernels of the ViT block: LayerNorm forward/backward (with the LoRA rank-r
+// side products folded in), patch im2col, class-token/pos-emb/ln_pre assembly, LoRA side
+// reductions, weight packing and the fused AdamW on the flat LoRA buffer.
+// All are one-warp-per-row, 16-byte vectorised, shuffle-reduced; no shared-memory round trips
+// except where a [C, r] factor is reused by every row.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default, reference models/clip/model.py:194-200
+constexpr int kMaxR = 8;
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: y = (x-mean)*rstd*g + b -> bf16; optional u = y . A^T appended at column D.
+// NV = D/128 float4 per lane.
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, int T, __nv_bfloat16* __restrict__ y, int ld_y,
+              const float* __restrict__ lora_A, int r) {
+  constexpr int D = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= T) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld_x);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + kLnEps);
+  float u[kMaxR];
+#pragma unroll
+  for (int j = 0; j < kMaxR; ++j) u[j] = 0.f;
+  uint2* yr = reinterpret_cast<uint2*>(y + (size_t)row * ld_y);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 o;
+    o.x = v[i].x * rstd * g.x + b.x;
+    o.y = v[i].y * rstd * g.y + b.y;
+    o.z = v[i].z * rstd * g.z + b.z;
+    o.w = v[i].w * rstd * g.w + b.w;
+    yr[c4] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    if (lora_A != nullptr) {
+#pragma unroll
+      for (int j = 0; j < kMaxR; ++j) {
+        if (j < r) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(lora_A + (size_t)j * D) + c4);
+          u[j] += o.x * a.x + o.y * a.y + o.z * a.z + o.w * a.w;
+        }
+      }
+    }
+  }
+  if (lora_A != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j) u[j] = warp_sum(u[j]);
+    if (lane < LLC_LORA_PAD / 2) {
+      // lane l writes padded columns 2l, 2l+1
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxR; ++j) {
+        if (j == 2 * lane && j < r) a = u[j];
+        if (j == 2 * lane + 1 && j < r) b = u[j];
+      }
+      reinterpret_cast<uint32_t*>(y + (size_t)row * ld_y + D)[lane] = pack_bf16(a, b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward w.r.t. the input only (affine parameters are frozen):
+//   xh = (x-mean)*rstd, g = dy*gamma, dx = rstd*(g - mean(g) - xh*mean(g*xh))
+// out = dx_in + dx -> fp32 (+ bf16 copy, + du = scale * out . B appended at column D of the copy)
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
+              const __nv_bfloat16* __restrict__ dy, int ld_dy, const float* dx_in, float* dx_out,
+              int T, __nv_bfloat16* __restrict__ dxb, int ld_dxb,
+              const float* __restrict__ lora_B, int r, float scale) {
+  constexpr int D = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= T) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld_x);
+  const uint2* dyr = reinterpret_cast<const uint2*>(dy + (size_t)row * ld_dy);
+  float4 v[NV], g[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + kLnEps);
+  float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const uint2 d = dyr[c4];
+    const float2 d01 = unpack_bf16(d.x), d23 = unpack_bf16(d.y);
+    v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xh
+    g[i].x = d01.x * gm.x; g[i].y = d01.y * gm.y; g[i].z = d23.x * gm.z; g[i].w = d23.y * gm.w;
+    c1 += g[i].x + g[i].y + g[i].z + g[i].w;
+    c2 += g[i].x * v[i].x + g[i].y * v[i].y + g[i].z * v[i].z + g[i].w * v[i].w;
+  }
+  c1 = warp_sum(c1) * (1.0f / D);
+  c2 = warp_sum(c2) * (1.0f / D);
+  float du[kMaxR];
+#pragma unroll
+  for (int j = 0; j < kMaxR; ++j) du[j] = 0.f;
+  const float4* dir = dx_in ? reinterpret_cast<const float4*>(dx_in + (size_t)row * D) : nullptr;
+  float4* dor = reinterpret_cast<float4*>(dx_out + (size_t)row * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    float4 o;
+    o.x = rstd * (g[i].x - c1 - v[i].x * c2);
+    o.y = rstd * (g[i].y - c1 - v[i].y * c2);
+    o.z = rstd * (g[i].z - c1 - v[i].z * c2);
+    o.w = rstd * (g[i].w - c1 - v[i].w * c2);
+    if (dir != nullptr) {
+      const float4 p = dir[c4];
+      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+    }
+    dor[c4] = o;
+    if (dxb != nullptr)
+      reinterpret_cast<uint2*>(dxb + (size_t)row * ld_dxb)[c4] =
+          make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    if (lora_B != nullptr) {
+      const int c = c4 * 4;
+#pragma unroll
+      for (int j = 0; j < kMaxR; ++j) {
+        if (j < r) {
+          du[j] += o.x * __ldg(lora_B + (size_t)(c + 0) * r + j) +
+                   o.y * __ldg(lora_B + (size_t)(c + 1) * r + j) +
+                   o.z * __ldg(lora_B + (size_t)(c + 2) * r + j) +
+                   o.w * __ldg(lora_B + (size_t)(c + 3) * r + j);
+        }
+      }
+    }
+  }
+  if (lora_B != nullptr && dxb != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kMaxR; ++j) du[j] = warp_sum(du[j]) * scale;
+    if (lane < LLC_LORA_PAD / 2) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxR; ++j) {
+        if (j == 2 * lane && j < r) a = du[j];
+        if (j == 2 * lane + 1 && j < r) b = du[j];
+      }
+      reinterpret_cast<uint32_t*>(dxb + (size_t)row * ld_dxb + D)[lane] = pack_bf16(a, b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LoRA side reductions over X bf16 [T, ld_x] (C columns), see llc.h.
+constexpr int kSideRows = 32;     // rows per chunk
+constexpr int kSideThreads = 256;
+constexpr int kSideMaxPairs = 8;  // column pairs per thread: C <= 2*256*8 = 4096
+
+template <int R>
+__global__ void __launch_bounds__(kSideThreads)
+lora_side_kernel(__nv_bfloat16* X, int ld_x, int T, int C, int r, const float* __restrict__ Mrd,
+                 int rd_sc, int rd_sj, float rd_scale, const __nv_bfloat16* __restrict__ w,
+                 int ld_w, float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  float* sM = sm;                         // [C][R] rowdot factor (if Mrd)
+  float* sW = sm + (Mrd ? C * R : 0);     // [kSideRows][R] colsum weights of the chunk
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (Mrd != nullptr) {
+    for (int i = tid; i < C * R; i += kSideThreads) {
+      const int c = i / R, j = i % R;
+      sM[i] = (j < r) ? Mrd[(size_t)c * rd_sc + (size_t)j * rd_sj] * rd_scale : 0.f;
+    }
+  }
+  float acc[kSideMaxPairs][2][R];
+#pragma unroll
+  for (int p = 0; p < kSideMaxPairs; ++p)
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[p][0][j] = acc[p][1][j] = 0.f;
+  __syncthreads();
+
+  const int n_chunks = (T + kSideRows - 1) / kSideRows;
+  const int n_pairs = C / 2;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int t0 = chunk * kSideRows;
+    if (w != nullptr) {
+      for (int i = tid; i < kSideRows * R; i += kSideThreads) {
+        const int t = t0 + i / R, j = i % R;
+        sW[i] = (t < T && j < r) ? __bfloat162float(w[(size_t)t * ld_w + j]) : 0.f;
+      }
+    }
+    __syncthreads();  // sW ready (also orders the previous chunk's reads)
+    if (Mrd != nullptr) {
+      // rowdot: one warp per row, lanes stride over 8-column vectors
+      for (int rr = warp; rr < kSideRows; rr += kSideThreads / 32) {
+        const int t = t0 + rr;
+        if (t >= T) break;
+        const uint4* xr = reinterpret_cast<const uint4*>(X + (size_t)t * ld_x);
+        float d[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) d[j] = 0.f;
+        for (int vi = lane; vi < C / 8; vi += 32) {
+          const uint4 pk = xr[vi];
+          const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16(pw[e]);
+            const float* m0 = sM + (vi * 8 + 2 * e) * R;
+#pragma unroll
+            for (int j = 0; j < R; ++j) d[j] += f.x * m0[j] + f.y * m0[R + j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) d[j] = warp_sum(d[j]);
+        if (lane < LLC_LORA_PAD / 2) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            if (j == 2 * lane) a = d[j];
+            if (j == 2 * lane + 1) b = d[j];
+          }
+          reinterpret_cast<uint32_t*>(X + (size_t)t * ld_x + C)[lane] = pack_bf16(a, b);
+        }
+      }
+    }
+    if (w != nullptr) {
+      // colsum: each thread owns column pairs tid + 256*p and walks the chunk's rows
+      const int rows = min(kSideRows, T - t0);
+      for (int rr = 0; rr < rows; ++rr) {
+        const uint32_t* xr = reinterpret_cast<const uint32_t*>(X + (size_t)(t0 + rr) * ld_x);
+        float wj[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) wj[j] = sW[rr * R + j];
+#pragma unroll
+        for (int p = 0; p < kSideMaxPairs; ++p) {
+          const int cp = tid + kSideThreads * p;
+          if (cp < n_pairs) {
+            const float2 f = unpack_bf16(xr[cp]);
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              acc[p][0][j] += f.x * wj[j];
+              acc[p][1][j] += f.y * wj[j];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (w != nullptr) {
+    float* out = partial + (size_t)blockIdx.x * C * R;
+#pragma unroll
+    for (int p = 0; p < kSideMaxPairs; ++p) {
+      const int cp = tid + kSideThreads * p;
+      if (cp < n_pairs) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          out[(size_t)(2 * cp) * R + j] = acc[p][0][j];
+          out[(size_t)(2 * cp + 1) * R + j] = acc[p][1][j];
+        }
+      }
+    }
+  }
+}
+
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int n_partials, int C,
+                                     int R, int r, float scale, float* __restrict__ out, int o_sc,
+                                     int o_sj) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * R) return;
+  const int c = i / R, j = i % R;
+  if (j >= r) return;
+  float s = 0.f;
+  for (int p = 0; p < n_partials; ++p) s += partial[(size_t)p * C * R + i];
+  out[(size_t)c * o_sc + (size_t)j * o_sj] = s * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ src, int rows, int cols,
+                                   int transpose, __nv_bfloat16* __restrict__ dst, int ld_dst) {
+  // dst[i, j], i < rows, j < cols; src is [rows, cols] or (transpose) [cols, rows]
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (!transpose) {
+    for (int k = ty; k < 32; k += 8) {
+      const int i = bi + k, j = bj + tx;
+      if (i < rows && j < cols)
+        dst[(size_t)i * ld_dst + j] = __float2bfloat16_rn(src[(size_t)i * cols + j]);
+    }
+  } else {
+    for (int k = ty; k < 32; k += 8) {
+      const int j = bj + k, i = bi + tx;  // read src[j, i] coalesced along i
+      if (i < rows && j < cols) tile[k][tx] = src[(size_t)j * rows + i];
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+      const int i = bi + k, j = bj + tx;
+      if (i < rows && j < cols) dst[(size_t)i * ld_dst + j] = __float2bfloat16_rn(tile[tx][k]);
+    }
+  }
+}
+
+__global__ void pack_lora_cols_kernel(const float* __restrict__ src, int rows, int r, int s_i,
+                                      int s_j, float scale, __nv_bfloat16* __restrict__ dst,
+                                      int ld_dst, int col0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * LLC_LORA_PAD) return;
+  const int i = idx / LLC_LORA_PAD, j = idx % LLC_LORA_PAD;
+  const float v = (j < r) ? scale * src[(size_t)i * s_i + (size_t)j * s_j] : 0.f;
+  dst[(size_t)i * ld_dst + col0 + j] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col of the stride-P patch conv: out[(n*G+py)*G+px, c*P*P + i*P + j] = img[n,c,py*P+i,px*P+j]
+// (two pixels per thread: P is even, so a pair never straddles a patch). Columns
+// [C*P*P, ld_out) are zero so that K can be padded to a multiple of 16 (ViT-L/14: 588 -> 592).
+__global__ void patchify_kernel(const float* __restrict__ img, int N, int C, int HW, int P,
+                                __nv_bfloat16* __restrict__ out, int ld_out) {
+  const int G = HW / P;
+  const size_t total = (size_t)N * C * HW * (HW / 2);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int x2 = (int)(idx % (HW / 2));
+    size_t rest = idx / (HW / 2);
+    const int yy = (int)(rest % HW); rest /= HW;
+    const int c = (int)(rest % C);
+    const int n = (int)(rest / C);
+    const float2 v = reinterpret_cast<const float2*>(img)[idx];
+    const int xx = x2 * 2;
+    const int px = xx / P, j = xx % P;
+    const int py = yy / P, i = yy % P;
+    const size_t row = ((size_t)n * G + py) * G + px;
+    const int col = c * P * P + i * P + j;
+    *reinterpret_cast<uint32_t*>(out + row * ld_out + col) = pack_bf16(v.x, v.y);
+  }
+  const int K = C * P * P, pad = ld_out - K;
+  if (pad > 0) {
+    const size_t rows = (size_t)N * G * G;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < rows * pad;
+         idx += (size_t)gridDim.x * blockDim.x)
+      out[(idx / pad) * ld_out + K + (idx % pad)] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// class token + positional embedding + ln_pre (reference model.py:759-766)
+template <int NV>
+__global__ void __launch_bounds__(256)
+embed_ln_pre_kernel(const float* __restrict__ patch_out, int ld_p, const float* __restrict__ cls,
+                    const float* __restrict__ pos, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int N, int L, float* __restrict__ x0) {
+  constexpr int D = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= N * L) return;
+  const int n = row / L, l = row % L;
+  const float4* src = (l == 0) ? reinterpret_cast<const float4*>(cls)
+                               : reinterpret_cast<const float4*>(
+                                     patch_out + ((size_t)n * (L - 1) + (l - 1)) * ld_p);
+  const float4* pr = reinterpret_cast<const float4*>(pos + (size_t)l * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = src[lane + 32 * i], p = __ldg(pr + lane + 32 * i);
+    v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + kLnEps);
+  float4* o = reinterpret_cast<float4*>(x0 + (size_t)row * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    o[c4] = make_float4(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y,
+                        v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+  }
+}
+
+// torch.optim.AdamW single-tensor update (decoupled weight decay), reference
+// utils/train_utils.py:27-28; g is multiplied by grad_scale first (1/world, GradScaler unscale)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                             float* __restrict__ m, float* __restrict__ v, int n, float lr,
+                             float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                             float grad_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  float pi = p[i] * (1.0f - lr * wd);
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi -= (lr / bc1) * (mi / denom);
+  p[i] = pi;
+}
+
+#define DISPATCH_NV(D, CALL)                                                      \
+  switch ((D) / 128) {                                                            \
+    case 4: { constexpr int NV = 4; CALL; } break;                                \
+    case 5: { constexpr int NV = 5; CALL; } break;                                \
+    case 6: { constexpr int NV = 6; CALL; } break;                                \
+    case 8: { constexpr int NV = 8; CALL; } break;                                \
+    case 10: { constexpr int NV = 10; CALL; } break;                              \
+    default:                                                                      \
+      llc_set_error("LayerNorm width %d unsupported (need 512/640/768/1024/1280)", (D)); \
+      return LLC_ERR_ARG;                                                         \
+  }
+
+}  // namespace
+
+extern "C" int llc_ln_fwd(const float* x, int ld_x, const float* gamma, const float* beta, int T,
+                          int D, void* y, int ld_y, const float* lora_A, int r, void* stream) {
+  LLC_REQUIRE(x && gamma && beta && y, "llc_ln_fwd: null pointer");
+  LLC_REQUIRE(T >= 0 && D % 128 == 0 && ld_x % 4 == 0 && ld_y % 8 == 0, "llc_ln_fwd: bad shape");
+  LLC_REQUIRE(lora_A == nullptr || (r >= 1 && r <= kMaxR && ld_y >= D + LLC_LORA_PAD),
+              "llc_ln_fwd: LoRA rank %d unsupported or ld_y too small", r);
+  if (T == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_NV(D, (ln_fwd_kernel<NV><<<(T + 7) / 8, 256, 0, st>>>(
+                     x, ld_x, gamma, beta, T, (__nv_bfloat16*)y, ld_y, lora_A, r)));
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("ln_fwd_kernel");
+  return 0;
+}
+
+extern "C" int llc_ln_bwd(const float* x, int ld_x, const float* gamma, const void* dy, int ld_dy,
+                          const float* dx_in, float* dx_out, int T, int D, void* dxb, int ld_dxb,
+                          const float* lora_B, int r, float scale, void* stream) {
+  LLC_REQUIRE(x && gamma && dy && dx_out, "llc_ln_bwd: null pointer");
+  LLC_REQUIRE(T >= 0 && D % 128 == 0 && ld_x % 4 == 0 && ld_dy % 4 == 0, "llc_ln_bwd: bad shape");
+  LLC_REQUIRE(dxb == nullptr || ld_dxb % 8 == 0, "llc_ln_bwd: ld_dxb %% 8");
+  LLC_REQUIRE(lora_B == nullptr || (r >= 1 && r <= kMaxR && dxb && ld_dxb >= D + LLC_LORA_PAD),
+              "llc_ln_bwd: LoRA rank %d unsupported or no room for du", r);
+  if (T == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_NV(D, (ln_bwd_kernel<NV><<<(T + 7) / 8, 256, 0, st>>>(
+                     x, ld_x, gamma, (const __nv_bfloat16*)dy, ld_dy, dx_in, dx_out, T,
+                     (__nv_bfloat16*)dxb, ld_dxb, lora_B, r, scale)));
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("ln_bwd_kernel");
+  return 0;
+}
+
+extern "C" int llc_lora_side_max_partials(void) { return 2 * llc_num_sms(); }
+
+extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float* Mrd, int rd_sc,
+                             int rd_sj, float rd_scale, const void* w, int ld_w, float* partial,
+                             int* n_partials, void* stream) {
+  LLC_REQUIRE(X && T > 0 && C > 0, "llc_lora_side: empty input");
+  LLC_REQUIRE(C % 8 == 0 && ld_x % 8 == 0 && C <= 2 * kSideThreads * kSideMaxPairs,
+              "llc_lora_side: C=%d unsupported", C);
+  LLC_REQUIRE(r >= 1 && r <= kMaxR, "llc_lora_side: rank %d unsupported", r);
+  LLC_REQUIRE(Mrd == nullptr || ld_x >= C + LLC_LORA_PAD, "llc_lora_side: no room for rowdot");
+  LLC_REQUIRE(w == nullptr || (partial && n_partials), "llc_lora_side: colsum needs partial");
+  const int R = r <= 4 ? 4 : 8;
+  const int chunks = (T + kSideRows - 1) / kSideRows;
+  const int grid = chunks < llc_lora_side_max_partials() ? chunks : llc_lora_side_max_partials();
+  const size_t smem = ((Mrd ? (size_t)C * R : 0) + (size_t)kSideRows * R) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R == 4) {
+    static bool cfg4 = false;
+    if (!cfg4) {
+      LLC_CUDA(cudaFuncSetAttribute(lora_side_kernel<4>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      cfg4 = true;
+    }
+    lora_side_kernel<4><<<grid, kSideThreads, smem, st>>>(
+        (__nv_bfloat16*)X, ld_x, T, C, r, Mrd, rd_sc, rd_sj, rd_scale, (const __nv_bfloat16*)w,
+        ld_w, partial);
+  } else {
+    static bool cfg8 = false;
+    if (!cfg8) {
+      LLC_CUDA(cudaFuncSetAttribute(lora_side_kernel<8>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      cfg8 = true;
+    }
+    lora_side_kernel<8><<<grid, kSideThreads, smem, st>>>(
+        (__nv_bfloat16*)X, ld_x, T, C, r, Mrd, rd_sc, rd_sj, rd_scale, (const __nv_bfloat16*)w,
+        ld_w, partial);
+  }
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("lora_side_kernel");
+  if (n_partials) *n_partials = grid;
+  return 0;
+}
+
+extern "C" int llc_lora_colsum_finish(const float* partial, int n_partials, int C, int r,
+                                      float cs_scale, float* out, int o_sc, int o_sj,
+                                      void* stream) {
+  LLC_REQUIRE(partial && out && n_partials > 0 && r >= 1 && r <= kMaxR,
+              "llc_lora_colsum_finish: bad args");
+  const int R = r <= 4 ? 4 : 8;
+  colsum_finish_kernel<<<(C * R + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      partial, n_partials, C, R, r, cs_scale, out, o_sc, o_sj);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("colsum_finish_kernel");
+  return 0;
+}
+
+extern "C" int llc_pack_weight(const float* src, int rows, int cols, int transpose, void* dst,
+                               int ld_dst, void* stream) {
+  LLC_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_dst >= cols, "llc_pack_weight: bad args");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  pack_weight_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, rows, cols, transpose,
+                                                               (__nv_bfloat16*)dst, ld_dst);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("pack_weight_kernel");
+  return 0;
+}
+
+extern "C" int llc_pack_lora_cols(const float* src, int rows, int r, int s_i, int s_j, float scale,
+                                  void* dst, int ld_dst, int col0, void* stream) {
+  LLC_REQUIRE(src && dst && rows > 0 && r >= 1 && r <= LLC_LORA_PAD &&
+                  ld_dst >= col0 + LLC_LORA_PAD,
+              "llc_pack_lora_cols: bad args");
+  const int n = rows * LLC_LORA_PAD;
+  pack_lora_cols_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      src, rows, r, s_i, s_j, scale, (__nv_bfloat16*)dst, ld_dst, col0);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("pack_lora_cols_kernel");
+  return 0;
+}
+
+extern "C" int llc_patchify(const float* img, int N, int C, int HW, int P, void* out, int ld_out,
+                            void* stream) {
+  LLC_REQUIRE(img && out && N > 0, "llc_patchify: bad args");
+  LLC_REQUIRE(P % 2 == 0 && HW % P == 0 && ld_out % 2 == 0 && ld_out >= C * P * P,
+              "llc_patchify: image %d / patch %d unsupported", HW, P);
+  const size_t total = (size_t)N * C * HW * (HW / 2);
+  const int grid = (int)((total + 255) / 256 < (size_t)(llc_num_sms() * 16)
+                             ? (total + 255) / 256
+                             : (size_t)(llc_num_sms() * 16));
+  patchify_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, C, HW, P, (__nv_bfloat16*)out,
+                                                          ld_out);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("patchify_kernel");
+  return 0;
+}
+
+extern "C" int llc_embed_ln_pre(const float* patch_out, int ld_p, const float* class_emb,
+                                const float* pos, const float* gamma, const float* beta, int N,
+                                int L, int D, float* x0, void* stream) {
+  LLC_REQUIRE(patch_out && class_emb && pos && gamma && beta && x0 && N > 0 && L > 1,
+              "llc_embed_ln_pre: bad args");
+  LLC_REQUIRE(D % 128 == 0 && ld_p % 4 == 0, "llc_embed_ln_pre: bad shape");
+  const int T = N * L;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_NV(D, (embed_ln_pre_kernel<NV><<<(T + 7) / 8, 256, 0, st>>>(
+                     patch_out, ld_p, class_emb, pos, gamma, beta, N, L, x0)));
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("embed_ln_pre_kernel");
+  return 0;
+}
+
+extern "C" int llc_adamw(float* p, const float* g, float* m, float* v, int n, float lr, float beta1,
+                         float beta2, float eps, float wd, int step, float grad_scale,
+                         void* stream) {
+  LLC_REQUIRE(p && g && m && v && n > 0 && step >= 1, "llc_adamw: bad args");
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  adamw_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2,
+                                                                  eps, wd, bc1, bc2_sqrt,
+                                                                  grad_scale);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("adamw_kernel");
+  return 0;
+}

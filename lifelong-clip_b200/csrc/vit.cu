@@ -1,0 +1,300 @@
+// Host-side orchestration of the image tower: the launch sequence of one
+// ResidualAttentionBlock_LoRA (reference models/clip/model.py:233-236,400-415 ->
+// models/clip/lora.py:825-840,950,1002-1074) forward and backward, and of the whole
+// VisualTransformer.forward (model.py:755-787). Pure launch code: every tensor lives in a caller
+// owned arena whose layout is defined here, so one C call replaces ~100 Python-dispatched ops and
+// the sequence is CUDA-graph capturable.
+#include "common.cuh"
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
+
+struct Dims {
+  int N, L, T, D, H, M, E, G, P, PK /* padded 3*P*P */, r, layers;
+};
+
+Dims make_dims(const llc_vit_cfg* c, int N) {
+  Dims d;
+  d.N = N;
+  d.G = c->image_size / c->patch;
+  d.L = d.G * d.G + 1;
+  d.T = N * d.L;
+  d.D = c->width;
+  d.H = c->heads;
+  d.M = c->mlp_dim;
+  d.E = c->embed_dim;
+  d.P = c->patch;
+  d.PK = (3 * c->patch * c->patch + 15) / 16 * 16;
+  d.r = c->lora_r;
+  d.layers = c->layers;
+  return d;
+}
+
+// Arena layout. Training keeps one activation set per layer (saved for backward); inference
+// reuses a single set.
+struct Arena {
+  size_t patches, patch_out, x /*[layers+1]*/, x_stride;
+  size_t h1, qkv, lse, o, x_mid, z, layer_stride;  // per-layer block (training) or shared
+  size_t h2, g;
+  size_t dxb, dz, dh, d_o, dqkv, partial;  // backward scratch
+  size_t total;
+};
+
+Arena plan(const Dims& d, int training) {
+  Arena a;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const size_t T = d.T;
+  a.patches = take((size_t)d.N * d.G * d.G * d.PK * 2);
+  a.patch_out = take((size_t)d.N * d.G * d.G * d.D * 4);
+  a.x_stride = align_up(T * d.D * 4);
+  a.x = take(a.x_stride * (training ? d.layers + 1 : 2));
+  const size_t l0 = off;
+  a.h1 = take(T * (d.D + LLC_LORA_PAD) * 2);
+  a.qkv = take(T * (3 * d.D + LLC_LORA_PAD) * 2);
+  a.lse = take((size_t)d.N * d.H * d.L * 4);
+  a.o = take(T * (d.D + LLC_LORA_PAD) * 2);
+  a.x_mid = take(T * d.D * 4);
+  a.z = take(T * d.M * 2);
+  a.layer_stride = off - l0;
+  if (training) off = l0 + a.layer_stride * d.layers;
+  a.h2 = take(T * d.D * 2);
+  a.g = take(T * d.M * 2);
+  if (training) {
+    a.dxb = take(T * (d.D + LLC_LORA_PAD) * 2);
+    a.dz = take(T * d.M * 2);
+    a.dh = take(T * d.D * 2);
+    a.d_o = take(T * d.D * 2);
+    a.dqkv = take(T * (3 * d.D + LLC_LORA_PAD) * 2);
+    a.partial = take((size_t)llc_lora_side_max_partials() * 3 * d.D * 8 * 4);
+  } else {
+    a.dxb = a.dz = a.dh = a.d_o = a.dqkv = a.partial = 0;
+  }
+  a.total = off;
+  return a;
+}
+
+int check_cfg(const llc_vit_cfg* c, const char* who) {
+  LLC_REQUIRE(c, "%s: null cfg", who);
+  LLC_REQUIRE(c->width % 128 == 0 && c->heads * 64 == c->width,
+              "%s: width %d / heads %d unsupported (head dim must be 64)", who, c->width, c->heads);
+  LLC_REQUIRE(c->patch % 2 == 0 && c->image_size % c->patch == 0, "%s: bad patch geometry", who);
+  LLC_REQUIRE(c->mlp_dim % 8 == 0 && c->layers > 0 && c->embed_dim > 0, "%s: bad dims", who);
+  LLC_REQUIRE(c->lora_r >= 1 && c->lora_r <= 8, "%s: LoRA rank %d unsupported (1..8)", who,
+              c->lora_r);
+  return 0;
+}
+
+void fill_bufs(const Dims& d, const Arena& a, uint8_t* base, int layer, int training,
+               llc_block_bufs* b) {
+  const size_t lo = training ? a.layer_stride * layer : 0;
+  const int xi = training ? layer : (layer & 1);
+  const int xo = training ? layer + 1 : ((layer + 1) & 1);
+  b->x_in = reinterpret_cast<float*>(base + a.x + a.x_stride * xi);
+  b->x_out = reinterpret_cast<float*>(base + a.x + a.x_stride * xo);
+  b->h1 = base + a.h1 + lo;
+  b->qkv = base + a.qkv + lo;
+  b->lse = reinterpret_cast<float*>(base + a.lse + lo);
+  b->o = base + a.o + lo;
+  b->x_mid = reinterpret_cast<float*>(base + a.x_mid + lo);
+  b->z = training ? base + a.z + lo : nullptr;
+  b->h2 = base + a.h2;
+  b->g = base + a.g;
+  (void)d;
+}
+
+#define RUN(call)            \
+  do {                       \
+    int _rc = (call);        \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+}  // namespace
+
+extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                                 const llc_block_bufs* b, int N, int L, int sn, int sl, int causal,
+                                 void* stream) {
+  RUN(check_cfg(cfg, "llc_block_forward"));
+  LLC_REQUIRE(w && b && N > 0 && L > 0, "llc_block_forward: bad args");
+  const int D = cfg->width, M = cfg->mlp_dim, H = cfg->heads, r = cfg->lora_r;
+  const int T = N * L, DA = D + LLC_LORA_PAD, QA = 3 * D + LLC_LORA_PAD;
+  llc_gemm_epi e;
+  // x -> ln_1 -> h1 | u = h1 A_in^T
+  RUN(llc_ln_fwd(b->x_in, D, w->ln1_g, w->ln1_b, T, D, b->h1, DA, w->in_A, r, stream));
+  // qkv = h1 W_in^T + b_in + s (h1 A^T) B^T   (one accumulator, K = D + 16)
+  e = llc_gemm_epi{};
+  e.bias = w->bqkv; e.out = b->qkv; e.ld_out = QA;
+  RUN(llc_gemm_bf16_tn(b->h1, DA, w->wqkv_aug, DA, T, 3 * D, DA, &e, stream));
+  RUN(llc_attn_fwd(b->qkv, QA, b->o, DA, b->lse, N, L, H, sn, sl, causal, stream));
+  // u_o = o A_o^T into o's pad columns
+  RUN(llc_lora_side(b->o, DA, T, D, r, w->out_A, 1, D, 1.0f, nullptr, 0, nullptr, nullptr,
+                    stream));
+  // x_mid = x + o W_o^T + b_o + s (o A_o^T) B_o^T
+  e = llc_gemm_epi{};
+  e.bias = w->bo; e.resid = b->x_in; e.ld_resid = D; e.out = b->x_mid; e.ld_out = D;
+  e.out_fp32 = 1;
+  RUN(llc_gemm_bf16_tn(b->o, DA, w->wo_aug, DA, T, D, DA, &e, stream));
+  // mlp
+  RUN(llc_ln_fwd(b->x_mid, D, w->ln2_g, w->ln2_b, T, D, b->h2, D, nullptr, 0, stream));
+  e = llc_gemm_epi{};
+  e.bias = w->bfc; e.act = 1; e.out = b->z; e.ld_out = M; e.out2 = b->g; e.ld_out2 = M;
+  RUN(llc_gemm_bf16_tn(b->h2, D, w->wfc, D, T, M, D, &e, stream));
+  e = llc_gemm_epi{};
+  e.bias = w->bproj; e.resid = b->x_mid; e.ld_resid = D; e.out = b->x_out; e.ld_out = D;
+  e.out_fp32 = 1;
+  RUN(llc_gemm_bf16_tn(b->g, M, w->wproj, M, T, D, M, &e, stream));
+  return 0;
+}
+
+extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                                  const llc_block_bufs* b, const llc_block_bwd_bufs* s, int N,
+                                  int L, int sn, int sl, int causal, int need_dx_in,
+                                  void* stream) {
+  RUN(check_cfg(cfg, "llc_block_backward"));
+  LLC_REQUIRE(w && b && s && N > 0 && L > 0, "llc_block_backward: bad args");
+  LLC_REQUIRE(b->z, "llc_block_backward: forward was not run in training mode");
+  const int D = cfg->width, M = cfg->mlp_dim, H = cfg->heads, r = cfg->lora_r;
+  const float sc = cfg->lora_scale;
+  const int T = N * L, DA = D + LLC_LORA_PAD, QA = 3 * D + LLC_LORA_PAD;
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(s->dxb);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(b->o);
+  __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(b->h1);
+  __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(s->dqkv);
+  int np = 0;
+  llc_gemm_epi e;
+  // dz = (dx W_proj) o QuickGELU'(z)
+  e = llc_gemm_epi{};
+  e.act = 2; e.aux = b->z; e.ld_aux = M; e.out = s->dz; e.ld_out = M;
+  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->wprojT, D, T, M, D, &e, stream));
+  // dh2 = dz W_fc
+  e = llc_gemm_epi{};
+  e.out = s->dh; e.ld_out = D;
+  RUN(llc_gemm_bf16_tn(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
+  // dx_mid = dx + LN2'(dh2); bf16 copy | du_o = s dx_mid B_o
+  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, w->out_B, r, sc,
+                 stream));
+  // out-proj LoRA grads: dB_o = s dx_mid^T u_o ; dA_o = du_o^T o
+  RUN(llc_lora_side(s->dxb, DA, T, D, r, nullptr, 0, 0, 0.f, o + D, DA, s->partial, &np, stream));
+  RUN(llc_lora_colsum_finish(s->partial, np, D, r, sc, w->g_out_B, r, 1, stream));
+  RUN(llc_lora_side(b->o, DA, T, D, r, nullptr, 0, 0, 0.f, dxb + D, DA, s->partial, &np, stream));
+  RUN(llc_lora_colsum_finish(s->partial, np, D, r, 1.0f, w->g_out_A, 1, D, stream));
+  // d_o = dx_mid W_o + du_o A_o
+  e = llc_gemm_epi{};
+  e.out = s->d_o; e.ld_out = D;
+  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->woT_aug, DA, T, D, DA, &e, stream));
+  RUN(llc_attn_bwd(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
+                   stream));
+  // in-proj LoRA grads: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
+  RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, w->in_B, r, 1, sc, h1 + D, DA, s->partial, &np,
+                    stream));
+  RUN(llc_lora_colsum_finish(s->partial, np, 3 * D, r, sc, w->g_in_B, r, 1, stream));
+  RUN(llc_lora_side(b->h1, DA, T, D, r, nullptr, 0, 0, 0.f, dqkv + 3 * D, QA, s->partial, &np,
+                    stream));
+  RUN(llc_lora_colsum_finish(s->partial, np, D, r, 1.0f, w->g_in_A, 1, D, stream));
+  if (need_dx_in) {
+    // dh1 = dqkv W_in + du A_in ; dx_in = dx_mid + LN1'(dh1)
+    e = llc_gemm_epi{};
+    e.out = s->dh; e.ld_out = D;
+    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->wqkvT_aug, QA, T, D, QA, &e, stream));
+    RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
+                   stream));
+  }
+  return 0;
+}
+
+extern "C" size_t llc_vit_arena_bytes(const llc_vit_cfg* cfg, int N, int training) {
+  if (check_cfg(cfg, "llc_vit_arena_bytes") != 0 || N <= 0) return 0;
+  return plan(make_dims(cfg, N), training).total;
+}
+
+extern "C" int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weights* w,
+                                    void* stream) {
+  RUN(check_cfg(cfg, "llc_vit_refresh_lora"));
+  LLC_REQUIRE(w && w->layers, "llc_vit_refresh_lora: null weights");
+  const int D = cfg->width, r = cfg->lora_r;
+  const int DA = D + LLC_LORA_PAD, QA = 3 * D + LLC_LORA_PAD;
+  const float sc = cfg->lora_scale;
+  for (int l = 0; l < cfg->layers; ++l) {
+    const llc_vit_layer* y = &w->layers[l];
+    // forward: [W_in | s B_in], [W_o | s B_o]; backward: [W_in^T | A_in^T], [W_o^T | A_o^T]
+    RUN(llc_pack_lora_cols(y->in_B, 3 * D, r, r, 1, sc, y->wqkv_aug, DA, D, stream));
+    RUN(llc_pack_lora_cols(y->out_B, D, r, r, 1, sc, y->wo_aug, DA, D, stream));
+    RUN(llc_pack_lora_cols(y->in_A, D, r, 1, D, 1.0f, y->wqkvT_aug, QA, 3 * D, stream));
+    RUN(llc_pack_lora_cols(y->out_A, D, r, 1, D, 1.0f, y->woT_aug, DA, D, stream));
+  }
+  return 0;
+}
+
+extern "C" int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w,
+                               const float* images, int N, void* arena, int training,
+                               float** x_final, void* stream) {
+  RUN(check_cfg(cfg, "llc_vit_forward"));
+  LLC_REQUIRE(w && w->layers && images && arena && N > 0, "llc_vit_forward: bad args");
+  const Dims d = make_dims(cfg, N);
+  const Arena a = plan(d, training);
+  uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  // patch embedding: im2col -> GEMM -> class token, positional embedding, ln_pre
+  RUN(llc_patchify(images, N, 3, cfg->image_size, cfg->patch, base + a.patches, d.PK, stream));
+  llc_gemm_epi e{};
+  e.out = base + a.patch_out; e.ld_out = d.D; e.out_fp32 = 1;
+  RUN(llc_gemm_bf16_tn(base + a.patches, d.PK, w->wpatch, d.PK, N * d.G * d.G, d.D, d.PK, &e,
+                       stream));
+  float* x0 = reinterpret_cast<float*>(base + a.x);
+  RUN(llc_embed_ln_pre(reinterpret_cast<float*>(base + a.patch_out), d.D, w->class_emb, w->pos_emb,
+                       w->ln_pre_g, w->ln_pre_b, N, d.L, d.D, x0, stream));
+  llc_block_bufs b;
+  for (int l = 0; l < d.layers; ++l) {
+    fill_bufs(d, a, base, l, training, &b);
+    RUN(llc_block_forward(cfg, &w->layers[l], &b, N, d.L, d.L, 1, 0, stream));
+  }
+  if (x_final) *x_final = b.x_out;
+  return 0;
+}
+
+__global__ void cast_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                      int T, int D, int ld_dst) {
+  const int per_row = D / 4;
+  const size_t total = (size_t)T * per_row;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / per_row;
+    const int c4 = (int)(i % per_row);
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    *reinterpret_cast<uint2*>(dst + row * ld_dst + c4 * 4) =
+        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N,
+                                void* arena, float* dx_final, void* stream) {
+  RUN(check_cfg(cfg, "llc_vit_backward"));
+  LLC_REQUIRE(w && w->layers && arena && dx_final && N > 0, "llc_vit_backward: bad args");
+  const Dims d = make_dims(cfg, N);
+  const Arena a = plan(d, 1);
+  uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  llc_block_bwd_bufs s;
+  s.dx = dx_final;
+  s.dxb = base + a.dxb;
+  s.dz = base + a.dz;
+  s.dh = base + a.dh;
+  s.d_o = base + a.d_o;
+  s.dqkv = base + a.dqkv;
+  s.partial = reinterpret_cast<float*>(base + a.partial);
+  {
+    const size_t total = (size_t)d.T * d.D / 4;
+    const int grid = (int)((total + 255) / 256 < (size_t)llc_num_sms() * 8
+                               ? (total + 255) / 256
+                               : (size_t)llc_num_sms() * 8);
+    cast_rows_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        dx_final, reinterpret_cast<__nv_bfloat16*>(s.dxb), d.T, d.D, d.D + LLC_LORA_PAD);
+    LLC_COUNT_LAUNCH();
+    LLC_LAUNCH_CHECK("cast_rows_bf16_kernel");
+  }
+  llc_block_bufs b;
+  for (int l = d.layers - 1; l >= 0; --l) {
+    fill_bufs(d, a, base, l, 1, &b);
+    RUN(llc_block_backward(cfg, &w->layers[l], &b, &s, N, d.L, d.L, 1, 0, l > 0, stream));
+  }
+  return 0;
+}

@@ -1,0 +1,282 @@
+"""ORACLE — test infrastructure only. Never imported by the product path (lifelong_clip_b200/*).
+
+CPU restatement of the reference's online-step hot path (qcNPU/LifeLong-CLIP, paths relative to
+the reference root): CLIP ViT image tower with LoRA on the attention projections + cosine-logit
+head + the reference's loss. Written as plain tensor math (no nn.Module from the reference), so it
+is dtype-generic: run it in float64 for a truth value or float32 to mirror the reference.
+Gradients come from torch autograd over this restatement.
+
+Pinning: tests/test_oracle_golden.py checks this file against tests/golden/*.npz, which were
+produced by tests/golden/make_golden.py from the reference's OWN classes (models/clip/model.py,
+models/clip/lora.py imported from /root/reference). The reference ships no tests or golden vectors
+of its own, so executing its classes is the only pin there is.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+@dataclass(frozen=True)
+class VitCfg:
+    image_size: int = 224
+    patch: int = 16
+    width: int = 768
+    layers: int = 12
+    heads: int = 12
+    embed_dim: int = 512
+    lora_r: int = 4          # models/adapter_clip.py:24-30 (hard-coded r=4, alpha=1)
+    lora_alpha: float = 1.0
+
+    @property
+    def mlp_dim(self) -> int:  # model.py:219-222: c_fc is d_model -> 4*d_model
+        return 4 * self.width
+
+    @property
+    def grid(self) -> int:
+        return self.image_size // self.patch
+
+    @property
+    def tokens(self) -> int:  # model.py:717-718: grid**2 + 1
+        return self.grid ** 2 + 1
+
+    @property
+    def lora_scale(self) -> float:  # lora.py:401 scaling = alpha / r
+        return self.lora_alpha / self.lora_r
+
+
+VIT_B16 = VitCfg()
+VIT_L14 = VitCfg(image_size=224, patch=14, width=1024, layers=24, heads=16, embed_dim=768)
+VIT_TINY = VitCfg(image_size=32, patch=8, width=128, layers=2, heads=2, embed_dim=64)
+
+
+def param_shapes(cfg: VitCfg) -> dict[str, tuple[int, ...]]:
+    """Vision-tower parameter names/shapes exactly as the reference's state_dict has them
+    (model.py:709-729 VisualTransformer, :209-222 block, lora.py:419-435 LoRA tensors)."""
+    D, r, P = cfg.width, cfg.lora_r, cfg.patch
+    s: dict[str, tuple[int, ...]] = {
+        "visual.conv1.weight": (D, 3, P, P),
+        "visual.class_embedding": (D,),
+        "visual.positional_embedding": (cfg.tokens, D),
+        "visual.ln_pre.weight": (D,), "visual.ln_pre.bias": (D,),
+        "visual.ln_post.weight": (D,), "visual.ln_post.bias": (D,),
+        "visual.proj": (D, cfg.embed_dim),
+    }
+    for i in range(cfg.layers):
+        p = f"visual.transformer.resblocks.{i}."
+        s[p + "attn.in_proj_weight"] = (3 * D, D)
+        s[p + "attn.in_proj_bias"] = (3 * D,)
+        s[p + "attn.in_proj_weight_lora_A"] = (r, D)
+        s[p + "attn.in_proj_weight_lora_B"] = (3 * D, r)
+        s[p + "attn.out_proj.weight"] = (D, D)
+        s[p + "attn.out_proj.bias"] = (D,)
+        s[p + "attn.out_proj.lora_A"] = (r, D)
+        s[p + "attn.out_proj.lora_B"] = (D, r)
+        s[p + "ln_1.weight"] = (D,); s[p + "ln_1.bias"] = (D,)
+        s[p + "ln_2.weight"] = (D,); s[p + "ln_2.bias"] = (D,)
+        s[p + "mlp.c_fc.weight"] = (cfg.mlp_dim, D); s[p + "mlp.c_fc.bias"] = (cfg.mlp_dim,)
+        s[p + "mlp.c_proj.weight"] = (D, cfg.mlp_dim); s[p + "mlp.c_proj.bias"] = (D,)
+    return s
+
+
+def synth_weights(cfg: VitCfg, seed: int = 0) -> dict[str, np.ndarray]:
+    """Deterministic random-init weights (numpy PCG64, stable across machines) with the scale of
+    the reference's initialisers (model.py:852-885, lora.py:123-139,451-452) but with every affine
+    term, bias and LoRA factor non-trivial so all gradient paths are exercised
+    (out_proj.lora_B is zero at the reference's init; SURVEY.md §8c asks to randomise it)."""
+    rng = np.random.default_rng(seed)
+    D = cfg.width
+    out: dict[str, np.ndarray] = {}
+    for name, shape in param_shapes(cfg).items():
+        if name.endswith(("ln_pre.weight", "ln_post.weight", "ln_1.weight", "ln_2.weight")):
+            v = 1.0 + 0.1 * rng.standard_normal(shape)
+        elif name.endswith(("ln_pre.bias", "ln_post.bias", "ln_1.bias", "ln_2.bias")):
+            v = 0.1 * rng.standard_normal(shape)
+        elif name.endswith("bias"):
+            v = 0.02 * rng.standard_normal(shape)
+        elif name.endswith("conv1.weight"):
+            v = rng.standard_normal(shape) / math.sqrt(3 * cfg.patch ** 2)
+        elif name.endswith(("class_embedding", "positional_embedding", "visual.proj")):
+            v = D ** -0.5 * rng.standard_normal(shape)
+        elif name.endswith("in_proj_weight"):
+            v = D ** -0.5 * rng.standard_normal(shape)
+        elif name.endswith(("out_proj.weight", "c_proj.weight")):
+            v = D ** -0.5 * (2 * cfg.layers) ** -0.5 * rng.standard_normal(shape)
+        elif name.endswith("c_fc.weight"):
+            v = (2 * D) ** -0.5 * rng.standard_normal(shape)
+        elif name.endswith(("lora_A", "lora_B")):
+            fan = shape[0] + shape[1]
+            bound = math.sqrt(6.0 / fan)  # xavier-uniform as lora.py:451-452
+            v = rng.uniform(-bound, bound, shape)
+        else:
+            raise KeyError(name)
+        out[name] = v.astype(np.float32)
+    return out
+
+
+def synth_text_features(num_classes: int, embed_dim: int, seed: int = 1) -> np.ndarray:
+    """Cached class text features: L2-normalised rows (what model.py:968-969 hands the head)."""
+    rng = np.random.default_rng(seed)
+    t = rng.standard_normal((num_classes, embed_dim))
+    t /= np.linalg.norm(t, axis=-1, keepdims=True)
+    return t.astype(np.float32)
+
+
+def to_torch(w: dict[str, np.ndarray], dtype=torch.float32, lora_grad: bool = True):
+    """numpy weights -> torch; only tensors whose name contains 'lora' get requires_grad, the
+    freeze policy of methods/adapter_clip.py:115-119."""
+    out = {}
+    for k, v in w.items():
+        t = torch.from_numpy(np.ascontiguousarray(v)).to(dtype)
+        if lora_grad and "lora" in k:
+            t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+# ------------------------------------------------------------------------------------- operators
+def layer_norm(x, g, b, eps: float = 1e-5):
+    """model.py:194-200 (nn.LayerNorm over the last dim, eps 1e-5, affine)."""
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * g + b
+
+
+def quick_gelu(x):
+    """model.py:203-206."""
+    return x * torch.sigmoid(1.702 * x)
+
+
+def lora_linear(x, W, b, A, B, s):
+    """lora.py:837-839 (in-proj) and :1072-1074 / lora.py:163-169 (out-proj):
+    F.linear(x, W, b) + F.linear(F.linear(x, A), B) * s."""
+    return x @ W.T + b + ((x @ A.T) @ B.T) * s
+
+
+def attention_core(q, k, v, heads: int, causal: bool = False):
+    """lora.py:950 (q scaled by hd^-0.5 after the bias), :1002-1006 (head of sample n / head h is
+    batch index n*H+h), :1043 bmm, :1063 softmax, :1068 bmm, :1070-1071 merge.
+    q, k, v: [N, L, D] sample-major (the reference holds [L, N, D]; same math)."""
+    N, L, D = q.shape
+    hd = D // heads
+    qh = (q * hd ** -0.5).reshape(N, L, heads, hd).permute(0, 2, 1, 3)
+    kh = k.reshape(N, L, heads, hd).permute(0, 2, 1, 3)
+    vh = v.reshape(N, L, heads, hd).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2)
+    if causal:  # model.py:926-932 additive -inf upper triangle (text tower)
+        mask = torch.full((L, L), float("-inf"), dtype=s.dtype).triu(1)
+        s = s + mask
+    p = torch.softmax(s, dim=-1)
+    o = p @ vh
+    return o.permute(0, 2, 1, 3).reshape(N, L, D)
+
+
+def block_forward(x, w, prefix: str, cfg: VitCfg, causal: bool = False):
+    """ResidualAttentionBlock.forward model.py:233-236 with the LoRA attention of :400-415."""
+    D, s = cfg.width, cfg.lora_scale
+    h = layer_norm(x, w[prefix + "ln_1.weight"], w[prefix + "ln_1.bias"])
+    qkv = lora_linear(h, w[prefix + "attn.in_proj_weight"], w[prefix + "attn.in_proj_bias"],
+                      w[prefix + "attn.in_proj_weight_lora_A"],
+                      w[prefix + "attn.in_proj_weight_lora_B"], s)
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]  # lora.py:840 chunk(3)
+    o = attention_core(q, k, v, cfg.heads, causal)
+    x = x + lora_linear(o, w[prefix + "attn.out_proj.weight"], w[prefix + "attn.out_proj.bias"],
+                        w[prefix + "attn.out_proj.lora_A"], w[prefix + "attn.out_proj.lora_B"], s)
+    h2 = layer_norm(x, w[prefix + "ln_2.weight"], w[prefix + "ln_2.bias"])
+    z = h2 @ w[prefix + "mlp.c_fc.weight"].T + w[prefix + "mlp.c_fc.bias"]
+    x = x + quick_gelu(z) @ w[prefix + "mlp.c_proj.weight"].T + w[prefix + "mlp.c_proj.bias"]
+    return x
+
+
+def patch_embed(images, w, cfg: VitCfg):
+    """model.py:756-766: stride-P conv (no bias) -> [N, G*G, D] -> prepend class token ->
+    + positional embedding -> ln_pre.  Returns x0 [N, L, D]."""
+    N = images.shape[0]
+    P, G, D = cfg.patch, cfg.grid, cfg.width
+    # im2col: rows (n, py, px), columns (c, i, j) == conv weight viewed [D, 3*P*P]
+    pt = images.reshape(N, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(N, G * G, 3 * P * P)
+    x = pt @ w["visual.conv1.weight"].reshape(D, -1).T
+    cls = w["visual.class_embedding"].expand(N, 1, D)
+    x = torch.cat([cls, x], dim=1) + w["visual.positional_embedding"]
+    return layer_norm(x, w["visual.ln_pre.weight"], w["visual.ln_pre.bias"])
+
+
+def vit_forward(images, w, cfg: VitCfg, return_tokens: bool = False):
+    """VisualTransformer.forward model.py:755-787 (prompt_module=None path): image features
+    [N, E] before normalisation."""
+    x = patch_embed(images, w, cfg)
+    for i in range(cfg.layers):
+        x = block_forward(x, w, f"visual.transformer.resblocks.{i}.", cfg)
+    y = layer_norm(x[:, 0, :], w["visual.ln_post.weight"], w["visual.ln_post.bias"])  # :782
+    feat = y @ w["visual.proj"]                                                        # :784-785
+    return (feat, x) if return_tokens else feat
+
+
+def head_forward(feat, text, logit_scale_exp: float, cls_idx=None, add_mask=None):
+    """model.py:966-973 + models/adapter_clip.py:99. `text` rows are already L2-normalised
+    (model.py:968-969). cls_idx = visible-class gather (methods/adapter_clip.py:53-61,84);
+    add_mask = additive seen-class mask (methods/mvp_clip.py:113-118). Returns
+    (probs, logits, f_normalised)."""
+    f = feat / feat.norm(dim=-1, keepdim=True)
+    t = text if cls_idx is None else text[cls_idx]
+    logits = logit_scale_exp * f @ t.T
+    if add_mask is not None:
+        logits = logits + add_mask
+    return torch.softmax(logits, dim=-1), logits, f
+
+
+def reference_loss(probs, labels, logits=None, double_softmax: bool = True):
+    """methods/adapter_clip.py:89 with criterion nn.CrossEntropyLoss (methods/_trainer.py:164):
+    the reference feeds the PROBABILITIES to cross-entropy (a second softmax). With
+    double_softmax=False the conventional CE on the logits is returned instead."""
+    if double_softmax:
+        return F.cross_entropy(probs, labels)
+    return F.cross_entropy(logits, labels)
+
+
+def predict(probs):
+    """methods/adapter_clip.py:90 topk(1) / :149 argmax -> int64 [N]."""
+    return probs.argmax(dim=-1)
+
+
+def label_remap(labels: np.ndarray, class_list: list[int]) -> np.ndarray:
+    """methods/adapter_clip.py:75-76: y[j] = train_class_list.index(y[j]) (bit-exact int64)."""
+    return np.asarray([class_list.index(int(v)) for v in labels], dtype=np.int64)
+
+
+def class_lut(class_list: list[int], size: int) -> np.ndarray:
+    """Dense inverse of class_list for the device kernel: lut[class id] = position, -1 if unseen."""
+    lut = np.full((size,), -1, dtype=np.int64)
+    for pos, c in enumerate(class_list):
+        lut[int(c)] = pos
+    return lut
+
+
+def online_step_oracle(images: np.ndarray, labels_local: np.ndarray, w_np: dict, text: np.ndarray,
+                       cfg: VitCfg, logit_scale_exp: float = 1.0 / 0.07, dtype=torch.float64,
+                       double_softmax: bool = True, cls_idx=None, inv_batch: float | None = None):
+    """One forward+backward of the hot path. Returns dict of numpy arrays: feat, probs, logits,
+    loss, pred and the LoRA gradients keyed by parameter name."""
+    w = to_torch(w_np, dtype)
+    x = torch.from_numpy(images).to(dtype)
+    t = torch.from_numpy(text).to(dtype)
+    y = torch.from_numpy(labels_local)
+    feat = vit_forward(x, w, cfg)
+    idx = None if cls_idx is None else torch.from_numpy(np.asarray(cls_idx))
+    probs, logits, f = head_forward(feat, t, logit_scale_exp, idx)
+    loss = reference_loss(probs, y, logits, double_softmax)
+    if inv_batch is not None:  # mean over a global batch larger than this shard
+        loss = loss * (inv_batch * len(y))
+    loss.backward()
+    out = {"feat": feat, "fnorm": f, "probs": probs, "logits": logits, "loss": loss,
+           "pred": predict(probs)}
+    res = {k: v.detach().cpu().numpy() for k, v in out.items()}
+    res["grads"] = {k: v.grad.detach().cpu().numpy() for k, v in w.items() if v.requires_grad}
+    return res

@@ -1,0 +1,61 @@
+"""Pins oracle/vit_oracle.py against golden vectors produced by the REFERENCE's own classes
+(tests/golden/make_golden.py). CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as vo
+from tests.golden.make_golden import CASES, synth_inputs
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+@pytest.mark.parametrize("name", ["tiny", "vitb16"])
+def test_oracle_matches_reference_golden(name, golden_dir):
+    cfg, n, c, seed = CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = vo.synth_weights(cfg, seed)
+    images, labels = synth_inputs(cfg, n, c, seed + 100)
+    text = vo.synth_text_features(c, cfg.embed_dim, seed + 200)
+    # fp32 like the reference for the big case (speed); fp64 truth for the tiny one
+    dtype = torch.float64 if name == "tiny" else torch.float32
+    out = vo.online_step_oracle(images, labels, w, text, cfg,
+                                logit_scale_exp=float(gold["logit_scale_exp"]), dtype=dtype)
+    # the reference ran in fp32: agreement is limited by ITS rounding
+    assert _rel(out["feat"], gold["feat"]) < 2e-5
+    assert _rel(out["logits"], gold["logits"]) < 2e-5
+    assert _rel(out["probs"], gold["probs"]) < 2e-5
+    assert abs(float(out["loss"]) - float(gold["loss"])) < 1e-5
+    np.testing.assert_array_equal(out["pred"], gold["pred"])  # integer: bit-exact
+    grads = {k[5:]: gold[k] for k in gold.files if k.startswith("grad:")}
+    assert set(grads) == set(out["grads"]) and len(grads) == 4 * cfg.layers
+    worst = max(_rel(out["grads"][k], v) for k, v in grads.items())
+    assert worst < 5e-4, worst
+
+
+def test_label_remap_matches_python_loop():
+    # methods/adapter_clip.py:75-76 restated; class list in order of first exposure
+    rng = np.random.default_rng(0)
+    class_list = [17, 3, 99, 42, 0, 8]
+    y = rng.choice(class_list, size=64).astype(np.int64)
+    local = vo.label_remap(y, class_list)
+    lut = vo.class_lut(class_list, 100)
+    np.testing.assert_array_equal(local, lut[y])
+    assert local.dtype == np.int64 and lut[5] == -1
+
+
+def test_double_softmax_loss_is_ce_on_probs():
+    # methods/adapter_clip.py:89: CE applied to probabilities
+    rng = np.random.default_rng(1)
+    logits = torch.from_numpy(rng.standard_normal((5, 7)))
+    y = torch.from_numpy(rng.integers(0, 7, size=(5,)))
+    p = logits.softmax(-1)
+    want = (-p[torch.arange(5), y] + torch.logsumexp(p, -1)).mean()
+    got = vo.reference_loss(p, y)
+    assert abs(float(want) - float(got)) < 1e-12
