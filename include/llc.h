@@ -131,6 +131,10 @@ typedef struct llc_head_args {
   float logit_scale;     /* exp(logit_scale) */
   int N, D, E, C;
   const int64_t* labels; /* [N] local (remapped) labels, or NULL (inference) */
+  const float* d_feat;   /* backward only: [N, E] extra gradient w.r.t. feat (pre-normalisation),
+                            added to the one coming from the logits; NULL if none */
+  int skip_logit_grad;   /* backward only: 1 = use d_feat alone (VisualTransformer.forward used
+                            without the head) */
   int double_softmax;    /* 1: CE applied to the probabilities (the reference's loss) */
   float inv_batch;       /* 1 / global batch (mean reduction) */
   /* outputs */
@@ -194,6 +198,8 @@ int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w, const floa
 /* dx_final fp32 [N*L, D] (the head's gradient; consumed/overwritten) -> LoRA grads in w->layers */
 int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N, void* arena,
                      float* dx_final, void* stream);
+/* dst bf16 [T, ld_dst] <- src fp32 [T, D] (contiguous rows) */
+int llc_cast_bf16(const float* src, void* dst, int T, int D, int ld_dst, void* stream);
 /* refresh the LoRA columns of the augmented weights from the live parameters */
 int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weights* w, void* stream);
 

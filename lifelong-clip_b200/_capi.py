@@ -31,7 +31,8 @@ class HeadArgs(C.Structure):
         ("ln_g", c_void), ("ln_b", c_void), ("proj", c_void), ("text", c_void),
         ("cls_idx", c_void), ("add_mask", c_void), ("logit_scale", c_float),
         ("N", c_int), ("D", c_int), ("E", c_int), ("C", c_int),
-        ("labels", c_void), ("double_softmax", c_int), ("inv_batch", c_float),
+        ("labels", c_void), ("d_feat", c_void), ("skip_logit_grad", c_int),
+        ("double_softmax", c_int), ("inv_batch", c_float),
         ("feat", c_void), ("fnorm", c_void), ("logits", c_void), ("probs", c_void),
         ("loss_rows", c_void), ("pred", c_void),
     ]
@@ -104,6 +105,7 @@ SIGNATURES = {
                                 c_int, C.POINTER(c_void), c_void]),
     "llc_vit_backward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitWeights), c_int, c_void, c_void,
                                  c_void]),
+    "llc_cast_bf16": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void]),
     "llc_vit_refresh_lora": (c_int, [C.POINTER(VitCfg), C.POINTER(VitWeights), c_void]),
     "llc_block_forward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitLayer), C.POINTER(BlockBufs),
                                   c_int, c_int, c_int, c_int, c_int, c_void]),

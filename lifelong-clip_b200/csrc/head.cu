@@ -50,6 +50,8 @@ struct HeadK {
   float inv_batch;
   float *feat, *fnorm, *logits, *probs, *loss_rows;
   int64_t* pred;
+  const float* d_feat;
+  int skip_logit_grad;
 };
 
 // smem: y[D] | f[E] | p[C] | red[32]
@@ -163,49 +165,58 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
   const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* pr = a.probs + (size_t)n * a.C;
 
-  // dL/dlogits
-  if (d_probs == nullptr && !a.double_softmax) {
-    const int64_t yv = a.labels[n];
-    for (int c = tid; c < a.C; c += kThreads)
-      sg[c] = (pr[c] - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
-  } else {
-    if (d_probs != nullptr) {
-      for (int c = tid; c < a.C; c += kThreads) sg[c] = d_probs[(size_t)n * a.C + c] * loss_scale;
-    } else {
+  if (!a.skip_logit_grad) {
+    // dL/dlogits
+    if (d_probs == nullptr && !a.double_softmax) {
       const int64_t yv = a.labels[n];
-      float z2 = 0.f;
-      for (int c = tid; c < a.C; c += kThreads) z2 += __expf(pr[c]);
-      z2 = block_sum(z2, red);
       for (int c = tid; c < a.C; c += kThreads)
-        sg[c] = (__expf(pr[c]) / z2 - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
+        sg[c] = (pr[c] - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
+    } else {
+      if (d_probs != nullptr) {
+        for (int c = tid; c < a.C; c += kThreads)
+          sg[c] = d_probs[(size_t)n * a.C + c] * loss_scale;
+      } else {
+        const int64_t yv = a.labels[n];
+        float z2 = 0.f;
+        for (int c = tid; c < a.C; c += kThreads) z2 += __expf(pr[c]);
+        z2 = block_sum(z2, red);
+        for (int c = tid; c < a.C; c += kThreads)
+          sg[c] = (__expf(pr[c]) / z2 - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
+      }
+      __syncthreads();
+      float dot = 0.f;
+      for (int c = tid; c < a.C; c += kThreads) dot += sg[c] * pr[c];
+      dot = block_sum(dot, red);
+      for (int c = tid; c < a.C; c += kThreads) sg[c] = pr[c] * (sg[c] - dot);
     }
+    for (int e = tid; e < a.E; e += kThreads) sf[e] = a.fnorm[(size_t)n * a.E + e];
     __syncthreads();
-    float dot = 0.f;
-    for (int c = tid; c < a.C; c += kThreads) dot += sg[c] * pr[c];
-    dot = block_sum(dot, red);
-    for (int c = tid; c < a.C; c += kThreads) sg[c] = pr[c] * (sg[c] - dot);
-  }
-  for (int e = tid; e < a.E; e += kThreads) sf[e] = a.fnorm[(size_t)n * a.E + e];
-  __syncthreads();
 
-  // df = scale * dlogits @ T ; dz = (df - f (f.df)) / |z|
-  float fd = 0.f, zz = 0.f;
-  for (int e = tid; e < a.E; e += kThreads) {
-    float acc = 0.f;
-    for (int c = 0; c < a.C; ++c) {
-      const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
-      acc += sg[c] * __ldg(a.text + (size_t)row * a.E + e);
+    // df = scale * dlogits @ T ; dz = (df - f (f.df)) / |z|
+    float fd = 0.f, zz = 0.f;
+    for (int e = tid; e < a.E; e += kThreads) {
+      float acc = 0.f;
+      for (int c = 0; c < a.C; ++c) {
+        const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
+        acc += sg[c] * __ldg(a.text + (size_t)row * a.E + e);
+      }
+      acc *= a.logit_scale;
+      sz[e] = acc;
+      fd += acc * sf[e];
+      const float zf = a.feat[(size_t)n * a.E + e];
+      zz += zf * zf;
     }
-    acc *= a.logit_scale;
-    sz[e] = acc;
-    fd += acc * sf[e];
-    const float zf = a.feat[(size_t)n * a.E + e];
-    zz += zf * zf;
+    fd = block_sum(fd, red);
+    zz = block_sum(zz, red);
+    const float inv_norm = 1.0f / sqrtf(zz);
+    for (int e = tid; e < a.E; e += kThreads) {
+      float v = (sz[e] - sf[e] * fd) * inv_norm;
+      if (a.d_feat) v += a.d_feat[(size_t)n * a.E + e] * loss_scale;
+      sz[e] = v;
+    }
+  } else {
+    for (int e = tid; e < a.E; e += kThreads) sz[e] = a.d_feat[(size_t)n * a.E + e] * loss_scale;
   }
-  fd = block_sum(fd, red);
-  zz = block_sum(zz, red);
-  const float inv_norm = 1.0f / sqrtf(zz);
-  for (int e = tid; e < a.E; e += kThreads) sz[e] = (sz[e] - sf[e] * fd) * inv_norm;
   __syncthreads();
 
   // dy = dz @ proj^T : one warp per k
@@ -272,6 +283,7 @@ int to_k(const llc_head_args* a, HeadK* k, const char* who) {
   k->double_softmax = a->double_softmax; k->inv_batch = a->inv_batch;
   k->feat = a->feat; k->fnorm = a->fnorm; k->logits = a->logits; k->probs = a->probs;
   k->loss_rows = a->loss_rows; k->pred = a->pred;
+  k->d_feat = a->d_feat; k->skip_logit_grad = a->skip_logit_grad;
   return 0;
 }
 
@@ -296,7 +308,9 @@ extern "C" int llc_head_bwd(const llc_head_args* a, const float* d_probs, float 
   HeadK k;
   if (int rc = to_k(a, &k, "llc_head_bwd")) return rc;
   LLC_REQUIRE(dx && ld_dx >= a->D, "llc_head_bwd: bad dx");
-  LLC_REQUIRE(d_probs || a->labels, "llc_head_bwd: need d_probs or labels");
+  LLC_REQUIRE(d_probs || a->labels || (a->skip_logit_grad && a->d_feat),
+              "llc_head_bwd: need d_probs, labels or d_feat");
+  LLC_REQUIRE(!a->skip_logit_grad || a->d_feat, "llc_head_bwd: skip_logit_grad needs d_feat");
   const size_t smem = (size_t)(a->C + 2 * a->E + 2 * a->D + 32) * sizeof(float);
   LLC_REQUIRE(smem <= 200 * 1024, "llc_head_bwd: sizes too large for one CTA");
   if (smem > 48 * 1024)
@@ -311,8 +325,9 @@ extern "C" int llc_head_bwd(const llc_head_args* a, const float* d_probs, float 
 
 extern "C" int llc_label_remap(const int64_t* y_global, const int64_t* lut, int lut_size,
                                int64_t* y_local, int n, void* stream) {
-  LLC_REQUIRE(y_global && lut && y_local && n >= 0 && lut_size > 0, "llc_label_remap: bad args");
-  if (n == 0) return 0;
+  LLC_REQUIRE(n >= 0, "llc_label_remap: negative count");
+  if (n == 0) return 0;  // empty batch: nothing to do, pointers may be NULL
+  LLC_REQUIRE(y_global && lut && y_local && lut_size > 0, "llc_label_remap: bad args");
   label_remap_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y_global, lut, lut_size,
                                                                         y_local, n);
   LLC_COUNT_LAUNCH();

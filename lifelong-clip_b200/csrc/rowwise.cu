@@ -428,13 +428,16 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 
 #define DISPATCH_NV(D, CALL)                                                      \
   switch ((D) / 128) {                                                            \
+    case 1: { constexpr int NV = 1; CALL; } break;                                \
+    case 2: { constexpr int NV = 2; CALL; } break;                                \
+    case 3: { constexpr int NV = 3; CALL; } break;                                \
     case 4: { constexpr int NV = 4; CALL; } break;                                \
     case 5: { constexpr int NV = 5; CALL; } break;                                \
     case 6: { constexpr int NV = 6; CALL; } break;                                \
     case 8: { constexpr int NV = 8; CALL; } break;                                \
     case 10: { constexpr int NV = 10; CALL; } break;                              \
     default:                                                                      \
-      llc_set_error("LayerNorm width %d unsupported (need 512/640/768/1024/1280)", (D)); \
+      llc_set_error("LayerNorm width %d unsupported (need a multiple of 128 up to 1280)", (D)); \
       return LLC_ERR_ARG;                                                         \
   }
 

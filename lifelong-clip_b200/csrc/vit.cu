@@ -112,6 +112,34 @@ void fill_bufs(const Dims& d, const Arena& a, uint8_t* base, int layer, int trai
 
 }  // namespace
 
+__global__ void cast_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                      int T, int D, int ld_dst) {
+  const int per_row = D / 4;
+  const size_t total = (size_t)T * per_row;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / per_row;
+    const int c4 = (int)(i % per_row);
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    *reinterpret_cast<uint2*>(dst + row * ld_dst + c4 * 4) =
+        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+extern "C" int llc_cast_bf16(const float* src, void* dst, int T, int D, int ld_dst, void* stream) {
+  LLC_REQUIRE(src && dst && T > 0 && D % 4 == 0 && ld_dst % 4 == 0 && ld_dst >= D,
+              "llc_cast_bf16: bad args");
+  const size_t total = (size_t)T * D / 4;
+  const int grid = (int)((total + 255) / 256 < (size_t)llc_num_sms() * 8
+                             ? (total + 255) / 256
+                             : (size_t)llc_num_sms() * 8);
+  cast_rows_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), T, D, ld_dst);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("cast_rows_bf16_kernel");
+  return 0;
+}
+
 extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
                                  const llc_block_bufs* b, int N, int L, int sn, int sl, int causal,
                                  void* stream) {
@@ -252,20 +280,6 @@ extern "C" int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w,
   return 0;
 }
 
-__global__ void cast_rows_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                      int T, int D, int ld_dst) {
-  const int per_row = D / 4;
-  const size_t total = (size_t)T * per_row;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = i / per_row;
-    const int c4 = (int)(i % per_row);
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
-    *reinterpret_cast<uint2*>(dst + row * ld_dst + c4 * 4) =
-        make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-  }
-}
-
 extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N,
                                 void* arena, float* dx_final, void* stream) {
   RUN(check_cfg(cfg, "llc_vit_backward"));
@@ -281,16 +295,7 @@ extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w
   s.d_o = base + a.d_o;
   s.dqkv = base + a.dqkv;
   s.partial = reinterpret_cast<float*>(base + a.partial);
-  {
-    const size_t total = (size_t)d.T * d.D / 4;
-    const int grid = (int)((total + 255) / 256 < (size_t)llc_num_sms() * 8
-                               ? (total + 255) / 256
-                               : (size_t)llc_num_sms() * 8);
-    cast_rows_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        dx_final, reinterpret_cast<__nv_bfloat16*>(s.dxb), d.T, d.D, d.D + LLC_LORA_PAD);
-    LLC_COUNT_LAUNCH();
-    LLC_LAUNCH_CHECK("cast_rows_bf16_kernel");
-  }
+  RUN(llc_cast_bf16(dx_final, s.dxb, d.T, d.D, d.D + LLC_LORA_PAD, stream));
   llc_block_bufs b;
   for (int l = d.layers - 1; l >= 0; --l) {
     fill_bufs(d, a, base, l, 1, &b);

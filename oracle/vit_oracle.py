@@ -171,7 +171,7 @@ def attention_core(q, k, v, heads: int, causal: bool = False):
     vh = v.reshape(N, L, heads, hd).permute(0, 2, 1, 3)
     s = qh @ kh.transpose(-1, -2)
     if causal:  # model.py:926-932 additive -inf upper triangle (text tower)
-        mask = torch.full((L, L), float("-inf"), dtype=s.dtype).triu(1)
+        mask = torch.full((L, L), float("-inf"), dtype=s.dtype, device=s.device).triu(1)
         s = s + mask
     p = torch.softmax(s, dim=-1)
     o = p @ vh

@@ -1,0 +1,315 @@
+"""Kernel-level parity: every libllc entry point (called through the C-ABI via ctypes) against the
+oracle's operator restatements evaluated in fp32/fp64 on the same seeded inputs.
+bf16-operand kernels: tensor rel-L2 <= 1e-2 (the north-star tolerance); integer work: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from lifelong_clip_b200 import ops as _ops
+    _ops.check_device(0)
+    return _ops
+
+
+def rel(a, b):
+    a = a.double().flatten(); b = b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf16_randn(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (300, 384, 784),
+                                   (197 * 3, 768, 2320), (2200, 2304, 784), (5000, 768, 3072)])
+def test_gemm_plain_bf16(ops, M, N, K):
+    A = bf16_randn(M, K + 8, seed=1)[:, :K]          # padded leading dim
+    B = bf16_randn(N, K, seed=2, scale=K ** -0.5)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(A, B, M, N, K, out)
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().T
+    assert rel(out.float(), want) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(197 * 4, 768, 784), (2200, 768, 3072)])
+def test_gemm_bias_residual_fp32(ops, M, N, K):
+    A = bf16_randn(M, K, seed=3)
+    B = bf16_randn(N, K, seed=4, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm_tn(A, B, M, N, K, out, bias=bias, resid=resid)
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().T + bias + resid
+    assert rel(out, want) < 1e-5
+    # in place on the residual stream
+    r2 = resid.clone()
+    ops.gemm_tn(A, B, M, N, K, r2, bias=bias, resid=r2)
+    torch.cuda.synchronize()
+    assert rel(r2, want) < 1e-5
+
+
+def test_gemm_quickgelu_forward_and_backward_epilogues(ops):
+    M, N, K = 197 * 5, 3072, 768
+    A = bf16_randn(M, K, seed=5)
+    B = bf16_randn(N, K, seed=6, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda") * 0.1
+    z = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    g = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(A, B, M, N, K, z, bias=bias, act=1, out2=g)
+    torch.cuda.synchronize()
+    zw = A.float() @ B.float().T + bias
+    assert rel(z.float(), zw) < 5e-3
+    assert rel(g.float(), vo.quick_gelu(zw)) < 1e-2
+    # act=2: out = (A B^T) * QuickGELU'(z)
+    M2, N2, K2 = M, 3072, 768
+    dz = torch.empty(M2, N2, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(A, B, M2, N2, K2, dz, act=2, aux=z)
+    torch.cuda.synchronize()
+    zf = z.float().requires_grad_(True)
+    vo.quick_gelu(zf).sum().backward()
+    want = (A.float() @ B.float().T) * zf.grad
+    assert rel(dz.float(), want) < 1e-2
+
+
+def test_gemm_rejects_bad_shapes(ops):
+    A = bf16_randn(64, 40); B = bf16_randn(64, 40)
+    out = torch.empty(64, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        ops.gemm_tn(A, B, 64, 64, 40, out)
+
+
+# --------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("T,D", [(37, 128), (197 * 3, 768), (257 * 2, 1024)])
+def test_ln_fwd_with_lora_rowdot(ops, T, D):
+    g0 = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(T, D, device="cuda", generator=g0) * 2 + 0.3
+    gamma = 1 + 0.1 * torch.randn(D, device="cuda", generator=g0)
+    beta = 0.1 * torch.randn(D, device="cuda", generator=g0)
+    A = torch.randn(4, D, device="cuda", generator=g0) * 0.05
+    y = torch.full((T, D + 16), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.ln_fwd(x, gamma, beta, y, lora_A=A, r=4)
+    torch.cuda.synchronize()
+    want = vo.layer_norm(x.double(), gamma.double(), beta.double())
+    assert rel(y[:, :D].float(), want) < 4e-3
+    assert rel(y[:, D:D + 4].float(), want @ A.double().T) < 4e-3
+    assert float(y[:, D + 4:].abs().max()) == 0.0  # pad columns are exact zeros
+
+
+@pytest.mark.parametrize("T,D", [(37, 128), (197 * 3, 768)])
+def test_ln_bwd_with_lora_du(ops, T, D):
+    g0 = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(T, D, device="cuda", generator=g0) * 2 + 0.3
+    gamma = 1 + 0.1 * torch.randn(D, device="cuda", generator=g0)
+    dy = bf16_randn(T, D, seed=9)
+    dx_in = torch.randn(T, D, device="cuda", generator=g0)
+    Bm = torch.randn(D, 4, device="cuda", generator=g0) * 0.05
+    dx_out = torch.empty(T, D, device="cuda")
+    dxb = torch.empty(T, D + 16, device="cuda", dtype=torch.bfloat16)
+    ops.ln_bwd(x, gamma, dy, dx_in, dx_out, dxb=dxb, lora_B=Bm, r=4, scale=0.25)
+    torch.cuda.synchronize()
+    xd = x.double().requires_grad_(True)
+    yv = vo.layer_norm(xd, gamma.double(), torch.zeros(D, device="cuda", dtype=torch.float64))
+    yv.backward(dy.double())
+    want = dx_in.double() + xd.grad
+    assert rel(dx_out, want) < 1e-5
+    assert rel(dxb[:, :D].float(), want) < 4e-3
+    assert rel(dxb[:, D:D + 4].float(), 0.25 * want @ Bm.double()) < 4e-3
+
+
+# --------------------------------------------------------------------------------------- attention
+def _attn_case(ops, N, L, H, causal, seq_first, seed):
+    D = H * 64
+    T = N * L
+    qkv = bf16_randn(T, 3 * D + 16, seed=seed)
+    sn, sl = (1, N) if seq_first else (L, 1)
+    o = torch.zeros(T, D + 16, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(N * H * L, device="cuda")
+    ops.attn_fwd(qkv, o, lse, N, L, H, sn, sl, causal)
+    d_o = bf16_randn(T, D, seed=seed + 1)
+    dqkv = torch.zeros(T, 3 * D + 16, device="cuda", dtype=torch.bfloat16)
+    ops.attn_bwd(qkv, o, d_o, lse, dqkv, N, L, H, sn, sl, causal)
+    torch.cuda.synchronize()
+
+    def to_nld(t, width):  # rows -> [N, L, width]
+        t = t[:, :width].double()
+        return t.reshape(L, N, width).transpose(0, 1) if seq_first else t.reshape(N, L, width)
+
+    x = to_nld(qkv, 3 * D).clone().requires_grad_(True)
+    ow = vo.attention_core(x[..., :D], x[..., D:2 * D], x[..., 2 * D:], H, causal)
+    ow.backward(to_nld(d_o, D))
+    assert rel(to_nld(o, D), ow.detach()) < 6e-3
+    got = to_nld(dqkv, 3 * D)
+    for i, name in enumerate("qkv"):
+        assert rel(got[..., i * D:(i + 1) * D], x.grad[..., i * D:(i + 1) * D]) < 1e-2, name
+
+
+@pytest.mark.parametrize("N,L,H,causal,seq_first", [
+    (3, 9, 2, False, False), (2, 17, 2, False, True), (2, 77, 8, True, False),
+    (2, 197, 12, False, False), (3, 197, 12, False, True), (1, 257, 16, False, False),
+    (2, 50, 2, True, True)])
+def test_attention_fwd_bwd(ops, N, L, H, causal, seq_first):
+    _attn_case(ops, N, L, H, causal, seq_first, seed=20 + L)
+
+
+# --------------------------------------------------------------------------------------- LoRA side
+@pytest.mark.parametrize("T,Cc", [(100, 128), (197 * 3, 768), (197 * 3, 2304)])
+def test_lora_side_rowdot_and_colsum(ops, T, Cc):
+    r = 4
+    X = bf16_randn(T, Cc + 16, seed=30)
+    Mrd = torch.randn(Cc, r, device="cuda") * 0.05
+    w = bf16_randn(T, 24, seed=31)
+    partial = torch.empty(ops.lora_side_max_partials() * Cc * 8, device="cuda")
+    n = ops.lora_side(X, T, Cc, r, Mrd=Mrd, rd_sc=r, rd_sj=1, rd_scale=0.25, w=w, ld_w=24,
+                      partial=partial)
+    out = torch.empty(Cc, r, device="cuda")
+    ops.lora_colsum_finish(partial, n, Cc, r, 0.5, out, r, 1)
+    outT = torch.empty(r, Cc, device="cuda")
+    ops.lora_colsum_finish(partial, n, Cc, r, 1.0, outT, 1, Cc)
+    torch.cuda.synchronize()
+    Xd = X[:, :Cc].double()
+    assert rel(X[:, Cc:Cc + r].float(), 0.25 * Xd @ Mrd.double()) < 4e-3
+    assert float(X[:, Cc + r:].abs().max()) == 0.0
+    want = Xd.T @ w[:, :r].double()
+    assert rel(out, 0.5 * want) < 1e-5
+    assert rel(outT, want.T) < 1e-5
+
+
+# -------------------------------------------------------------------------------------- front end
+def test_pack_weight_and_lora_cols(ops):
+    W = torch.randn(96, 160, device="cuda")
+    d1 = torch.zeros(96, 176, device="cuda", dtype=torch.bfloat16)
+    ops.pack_weight(W, d1)
+    d2 = torch.zeros(160, 112, device="cuda", dtype=torch.bfloat16)
+    ops.pack_weight(W, d2, transpose=True)
+    Bm = torch.randn(96, 4, device="cuda")
+    ops.pack_lora_cols(Bm, 96, 4, 4, 1, 0.25, d1, 160)
+    torch.cuda.synchronize()
+    assert torch.equal(d1[:, :160], W.to(torch.bfloat16))
+    assert torch.equal(d2[:, :96], W.T.to(torch.bfloat16))
+    assert torch.equal(d1[:, 160:164], (0.25 * Bm).to(torch.bfloat16))
+    assert float(d1[:, 164:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cfg", [vo.VIT_TINY, vo.VitCfg(image_size=28, patch=14, width=128,
+                                                        layers=1, heads=2, embed_dim=64)])
+def test_patchify_and_embed(ops, cfg):
+    N = 3
+    w = {k: torch.from_numpy(v).cuda() for k, v in vo.synth_weights(cfg, 3).items()}
+    img = torch.randn(N, 3, cfg.image_size, cfg.image_size, device="cuda")
+    K = 3 * cfg.patch ** 2
+    PK = (K + 15) // 16 * 16
+    G2 = cfg.grid ** 2
+    patches = torch.full((N * G2, PK), 3.0, device="cuda", dtype=torch.bfloat16)
+    ops.patchify(img, cfg.patch, patches)
+    torch.cuda.synchronize()
+    P, G = cfg.patch, cfg.grid
+    want = img.reshape(N, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(N * G2, K)
+    assert torch.equal(patches[:, :K], want.to(torch.bfloat16))
+    assert float(patches[:, K:].abs().max() if PK > K else 0.0) == 0.0
+    # GEMM + class token + positional embedding + ln_pre against the oracle's patch_embed
+    wp = torch.zeros(cfg.width, PK, device="cuda", dtype=torch.bfloat16)
+    ops.pack_weight(w["visual.conv1.weight"].reshape(cfg.width, K).contiguous(), wp)
+    po = torch.empty(N * G2, cfg.width, device="cuda")
+    ops.gemm_tn(patches, wp, N * G2, cfg.width, PK, po)
+    x0 = torch.empty(N * cfg.tokens, cfg.width, device="cuda")
+    ops.embed_ln_pre(po, w["visual.class_embedding"], w["visual.positional_embedding"],
+                     w["visual.ln_pre.weight"], w["visual.ln_pre.bias"], N, cfg.tokens, cfg.width,
+                     x0)
+    torch.cuda.synchronize()
+    wd = {k: v.double() for k, v in w.items()}
+    want0 = vo.patch_embed(img.double(), wd, cfg).reshape(N * cfg.tokens, cfg.width)
+    assert rel(x0, want0) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------- head
+@pytest.mark.parametrize("double_softmax,gather", [(True, False), (True, True), (False, False)])
+def test_head_forward_backward(ops, double_softmax, gather):
+    N, L, D, E, Call = 6, 5, 128, 64, 20
+    g0 = torch.Generator(device="cuda").manual_seed(40)
+    x = torch.randn(N * L, D, device="cuda", generator=g0)
+    ln_g = 1 + 0.1 * torch.randn(D, device="cuda", generator=g0)
+    ln_b = 0.1 * torch.randn(D, device="cuda", generator=g0)
+    proj = torch.randn(D, E, device="cuda", generator=g0) * D ** -0.5
+    text = torch.from_numpy(vo.synth_text_features(Call, E, 5)).cuda()
+    cls_idx = torch.tensor([7, 2, 19, 4, 11, 0, 3], device="cuda") if gather else None
+    Cn = 7 if gather else Call
+    labels = torch.randint(0, Cn, (N,), device="cuda", generator=g0)
+    scale = 1 / 0.07
+    h = ops.Head(x, L, ln_g, ln_b, proj, text, scale, N, cls_idx=cls_idx, labels=labels,
+                 double_softmax=double_softmax).forward()
+    dx = torch.zeros(N * L, D, device="cuda")
+    h.backward(dx)
+    torch.cuda.synchronize()
+    xd = x.double().requires_grad_(True)
+    y = vo.layer_norm(xd.reshape(N, L, D)[:, 0], ln_g.double(), ln_b.double())
+    feat = y @ proj.double()
+    probs, logits, f = vo.head_forward(feat, text.double(), scale, cls_idx)
+    loss = vo.reference_loss(probs, labels, logits, double_softmax)
+    loss.backward()
+    assert rel(h.feat, feat.detach()) < 1e-5
+    assert rel(h.logits, logits.detach()) < 1e-5
+    assert rel(h.probs, probs.detach()) < 1e-4
+    assert abs(float(h.loss_rows.sum()) - float(loss)) < 1e-5
+    assert torch.equal(h.pred, vo.predict(probs))  # integer: bit-exact
+    assert rel(dx, xd.grad) < 1e-4
+    # external d_probs path (torch autograd feeding the kernel) must agree with the analytic one
+    p2 = h.probs.clone().requires_grad_(True)
+    vo.reference_loss(p2, labels, None, True).backward()
+    dx2 = torch.zeros_like(dx)
+    if double_softmax:
+        h.backward(dx2, d_probs=p2.grad)
+        torch.cuda.synchronize()
+        assert rel(dx2, xd.grad) < 1e-4
+
+
+def test_head_additive_mask_variant(ops):
+    # methods/mvp_clip.py:113-118: logit + mask with -inf on unseen classes
+    N, L, D, E, Cn = 4, 3, 128, 64, 12
+    x = torch.randn(N * L, D, device="cuda")
+    ln_g = torch.ones(D, device="cuda"); ln_b = torch.zeros(D, device="cuda")
+    proj = torch.randn(D, E, device="cuda") * D ** -0.5
+    text = torch.from_numpy(vo.synth_text_features(Cn, E, 6)).cuda()
+    mask = torch.full((Cn,), float("-inf"), device="cuda"); mask[:5] = 0
+    h = ops.Head(x, L, ln_g, ln_b, proj, text, 10.0, N, add_mask=mask).forward()
+    torch.cuda.synchronize()
+    y = vo.layer_norm(x.double().reshape(N, L, D)[:, 0], ln_g.double(), ln_b.double())
+    probs, _, _ = vo.head_forward(y @ proj.double(), text.double(), 10.0, None, mask.double())
+    assert rel(h.probs, probs) < 1e-4
+    assert float(h.probs[:, 5:].abs().max()) == 0.0
+    assert torch.equal(h.pred, probs.argmax(-1))
+
+
+def test_label_remap_bit_exact(ops):
+    class_list = [17, 3, 99, 42, 0, 8]
+    rng = np.random.default_rng(0)
+    y = rng.choice(class_list + [5], size=257).astype(np.int64)  # 5 is unseen -> -1
+    lut = torch.from_numpy(vo.class_lut(class_list, 100)).cuda()
+    got = ops.label_remap(torch.from_numpy(y).cuda(), lut).cpu().numpy()
+    want = np.array([class_list.index(v) if v in class_list else -1 for v in y], dtype=np.int64)
+    np.testing.assert_array_equal(got, want)
+    assert ops.label_remap(torch.empty(0, dtype=torch.int64, device="cuda"), lut).numel() == 0
+
+
+def test_adamw_matches_torch(ops):
+    n = 1000
+    p0 = torch.randn(n, device="cuda")
+    p = p0.clone(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([pt], lr=1e-2, weight_decay=1e-5)
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        pt.grad = g.clone()
+        opt.step()
+        ops.adamw(p, g, m, v, 1e-2, 0.9, 0.999, 1e-8, 1e-5, step)
+    torch.cuda.synchronize()
+    assert rel(p, pt.detach()) < 1e-6
