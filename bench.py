@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py - train images/s of the CLIP ViT-B/16 LoRA online step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one combined stream+replay batch: image tower forward,
+head + loss, backward to the LoRA factors (frozen-backbone weight gradients skipped), all-reduce
+of the flat LoRA gradient (N > 1) and AdamW. Workload = BASELINE.json configs[1] on one GPU:
+ViT-B/16, batch 256 per GPU (weak scaling: every rank holds its own 256), 100 visible classes,
+synthetic images, random-init weights.
+
+  value   images/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e     images/s through the public API LoRAClipTrainer.online_step(images, labels, idx) fed
+          from pinned HOST memory: the H2D copy of every step's images and labels and the D2H read
+          of (loss, acc) are inside the timed region
+  roofline       the tcgen05 GEMM kernel: algorithmic FLOPs / CUDA-event time per launch
+  cpu_baseline   the oracle port of the reference path on this box's host cores (bounded sample)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train img/s, CLIP ViT-B/16 LoRA online step"
+UNIT = "img/s"
+MODELS = {  # name -> (image, patch, width, layers, heads, embed)
+    "ViT-B/16": (224, 16, 768, 12, 12, 512),
+    "ViT-L/14": (224, 14, 1024, 24, 16, 768),
+}
+
+
+def train_flops_per_image(model: str) -> float:
+    """BASELINE.md §4 / SURVEY.md §8d: forward + activation-gradient backward, no frozen dW."""
+    S, p, D, layers, H, E = MODELS[model]
+    L, m, r, hd = (S // p) ** 2 + 1, 4 * D, 4, 64
+    lin = 2 * L * (3 * D * D + D * D + 2 * D * m)
+    attn = 2 * 2 * H * L * L * hd
+    lora = 2 * L * (D * r + r * 3 * D + D * r + r * D)
+    fwd = 2 * (L - 1) * D * 3 * p * p + layers * (lin + attn + lora) + 2 * D * E
+    bwd = layers * (lin + 2 * attn + 2 * lora) + 2 * D * E
+    return float(fwd + bwd)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained"),
+                "hbm": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/llc_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        with open(self.path) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 8:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples in the upper half of the observed power range
+        lo = (min(pw) + max(pw)) / 2
+        load = [s for s, p in zip(sm, pw) if p >= lo] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx),
+                "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+class CpuReference:
+    """The reference's CPU path as restated by oracle/vit_oracle.py (the reference itself is
+    Python and absent on the GPU box; kind = "port"): fp32 torch CPU ops on all host threads,
+    forward + reference loss + backward + AdamW over the LoRA tensors."""
+
+    def __init__(self, model: str, classes: int, batch: int, seed: int = 0):
+        import numpy as np
+        import torch
+        from oracle import vit_oracle as vo
+        self.torch, self.vo = torch, vo
+        S, p, D, layers, H, E = MODELS[model]
+        self.cfg = vo.VitCfg(image_size=S, patch=p, width=D, layers=layers, heads=H, embed_dim=E)
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.w = vo.to_torch(vo.synth_weights(self.cfg, seed), torch.float32)
+        self.text = torch.from_numpy(vo.synth_text_features(classes, E, seed + 1))
+        rng = np.random.default_rng(seed + 2)
+        self.x = torch.from_numpy(rng.standard_normal((batch, 3, S, S)).astype(np.float32))
+        self.y = torch.from_numpy(rng.integers(0, classes, size=(batch,)).astype(np.int64))
+        self.opt = torch.optim.AdamW([t for t in self.w.values() if t.requires_grad], lr=1e-3,
+                                     weight_decay=1e-5)
+        self.batch = batch
+
+    def step(self) -> float:
+        vo = self.vo
+        self.opt.zero_grad(set_to_none=True)
+        feat = vo.vit_forward(self.x, self.w, self.cfg)
+        probs, logits, _ = vo.head_forward(feat, self.text, 1.0 / 0.07)
+        loss = vo.reference_loss(probs, self.y, logits, True)
+        loss.backward()
+        self.opt.step()
+        return float(loss)
+
+    def time_steps(self, steps: int, warmup: int) -> float:
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args):
+    """--impl reference: rank 0 alone times the CPU path; other ranks exit 0 without work."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = args.cpu_batch
+    ref = CpuReference(args.model, args.classes, b)
+    sec = ref.time_steps(args.steps, args.warmup)
+    v = b / sec
+    sample = (f"{b}-image batch per step (of the {args.batch}-image workload), fp32 oracle port of "
+              f"the reference's PyTorch path, fwd+loss+bwd+AdamW, {ref.cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "classes": args.classes},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def workload_name(args) -> str:
+    return (f"CLIP {args.model} LoRA online step, stream+replay batch {args.batch} per GPU "
+            f"(BASELINE.json configs[1] on one GPU; weak scaling), bf16 operands")
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun (one process per GPU): python -m "
+                             f"torch.distributed.run --nnodes=1 --nproc-per-node {args.gpus} "
+                             f"--master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from lifelong_clip_b200 import ops
+    from lifelong_clip_b200.adapter_clip import AdapterCLIP
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+
+    S, p, D, layers, H, E = MODELS[args.model]
+    B, C = args.batch, args.classes
+    torch.manual_seed(0)                       # identical replicas on every rank
+    model = AdapterCLIP(vision_config=(S, p, D, layers, E)).to(dev)
+    names = [f"class {i}" for i in range(C)]
+    g = torch.Generator().manual_seed(1)
+    model.set_text_features(names, torch.randn(C, E, generator=g))
+    trainer = LoRAClipTrainer(model, names, n_classes=C, n_tasks=5, lr=1e-3, online_iter=1,
+                              visible_classes="all", sharded_input=True)
+    trainer.online_before_task(0)
+
+    # synthetic stream: a pool of distinct pinned host batches (each 154 MB fp32 at B=256, i.e.
+    # larger than the 126 MB L2, so no step finds its input cached)
+    n_pool = 3
+    gen = torch.Generator().manual_seed(100 + rank)
+    host_x = [torch.randn(B, 3, S, S, generator=gen).pin_memory() for _ in range(n_pool)]
+    host_y = [torch.randint(0, C, (B,), generator=gen).pin_memory() for _ in range(n_pool)]
+    idx = torch.arange(B)
+
+    # every class exposed once up front so the visible-class list (C columns) is fixed
+    trainer.add_new_class(torch.arange(C))
+    model.set_token(trainer.exposed_classes_names)
+    lut = trainer._class_lut(trainer.exposed_classes)
+    dev_x = [x.to(dev) for x in host_x[:2]]
+    dev_y = [ops.label_remap(y.to(dev), lut) for y in host_y[:2]]
+    gB = B * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- device-resident: `value`
+    for i in range(args.warmup):
+        trainer.fused_step(dev_x[i % 2], dev_y[i % 2], gB, sync=False)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        trainer.fused_step(dev_x[i % 2], dev_y[i % 2], gB, sync=False)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    value = gB / (ms_dev * 1e-3)
+
+    # ---------------------------------------------------------------- end to end: `e2e`
+    for i in range(max(1, args.warmup // 2)):
+        trainer.online_step(host_x[i % n_pool], host_y[i % n_pool], idx)
+    barrier()
+    e0.record()
+    last = None
+    for i in range(args.steps):
+        last = trainer.online_step(host_x[i % n_pool], host_y[i % n_pool], idx)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = gB / (ms_e2e * 1e-3)
+    h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
+    d2h = 8
+
+    # ---------------------------------------------------------------- per-kernel pass (roofline)
+    ops.prof_enable(True)
+    for i in range(args.prof_steps):
+        trainer.fused_step(dev_x[i % 2], dev_y[i % 2], gB, sync=False)
+    torch.cuda.synchronize()
+    recs = ops.prof_read()
+    ops.prof_enable(False)
+    by_kind = {}
+    for kind, m, n, k, ms, fl, by in recs:
+        d = by_kind.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["launches"] += 1; d["ms"] += ms; d["flops"] += fl; d["bytes"] += by
+    peaks = load_peaks()
+    gemm = by_kind.get("gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
+    total_ms = sum(d["ms"] for d in by_kind.values()) or 1.0
+    roof = None
+    if gemm["launches"]:
+        achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05/TMEM, all shapes of the step)",
+                "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16"], "traffic": None,
+                "peak_source": peaks["source"] + ", burst",
+                "flop_per_launch": gemm["flops"] / gemm["launches"],
+                "us_per_launch": gemm["ms"] * 1e3 / gemm["launches"],
+                "launches_per_step": gemm["launches"] / args.prof_steps,
+                "share_of_step": gemm["ms"] / total_ms,
+                "timed": f"CUDA events around each launch, {args.prof_steps} instrumented steps "
+                         "right after the timed region"}
+    breakdown = {k: {"ms_per_step": d["ms"] / args.prof_steps,
+                     "launches_per_step": d["launches"] / args.prof_steps,
+                     "tflops": (d["flops"] / (d["ms"] * 1e-3) / 1e12) if d["ms"] else 0.0,
+                     "gbs": (d["bytes"] / (d["ms"] * 1e-3) / 1e9) if d["ms"] else 0.0}
+                 for k, d in sorted(by_kind.items())}
+    if args.dump_prof and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.dump_prof)), exist_ok=True)
+        with open(args.dump_prof, "w") as f:
+            json.dump({"records": recs, "by_kind": breakdown}, f)
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(args.model, C, args.cpu_batch)
+        sec = ref.time_steps(2, 1)
+        cpu = {"value": args.cpu_batch / sec, "unit": UNIT, "cores": ref.cores, "kind": "port",
+               "sample": f"{args.cpu_batch}-image batch x 2 timed steps (1 warm-up) of the same "
+                         "model/classes: fp32 oracle port of the reference's PyTorch path, "
+                         "fwd+loss+bwd+AdamW"}
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    fl = train_flops_per_image(args.model)
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(args), "model": args.model,
+                   "batch_per_gpu": B, "global_batch": gB, "classes": C, "tokens": (S // p) ** 2 + 1,
+                   "parallelism": f"dp{world}", "weights": "random-init",
+                   "l2": "inputs larger than L2 (154 MB images per step; activations 1 GB/layer)",
+                   "loss": "CE on probabilities (reference double softmax)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                "api": "LoRAClipTrainer.online_step(images, labels, idx) from pinned host tensors",
+                "last_loss_acc": list(last) if last else None},
+        "gpu_launches": launches * world,
+        "step_tensor_frac": {"achieved_tflops_per_gpu": value / world * fl / 1e12,
+                             "of_burst_peak": value / world * fl / 1e12 / peaks["bf16"],
+                             "of_sustained_peak": (value / world * fl / 1e12 / peaks["bf16_sustained"]
+                                                   if peaks["bf16_sustained"] else None),
+                             "flop_per_image": fl},
+        "roofline": roof,
+        "kernel_breakdown": breakdown,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="ViT-B/16", choices=sorted(MODELS))
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--classes", type=int, default=100)
+    ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
+    ap.add_argument("--prof-steps", type=int, default=2)
+    ap.add_argument("--dump-prof", default=None, help="write per-launch records (json) here")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,24 @@ int llc_check_device(int dev);
 /* number of kernels this process has launched through the library (bench.py: gpu_launches) */
 unsigned long long llc_launch_count(void);
 
+/* ---- per-launch device timing (bench.py roofline: CUDA events on the launching stream) --------
+ * When enabled every llc_* launch is bracketed by two events; llc_prof_read synchronises on them
+ * and returns one record per launch. Off by default (events cost ~1 us each). Not graph-capturable
+ * while enabled. */
+enum {
+  LLC_K_GEMM = 0, LLC_K_ATTN_FWD = 1, LLC_K_ATTN_BWD = 2, LLC_K_LN_FWD = 3, LLC_K_LN_BWD = 4,
+  LLC_K_LORA_SIDE = 5, LLC_K_HEAD = 6, LLC_K_EMBED = 7, LLC_K_OTHER = 8, LLC_K_COUNT = 9
+};
+typedef struct llc_prof_rec {
+  int kind, m, n, k;   /* m,n,k: GEMM shape, or rows/cols of the pass (k = 0) */
+  float ms;            /* device time of this launch */
+  double flops, bytes; /* algorithmic work the caller attributes to it */
+} llc_prof_rec;
+int llc_prof_enable(int on); /* 1: start recording (clears old records); 0: stop */
+/* copies up to max records into out (may be NULL to just count); returns the record count, <0 on
+ * error */
+int llc_prof_read(llc_prof_rec* out, int max);
+
 /* ---- dense contraction: out[M,N] = epi(A[M,K] . B[N,K]^T), bf16 operands, fp32 accumulate ----
  * TMA-fed tcgen05/TMEM GEMM. Replaces every F.linear on the path: in-proj lora.py:837-839,
  * out-proj lora.py:1072-1074, mlp model.py:219-222, and their activation-gradient transposes.

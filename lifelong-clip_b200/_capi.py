@@ -67,8 +67,18 @@ class BlockBwdBufs(C.Structure):
     _fields_ = [(n, c_void) for n in ("dx", "dxb", "dz", "dh", "d_o", "dqkv", "partial")]
 
 
+class ProfRec(C.Structure):
+    _fields_ = [("kind", c_int), ("m", c_int), ("n", c_int), ("k", c_int), ("ms", c_float),
+                ("flops", C.c_double), ("bytes", C.c_double)]
+
+
+PROF_KINDS = ("gemm", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "lora_side", "head", "embed",
+              "other")
+
 # name -> (restype, argtypes); every symbol llc.h declares
 SIGNATURES = {
+    "llc_prof_enable": (c_int, [c_int]),
+    "llc_prof_read": (c_int, [C.POINTER(ProfRec), c_int]),
     "llc_version": (c_int, []),
     "llc_last_error": (C.c_char_p, []),
     "llc_check_device": (c_int, [c_int]),

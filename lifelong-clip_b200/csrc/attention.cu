@@ -452,8 +452,11 @@ int launch_fwd(const __nv_bfloat16* qkv, int ld_qkv, __nv_bfloat16* o, int ld_o,
                                   smem));
     configured = true;
   }
+  LLC_PROF_BEGIN(LLC_K_ATTN_FWD, N * H, L, 0, 4.0 * N * H * (double)L * L * HD,
+                 8.0 * N * H * (double)L * HD, st);
   attn_fwd_kernel<LP><<<N * H, kWarps * 32, smem, st>>>(qkv, ld_qkv, o, ld_o, lse, L, H, sn, sl,
                                                         causal);
+  LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("attn_fwd_kernel");
   return 0;
@@ -470,8 +473,11 @@ int launch_bwd(const __nv_bfloat16* qkv, int ld_qkv, const __nv_bfloat16* o, int
                                   smem));
     configured = true;
   }
+  LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
+                 16.0 * N * H * (double)L * HD, st);
   attn_bwd_kernel<LP><<<N * H, kWarps * 32, smem, st>>>(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse,
                                                         dqkv, ld_dqkv, L, H, sn, sl, causal);
+  LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("attn_bwd_kernel");
   return 0;

@@ -37,6 +37,19 @@ int llc_check_cuda(cudaError_t e, const char* what);
 extern unsigned long long g_llc_launches;
 #define LLC_COUNT_LAUNCH() (++g_llc_launches)
 
+// per-launch event timing (llc_prof_enable / llc_prof_read)
+extern int g_llc_prof_on;
+void llc_prof_begin(int kind, int m, int n, int k, double flops, double bytes, cudaStream_t st);
+void llc_prof_end(cudaStream_t st);
+#define LLC_PROF_BEGIN(kind, m, n, k, flops, bytes, st)                       \
+  do {                                                                        \
+    if (g_llc_prof_on) llc_prof_begin(kind, m, n, k, flops, bytes, st);       \
+  } while (0)
+#define LLC_PROF_END(st)                  \
+  do {                                    \
+    if (g_llc_prof_on) llc_prof_end(st);  \
+  } while (0)
+
 // TMA descriptor encode (driver entry point fetched through the runtime, no -lcuda)
 int llc_encode_tmap_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int elem_bytes,
                        uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,

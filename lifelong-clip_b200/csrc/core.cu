@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -22,6 +24,66 @@ int llc_check_cuda(cudaError_t e, const char* what) {
 extern "C" int llc_version(void) { return LLC_VERSION; }
 extern "C" const char* llc_last_error(void) { return g_err; }
 extern "C" unsigned long long llc_launch_count(void) { return g_llc_launches; }
+
+// ---------------------------------------------------------------- per-launch event timing
+int g_llc_prof_on = 0;
+namespace {
+struct ProfSlot {
+  llc_prof_rec rec;
+  cudaEvent_t e0, e1;
+};
+std::vector<ProfSlot> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void release_all() {
+  for (auto& s : g_prof) {
+    g_event_pool.push_back(s.e0);
+    g_event_pool.push_back(s.e1);
+  }
+  g_prof.clear();
+}
+}  // namespace
+
+void llc_prof_begin(int kind, int m, int n, int k, double flops, double bytes, cudaStream_t st) {
+  ProfSlot s;
+  s.rec.kind = kind; s.rec.m = m; s.rec.n = n; s.rec.k = k;
+  s.rec.ms = 0.f; s.rec.flops = flops; s.rec.bytes = bytes;
+  s.e0 = take_event();
+  s.e1 = take_event();
+  cudaEventRecord(s.e0, st);
+  g_prof.push_back(s);
+}
+void llc_prof_end(cudaStream_t st) {
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().e1, st);
+}
+
+extern "C" int llc_prof_enable(int on) {
+  if (on) release_all();
+  g_llc_prof_on = on ? 1 : 0;
+  return 0;
+}
+
+extern "C" int llc_prof_read(llc_prof_rec* out, int max) {
+  for (auto& s : g_prof) {
+    cudaError_t e = cudaEventSynchronize(s.e1);
+    if (e != cudaSuccess) return -llc_check_cuda(e, "llc_prof_read: cudaEventSynchronize");
+    e = cudaEventElapsedTime(&s.rec.ms, s.e0, s.e1);
+    if (e != cudaSuccess) return -llc_check_cuda(e, "llc_prof_read: cudaEventElapsedTime");
+  }
+  const int n = (int)g_prof.size();
+  if (out != nullptr)
+    for (int i = 0; i < n && i < max; ++i) out[i] = g_prof[i].rec;
+  return n;
+}
 
 extern "C" int llc_check_device(int dev) {
   int n = 0;

@@ -285,7 +285,11 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, in
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < llc_num_sms() ? tiles : llc_num_sms();
+  LLC_PROF_BEGIN(LLC_K_GEMM, M, N, K, 2.0 * M * N * K,
+                 2.0 * ((double)M * K + (double)N * K) + (double)M * N * (ep.out_fp32 ? 4 : 2),
+                 stream);
   gemm_tn_kernel<BN><<<grid, kThreads, C::kSmem, stream>>>(tmA, tmB, M, N, K, ep);
+  LLC_PROF_END(stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("gemm_tn_kernel");
   return 0;

@@ -297,7 +297,10 @@ extern "C" int llc_head_fwd(const llc_head_args* a, void* stream) {
   if (smem > 48 * 1024)
     LLC_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
+  LLC_PROF_BEGIN(LLC_K_HEAD, a->N, a->C, 0, 2.0 * a->N * ((double)a->D * a->E + (double)a->E * a->C),
+                 4.0 * a->N * (a->D + 2 * a->E + 2 * a->C), (cudaStream_t)stream);
   head_fwd_kernel<<<a->N, kThreads, smem, (cudaStream_t)stream>>>(k);
+  LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("head_fwd_kernel");
   return 0;
@@ -316,8 +319,11 @@ extern "C" int llc_head_bwd(const llc_head_args* a, const float* d_probs, float 
   if (smem > 48 * 1024)
     LLC_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
+  LLC_PROF_BEGIN(LLC_K_HEAD, a->N, a->C, 1, 2.0 * a->N * ((double)a->D * a->E + (double)a->E * a->C),
+                 4.0 * a->N * (2 * a->D + 2 * a->E + a->C), (cudaStream_t)stream);
   head_bwd_kernel<<<a->N, kThreads, smem, (cudaStream_t)stream>>>(k, d_probs, loss_scale, dx,
                                                                   ld_dx);
+  LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("head_bwd_kernel");
   return 0;

@@ -451,8 +451,10 @@ extern "C" int llc_ln_fwd(const float* x, int ld_x, const float* gamma, const fl
               "llc_ln_fwd: LoRA rank %d unsupported or ld_y too small", r);
   if (T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  LLC_PROF_BEGIN(LLC_K_LN_FWD, T, D, 0, 0.0, 6.0 * T * D, st);
   DISPATCH_NV(D, (ln_fwd_kernel<NV><<<(T + 7) / 8, 256, 0, st>>>(
                      x, ld_x, gamma, beta, T, (__nv_bfloat16*)y, ld_y, lora_A, r)));
+  LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("ln_fwd_kernel");
   return 0;
@@ -468,9 +470,12 @@ extern "C" int llc_ln_bwd(const float* x, int ld_x, const float* gamma, const vo
               "llc_ln_bwd: LoRA rank %d unsupported or no room for du", r);
   if (T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  LLC_PROF_BEGIN(LLC_K_LN_BWD, T, D, 0, 0.0,
+                 (double)T * D * (4 + 2 + (dx_in ? 4 : 0) + 4 + (dxb ? 2 : 0)), st);
   DISPATCH_NV(D, (ln_bwd_kernel<NV><<<(T + 7) / 8, 256, 0, st>>>(
                      x, ld_x, gamma, (const __nv_bfloat16*)dy, ld_dy, dx_in, dx_out, T,
                      (__nv_bfloat16*)dxb, ld_dxb, lora_B, r, scale)));
+  LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("ln_bwd_kernel");
   return 0;
@@ -492,6 +497,7 @@ extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float
   const int grid = chunks < llc_lora_side_max_partials() ? chunks : llc_lora_side_max_partials();
   const size_t smem = ((Mrd ? (size_t)C * R : 0) + (size_t)kSideRows * R) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 0, 0.0, 2.0 * T * C, st);
   if (R == 4) {
     static bool cfg4 = false;
     if (!cfg4) {
@@ -513,6 +519,7 @@ extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float
         (__nv_bfloat16*)X, ld_x, T, C, r, Mrd, rd_sc, rd_sj, rd_scale, (const __nv_bfloat16*)w,
         ld_w, partial);
   }
+  LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("lora_side_kernel");
   if (n_partials) *n_partials = grid;
@@ -525,8 +532,11 @@ extern "C" int llc_lora_colsum_finish(const float* partial, int n_partials, int 
   LLC_REQUIRE(partial && out && n_partials > 0 && r >= 1 && r <= kMaxR,
               "llc_lora_colsum_finish: bad args");
   const int R = r <= 4 ? 4 : 8;
+  LLC_PROF_BEGIN(LLC_K_LORA_SIDE, n_partials, C, 1, 0.0, 4.0 * n_partials * C * R,
+                 (cudaStream_t)stream);
   colsum_finish_kernel<<<(C * R + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       partial, n_partials, C, R, r, cs_scale, out, o_sc, o_sj);
+  LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("colsum_finish_kernel");
   return 0;
@@ -565,8 +575,11 @@ extern "C" int llc_patchify(const float* img, int N, int C, int HW, int P, void*
   const int grid = (int)((total + 255) / 256 < (size_t)(llc_num_sms() * 16)
                              ? (total + 255) / 256
                              : (size_t)(llc_num_sms() * 16));
+  LLC_PROF_BEGIN(LLC_K_EMBED, N, C * HW * HW, 0, 0.0, 6.0 * N * C * HW * HW,
+                 (cudaStream_t)stream);
   patchify_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, N, C, HW, P, (__nv_bfloat16*)out,
                                                           ld_out);
+  LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("patchify_kernel");
   return 0;
@@ -580,8 +593,10 @@ extern "C" int llc_embed_ln_pre(const float* patch_out, int ld_p, const float* c
   LLC_REQUIRE(D % 128 == 0 && ld_p % 4 == 0, "llc_embed_ln_pre: bad shape");
   const int T = N * L;
   cudaStream_t st = (cudaStream_t)stream;
+  LLC_PROF_BEGIN(LLC_K_EMBED, T, D, 1, 0.0, 8.0 * T * D, st);
   DISPATCH_NV(D, (embed_ln_pre_kernel<NV><<<(T + 7) / 8, 256, 0, st>>>(
                      patch_out, ld_p, class_emb, pos, gamma, beta, N, L, x0)));
+  LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("embed_ln_pre_kernel");
   return 0;
@@ -593,9 +608,11 @@ extern "C" int llc_adamw(float* p, const float* g, float* m, float* v, int n, fl
   LLC_REQUIRE(p && g && m && v && n > 0 && step >= 1, "llc_adamw: bad args");
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  LLC_PROF_BEGIN(LLC_K_OTHER, n, 0, 0, 0.0, 28.0 * n, (cudaStream_t)stream);
   adamw_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2,
                                                                   eps, wd, bc1, bc2_sqrt,
                                                                   grad_scale);
+  LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("adamw_kernel");
   return 0;

@@ -133,8 +133,10 @@ extern "C" int llc_cast_bf16(const float* src, void* dst, int T, int D, int ld_d
   const int grid = (int)((total + 255) / 256 < (size_t)llc_num_sms() * 8
                              ? (total + 255) / 256
                              : (size_t)llc_num_sms() * 8);
+  LLC_PROF_BEGIN(LLC_K_OTHER, T, D, 1, 0.0, 6.0 * T * D, (cudaStream_t)stream);
   cast_rows_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), T, D, ld_dst);
+  LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("cast_rows_bf16_kernel");
   return 0;

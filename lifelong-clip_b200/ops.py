@@ -38,6 +38,22 @@ def launch_count() -> int:
     return int(_lib().llc_launch_count())
 
 
+def prof_enable(on: bool) -> None:
+    K.check(_lib().llc_prof_enable(int(on)), "llc_prof_enable")
+
+
+def prof_read():
+    """Per-launch records [(kind, m, n, k, ms, flops, bytes)] since prof_enable(True); blocks on
+    the recorded events."""
+    lib = _lib()
+    n = lib.llc_prof_read(None, 0)
+    if n < 0:
+        K.check(n, "llc_prof_read")
+    buf = (K.ProfRec * max(n, 1))()
+    n = lib.llc_prof_read(buf, n)
+    return [(K.PROF_KINDS[r.kind], r.m, r.n, r.k, r.ms, r.flops, r.bytes) for r in buf[:n]]
+
+
 def gemm_tn(A, B, M, N, Kdim, out, *, bias=None, resid=None, act=0, aux=None, out2=None):
     """out[M,N] = epi(A[M,K] @ B[N,K]^T). A, B bf16 2-D (row stride = leading dim)."""
     _req(A, torch.bfloat16, "A"); _req(B, torch.bfloat16, "B")

@@ -1,0 +1,213 @@
+"""Trainer mirror of the reference's methods/adapter_clip.AdapterCLIP (on methods/_trainer._Trainer)
+for the lora-clip method: same online_step / online_train / online_before_task / online_after_task /
+online_evaluate interface and class bookkeeping, with the hot loop routed through the fused
+tower + head kernels and sharded data-parallel over one process per GPU.
+
+What changed under the same interface:
+  * label remap: the O(N*C) Python `list.index` loop (methods/adapter_clip.py:75-76) is a device
+    LUT gather (llc_label_remap), bit-exact;
+  * per-step tokenisation + text tower (set_token, :84) is a gather index into cached features;
+  * forward/backward/AdamW are llc_* calls; loss and accuracy come back in ONE 2-float read
+    (the reference syncs twice, :103-104);
+  * nn.DataParallel (methods/_trainer.py:167-168: ~600 MB replicate per step) is replaced by
+    persistent replicas, a rank::world shard of the combined stream+replay batch and ONE NCCL
+    all-reduce of the flat LoRA gradient buffer (+2 floats for loss / #correct).
+The replay memory (utils/memory.py) and the Si-Blurry sampler (utils/online_sampler.py) are used
+unchanged: pass the reference's objects in.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import dp, ops
+from .adapter_clip import AdapterCLIP
+from .engine import FlatAdamW
+
+
+class LoRAClipTrainer:
+    def __init__(self, model: AdapterCLIP, class_names, *, n_classes=None, n_tasks=5, lr=1e-3,
+                 online_iter=1, visible_classes='batch', memory=None, memory_provider=None,
+                 memory_batchsize=0, memory_size=0, train_transform=None, test_transform=None,
+                 use_amp=True, topk=1, double_softmax=True, device=None, rank=None,
+                 world_size=None, sharded_input=False):
+        self.custom_clip = model
+        self.model = model
+        self.device = device or model.model.visual.proj.device
+        self.all_classnames = list(class_names)
+        self.n_classes = n_classes or len(class_names)
+        self.n_tasks = n_tasks
+        self.lr, self.online_iter, self.topk = lr, online_iter, topk
+        self.visible_classes = visible_classes
+        self.memory, self.memory_provider = memory, memory_provider
+        self.memory_batchsize, self.memory_size = memory_batchsize, memory_size
+        self.train_transform = train_transform or (lambda x: x)
+        self.test_transform = test_transform or (lambda x: x)
+        self.use_amp = use_amp          # bf16 tensor-core operands are always on; no GradScaler
+        self.double_softmax = double_softmax
+        self.exposed_classes, self.exposed_classes_names = [], []
+        self.batch_exposed_classes, self.batch_exposed_classes_names = [], []
+        self._total_classes = 0
+        ddp = dist.is_available() and dist.is_initialized()
+        self.rank = rank if rank is not None else (dist.get_rank() if ddp else 0)
+        self.world = world_size if world_size is not None else (dist.get_world_size() if ddp else 1)
+        # sharded_input=True: the loader already yields this rank's shard (DistributedSampler
+        # style; utils/online_sampler.py:33-48 has the num_replicas/rank plumbing); False: every
+        # rank sees the global batch (the reference's single DataLoader) and slices rank::world.
+        self.sharded_input = sharded_input
+        self.optimizer = None
+        self._lut = torch.full((self.n_classes,), -1, dtype=torch.int64, device=self.device)
+        self._lut_src = None
+        self._scal = torch.zeros(2, device=self.device)
+
+    # ---- class bookkeeping (methods/_trainer.py:404-416, methods/adapter_clip.py:256-283) ------
+    def add_new_class(self, class_name):
+        for label in class_name.tolist():
+            if label not in self.exposed_classes:
+                self.exposed_classes.append(label)
+        if self.memory is not None:
+            self.memory.add_new_class(cls_list=self.exposed_classes)
+        self.exposed_classes_names = [self.all_classnames[i] for i in self.exposed_classes]
+        self.batch_exposed_classes, self.batch_exposed_classes_names = [], []
+        if self.memory_size > 0:
+            self.batch_exposed_classes = self.exposed_classes
+            self.batch_exposed_classes_names = self.exposed_classes_names
+        else:
+            for label in class_name.tolist():
+                if label not in self.batch_exposed_classes:
+                    self.batch_exposed_classes.append(label)
+            self.batch_exposed_classes_names = [self.all_classnames[i]
+                                                for i in self.batch_exposed_classes]
+
+    def _class_lut(self, class_list):
+        """Device LUT class id -> position in class_list; rebuilt only when the list changes."""
+        key = tuple(class_list)
+        if key != self._lut_src:
+            lut = torch.full((self.n_classes,), -1, dtype=torch.int64)
+            lut[torch.tensor(class_list, dtype=torch.int64)] = torch.arange(len(class_list))
+            self._lut.copy_(lut, non_blocking=True)
+            self._lut_src = key
+        return self._lut
+
+    # ---- task hooks ----------------------------------------------------------------------------
+    def online_before_task(self, task_id):
+        """methods/adapter_clip.py:115-127: freeze everything but LoRA, rebuild the optimizer."""
+        for k, v in self.custom_clip.named_parameters():
+            if "adaptmlp" not in k and "lora" not in k:
+                v.requires_grad = False
+        self.reset_opt()
+
+    def reset_opt(self):
+        """utils/train_utils.py:27-28: AdamW(lr, weight_decay=1e-5) over the trainable tensors."""
+        self.optimizer = FlatAdamW(self.custom_clip.model.visual.engine(), lr=self.lr,
+                                   weight_decay=1e-5)
+
+    def online_after_task(self, task_id):
+        """methods/adapter_clip.py:129-130: evaluation sees every class exposed so far."""
+        self._total_classes = len(self.exposed_classes)
+        self.custom_clip.set_token(self.exposed_classes_names)
+
+    # ---- hot loop ------------------------------------------------------------------------------
+    def online_step(self, images, labels, idx=None):
+        """methods/adapter_clip.py:34-47."""
+        seen = labels
+        if self.sharded_input and self.world > 1:
+            # class bookkeeping must see the GLOBAL batch's labels
+            seen = dp.gather_labels(labels, self.world, self.device)
+        self.add_new_class(seen)
+        self.custom_clip.update_class_names(self.exposed_classes_names)
+        _loss, _acc, _iter = 0.0, 0.0, 0
+        for _ in range(int(self.online_iter)):
+            loss, acc = self.online_train([images, labels])  # nothing below writes in place
+            _loss += loss
+            _acc += acc
+            _iter += 1
+        return _loss / _iter, _acc / _iter
+
+    def online_train(self, data):
+        """methods/adapter_clip.py:49-107. Returns (loss: float, acc: float) of the GLOBAL batch."""
+        if self.optimizer is None:
+            self.reset_opt()
+        if self.visible_classes == 'batch':
+            train_class_list = self.batch_exposed_classes
+            train_class_name_list = self.batch_exposed_classes_names
+        else:
+            train_class_list = self.exposed_classes
+            train_class_name_list = self.exposed_classes_names
+        x, y = data
+        if self.memory is not None and len(self.memory) > 0 and self.memory_batchsize > 0:
+            memory_images, memory_labels = next(self.memory_provider)
+            for i in memory_labels.unique().tolist():
+                if i not in train_class_list:
+                    train_class_list.append(i)
+                    train_class_name_list.append(
+                        self.exposed_classes_names[self.exposed_classes.index(i)])
+            x = torch.cat([x, memory_images], dim=0)
+            y = torch.cat([y, memory_labels], dim=0)
+        B = y.shape[0]
+        # data-parallel shard of the combined stream+replay batch
+        if self.world > 1:
+            if self.sharded_input:
+                B = B * self.world
+            else:
+                x, y = dp.shard_batch(x, y, self.rank, self.world)
+        x = x.to(self.device, non_blocking=True)
+        y = y.to(self.device, non_blocking=True)
+        y_local = ops.label_remap(y, self._class_lut(train_class_list))
+        x = self.train_transform(x)
+        self.custom_clip.set_token(train_class_name_list)
+        loss_sum, n_correct = self.fused_step(x, y_local, B)
+        return loss_sum, n_correct / B
+
+    def fused_step(self, x, y_local, global_batch, sync=True):
+        """forward + loss + backward + gradient all-reduce + AdamW, all on the device."""
+        m = self.custom_clip
+        eng = m.model.visual.engine()
+        eng.forward(x, training=True)
+        head = eng.head(m._text_all, m.model.logit_scale_exp(),
+                        cls_idx=m._cls_idx, add_mask=m._add_mask, labels=y_local,
+                        double_softmax=self.double_softmax, inv_batch=1.0 / global_batch)
+        eng.backward_from_head(head)
+        ops.loss_acc(head.loss_rows, head.pred, y_local, self._scal)
+        dp.allreduce_step(eng.grad_flat, self._scal, self.world)
+        self.optimizer.step()
+        self.last_head = head
+        if not sync:
+            return self._scal
+        loss_sum, n_correct = self._scal.tolist()  # the step's only host sync
+        return loss_sum, n_correct
+
+    # ---- evaluation (methods/adapter_clip.py:132-176, methods/_trainer.py:519-534) --------------
+    @torch.no_grad()
+    def online_evaluate(self, test_loader, samples_cnt=None):
+        from sklearn.metrics import confusion_matrix
+        correct_l = torch.zeros(self.n_tasks)
+        num_data_l = torch.zeros(self.n_tasks)
+        label, pred_list = [], []
+        self.custom_clip.eval()
+        m = self.custom_clip
+        eng = m.model.visual.engine()
+        for x, y in test_loader:
+            x = self.test_transform(x.to(self.device))
+            y = y.to(self.device)
+            eng.forward(x, training=False)
+            head = eng.head(m._text_all, m.model.logit_scale_exp(),
+                            cls_idx=m._cls_idx, add_mask=m._add_mask)
+            pred = head.pred
+            xlabel_cnt, correct_xlabel_cnt = self._interpret_pred(y, pred)
+            correct_l += correct_xlabel_cnt
+            num_data_l += xlabel_cnt
+            label += y.tolist()
+            pred_list += pred.tolist()
+        avg_acc = torch.sum(correct_l) / torch.sum(num_data_l)
+        task_acc = (correct_l / (num_data_l + 1e-5)).numpy().tolist()
+        cm = confusion_matrix(label, pred_list)
+        return {"avg_loss": 0.0 / torch.sum(num_data_l), "avg_acc": avg_acc, "cls_acc": task_acc,
+                "task_acc": task_acc, "confusion_matrix": cm.tolist()}
+
+    def _interpret_pred(self, y, pred):
+        """methods/_trainer.py:519-534 (per-task counts via y // n_tasks), on the device."""
+        cls = (y // self.n_tasks).clamp(0, self.n_tasks - 1)
+        num = torch.bincount(cls, minlength=self.n_tasks).float().cpu()[:self.n_tasks]
+        ok = torch.bincount(cls[y == pred], minlength=self.n_tasks).float().cpu()[:self.n_tasks]
+        return num, ok
