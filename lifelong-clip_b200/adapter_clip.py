@@ -63,7 +63,7 @@ class _ProbsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, images, text, cls_idx, add_mask, *lora):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in lora)
+        need_grad = any(ctx.needs_input_grad)
         eng = model.visual.engine()
         eng.forward(images, training=need_grad)
         head = eng.head(text, model.logit_scale_exp(), cls_idx=cls_idx,

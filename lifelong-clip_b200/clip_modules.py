@@ -162,8 +162,8 @@ class _BlockFn(torch.autograd.Function):
         L, N, D = x.shape
         T, M, dev = L * N, blk.mlp.c_fc.out_features, x.device
         x2 = x.detach().float().contiguous().view(T, D)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad
-                                                                       for p in lora))
+        # (grad mode is off inside Function.forward: ask autograd which inputs need gradients)
+        need_grad = any(ctx.needs_input_grad)
         bufs = dict(
             x_in=x2, h1=_bf16(T, D + PAD, dev), qkv=_bf16(T, 3 * D + PAD, dev),
             lse=torch.empty(N * blk.n_head * L, device=dev), o=_bf16(T, D + PAD, dev),
@@ -318,7 +318,7 @@ class _TowerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, vit, images, *lora):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in lora)
+        need_grad = any(ctx.needs_input_grad)
         eng = vit.engine()
         eng.forward(images, training=need_grad)
         head = eng.features_only()

@@ -1,0 +1,221 @@
+// CTA-pair tcgen05 GEMM for sm_100a: out[M,N] = epi(A[M,K] . B[N,K]^T), bf16 -> fp32 in TMEM.
+//
+// The production-shape path of llc_gemm_bf16_tn (token counts in the thousands, N % 256 == 0).
+// A cluster of two CTAs (one SM each) owns a 256 x 256 output tile: tcgen05.mma.cta_group::2 with
+// M = 256 reads A rows [128 r, 128 r + 128) and B rows [128 r, 128 r + 128) from CTA r's shared
+// memory and leaves 128 accumulator rows x 256 columns in each CTA's TMEM. Per k-block each CTA
+// fetches 32 KB through TMA for 2 x 128 x 256 x 64 MACs of its own - half the L2->SM bytes per
+// FLOP of the single-CTA 128 x 256 kernel, which measured L2-feed-bound (profiles/).
+//
+//   warp 0      TMA producer (one lane per CTA): 6-stage ring; both CTAs complete bytes on the
+//               LEADER's full barrier
+//   warp 1      MMA issuer (leader CTA, one lane); commits multicast to both CTAs' barriers
+//   warps 2..9  epilogue (gemm_epilogue.cuh): two warps per TMEM lane quarter, 128 columns each
+// TMEM holds two 256-column accumulators, so a tile's epilogue overlaps the next tile's mainloop.
+#include "gemm_epilogue.cuh"
+
+namespace {
+
+constexpr int BM = 256;       // per pair; 128 rows per CTA
+constexpr int BN = 256;
+constexpr int BK = 64;        // 128 B swizzle row
+constexpr int kStages = 6;
+constexpr int kPrefetchKb = 8;  // A blocks requested into L2 this many k-blocks ahead of the ring
+constexpr int kABytes = 128 * BK * 2;
+constexpr int kBBytes = 128 * BK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;       // per CTA
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
+constexpr int kBarBytes = 256;
+constexpr int kSmem = 1024 + kStages * kStageBytes + kEpiBytes + kBarBytes;
+constexpr int kTmemCols = 512;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             int M, int N, int K, EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint8_t* smem_ab = smem;
+  uint8_t* smem_epi = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes + kEpiBytes);
+  uint64_t* full_bar = bars;                   // [kStages]  used in the leader CTA only
+  uint64_t* empty_bar = bars + kStages;        // [kStages]  one per CTA (multicast commit)
+  uint64_t* tfull_bar = bars + 2 * kStages;    // [2]        one per CTA (multicast commit)
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]     leader only: both CTAs' epilogues
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_n = N / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      // one arrival (the leader's expect_tx, armed with BOTH CTAs' bytes); the peer's TMA only
+      // completes bytes on it. Early peer bytes just drive the tx-count negative until the
+      // leader arms the phase, and a peer TMA can never reach the next phase early because its
+      // own empty barrier fires only after the MMAs that waited on this phase retired.
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull_bar[b]), 1);
+      mbar_init(smem_u32(&tempty_bar[b]), 2 * kEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_cg2<kTmemCols>(smem_u32(tmem_slot));
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits and the TMEM allocation are visible to both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / tiles_n) * BM + (int)rank * 128;
+        const int n0 = (tile % tiles_n) * BN + (int)rank * 128;
+        const int next_tile = tile + num_pairs;
+        const int m0_next = (next_tile / tiles_n) * BM + (int)rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          // A (activations) streams from HBM once per GEMM: pull it into L2 well ahead of the
+          // smem ring so the ring's own loads see L2 latency. B (weights) stays L2-resident.
+          {
+            const int pk = kb + kPrefetchKb;
+            if (pk < num_kb) tma_prefetch_2d(&tmA, pk * BK, m0);
+            else if (next_tile < num_tiles && pk - num_kb < num_kb)
+              tma_prefetch_2d(&tmA, (pk - num_kb) * BK, m0_next);
+          }
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb_local = smem_u32(&full_bar[stage]);
+          const uint32_t fb_leader = mapa_shared(fb_local, 0);
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * kStageBytes);
+          const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
+          tma_load_2d_cg2(sa, &tmA, fb_leader, kb * BK, m0);
+          tma_load_2d_cg2(sa + kABytes, &tmB, fb_leader, kb * BK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1);  // both epilogues drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+          const int ksteps = min(BK / 16, (K - kb * BK) / 16);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_mc(smem_u32(&empty_bar[stage]), 0x3);  // frees the slot in both CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_mc(smem_u32(&tfull_bar[buf]), 0x3);  // accumulator complete in both CTAs
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;
+    const int q = warp & 3;    // TMEM lane quarter this warp may access
+    const int hh = ew >> 2;    // column half
+    uint8_t* tile_s = smem_epi + ew * kEpiWarpBytes;
+    const uint32_t te_leader = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      const int row0 = (tile / tiles_n) * BM + (int)rank * 128 + q * 32;
+      const int col0 = (tile % tiles_n) * BN + hh * (BN / 2);
+      mbar_wait(smem_u32(&tfull_bar[buf]), bphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + buf * BN + hh * (BN / 2) + ((uint32_t)(q * 32) << 16);
+      epi_warp_tile<MODE, BN / 2 / 32>(ep, t_addr, tile_s, row0, col0, M, N, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(te_leader + buf * 8);
+    }
+  }
+
+  // no CTA may exit (or free TMEM) while its peer can still signal its barriers / read its smem
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2<kTmemCols>(tmem_base);
+  }
+}
+
+template <int MODE>
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                 const EpiParams& ep, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    LLC_CUDA(cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmem));
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int pairs = llc_num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  LLC_PROF_BEGIN(LLC_K_GEMM, M, N, K, 2.0 * M * N * K,
+                 2.0 * ((double)M * K + (double)N * K) + (double)M * N * (ep.out_fp32 ? 4 : 2),
+                 stream);
+  gemm2_kernel<MODE><<<grid, kThreads, kSmem, stream>>>(tmA, tmB, M, N, K, ep);
+  LLC_PROF_END(stream);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("gemm2_kernel");
+  return 0;
+}
+
+}  // namespace
+
+// Chosen by llc_gemm_bf16_tn for shapes that fill the machine with 256 x 256 pair tiles.
+bool llc_gemm2_eligible(int M, int N, int K) {
+  if (N % BN != 0 || K < BK) return false;
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  return tiles >= llc_num_sms() / 2;
+}
+
+int llc_gemm2_launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                     const EpiParams& ep, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  int rc = llc_encode_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K,
+                              (uint64_t)M, (uint64_t)lda * 2, BK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = llc_encode_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N,
+                          (uint64_t)ldb * 2, BK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  switch (epi_mode_of(ep)) {
+    case EPI_GELU: return launch_gemm2<EPI_GELU>(tmA, tmB, M, N, K, ep, stream);
+    case EPI_DGELU: return launch_gemm2<EPI_DGELU>(tmA, tmB, M, N, K, ep, stream);
+    case EPI_F32: return launch_gemm2<EPI_F32>(tmA, tmB, M, N, K, ep, stream);
+    default: return launch_gemm2<EPI_BF16>(tmA, tmB, M, N, K, ep, stream);
+  }
+}

@@ -1,0 +1,229 @@
+// Epilogue of the tcgen05 GEMMs: TMEM accumulator -> registers -> fused element-wise work of the
+// ViT block -> per-warp smem transpose -> coalesced 16-byte global I/O.
+//   EPI_BF16   out = bf16(acc + bias)                                  (qkv, d_o, dh)
+//   EPI_GELU   z = bf16(acc + bias) (optional), out2 = bf16(QuickGELU(z))   model.py:203-206,219-222
+//   EPI_DGELU  out = bf16(acc * QuickGELU'(aux))                         backward of the above
+//   EPI_F32    out = fp32(acc + bias + resid)                            residual stream model.py:234-235
+// One warp owns 32 accumulator rows (its TMEM lane quarter; thread = row after tcgen05.ld 32x32b)
+// and walks NCH chunks of 32 columns.
+//
+// bf16 modes do all math in the row-per-thread layout straight out of TMEM (32 independent
+// elements per thread: no shared-memory latency in the dependency chain), then transpose the
+// PACKED bf16 result through a 2 KB XOR-swizzled staging tile so that global stores are 16 B per
+// lane with 4 lanes per 64 B row segment. EPI_DGELU brings its aux operand in through the same
+// tile in the opposite direction (coalesced load -> row-per-thread). EPI_F32 transposes the fp32
+// accumulator (4 KB tile) and adds bias/residual in the coalesced layout, where the residual
+// loads are 16 B per lane. Global inputs of chunk c+1 are requested before chunk c is processed.
+#pragma once
+#include "common.cuh"
+
+enum { EPI_BF16 = 0, EPI_GELU = 1, EPI_DGELU = 2, EPI_F32 = 3 };
+
+struct EpiParams {
+  const float* bias;
+  const float* resid;
+  int ld_resid;
+  int act;
+  const __nv_bfloat16* aux;
+  int ld_aux;
+  void* out;
+  int ld_out;
+  int out_fp32;
+  __nv_bfloat16* out2;
+  int ld_out2;
+};
+
+constexpr int kEpiWarpBytes = 4096;  // two 2 KB bf16 tiles, or one 4 KB fp32 tile
+
+// QuickGELU x*sigmoid(1.702x) with sigmoid(y) = 0.5 + 0.5 tanh(y/2): one MUFU op per element
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float quick_gelu_fast(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(0.851f * x), hx);
+}
+__device__ __forceinline__ float quick_gelu_grad_fast(float x) {
+  const float s = fmaf(0.5f, tanh_approx(0.851f * x), 0.5f);
+  return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
+}
+
+// ---- staging tiles ------------------------------------------------------------------------------
+// bf16 tile: 32 rows x 64 B, 16 B chunk c of row r stored at chunk c ^ ((r >> 1) & 3): both the
+// row-per-thread side (8 consecutive rows, one chunk) and the coalesced side (2 rows x 4 chunks)
+// touch 32 distinct banks per 8-lane phase.
+__device__ __forceinline__ uint32_t bf_tile_off(int row, int chunk) {
+  return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+// fp32 tile: 32 rows x 128 B, chunk c of row r at c ^ (r & 7)
+__device__ __forceinline__ uint32_t f32_tile_off(int row, int chunk) {
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int MODE>
+struct EpiPre {
+  float4 bias[8];  // bf16 modes: the chunk's 32 bias values (uniform); F32: [0] = this lane's 4
+  uint4 aux[4];    // DGELU: this lane's 16 B of 4 rows (coalesced mapping)
+  float4 rs[8];    // F32: this lane's 16 B of 8 rows
+};
+
+template <int MODE>
+__device__ __forceinline__ void epi_prefetch(EpiPre<MODE>& p, const EpiParams& ep, int row0,
+                                             int col, int M, int N, int lane) {
+  if (MODE == EPI_F32) {
+    const int cc = col + (lane & 7) * 4;
+    p.bias[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr && cc < N)
+      p.bias[0] = __ldg(reinterpret_cast<const float4*>(ep.bias + cc));
+    if (ep.resid != nullptr) {
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int row = row0 + pass * 4 + (lane >> 3);
+        p.rs[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < M && cc < N)
+          p.rs[pass] = *reinterpret_cast<const float4*>(ep.resid + (size_t)row * ep.ld_resid + cc);
+      }
+    }
+  } else {
+    if (MODE != EPI_DGELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p.bias[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias != nullptr && col + 4 * j < N)  // same address in every lane: one wavefront
+          p.bias[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4 * j));
+      }
+    } else {
+      const int cc = col + (lane & 3) * 8;
+#pragma unroll
+      for (int pass = 0; pass < 4; ++pass) {
+        const int row = row0 + pass * 8 + (lane >> 2);
+        p.aux[pass] = make_uint4(0, 0, 0, 0);
+        if (row < M && cc < N)
+          p.aux[pass] = *reinterpret_cast<const uint4*>(ep.aux + (size_t)row * ep.ld_aux + cc);
+      }
+    }
+  }
+}
+
+// packed bf16 row (32 columns = 4 x 16 B) of this thread -> staging tile
+__device__ __forceinline__ void stage_row_bf16(uint8_t* tile, int lane, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(tile + bf_tile_off(lane, c)) =
+        make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+// staging tile -> global, 4 lanes per row, 8 rows per instruction
+__device__ __forceinline__ void store_tile_bf16(const uint8_t* tile, __nv_bfloat16* out, int ld,
+                                                int row0, int col, int M, int N, int lane) {
+  const int cc = col + (lane & 3) * 8;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int rr = pass * 8 + (lane >> 2), row = row0 + rr;
+    const uint4 v = *reinterpret_cast<const uint4*>(tile + bf_tile_off(rr, lane & 3));
+    if (row < M && cc < N) *reinterpret_cast<uint4*>(out + (size_t)row * ld + cc) = v;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_chunk(const EpiPre<MODE>& p, const EpiParams& ep,
+                                          const uint32_t (&acc)[32], uint8_t* tile, int row0,
+                                          int col, int M, int N, int lane) {
+  if (MODE == EPI_F32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(tile + f32_tile_off(lane, j)) =
+          make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    __syncwarp();
+    const int c4 = lane & 7, cc = col + c4 * 4;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int rr = pass * 4 + (lane >> 3), row = row0 + rr;
+      float4 v = *reinterpret_cast<const float4*>(tile + f32_tile_off(rr, c4));
+      v.x += p.bias[0].x; v.y += p.bias[0].y; v.z += p.bias[0].z; v.w += p.bias[0].w;
+      if (ep.resid != nullptr) {
+        v.x += p.rs[pass].x; v.y += p.rs[pass].y; v.z += p.rs[pass].z; v.w += p.rs[pass].w;
+      }
+      if (row < M && cc < N)
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ld_out + cc) = v;
+    }
+    __syncwarp();
+    return;
+  }
+  uint8_t* t0 = tile;
+  uint8_t* t1 = tile + 2048;
+  float v[32];
+  if (MODE == EPI_DGELU) {
+    // aux arrives in the coalesced mapping; turn it into this thread's row through tile 1
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass)
+      *reinterpret_cast<uint4*>(t1 + bf_tile_off(pass * 8 + (lane >> 2), lane & 3)) = p.aux[pass];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 zq = *reinterpret_cast<const uint4*>(t1 + bf_tile_off(lane, c));
+      const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 z = unpack_bf16(zw[e]);
+        v[8 * c + 2 * e] = __uint_as_float(acc[8 * c + 2 * e]) * quick_gelu_grad_fast(z.x);
+        v[8 * c + 2 * e + 1] = __uint_as_float(acc[8 * c + 2 * e + 1]) * quick_gelu_grad_fast(z.y);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] = __uint_as_float(acc[4 * j]) + p.bias[j].x;
+      v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + p.bias[j].y;
+      v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + p.bias[j].z;
+      v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + p.bias[j].w;
+    }
+  }
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+  if (MODE == EPI_GELU) {
+    if (out != nullptr) stage_row_bf16(t0, lane, pk);
+    // the activation is applied to the bf16-rounded pre-activation, so that backward (which only
+    // sees the saved bf16 z) differentiates exactly the function forward evaluated
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 z = unpack_bf16(pk[i]);
+      pk[i] = pack_bf16(quick_gelu_fast(z.x), quick_gelu_fast(z.y));
+    }
+    stage_row_bf16(t1, lane, pk);
+    __syncwarp();
+    if (out != nullptr) store_tile_bf16(t0, out, ep.ld_out, row0, col, M, N, lane);
+    store_tile_bf16(t1, ep.out2, ep.ld_out2, row0, col, M, N, lane);
+  } else {
+    stage_row_bf16(t0, lane, pk);
+    __syncwarp();
+    store_tile_bf16(t0, out, ep.ld_out, row0, col, M, N, lane);
+  }
+  __syncwarp();  // tiles are rewritten by the next chunk
+}
+
+// One warp drains NCH chunks (32 rows x 32 columns each) starting at TMEM address t_addr.
+template <int MODE, int NCH>
+__device__ __forceinline__ void epi_warp_tile(const EpiParams& ep, uint32_t t_addr, uint8_t* tile,
+                                              int row0, int col0, int M, int N, int lane) {
+  EpiPre<MODE> cur, nxt;
+  epi_prefetch<MODE>(cur, ep, row0, col0, M, N, lane);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c + 1 < NCH) epi_prefetch<MODE>(nxt, ep, row0, col0 + (c + 1) * 32, M, N, lane);
+    uint32_t acc[32];
+    tmem_ld_32x32(t_addr + c * 32, acc);
+    tmem_ld_wait();
+    epi_chunk<MODE>(cur, ep, acc, tile, row0, col0 + c * 32, M, N, lane);
+    if (c + 1 < NCH) cur = nxt;
+  }
+}
+
+inline int epi_mode_of(const EpiParams& ep) {
+  if (ep.act == 1) return EPI_GELU;
+  if (ep.act == 2) return EPI_DGELU;
+  return ep.out_fp32 ? EPI_F32 : EPI_BF16;
+}

@@ -95,13 +95,21 @@ ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g
   if (row >= T) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld_x);
   const uint2* dyr = reinterpret_cast<const uint2*>(dy + (size_t)row * ld_dy);
-  float4 v[NV], g[NV];
+  const float4* dir = dx_in ? reinterpret_cast<const float4*>(dx_in + (size_t)row * D) : nullptr;
+  // every global input of the row is requested before the first reduction: ~2.3 KB in flight
+  // per warp instead of three dependent load phases
+  float4 v[NV], g[NV], pin[NV];
+  uint2 dq[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dq[i] = dyr[lane + 32 * i];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    pin[i] = dir ? dir[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
-  }
+  for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
   const float mean = warp_sum(s) * (1.0f / D);
   float q = 0.f;
 #pragma unroll
@@ -115,8 +123,7 @@ ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g
   for (int i = 0; i < NV; ++i) {
     const int c4 = lane + 32 * i;
     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
-    const uint2 d = dyr[c4];
-    const float2 d01 = unpack_bf16(d.x), d23 = unpack_bf16(d.y);
+    const float2 d01 = unpack_bf16(dq[i].x), d23 = unpack_bf16(dq[i].y);
     v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;  // xh
     g[i].x = d01.x * gm.x; g[i].y = d01.y * gm.y; g[i].z = d23.x * gm.z; g[i].w = d23.y * gm.w;
     c1 += g[i].x + g[i].y + g[i].z + g[i].w;
@@ -127,33 +134,37 @@ ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g
   float du[kMaxR];
 #pragma unroll
   for (int j = 0; j < kMaxR; ++j) du[j] = 0.f;
-  const float4* dir = dx_in ? reinterpret_cast<const float4*>(dx_in + (size_t)row * D) : nullptr;
   float4* dor = reinterpret_cast<float4*>(dx_out + (size_t)row * D);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c4 = lane + 32 * i;
     float4 o;
-    o.x = rstd * (g[i].x - c1 - v[i].x * c2);
-    o.y = rstd * (g[i].y - c1 - v[i].y * c2);
-    o.z = rstd * (g[i].z - c1 - v[i].z * c2);
-    o.w = rstd * (g[i].w - c1 - v[i].w * c2);
-    if (dir != nullptr) {
-      const float4 p = dir[c4];
-      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-    }
+    o.x = rstd * (g[i].x - c1 - v[i].x * c2) + pin[i].x;
+    o.y = rstd * (g[i].y - c1 - v[i].y * c2) + pin[i].y;
+    o.z = rstd * (g[i].z - c1 - v[i].z * c2) + pin[i].z;
+    o.w = rstd * (g[i].w - c1 - v[i].w * c2) + pin[i].w;
     dor[c4] = o;
     if (dxb != nullptr)
       reinterpret_cast<uint2*>(dxb + (size_t)row * ld_dxb)[c4] =
           make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
     if (lora_B != nullptr) {
       const int c = c4 * 4;
+      if (r == 4) {  // B rows of 4 floats: one 16-byte load per column
+        const float4* bp = reinterpret_cast<const float4*>(lora_B) + c;
+        const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
+        du[0] += o.x * b0.x + o.y * b1.x + o.z * b2.x + o.w * b3.x;
+        du[1] += o.x * b0.y + o.y * b1.y + o.z * b2.y + o.w * b3.y;
+        du[2] += o.x * b0.z + o.y * b1.z + o.z * b2.z + o.w * b3.z;
+        du[3] += o.x * b0.w + o.y * b1.w + o.z * b2.w + o.w * b3.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < kMaxR; ++j) {
-        if (j < r) {
-          du[j] += o.x * __ldg(lora_B + (size_t)(c + 0) * r + j) +
-                   o.y * __ldg(lora_B + (size_t)(c + 1) * r + j) +
-                   o.z * __ldg(lora_B + (size_t)(c + 2) * r + j) +
-                   o.w * __ldg(lora_B + (size_t)(c + 3) * r + j);
+        for (int j = 0; j < kMaxR; ++j) {
+          if (j < r) {
+            du[j] += o.x * __ldg(lora_B + (size_t)(c + 0) * r + j) +
+                     o.y * __ldg(lora_B + (size_t)(c + 1) * r + j) +
+                     o.z * __ldg(lora_B + (size_t)(c + 2) * r + j) +
+                     o.w * __ldg(lora_B + (size_t)(c + 3) * r + j);
+          }
         }
       }
     }
@@ -174,127 +185,157 @@ ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g
 }
 
 // ------------------------------------------------------------------------------------------------
-// LoRA side reductions over X bf16 [T, ld_x] (C columns), see llc.h.
-constexpr int kSideRows = 32;     // rows per chunk
+// LoRA side reductions over X bf16 [T, ld_x] (C columns), see llc.h. Two streaming kernels, both
+// one-warp-per-row with 16-byte loads (a warp reads 512 B of one row per instruction):
+//   rowdot  u[t, j] = scale * sum_c X[t, c] * M[c, j]      -> bf16 into X's 16 pad columns
+//   colsum  P[c, j] = sum_t X[t, c] * w[t, j]              -> per-CTA partials, reduced in fixed
+//                                                             order by colsum_finish (deterministic)
 constexpr int kSideThreads = 256;
-constexpr int kSideMaxPairs = 8;  // column pairs per thread: C <= 2*256*8 = 4096
+constexpr int kSideGroup = 256;  // columns per colsum CTA: one 16 B vector per lane
 
 template <int R>
 __global__ void __launch_bounds__(kSideThreads)
-lora_side_kernel(__nv_bfloat16* X, int ld_x, int T, int C, int r, const float* __restrict__ Mrd,
-                 int rd_sc, int rd_sj, float rd_scale, const __nv_bfloat16* __restrict__ w,
-                 int ld_w, float* __restrict__ partial) {
-  extern __shared__ float sm[];
-  float* sM = sm;                         // [C][R] rowdot factor (if Mrd)
-  float* sW = sm + (Mrd ? C * R : 0);     // [kSideRows][R] colsum weights of the chunk
+lora_rowdot_kernel(__nv_bfloat16* X, int ld_x, int T, int C, int r, const float* __restrict__ Mrd,
+                   int rd_sc, int rd_sj, float rd_scale) {
+  // factor staged as sM[(e * R + j) * nvec + v] (e = column within the 8-wide vector v): lanes
+  // read consecutive words -> no bank conflicts
+  extern __shared__ float sM[];
+  const int nvec = C / 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (Mrd != nullptr) {
-    for (int i = tid; i < C * R; i += kSideThreads) {
-      const int c = i / R, j = i % R;
-      sM[i] = (j < r) ? Mrd[(size_t)c * rd_sc + (size_t)j * rd_sj] * rd_scale : 0.f;
-    }
+  for (int i = tid; i < C * R; i += kSideThreads) {
+    const int c = i / R, j = i % R;
+    const float m = (j < r) ? Mrd[(size_t)c * rd_sc + (size_t)j * rd_sj] * rd_scale : 0.f;
+    sM[((c & 7) * R + j) * nvec + (c >> 3)] = m;
   }
-  float acc[kSideMaxPairs][2][R];
-#pragma unroll
-  for (int p = 0; p < kSideMaxPairs; ++p)
-#pragma unroll
-    for (int j = 0; j < R; ++j) acc[p][0][j] = acc[p][1][j] = 0.f;
   __syncthreads();
-
-  const int n_chunks = (T + kSideRows - 1) / kSideRows;
-  const int n_pairs = C / 2;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int t0 = chunk * kSideRows;
-    if (w != nullptr) {
-      for (int i = tid; i < kSideRows * R; i += kSideThreads) {
-        const int t = t0 + i / R, j = i % R;
-        sW[i] = (t < T && j < r) ? __bfloat162float(w[(size_t)t * ld_w + j]) : 0.f;
+  const int gw = blockIdx.x * (kSideThreads / 32) + warp;
+  const int nw = gridDim.x * (kSideThreads / 32);
+  for (int t = gw; t < T; t += nw) {
+    const uint4* xr = reinterpret_cast<const uint4*>(X + (size_t)t * ld_x);
+    float d[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) d[j] = 0.f;
+#pragma unroll 3
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 pk = xr[v];
+      const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(pw[e]);
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          d[j] += f.x * sM[((2 * e) * R + j) * nvec + v] + f.y * sM[((2 * e + 1) * R + j) * nvec + v];
       }
     }
-    __syncthreads();  // sW ready (also orders the previous chunk's reads)
-    if (Mrd != nullptr) {
-      // rowdot: one warp per row, lanes stride over 8-column vectors
-      for (int rr = warp; rr < kSideRows; rr += kSideThreads / 32) {
-        const int t = t0 + rr;
-        if (t >= T) break;
-        const uint4* xr = reinterpret_cast<const uint4*>(X + (size_t)t * ld_x);
-        float d[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) d[j] = 0.f;
-        for (int vi = lane; vi < C / 8; vi += 32) {
-          const uint4 pk = xr[vi];
-          const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+    for (int j = 0; j < R; ++j) d[j] = warp_sum(d[j]);
+    if (lane < LLC_LORA_PAD / 2) {
+      float a = 0.f, b = 0.f;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = unpack_bf16(pw[e]);
-            const float* m0 = sM + (vi * 8 + 2 * e) * R;
-#pragma unroll
-            for (int j = 0; j < R; ++j) d[j] += f.x * m0[j] + f.y * m0[R + j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < R; ++j) d[j] = warp_sum(d[j]);
-        if (lane < LLC_LORA_PAD / 2) {
-          float a = 0.f, b = 0.f;
-#pragma unroll
-          for (int j = 0; j < R; ++j) {
-            if (j == 2 * lane) a = d[j];
-            if (j == 2 * lane + 1) b = d[j];
-          }
-          reinterpret_cast<uint32_t*>(X + (size_t)t * ld_x + C)[lane] = pack_bf16(a, b);
-        }
+      for (int j = 0; j < R; ++j) {
+        if (j == 2 * lane) a = d[j];
+        if (j == 2 * lane + 1) b = d[j];
       }
-    }
-    if (w != nullptr) {
-      // colsum: each thread owns column pairs tid + 256*p and walks the chunk's rows
-      const int rows = min(kSideRows, T - t0);
-      for (int rr = 0; rr < rows; ++rr) {
-        const uint32_t* xr = reinterpret_cast<const uint32_t*>(X + (size_t)(t0 + rr) * ld_x);
-        float wj[R];
-#pragma unroll
-        for (int j = 0; j < R; ++j) wj[j] = sW[rr * R + j];
-#pragma unroll
-        for (int p = 0; p < kSideMaxPairs; ++p) {
-          const int cp = tid + kSideThreads * p;
-          if (cp < n_pairs) {
-            const float2 f = unpack_bf16(xr[cp]);
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-              acc[p][0][j] += f.x * wj[j];
-              acc[p][1][j] += f.y * wj[j];
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (w != nullptr) {
-    float* out = partial + (size_t)blockIdx.x * C * R;
-#pragma unroll
-    for (int p = 0; p < kSideMaxPairs; ++p) {
-      const int cp = tid + kSideThreads * p;
-      if (cp < n_pairs) {
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          out[(size_t)(2 * cp) * R + j] = acc[p][0][j];
-          out[(size_t)(2 * cp + 1) * R + j] = acc[p][1][j];
-        }
-      }
+      reinterpret_cast<uint32_t*>(X + (size_t)t * ld_x + C)[lane] = pack_bf16(a, b);
     }
   }
 }
 
-__global__ void colsum_finish_kernel(const float* __restrict__ partial, int n_partials, int C,
-                                     int R, int r, float scale, float* __restrict__ out, int o_sc,
-                                     int o_sj) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * R) return;
-  const int c = i / R, j = i % R;
-  if (j >= r) return;
+template <int R>
+__global__ void __launch_bounds__(kSideThreads)
+lora_colsum_kernel(const __nv_bfloat16* __restrict__ X, int ld_x, int T, int C, int r,
+                   const __nv_bfloat16* __restrict__ w, int ld_w, int w_vec,
+                   float* __restrict__ partial) {
+  __shared__ float red[8 * R * 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int col = blockIdx.y * kSideGroup + lane * 8;  // this lane's 8 columns
+  const bool live = col < C;
+  float acc[8][R];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[e][j] = 0.f;
+  const int gw = blockIdx.x * (kSideThreads / 32) + warp;
+  const int nw = gridDim.x * (kSideThreads / 32);
+  constexpr int U = 4;  // rows in flight per warp
+  for (int t0 = gw; t0 < T; t0 += nw * U) {
+    uint4 xv[U];
+    float wj[U][R];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * nw;
+      xv[u] = make_uint4(0, 0, 0, 0);
+      if (t < T && live) xv[u] = *reinterpret_cast<const uint4*>(X + (size_t)t * ld_x + col);
+      if (R == 4 && w_vec) {  // the 4 weights of a row in one 8-byte broadcast load
+        uint2 q = make_uint2(0, 0);
+        if (t < T) q = *reinterpret_cast<const uint2*>(w + (size_t)t * ld_w);
+        const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y);
+        wj[u][0] = a.x; wj[u][1] = r > 1 ? a.y : 0.f;
+        wj[u][2] = r > 2 ? b.x : 0.f; wj[u][3] = r > 3 ? b.y : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          wj[u][j] = (t < T && j < r) ? __bfloat162float(w[(size_t)t * ld_w + j]) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t pw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(pw[e]);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          acc[2 * e][j] += f.x * wj[u][j];
+          acc[2 * e + 1][j] += f.y * wj[u][j];
+        }
+      }
+    }
+  }
+  // fixed-order cross-warp sum: red[(e * R + j) * 32 + lane]
+  for (int wv = 0; wv < kSideThreads / 32; ++wv) {
+    if (warp == wv) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          float* p = &red[(e * R + j) * 32 + lane];
+          *p = (wv == 0) ? acc[e][j] : *p + acc[e][j];
+        }
+    }
+    __syncthreads();
+  }
+  // partial[blockIdx.x][c][j], c = blockIdx.y * 256 + l * 8 + e
+  float* out = partial + ((size_t)blockIdx.x * C + (size_t)blockIdx.y * kSideGroup) * R;
+  for (int i = tid; i < kSideGroup * R; i += kSideThreads) {
+    const int cl = i / R, j = i % R;
+    if (blockIdx.y * kSideGroup + cl < C) out[i] = red[((cl & 7) * R + j) * 32 + (cl >> 3)];
+  }
+}
+
+// out[c, j] = scale * sum_p partial[p][c][j]: 8 slices of the partials per output, summed in a
+// fixed order (bit-deterministic)
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ partial, int n_partials, int C, int R, int r,
+                     float scale, float* __restrict__ out, int o_sc, int o_sj) {
+  __shared__ float red[8][32];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;
+  const int n = C * R;
   float s = 0.f;
-  for (int p = 0; p < n_partials; ++p) s += partial[(size_t)p * C * R + i];
-  out[(size_t)c * o_sc + (size_t)j * o_sj] = s * scale;
+  if (i < n) {
+#pragma unroll 4
+    for (int p = sl; p < n_partials; p += 8) s += partial[(size_t)p * n + i];
+  }
+  red[sl][o] = s;
+  __syncthreads();
+  if (sl == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][o];
+    const int c = i / R, j = i % R;
+    if (j < r) out[(size_t)c * o_sc + (size_t)j * o_sj] = t * scale;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,6 +509,8 @@ extern "C" int llc_ln_bwd(const float* x, int ld_x, const float* gamma, const vo
   LLC_REQUIRE(dxb == nullptr || ld_dxb % 8 == 0, "llc_ln_bwd: ld_dxb %% 8");
   LLC_REQUIRE(lora_B == nullptr || (r >= 1 && r <= kMaxR && dxb && ld_dxb >= D + LLC_LORA_PAD),
               "llc_ln_bwd: LoRA rank %d unsupported or no room for du", r);
+  LLC_REQUIRE(lora_B == nullptr || r != 4 || ((uintptr_t)lora_B & 15) == 0,
+              "llc_ln_bwd: lora_B must be 16-byte aligned");
   if (T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   LLC_PROF_BEGIN(LLC_K_LN_BWD, T, D, 0, 0.0,
@@ -481,48 +524,68 @@ extern "C" int llc_ln_bwd(const float* x, int ld_x, const float* gamma, const vo
   return 0;
 }
 
-extern "C" int llc_lora_side_max_partials(void) { return 2 * llc_num_sms(); }
+extern "C" int llc_lora_side_max_partials(void) { return 4 * llc_num_sms(); }
 
 extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float* Mrd, int rd_sc,
                              int rd_sj, float rd_scale, const void* w, int ld_w, float* partial,
                              int* n_partials, void* stream) {
   LLC_REQUIRE(X && T > 0 && C > 0, "llc_lora_side: empty input");
-  LLC_REQUIRE(C % 8 == 0 && ld_x % 8 == 0 && C <= 2 * kSideThreads * kSideMaxPairs,
-              "llc_lora_side: C=%d unsupported", C);
+  LLC_REQUIRE(C % 8 == 0 && ld_x % 8 == 0 && ((uintptr_t)X & 15) == 0,
+              "llc_lora_side: C=%d / ld_x=%d must be multiples of 8, X 16-byte aligned", C, ld_x);
   LLC_REQUIRE(r >= 1 && r <= kMaxR, "llc_lora_side: rank %d unsupported", r);
   LLC_REQUIRE(Mrd == nullptr || ld_x >= C + LLC_LORA_PAD, "llc_lora_side: no room for rowdot");
   LLC_REQUIRE(w == nullptr || (partial && n_partials), "llc_lora_side: colsum needs partial");
   const int R = r <= 4 ? 4 : 8;
-  const int chunks = (T + kSideRows - 1) / kSideRows;
-  const int grid = chunks < llc_lora_side_max_partials() ? chunks : llc_lora_side_max_partials();
-  const size_t smem = ((Mrd ? (size_t)C * R : 0) + (size_t)kSideRows * R) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 0, 0.0, 2.0 * T * C, st);
-  if (R == 4) {
-    static bool cfg4 = false;
-    if (!cfg4) {
-      LLC_CUDA(cudaFuncSetAttribute(lora_side_kernel<4>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      cfg4 = true;
+  if (Mrd != nullptr) {
+    const size_t smem = (size_t)C * R * sizeof(float);
+    LLC_REQUIRE(smem <= 160 * 1024, "llc_lora_side: C=%d too wide for the staged factor", C);
+    const int grid = min((T + 7) / 8, 4 * llc_num_sms());
+    LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 0, 2.0 * T * C * r, 2.0 * T * C, st);
+    if (R == 4) {
+      static bool cfg4 = false;
+      if (!cfg4) {
+        LLC_CUDA(cudaFuncSetAttribute(lora_rowdot_kernel<4>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        cfg4 = true;
+      }
+      lora_rowdot_kernel<4><<<grid, kSideThreads, smem, st>>>((__nv_bfloat16*)X, ld_x, T, C, r, Mrd,
+                                                             rd_sc, rd_sj, rd_scale);
+    } else {
+      static bool cfg8 = false;
+      if (!cfg8) {
+        LLC_CUDA(cudaFuncSetAttribute(lora_rowdot_kernel<8>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        cfg8 = true;
+      }
+      lora_rowdot_kernel<8><<<grid, kSideThreads, smem, st>>>((__nv_bfloat16*)X, ld_x, T, C, r, Mrd,
+                                                             rd_sc, rd_sj, rd_scale);
     }
-    lora_side_kernel<4><<<grid, kSideThreads, smem, st>>>(
-        (__nv_bfloat16*)X, ld_x, T, C, r, Mrd, rd_sc, rd_sj, rd_scale, (const __nv_bfloat16*)w,
-        ld_w, partial);
-  } else {
-    static bool cfg8 = false;
-    if (!cfg8) {
-      LLC_CUDA(cudaFuncSetAttribute(lora_side_kernel<8>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      cfg8 = true;
-    }
-    lora_side_kernel<8><<<grid, kSideThreads, smem, st>>>(
-        (__nv_bfloat16*)X, ld_x, T, C, r, Mrd, rd_sc, rd_sj, rd_scale, (const __nv_bfloat16*)w,
-        ld_w, partial);
+    LLC_PROF_END(st);
+    LLC_COUNT_LAUNCH();
+    LLC_LAUNCH_CHECK("lora_rowdot_kernel");
   }
-  LLC_PROF_END(st);
-  LLC_COUNT_LAUNCH();
-  LLC_LAUNCH_CHECK("lora_side_kernel");
-  if (n_partials) *n_partials = grid;
+  if (w != nullptr) {
+    const int groups = (C + kSideGroup - 1) / kSideGroup;
+    int gx = llc_lora_side_max_partials() / groups;
+    const int by_rows = (T + 31) / 32;  // at least ~4 rows per warp
+    if (gx > by_rows) gx = by_rows;
+    if (gx < 1) gx = 1;
+    LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 2, 2.0 * T * C * r, 2.0 * T * C, st);
+    const int w_vec = (((uintptr_t)w & 7) == 0 && ld_w % 4 == 0) ? 1 : 0;
+    if (R == 4)
+      lora_colsum_kernel<4><<<dim3(gx, groups), kSideThreads, 0, st>>>(
+          (const __nv_bfloat16*)X, ld_x, T, C, r, (const __nv_bfloat16*)w, ld_w, w_vec, partial);
+    else
+      lora_colsum_kernel<8><<<dim3(gx, groups), kSideThreads, 0, st>>>(
+          (const __nv_bfloat16*)X, ld_x, T, C, r, (const __nv_bfloat16*)w, ld_w, 0, partial);
+    LLC_PROF_END(st);
+    LLC_COUNT_LAUNCH();
+    LLC_LAUNCH_CHECK("lora_colsum_kernel");
+    *n_partials = gx;
+  } else if (n_partials) {
+    *n_partials = 0;
+  }
   return 0;
 }
 
@@ -534,7 +597,7 @@ extern "C" int llc_lora_colsum_finish(const float* partial, int n_partials, int 
   const int R = r <= 4 ? 4 : 8;
   LLC_PROF_BEGIN(LLC_K_LORA_SIDE, n_partials, C, 1, 0.0, 4.0 * n_partials * C * R,
                  (cudaStream_t)stream);
-  colsum_finish_kernel<<<(C * R + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  colsum_finish_kernel<<<(C * R + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
       partial, n_partials, C, R, r, cs_scale, out, o_sc, o_sj);
   LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();

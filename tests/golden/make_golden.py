@@ -101,7 +101,7 @@ def run_reference(cfg: vo.VitCfg, n: int, num_classes: int, seed: int):
 CASES = {
     # name: (cfg, batch, classes, seed)
     "tiny": (vo.VIT_TINY, 3, 10, 11),
-    "vitb16": (vo.VIT_B16, 2, 100, 7),
+    "vitb16": (vo.VIT_B16, 8, 100, 7),
 }
 
 

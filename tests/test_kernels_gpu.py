@@ -81,6 +81,41 @@ def test_gemm_quickgelu_forward_and_backward_epilogues(ops):
     assert rel(dz.float(), want) < 1e-2
 
 
+# CTA-pair (cta_group::2) kernel: shapes with >= 74 tiles of 256 x 256; M deliberately not a
+# multiple of 256 (row tail), K with a partial last k-block (784, 2320)
+@pytest.mark.parametrize("M,N,K", [(6304, 768, 784), (6304, 2304, 784), (6304, 768, 2320),
+                                   (5000, 1024, 64), (19700, 256, 3072)])
+def test_gemm_pair_kernel_all_epilogues(ops, M, N, K):
+    A = bf16_randn(M, K, seed=11)
+    B = bf16_randn(N, K, seed=12, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda") * 0.1
+    ref = A.float() @ B.float().T
+    # bf16 out + bias
+    o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(A, B, M, N, K, o, bias=bias)
+    assert rel(o.float(), ref + bias) < 5e-3
+    # fp32 out + bias + residual (in place on the residual stream as well)
+    resid = torch.randn(M, N, device="cuda")
+    o32 = torch.empty(M, N, device="cuda")
+    ops.gemm_tn(A, B, M, N, K, o32, bias=bias, resid=resid)
+    assert rel(o32, ref + bias + resid) < 1e-5
+    r2 = resid.clone()
+    ops.gemm_tn(A, B, M, N, K, r2, bias=bias, resid=r2)
+    assert rel(r2, ref + bias + resid) < 1e-5
+    # QuickGELU forward (z and g) and backward epilogues
+    z = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    g = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(A, B, M, N, K, z, bias=bias, act=1, out2=g)
+    assert rel(z.float(), ref + bias) < 5e-3
+    assert rel(g.float(), vo.quick_gelu(ref + bias)) < 1e-2
+    dz = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(A, B, M, N, K, dz, act=2, aux=z)
+    zf = z.float().requires_grad_(True)
+    vo.quick_gelu(zf).sum().backward()
+    assert rel(dz.float(), ref * zf.grad) < 1e-2
+    torch.cuda.synchronize()
+
+
 def test_gemm_rejects_bad_shapes(ops):
     A = bf16_randn(64, 40); B = bf16_randn(64, 40)
     out = torch.empty(64, 64, device="cuda", dtype=torch.bfloat16)
