@@ -33,6 +33,8 @@ extern "C" {
 #define LLC_ERR_ARG (-1)
 #define LLC_ERR_ARCH (-2)
 #define LLC_LORA_PAD 16 /* rank-r LoRA columns are padded to one UMMA K step (16 bf16) */
+#define LLC_LORA_LD 64  /* ...and the ROW PITCH of an augmented buffer grows by 64 elements (128 B),
+                           so every row still starts on a cache-line boundary for TMA */
 
 int llc_version(void);
 const char* llc_last_error(void);
@@ -188,6 +190,7 @@ typedef struct llc_vit_cfg {
 
 typedef struct llc_vit_layer {
   /* frozen, prepared bf16 K-major (llc_pack_weight); *_aug carry LLC_LORA_PAD extra K columns */
+  /* "+16" = LLC_LORA_PAD K columns; the row pitch of these buffers is +LLC_LORA_LD (64) */
   void* wqkv_aug;  /* [3D, D+16]: W_in | s*B_in        */
   void* wo_aug;    /* [D, D+16]:  W_o  | s*B_o         */
   void* wfc;       /* [mlp, D]                          */
@@ -222,6 +225,7 @@ int llc_cast_bf16(const float* src, void* dst, int T, int D, int ld_dst, void* s
 int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weights* w, void* stream);
 
 /* one transformer block on [T, D] fp32 (ResidualAttentionBlock.forward model.py:233-236) */
+/* buffers written "[T, X+16]" have row pitch X + LLC_LORA_LD */
 typedef struct llc_block_bufs {
   float* x_in;   /* [T, D] fp32 input (saved)                     */
   void* h1;      /* [T, D+16] bf16  LN1 out | u_in (saved)        */

@@ -9,7 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libllc.so")
 
-LORA_PAD = 16
+LORA_PAD = 16   # K columns appended for the rank-r factors
+LORA_LD = 64    # row-pitch growth of an augmented buffer (keeps rows 128 B aligned)
 
 c_void = C.c_void_p
 c_int = C.c_int

@@ -89,6 +89,26 @@ __device__ __forceinline__ float quick_gelu_grad(float x) {
   return s * (1.0f + 1.702f * x * (1.0f - s));
 }
 
+// One lane of a fully converged warp. Single-thread instructions (TMA, tcgen05.mma/commit) are
+// issued as `if (elect_one()) ...` from warp-uniform code so that their operands stay in uniform
+// registers; issuing them from inside `if (lane == 0)` makes ptxas wrap every one in an
+// R2UR "waterfall" loop, which measured ~230 cycles per tcgen05.mma (profiles/).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a provably warp-uniform value
+__device__ __forceinline__ int uniform_warp_idx() {
+  return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+}
+
 // ---------------------------------------------------------------- smem / mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

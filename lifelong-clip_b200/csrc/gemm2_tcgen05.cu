@@ -12,6 +12,8 @@
 //   warp 1      MMA issuer (leader CTA, one lane); commits multicast to both CTAs' barriers
 //   warps 2..9  epilogue (gemm_epilogue.cuh): two warps per TMEM lane quarter, 128 columns each
 // TMEM holds two 256-column accumulators, so a tile's epilogue overlaps the next tile's mainloop.
+#include <stdlib.h>
+
 #include "gemm_epilogue.cuh"
 
 namespace {
@@ -34,7 +36,10 @@ constexpr int kTmemCols = 512;
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             int M, int N, int K, EpiParams ep) {
+             int M, int N, int K, EpiParams ep, int dbg) {
+  // dbg (LLC_GEMM_DBG, development only): 1 = epilogue does no work, 2 = producer issues no TMA,
+  // 4 = no MMA is issued, 8 = no L2 prefetch, 32 = producer does not wait for free slots,
+  // 64 = MMA issuer does not wait for data, 128 = no per-stage commit (wrong results: timing only)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -47,7 +52,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]     leader only: both CTAs' epilogues
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
@@ -79,41 +84,47 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_before();
   cluster_sync_all();   // barrier inits and the TMEM allocation are visible to both CTAs
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m0 = (tile / tiles_n) * BM + (int)rank * 128;
-        const int n0 = (tile % tiles_n) * BN + (int)rank * 128;
-        const int next_tile = tile + num_pairs;
-        const int m0_next = (next_tile / tiles_n) * BM + (int)rank * 128;
-        for (int kb = 0; kb < num_kb; ++kb) {
+    // the whole warp runs the loop; one elected lane issues (operands stay uniform)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / tiles_n) * BM + (int)rank * 128;
+      const int n0 = (tile % tiles_n) * BN + (int)rank * 128;
+      const int next_tile = tile + num_pairs;
+      const int m0_next = (next_tile / tiles_n) * BM + (int)rank * 128;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (!(dbg & 32)) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb_local = smem_u32(&full_bar[stage]);
+        const uint32_t fb_leader = mapa_shared(fb_local, 0);
+        const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
+        if (elect_one()) {
           // A (activations) streams from HBM once per GEMM: pull it into L2 well ahead of the
           // smem ring so the ring's own loads see L2 latency. B (weights) stays L2-resident.
-          {
+          if (!(dbg & 8)) {
             const int pk = kb + kPrefetchKb;
             if (pk < num_kb) tma_prefetch_2d(&tmA, pk * BK, m0);
             else if (next_tile < num_tiles && pk - num_kb < num_kb)
               tma_prefetch_2d(&tmA, (pk - num_kb) * BK, m0_next);
           }
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb_local = smem_u32(&full_bar[stage]);
-          const uint32_t fb_leader = mapa_shared(fb_local, 0);
-          if (rank == 0) mbar_expect_tx(fb_local, 2 * kStageBytes);
-          const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
-          tma_load_2d_cg2(sa, &tmA, fb_leader, kb * BK, m0);
-          tma_load_2d_cg2(sa + kABytes, &tmB, fb_leader, kb * BK, n0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (dbg & 2) {
+            if (rank == 0) mbar_arrive(fb_local);
+          } else {
+            if (rank == 0) mbar_expect_tx(fb_local, 2 * kStageBytes);
+            tma_load_2d_cg2(sa, &tmA, fb_leader, kb * BK, m0);
+            tma_load_2d_cg2(sa + kABytes, &tmB, fb_leader, kb * BK, n0);
+          }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -125,18 +136,24 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (!(dbg & 64)) mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
           const int ksteps = min(BK / 16, (K - kb * BK) / 16);
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_mc(smem_u32(&empty_bar[stage]), 0x3);  // frees the slot in both CTAs
+          if (elect_one()) {
+            if (!(dbg & 4))
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (!(dbg & 128))
+              umma_commit_mc(smem_u32(&empty_bar[stage]), 0x3);  // frees the slot in both CTAs
+            if (kb == num_kb - 1)
+              umma_commit_mc(smem_u32(&tfull_bar[buf]), 0x3);  // accumulator complete (both CTAs)
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_mc(smem_u32(&tfull_bar[buf]), 0x3);  // accumulator complete in both CTAs
       }
     }
   } else {
@@ -152,10 +169,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t bphase = (it >> 1) & 1;
       const int row0 = (tile / tiles_n) * BM + (int)rank * 128 + q * 32;
       const int col0 = (tile % tiles_n) * BN + hh * (BN / 2);
+      {  // while this tile's mainloop runs: pull the NEXT tile's aux / residual rows into L2
+        const int nt = tile + num_pairs;
+        if (nt < num_tiles)
+          epi_l2_prefetch<MODE, BN / 2 / 32>(ep, (nt / tiles_n) * BM + (int)rank * 128 + q * 32,
+                                             (nt % tiles_n) * BN + hh * (BN / 2), M, lane);
+      }
       mbar_wait(smem_u32(&tfull_bar[buf]), bphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * BN + hh * (BN / 2) + ((uint32_t)(q * 32) << 16);
-      epi_warp_tile<MODE, BN / 2 / 32>(ep, t_addr, tile_s, row0, col0, M, N, lane);
+      if (!(dbg & 1)) epi_warp_tile<MODE, BN / 2 / 32>(ep, t_addr, tile_s, row0, col0, M, N, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(te_leader + buf * 8);
@@ -187,7 +210,8 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, i
   LLC_PROF_BEGIN(LLC_K_GEMM, M, N, K, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + (double)M * N * (ep.out_fp32 ? 4 : 2),
                  stream);
-  gemm2_kernel<MODE><<<grid, kThreads, kSmem, stream>>>(tmA, tmB, M, N, K, ep);
+  static const int dbg = getenv("LLC_GEMM_DBG") ? atoi(getenv("LLC_GEMM_DBG")) : 0;
+  gemm2_kernel<MODE><<<grid, kThreads, kSmem, stream>>>(tmA, tmB, M, N, K, ep, dbg);
   LLC_PROF_END(stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("gemm2_kernel");

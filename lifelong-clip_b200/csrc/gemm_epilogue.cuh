@@ -205,10 +205,51 @@ __device__ __forceinline__ void epi_chunk(const EpiPre<MODE>& p, const EpiParams
   __syncwarp();  // tiles are rewritten by the next chunk
 }
 
+// DRAM -> L2 request for the rows a warp will read as aux / residual one tile later
+// (row0/col0 of that tile; the warp covers 32 rows x NCH*32 columns)
+template <int MODE, int NCH>
+__device__ __forceinline__ void epi_l2_prefetch(const EpiParams& ep, int row0, int col0, int M,
+                                                int lane) {
+  const char* base = nullptr;
+  size_t pitch = 0;
+  int row_bytes = 0;
+  if (MODE == EPI_F32 && ep.resid != nullptr) {
+    base = reinterpret_cast<const char*>(ep.resid + col0);
+    pitch = (size_t)ep.ld_resid * 4;
+    row_bytes = NCH * 32 * 4;
+  } else if (MODE == EPI_DGELU) {
+    base = reinterpret_cast<const char*>(ep.aux + col0);
+    pitch = (size_t)ep.ld_aux * 2;
+    row_bytes = NCH * 32 * 2;
+  } else {
+    return;
+  }
+  const int lines = row_bytes / 128;  // per row
+  for (int i = lane; i < 32 * lines; i += 32) {
+    const int r = i / lines, l = i % lines;
+    if (row0 + r < M)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(row0 + r) * pitch + l * 128));
+  }
+}
+
 // One warp drains NCH chunks (32 rows x 32 columns each) starting at TMEM address t_addr.
 template <int MODE, int NCH>
 __device__ __forceinline__ void epi_warp_tile(const EpiParams& ep, uint32_t t_addr, uint8_t* tile,
                                               int row0, int col0, int M, int N, int lane) {
+  if (MODE == EPI_F32) {
+    // 8 x 16 B of residual per lane and chunk: not double-buffered (registers); the loads were
+    // requested into L2 one tile ahead by epi_l2_prefetch
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      EpiPre<MODE> cur;
+      epi_prefetch<MODE>(cur, ep, row0, col0 + c * 32, M, N, lane);
+      uint32_t acc[32];
+      tmem_ld_32x32(t_addr + c * 32, acc);
+      tmem_ld_wait();
+      epi_chunk<MODE>(cur, ep, acc, tile, row0, col0 + c * 32, M, N, lane);
+    }
+    return;
+  }
   EpiPre<MODE> cur, nxt;
   epi_prefetch<MODE>(cur, ep, row0, col0, M, N, lane);
 #pragma unroll

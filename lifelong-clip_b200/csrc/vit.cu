@@ -51,10 +51,10 @@ Arena plan(const Dims& d, int training) {
   a.x_stride = align_up(T * d.D * 4);
   a.x = take(a.x_stride * (training ? d.layers + 1 : 2));
   const size_t l0 = off;
-  a.h1 = take(T * (d.D + LLC_LORA_PAD) * 2);
-  a.qkv = take(T * (3 * d.D + LLC_LORA_PAD) * 2);
+  a.h1 = take(T * (d.D + LLC_LORA_LD) * 2);
+  a.qkv = take(T * (3 * d.D + LLC_LORA_LD) * 2);
   a.lse = take((size_t)d.N * d.H * d.L * 4);
-  a.o = take(T * (d.D + LLC_LORA_PAD) * 2);
+  a.o = take(T * (d.D + LLC_LORA_LD) * 2);
   a.x_mid = take(T * d.D * 4);
   a.z = take(T * d.M * 2);
   a.layer_stride = off - l0;
@@ -62,11 +62,11 @@ Arena plan(const Dims& d, int training) {
   a.h2 = take(T * d.D * 2);
   a.g = take(T * d.M * 2);
   if (training) {
-    a.dxb = take(T * (d.D + LLC_LORA_PAD) * 2);
+    a.dxb = take(T * (d.D + LLC_LORA_LD) * 2);
     a.dz = take(T * d.M * 2);
     a.dh = take(T * d.D * 2);
     a.d_o = take(T * d.D * 2);
-    a.dqkv = take(T * (3 * d.D + LLC_LORA_PAD) * 2);
+    a.dqkv = take(T * (3 * d.D + LLC_LORA_LD) * 2);
     a.partial = take((size_t)llc_lora_side_max_partials() * 3 * d.D * 8 * 4);
   } else {
     a.dxb = a.dz = a.dh = a.d_o = a.dqkv = a.partial = 0;
@@ -148,14 +148,15 @@ extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   RUN(check_cfg(cfg, "llc_block_forward"));
   LLC_REQUIRE(w && b && N > 0 && L > 0, "llc_block_forward: bad args");
   const int D = cfg->width, M = cfg->mlp_dim, H = cfg->heads, r = cfg->lora_r;
-  const int T = N * L, DA = D + LLC_LORA_PAD, QA = 3 * D + LLC_LORA_PAD;
+  const int T = N * L, DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;  // row pitches
+  const int KA = D + LLC_LORA_PAD, KQ = 3 * D + LLC_LORA_PAD;              // K extents
   llc_gemm_epi e;
   // x -> ln_1 -> h1 | u = h1 A_in^T
   RUN(llc_ln_fwd(b->x_in, D, w->ln1_g, w->ln1_b, T, D, b->h1, DA, w->in_A, r, stream));
   // qkv = h1 W_in^T + b_in + s (h1 A^T) B^T   (one accumulator, K = D + 16)
   e = llc_gemm_epi{};
   e.bias = w->bqkv; e.out = b->qkv; e.ld_out = QA;
-  RUN(llc_gemm_bf16_tn(b->h1, DA, w->wqkv_aug, DA, T, 3 * D, DA, &e, stream));
+  RUN(llc_gemm_bf16_tn(b->h1, DA, w->wqkv_aug, DA, T, 3 * D, KA, &e, stream));
   RUN(llc_attn_fwd(b->qkv, QA, b->o, DA, b->lse, N, L, H, sn, sl, causal, stream));
   // u_o = o A_o^T into o's pad columns
   RUN(llc_lora_side(b->o, DA, T, D, r, w->out_A, 1, D, 1.0f, nullptr, 0, nullptr, nullptr,
@@ -164,7 +165,7 @@ extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   e = llc_gemm_epi{};
   e.bias = w->bo; e.resid = b->x_in; e.ld_resid = D; e.out = b->x_mid; e.ld_out = D;
   e.out_fp32 = 1;
-  RUN(llc_gemm_bf16_tn(b->o, DA, w->wo_aug, DA, T, D, DA, &e, stream));
+  RUN(llc_gemm_bf16_tn(b->o, DA, w->wo_aug, DA, T, D, KA, &e, stream));
   // mlp
   RUN(llc_ln_fwd(b->x_mid, D, w->ln2_g, w->ln2_b, T, D, b->h2, D, nullptr, 0, stream));
   e = llc_gemm_epi{};
@@ -186,7 +187,8 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   LLC_REQUIRE(b->z, "llc_block_backward: forward was not run in training mode");
   const int D = cfg->width, M = cfg->mlp_dim, H = cfg->heads, r = cfg->lora_r;
   const float sc = cfg->lora_scale;
-  const int T = N * L, DA = D + LLC_LORA_PAD, QA = 3 * D + LLC_LORA_PAD;
+  const int T = N * L, DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;  // row pitches
+  const int KA = D + LLC_LORA_PAD, KQ = 3 * D + LLC_LORA_PAD;              // K extents
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(s->dxb);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(b->o);
   __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(b->h1);
@@ -212,7 +214,7 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   // d_o = dx_mid W_o + du_o A_o
   e = llc_gemm_epi{};
   e.out = s->d_o; e.ld_out = D;
-  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->woT_aug, DA, T, D, DA, &e, stream));
+  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->woT_aug, DA, T, D, KA, &e, stream));
   RUN(llc_attn_bwd(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
                    stream));
   // in-proj LoRA grads: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
@@ -226,7 +228,7 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
     // dh1 = dqkv W_in + du A_in ; dx_in = dx_mid + LN1'(dh1)
     e = llc_gemm_epi{};
     e.out = s->dh; e.ld_out = D;
-    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->wqkvT_aug, QA, T, D, QA, &e, stream));
+    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->wqkvT_aug, QA, T, D, KQ, &e, stream));
     RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
                    stream));
   }
@@ -243,7 +245,7 @@ extern "C" int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weight
   RUN(check_cfg(cfg, "llc_vit_refresh_lora"));
   LLC_REQUIRE(w && w->layers, "llc_vit_refresh_lora: null weights");
   const int D = cfg->width, r = cfg->lora_r;
-  const int DA = D + LLC_LORA_PAD, QA = 3 * D + LLC_LORA_PAD;
+  const int DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;
   const float sc = cfg->lora_scale;
   for (int l = 0; l < cfg->layers; ++l) {
     const llc_vit_layer* y = &w->layers[l];
@@ -297,7 +299,7 @@ extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w
   s.d_o = base + a.d_o;
   s.dqkv = base + a.dqkv;
   s.partial = reinterpret_cast<float*>(base + a.partial);
-  RUN(llc_cast_bf16(dx_final, s.dxb, d.T, d.D, d.D + LLC_LORA_PAD, stream));
+  RUN(llc_cast_bf16(dx_final, s.dxb, d.T, d.D, d.D + LLC_LORA_LD, stream));
   llc_block_bufs b;
   for (int l = d.layers - 1; l >= 0; --l) {
     fill_bufs(d, a, base, l, 1, &b);

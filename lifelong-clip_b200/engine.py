@@ -14,7 +14,7 @@ import torch
 from . import _capi as K
 from . import ops
 
-PAD = K.LORA_PAD
+PAD = K.LORA_LD   # row-pitch pad of augmented buffers (the K extension itself is LORA_PAD)
 
 
 class VitEngine:

@@ -10,7 +10,7 @@ import torch
 
 from . import _capi as K
 
-PAD = K.LORA_PAD
+PAD = K.LORA_LD   # row-pitch pad of augmented buffers (the K extension itself is LORA_PAD)
 
 
 def _lib():
