@@ -8,7 +8,17 @@
 // warp owns 16-row tiles and keeps scores in registers. Backward runs two phases over the same
 // staged tiles (query-owned rows -> dQ, key-owned rows -> dK, dV), so nothing is accumulated
 // across warps: no atomics, bit-deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
+
+// tcgen05/TMEM path (attention_tc.cu)
+bool llc_attn_tc_eligible(int L);
+int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o, int ld_do,
+                    const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H, int sn, int sl,
+                    int causal, cudaStream_t st);
+int llc_attn_fwd_tc(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L, int H,
+                    int sn, int sl, int causal, cudaStream_t st);
 
 namespace {
 
@@ -512,6 +522,12 @@ extern "C" int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, floa
   if (int rc = check_common(qkv, ld_qkv, N, L, H, "llc_attn_fwd")) return rc;
   LLC_REQUIRE(o && ld_o % 8 == 0 && ld_o >= H * HD && ((uintptr_t)o & 15) == 0,
               "llc_attn_fwd: bad output");
+  // sequences up to 256 tokens run on the tensor cores through TMEM; LLC_ATTN_LEGACY=1 keeps the
+  // mma.sync kernels (development A/B only)
+  static const bool legacy = getenv("LLC_ATTN_LEGACY") != nullptr;
+  if (!legacy && llc_attn_tc_eligible(L))
+    return llc_attn_fwd_tc(qkv, ld_qkv, o, ld_o, lse, N, L, H, tok_stride_n, tok_stride_l, causal,
+                           (cudaStream_t)stream);
   DISPATCH_LP(L, (launch_fwd<LP>((const __nv_bfloat16*)qkv, ld_qkv, (__nv_bfloat16*)o, ld_o, lse,
                                  N, L, H, tok_stride_n, tok_stride_l, causal,
                                  (cudaStream_t)stream)));
@@ -526,6 +542,10 @@ extern "C" int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o
               "llc_attn_bwd: bad leading dimension");
   LLC_REQUIRE((((uintptr_t)o | (uintptr_t)d_o) & 15) == 0 && ((uintptr_t)dqkv & 3) == 0,
               "llc_attn_bwd: misaligned pointer");
+  static const bool legacy = getenv("LLC_ATTN_LEGACY") != nullptr;
+  if (!legacy && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
+    return llc_attn_bwd_tc(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
+                           tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream);
   DISPATCH_LP(L, (launch_bwd<LP>((const __nv_bfloat16*)qkv, ld_qkv, (const __nv_bfloat16*)o, ld_o,
                                  (const __nv_bfloat16*)d_o, ld_do, lse, (__nv_bfloat16*)dqkv,
                                  ld_dqkv, N, L, H, tok_stride_n, tok_stride_l, causal,

@@ -1,0 +1,619 @@
+// tcgen05/TMEM attention core for sm_100a (sequence length <= 256; the mma.sync kernels in
+// attention.cu remain for longer sequences).
+// Reference math: models/clip/lora.py:950 (q * hd^-0.5), :1002-1006 (head n*H+h), :1043 bmm(q,k^T),
+// :1063 softmax, :1068 bmm(P,v), :1070-1071 merge heads. P [N*H, L, L] is never materialised.
+//
+// One CTA walks (sample, head) pairs. Per pair, with LK = L rounded up to 32 and M-tiles of 128
+// query rows:
+//   S_t  = Q_t K^T        tcgen05.mma SS, M=128, N=LK, K=64      -> TMEM region t, fp32
+//   P_t  = exp2(..)       one thread per query row straight out of TMEM (no shuffles), written
+//                         back to TMEM IN PLACE as packed bf16 pairs (tcgen05.st)
+//   O_t  = P_t V          tcgen05.mma with A from TMEM, B = V as loaded ([key][hd], MN-major)
+// Warp roles: 0 = TMA producer (Q,K,V tiles of the next pair land while this one computes),
+// 1 = MMA issuer, 2..5 / 6..9 = softmax + epilogue for M-tile 0 / 1.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int kThreads = 320;
+constexpr int kTileBytes = 128 * 128;          // 128 rows x 64 bf16
+constexpr int kMatBytes = 2 * kTileBytes;      // up to 256 rows
+constexpr int kStageBytes = 3 * kMatBytes;     // Q | K | V
+constexpr int kFwdSmem = 1024 + 2 * kStageBytes + 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,"
+      "%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct FwdParams {
+  __nv_bfloat16* o;
+  int ld_o;
+  float* lse;
+  int N, L, H, LK, NT, sn, sl, causal, dbg;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes);
+  uint64_t* kv_full = bars;        // [2] TMA landed Q,K,V of a pair
+  uint64_t* kv_empty = bars + 2;   // [2] all MMAs reading the stage retired
+  uint64_t* s_full = bars + 4;     // [2] per M-tile: S complete
+  uint64_t* p_ready = bars + 6;    // [2] per M-tile: P written to TMEM (128 arrivals)
+  uint64_t* o_full = bars + 8;     // [2] per M-tile: O complete
+  uint64_t* s_free = bars + 10;    // [2] per M-tile: O drained, region reusable (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int pairs = p.N * p.H;
+  const int D = p.H * HD;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&kv_full[i]), 1);
+      mbar_init(smem_u32(&kv_empty[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_ready[i]), 128);
+      mbar_init(smem_u32(&o_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int it = 0;
+    for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int n = pr / p.H, h = pr % p.H;
+      mbar_wait(smem_u32(&kv_empty[st]), ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&kv_full[st]);
+        mbar_expect_tx(fb, 3 * p.NT * kTileBytes);
+        const uint32_t base = smem_u32(smem + st * kStageBytes);
+        for (int m = 0; m < 3; ++m)        // Q, K, V: column blocks h*64 + {0, D, 2D}
+          for (int t = 0; t < p.NT; ++t)
+            tma_load_3d(base + m * kMatBytes + t * kTileBytes, &tmQKV, fb, m * D + h * HD, t * 128,
+                        n);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(128, p.LK, 0, 0);
+    const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);  // B = V is MN-major
+    const int ksteps_o = p.LK / 16;
+    int it = 0;
+    for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1, tp = it & 1;
+      const uint32_t base = smem_u32(smem + st * kStageBytes);
+      mbar_wait(smem_u32(&kv_full[st]), ph);
+      tc_fence_after();
+      for (int t = 0; t < p.NT; ++t) {
+        mbar_wait(smem_u32(&s_free[t]), tp ^ 1);   // previous pair's O_t drained
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = umma_desc_k_sw128(base + t * kTileBytes);
+          const uint64_t bdesc = umma_desc_k_sw128(base + kMatBytes);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(tmem_base + t * 256, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(smem_u32(&s_full[t]));
+        }
+        __syncwarp();
+      }
+      for (int t = 0; t < p.NT; ++t) {
+        mbar_wait(smem_u32(&p_ready[t]), tp);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps_o; ++ks) {
+            // V rows [16 ks, 16 ks + 16): two 8-row groups of 1024 B
+            const uint64_t bdesc = umma_desc_mn_sw128(base + 2 * kMatBytes + ks * 2048, 8192, 1024);
+            umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + ks * 8, bdesc, idesc_o,
+                         ks != 0);
+          }
+          umma_commit(smem_u32(&o_full[t]));
+          if (t == p.NT - 1) umma_commit(smem_u32(&kv_empty[st]));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue
+    const int t = (warp - 2) >> 2;   // M-tile of this warp group
+    const int q = warp & 3;          // TMEM lane quarter
+    if (t < p.NT) {
+      const int row = t * 128 + q * 32 + lane;   // query index within the pair
+      const uint32_t treg = tmem_base + t * 256 + ((uint32_t)(q * 32) << 16);
+      const float c2 = 0.125f * kLog2e;          // hd^-0.5 = 1/8 for hd = 64
+      const int nch = p.LK / 32;
+      int it = 0;
+      for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
+        const uint32_t tp = it & 1;
+        const int n = pr / p.H, h = pr % p.H;
+        const int kmax = p.causal ? min(p.L, row + 1) : p.L;   // keys [0, kmax) are visible
+        mbar_wait(smem_u32(&s_full[t]), tp);
+        tc_fence_after();
+        // pass 1: row maximum
+        float m = -INFINITY;
+        if (p.dbg & 1) m = 0.f;
+        for (int c = 0; c < ((p.dbg & 1) ? 0 : nch); ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(treg + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < kmax) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        const float mc = (m == -INFINITY) ? 0.f : m * c2;
+        // pass 2: p = exp2(s c2 - m c2), row sum, packed bf16 pairs back into the S columns
+        float l = 0.f;
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32], w[16];
+          tmem_ld_32x32(treg + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = (c * 32 + j < kmax) ? ex2(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
+            const float p1 =
+                (c * 32 + j + 1 < kmax) ? ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mc)) : 0.f;
+            l += p0 + p1;
+            w[j >> 1] = pack_bf16(p0, p1);
+          }
+          tmem_st_x16(treg + c * 16, w);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&p_ready[t]));
+        if (p.lse != nullptr && row < p.L)
+          p.lse[(size_t)pr * p.L + row] = m * 0.125f + logf(l);
+        const float inv = 1.0f / l;
+        // epilogue: O row (64 fp32) -> bf16 -> one 128 B row segment per thread
+        mbar_wait(smem_u32(&o_full[t]), tp);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(treg + 128, o0);
+        tmem_ld_32x32(treg + 160, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&s_free[t]));
+        if (row < p.L && !(p.dbg & 2)) {
+          uint4* dst = reinterpret_cast<uint4*>(p.o + (size_t)(n * p.sn + row * p.sl) * p.ld_o +
+                                                h * HD);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dst[j] = make_uint4(
+                pack_bf16(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv),
+                pack_bf16(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv),
+                pack_bf16(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv),
+                pack_bf16(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv));
+            dst[4 + j] = make_uint4(
+                pack_bf16(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv),
+                pack_bf16(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv),
+                pack_bf16(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv),
+                pack_bf16(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv));
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Backward. With P = softmax(S), S = q k^T / 8, delta_q = sum_c dO[q,c] O[q,c]:
+//   dP = dO V^T, dS = P o (dP - delta), dQ = dS K / 8, dK = dS^T Q / 8, dV = P^T dO.
+// Per (sample, head) the CTA runs 2 NT tile-phases of 128 accumulator rows, all on tcgen05:
+//   type A (query rows):  R0 = Q_t K^T, R1 = dO_t V^T  -> dS (bf16, into R1)   -> dQ_t = dS K
+//   type B (key rows):    R0 = K_t Q^T, R1 = V_t dO^T  -> P^T (R0), dS^T (R1)  -> dV_t = P^T dO,
+//                                                                                 dK_t = dS^T Q
+// R0/R1 = TMEM columns [0,256) / [256,512). 256 threads work on a phase: thread = (row, column
+// half). Each half writes its packed bf16 operands over columns of ITS OWN half that it has
+// already consumed (half 0 at [0, LK/4), half 1 at [LK/2, 3LK/4)), so no thread overwrites data
+// another thread still has to read; the MMA walks the two areas k-step by k-step. The second
+// operands (K, dO, Q as "[k][hd]" MN-major B) are the tiles exactly as TMA loaded them.
+struct BwdParams {
+  const __nv_bfloat16* o;
+  int ld_o;
+  const float* lse;
+  __nv_bfloat16* dqkv;
+  int ld_dqkv;
+  int N, L, H, LK, NT, sn, sl, causal;
+};
+constexpr int kBwdStage = 4 * kMatBytes;  // Q | K | V | dO
+constexpr int kBwdSmem = 1024 + kBwdStage + 2 * 256 * 4 + 256;
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~(uintptr_t)1023);
+  float* sLse = reinterpret_cast<float*>(smem + kBwdStage);   // [256] lse * log2e per query
+  float* sDelta = sLse + 256;                                 // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  uint64_t* ld_full = bars;       // TMA landed Q,K,V,dO
+  uint64_t* ld_empty = bars + 1;  // every MMA of the pair retired
+  uint64_t* s_full = bars + 2;    // R0/R1 hold the phase's S-type products
+  uint64_t* p_ready = bars + 3;   // operands written back to TMEM (256 arrivals)
+  uint64_t* o_full = bars + 4;    // output accumulators complete
+  uint64_t* acc_free = bars + 5;  // accumulators drained (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int pairs = p.N * p.H;
+  const int D = p.H * HD;
+  const int LK = p.LK, NT = p.NT, half = LK / 2;
+  const int out_b = (3 * LK / 4 + 31) & ~31;   // dV / dK accumulator columns inside R0 / R1
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(smem_u32(ld_full), 1);
+    mbar_init(smem_u32(ld_empty), 1);
+    mbar_init(smem_u32(s_full), 1);
+    mbar_init(smem_u32(p_ready), 256);
+    mbar_init(smem_u32(o_full), 1);
+    mbar_init(smem_u32(acc_free), 256);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t sQ = smem_u32(smem), sK = sQ + kMatBytes, sV = sQ + 2 * kMatBytes,
+                 sD = sQ + 3 * kMatBytes;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int it = 0;
+    for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
+      const int n = pr / p.H, h = pr % p.H;
+      mbar_wait(smem_u32(ld_empty), (it & 1) ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(ld_full);
+        mbar_expect_tx(fb, 4 * NT * kTileBytes);
+        for (int t = 0; t < NT; ++t) {
+          tma_load_3d(sQ + t * kTileBytes, &tmQKV, fb, h * HD, t * 128, n);
+          tma_load_3d(sK + t * kTileBytes, &tmQKV, fb, D + h * HD, t * 128, n);
+          tma_load_3d(sV + t * kTileBytes, &tmQKV, fb, 2 * D + h * HD, t * 128, n);
+          tma_load_3d(sD + t * kTileBytes, &tmDO, fb, h * HD, t * 128, n);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(128, LK, 0, 0);
+    const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
+    const uint32_t R0 = tmem_base, R1 = tmem_base + 256;
+    int it = 0, g = 0;
+    for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
+      mbar_wait(smem_u32(ld_full), it & 1);
+      tc_fence_after();
+      for (int ph = 0; ph < 2 * NT; ++ph, ++g) {
+        const bool type_a = ph < NT;
+        const int t = type_a ? ph : ph - NT;
+        mbar_wait(smem_u32(acc_free), (g & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a0 = umma_desc_k_sw128((type_a ? sQ : sK) + t * kTileBytes);
+          const uint64_t b0 = umma_desc_k_sw128(type_a ? sK : sQ);
+          const uint64_t a1 = umma_desc_k_sw128((type_a ? sD : sV) + t * kTileBytes);
+          const uint64_t b1 = umma_desc_k_sw128(type_a ? sV : sD);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(R0, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(R1, a1 + 2 * k, b1 + 2 * k, idesc_s, k != 0);
+          umma_commit(smem_u32(s_full));
+        }
+        __syncwarp();
+        mbar_wait(smem_u32(p_ready), g & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const int ksteps = LK / 16, kh = LK / 32;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t aoff = ks < kh ? ks * 8 : half + (ks - kh) * 8;
+            if (type_a) {   // dQ_t = dS K
+              umma_bf16_ts(R0, R1 + aoff, umma_desc_mn_sw128(sK + ks * 2048, 8192, 1024), idesc_o,
+                           ks != 0);
+            } else {        // dV_t = P^T dO ; dK_t = dS^T Q
+              umma_bf16_ts(R0 + out_b, R0 + aoff, umma_desc_mn_sw128(sD + ks * 2048, 8192, 1024),
+                           idesc_o, ks != 0);
+              umma_bf16_ts(R1 + out_b, R1 + aoff, umma_desc_mn_sw128(sQ + ks * 2048, 8192, 1024),
+                           idesc_o, ks != 0);
+            }
+          }
+          umma_commit(smem_u32(o_full));
+          if (ph == 2 * NT - 1) umma_commit(smem_u32(ld_empty));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ element-wise + epilogue
+    const int q = warp & 3;             // TMEM lane quarter
+    const int hh = (warp - 2) >> 2;     // column half
+    const int r = q * 32 + lane;        // accumulator row within a phase
+    const int tid2 = (warp - 2) * 32 + lane;   // 0..255: the query this thread preprocesses
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t R0 = tmem_base + lane_sel, R1 = tmem_base + 256 + lane_sel;
+    const float c2 = 0.125f * kLog2e;
+    const int nchunk = half / 16;
+    int it = 0, g = 0;
+    for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
+      const int n = pr / p.H, h = pr % p.H;
+      const int tok0 = n * p.sn;
+      mbar_wait(smem_u32(ld_full), it & 1);
+      // delta and lse of query tid2 (dO row from the landed tile, O row from global)
+      {
+        float d = 0.f, l2 = 0.f;
+        if (tid2 < p.L) {
+          const uint8_t* drow = smem + 3 * kMatBytes + (tid2 >> 7) * kTileBytes + (tid2 & 127) * 128;
+          const uint4* orow = reinterpret_cast<const uint4*>(
+              p.o + (size_t)(tok0 + tid2 * p.sl) * p.ld_o + h * HD);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 dv = *reinterpret_cast<const uint4*>(drow + ((c ^ (tid2 & 7)) << 4));
+            const uint4 ov = orow[c];
+            const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 a = unpack_bf16(dw[e]), b = unpack_bf16(ow[e]);
+              d += a.x * b.x + a.y * b.y;
+            }
+          }
+          l2 = p.lse[(size_t)pr * p.L + tid2] * kLog2e;
+        }
+        sDelta[tid2] = d;
+        sLse[tid2] = l2;
+      }
+      named_bar_sync(1, 256);
+      for (int ph = 0; ph < 2 * NT; ++ph, ++g) {
+        const bool type_a = ph < NT;
+        const int t = type_a ? ph : ph - NT;
+        const int gr = t * 128 + r;     // global row: query (A) or key (B) index
+        mbar_wait(smem_u32(s_full), g & 1);
+        tc_fence_after();
+        const float lse_r = sLse[gr & 255], del_r = sDelta[gr & 255];
+        for (int c = 0; c < nchunk; ++c) {
+          const int col0 = hh * half + c * 16;
+          uint32_t sv[16], dv[16], wp[8], wd[8];
+          tmem_ld_x16(R0 + col0, sv);
+          tmem_ld_x16(R1 + col0, dv);
+          tmem_ld_wait();
+          if (type_a) {
+            // row = query gr, columns = keys
+            const int kmax = (gr < p.L) ? (p.causal ? min(p.L, gr + 1) : p.L) : 0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              float ds[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float pe = (col0 + j + e < kmax)
+                                     ? ex2(fmaf(__uint_as_float(sv[j + e]), c2, -lse_r)) : 0.f;
+                ds[e] = pe * (__uint_as_float(dv[j + e]) - del_r);
+              }
+              wd[j >> 1] = pack_bf16(ds[0], ds[1]);
+            }
+            tmem_st_x8(R1 + hh * half + c * 8, wd);
+          } else {
+            // row = key gr, columns = queries: lse / delta per column (smem broadcast)
+            const int qmin = p.causal ? gr : 0;   // visible iff qmin <= query < L
+            const bool krow = gr < p.L;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              float pe[2], ds[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int qi = col0 + j + e;
+                const bool ok = krow && qi < p.L && qi >= qmin;
+                pe[e] = ok ? ex2(fmaf(__uint_as_float(sv[j + e]), c2, -sLse[qi & 255])) : 0.f;
+                ds[e] = pe[e] * (__uint_as_float(dv[j + e]) - sDelta[qi & 255]);
+              }
+              wp[j >> 1] = pack_bf16(pe[0], pe[1]);
+              wd[j >> 1] = pack_bf16(ds[0], ds[1]);
+            }
+            tmem_st_x8(R0 + hh * half + c * 8, wp);
+            tmem_st_x8(R1 + hh * half + c * 8, wd);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(p_ready));
+        // epilogue of the phase
+        mbar_wait(smem_u32(o_full), g & 1);
+        tc_fence_after();
+        if (type_a) {
+          uint32_t a[32];
+          tmem_ld_32x32(R0 + hh * 32, a);   // dQ columns [32 hh, 32 hh + 32)
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(smem_u32(acc_free));
+          if (gr < p.L) {
+            uint4* dst = reinterpret_cast<uint4*>(
+                p.dqkv + (size_t)(tok0 + gr * p.sl) * p.ld_dqkv + h * HD + hh * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(
+                  pack_bf16(__uint_as_float(a[8 * j]) * 0.125f, __uint_as_float(a[8 * j + 1]) * 0.125f),
+                  pack_bf16(__uint_as_float(a[8 * j + 2]) * 0.125f, __uint_as_float(a[8 * j + 3]) * 0.125f),
+                  pack_bf16(__uint_as_float(a[8 * j + 4]) * 0.125f, __uint_as_float(a[8 * j + 5]) * 0.125f),
+                  pack_bf16(__uint_as_float(a[8 * j + 6]) * 0.125f, __uint_as_float(a[8 * j + 7]) * 0.125f));
+          }
+        } else {
+          // half 0 stores dV (R0), half 1 stores dK (R1, scaled by hd^-0.5)
+          uint32_t a[32], b[32];
+          const uint32_t src = (hh == 0 ? R0 : R1) + out_b;
+          tmem_ld_32x32(src, a);
+          tmem_ld_32x32(src + 32, b);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(smem_u32(acc_free));
+          if (gr < p.L) {
+            const float sc = hh == 0 ? 1.0f : 0.125f;
+            uint4* dst = reinterpret_cast<uint4*>(
+                p.dqkv + (size_t)(tok0 + gr * p.sl) * p.ld_dqkv + (hh == 0 ? 2 * D : D) + h * HD);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              dst[j] = make_uint4(
+                  pack_bf16(__uint_as_float(a[8 * j]) * sc, __uint_as_float(a[8 * j + 1]) * sc),
+                  pack_bf16(__uint_as_float(a[8 * j + 2]) * sc, __uint_as_float(a[8 * j + 3]) * sc),
+                  pack_bf16(__uint_as_float(a[8 * j + 4]) * sc, __uint_as_float(a[8 * j + 5]) * sc),
+                  pack_bf16(__uint_as_float(a[8 * j + 6]) * sc, __uint_as_float(a[8 * j + 7]) * sc));
+              dst[4 + j] = make_uint4(
+                  pack_bf16(__uint_as_float(b[8 * j]) * sc, __uint_as_float(b[8 * j + 1]) * sc),
+                  pack_bf16(__uint_as_float(b[8 * j + 2]) * sc, __uint_as_float(b[8 * j + 3]) * sc),
+                  pack_bf16(__uint_as_float(b[8 * j + 4]) * sc, __uint_as_float(b[8 * j + 5]) * sc),
+                  pack_bf16(__uint_as_float(b[8 * j + 6]) * sc, __uint_as_float(b[8 * j + 7]) * sc));
+            }
+          }
+        }
+      }
+      // sLse / sDelta are rewritten for the next pair only after every thread left the last phase
+      named_bar_sync(1, 256);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+
+// 3-D view of a token-major activation buffer: (column, token l of a sample, sample n)
+static int encode_tokens_map(CUtensorMap* tm, const void* base, int cols, int ld, int L, int N,
+                             int sn, int sl) {
+  return llc_encode_tmap_3d(tm, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)cols,
+                            (uint64_t)L, (uint64_t)N, (uint64_t)ld * 2 * sl, (uint64_t)ld * 2 * sn,
+                            HD, 128, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+bool llc_attn_tc_eligible(int L) { return L <= 256; }
+
+int llc_attn_fwd_tc(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L, int H,
+                    int sn, int sl, int causal, cudaStream_t st) {
+  CUtensorMap tm;
+  // a sample-major [N, L, .] buffer with ONE sample still needs a non-zero outer stride
+  if (int rc = encode_tokens_map(&tm, qkv, 3 * H * HD, ld_qkv, L, N, sn, sl)) return rc;
+  FwdParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o); p.ld_o = ld_o; p.lse = lse;
+  p.N = N; p.L = L; p.H = H; p.LK = (L + 31) / 32 * 32; p.NT = (L + 127) / 128;
+  p.sn = sn; p.sl = sl; p.causal = causal;
+  static const int dbg = getenv("LLC_ATTN_DBG") ? atoi(getenv("LLC_ATTN_DBG")) : 0;
+  p.dbg = dbg;
+  static bool configured = false;
+  if (!configured) {
+    LLC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kFwdSmem));
+    configured = true;
+  }
+  const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
+  LLC_PROF_BEGIN(LLC_K_ATTN_FWD, N * H, L, 0, 4.0 * N * H * (double)L * L * HD,
+                 8.0 * N * H * (double)L * HD, st);
+  attn_fwd_tc_kernel<<<grid, kThreads, kFwdSmem, st>>>(tm, p);
+  LLC_PROF_END(st);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("attn_fwd_tc_kernel");
+  return 0;
+}
+
+int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o, int ld_do,
+                    const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H, int sn, int sl,
+                    int causal, cudaStream_t st) {
+  CUtensorMap tq, td;
+  if (int rc = encode_tokens_map(&tq, qkv, 3 * H * HD, ld_qkv, L, N, sn, sl)) return rc;
+  if (int rc = encode_tokens_map(&td, d_o, H * HD, ld_do, L, N, sn, sl)) return rc;
+  BwdParams p;
+  p.o = reinterpret_cast<const __nv_bfloat16*>(o); p.ld_o = ld_o; p.lse = lse;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); p.ld_dqkv = ld_dqkv;
+  p.N = N; p.L = L; p.H = H; p.LK = (L + 31) / 32 * 32; p.NT = (L + 127) / 128;
+  p.sn = sn; p.sl = sl; p.causal = causal;
+  static bool configured = false;
+  if (!configured) {
+    LLC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kBwdSmem));
+    configured = true;
+  }
+  const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
+  LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
+                 16.0 * N * H * (double)L * HD, st);
+  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmem, st>>>(tq, td, p);
+  LLC_PROF_END(st);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("attn_bwd_tc_kernel");
+  return 0;
+}
