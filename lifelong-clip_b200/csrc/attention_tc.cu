@@ -173,33 +173,75 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, FwdParams p) {
         const int kmax = p.causal ? min(p.L, row + 1) : p.L;   // keys [0, kmax) are visible
         mbar_wait(smem_u32(&s_full[t]), tp);
         tc_fence_after();
-        // pass 1: row maximum
+        // pass 1: row maximum. Chunks that lie entirely below kmax take the predicate-free
+        // path; the TMEM load of chunk c+1 is in flight while chunk c is reduced.
         float m = -INFINITY;
-        if (p.dbg & 1) m = 0.f;
-        for (int c = 0; c < ((p.dbg & 1) ? 0 : nch); ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(treg + c * 32, v);
-          tmem_ld_wait();
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(treg, va);
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld_32x32(treg + (c + 1) * 32, vb);
+            if (c * 32 + 32 <= kmax) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < kmax) m = fmaxf(m, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(va[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c * 32 + j < kmax) m = fmaxf(m, __uint_as_float(va[j]));
+            }
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld_32x32(treg + (c + 2) * 32, va);
+              if (c * 32 + 64 <= kmax) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(vb[j]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c * 32 + 32 + j < kmax) m = fmaxf(m, __uint_as_float(vb[j]));
+              }
+            }
+          }
         }
         const float mc = (m == -INFINITY) ? 0.f : m * c2;
         // pass 2: p = exp2(s c2 - m c2), row sum, packed bf16 pairs back into the S columns
         float l = 0.f;
-        for (int c = 0; c < nch; ++c) {
-          uint32_t v[32], w[16];
-          tmem_ld_32x32(treg + c * 32, v);
-          tmem_ld_wait();
+        {
+          uint32_t va[32], vb[32], w[16];
+          auto chunk = [&](const uint32_t (&v)[32], int c) {
+            if (c * 32 + 32 <= kmax) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = (c * 32 + j < kmax) ? ex2(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
-            const float p1 =
-                (c * 32 + j + 1 < kmax) ? ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mc)) : 0.f;
-            l += p0 + p1;
-            w[j >> 1] = pack_bf16(p0, p1);
+              for (int j = 0; j < 32; j += 2) {
+                const float p0 = ex2(fmaf(__uint_as_float(v[j]), c2, -mc));
+                const float p1 = ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mc));
+                l += p0 + p1;
+                w[j >> 1] = pack_bf16(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float p0 =
+                    (c * 32 + j < kmax) ? ex2(fmaf(__uint_as_float(v[j]), c2, -mc)) : 0.f;
+                const float p1 =
+                    (c * 32 + j + 1 < kmax) ? ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mc)) : 0.f;
+                l += p0 + p1;
+                w[j >> 1] = pack_bf16(p0, p1);
+              }
+            }
+            tmem_st_x16(treg + c * 16, w);
+          };
+          tmem_ld_32x32(treg, va);
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld_32x32(treg + (c + 1) * 32, vb);
+            chunk(va, c);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld_32x32(treg + (c + 2) * 32, va);
+              chunk(vb, c + 1);
+            }
           }
-          tmem_st_x16(treg + c * 16, w);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -265,7 +307,7 @@ struct BwdParams {
   const float* lse;
   __nv_bfloat16* dqkv;
   int ld_dqkv;
-  int N, L, H, LK, NT, sn, sl, causal;
+  int N, L, H, LK, NT, sn, sl, causal, dbg;
 };
 constexpr int kBwdStage = 4 * kMatBytes;  // Q | K | V | dO
 constexpr int kBwdSmem = 1024 + kBwdStage + 2 * 256 * 4 + 256;
@@ -369,10 +411,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           const uint64_t b0 = umma_desc_k_sw128(type_a ? sK : sQ);
           const uint64_t a1 = umma_desc_k_sw128((type_a ? sD : sV) + t * kTileBytes);
           const uint64_t b1 = umma_desc_k_sw128(type_a ? sV : sD);
+          if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16(R0, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
+            for (int k = 0; k < HD / 16; ++k) umma_bf16(R0, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16(R1, a1 + 2 * k, b1 + 2 * k, idesc_s, k != 0);
+            for (int k = 0; k < HD / 16; ++k) umma_bf16(R1, a1 + 2 * k, b1 + 2 * k, idesc_s, k != 0);
+          }
           umma_commit(smem_u32(s_full));
         }
         __syncwarp();
@@ -380,7 +424,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         tc_fence_after();
         if (elect_one()) {
           const int ksteps = LK / 16, kh = LK / 32;
-          for (int ks = 0; ks < ksteps; ++ks) {
+          for (int ks = 0; ks < ((p.dbg & 2) ? 0 : ksteps); ++ks) {
             const uint32_t aoff = ks < kh ? ks * 8 : half + (ks - kh) * 8;
             if (type_a) {   // dQ_t = dS K
               umma_bf16_ts(R0, R1 + aoff, umma_desc_mn_sw128(sK + ks * 2048, 8192, 1024), idesc_o,
@@ -416,7 +460,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       // delta and lse of query tid2 (dO row from the landed tile, O row from global)
       {
         float d = 0.f, l2 = 0.f;
-        if (tid2 < p.L) {
+        if (tid2 < p.L && !(p.dbg & 16)) {
           const uint8_t* drow = smem + 3 * kMatBytes + (tid2 >> 7) * kTileBytes + (tid2 & 127) * 128;
           const uint4* orow = reinterpret_cast<const uint4*>(
               p.o + (size_t)(tok0 + tid2 * p.sl) * p.ld_o + h * HD);
@@ -444,43 +488,77 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         mbar_wait(smem_u32(s_full), g & 1);
         tc_fence_after();
         const float lse_r = sLse[gr & 255], del_r = sDelta[gr & 255];
-        for (int c = 0; c < nchunk; ++c) {
+        // Out-of-range rows/columns need no masking in the non-causal case: TMA zero-filled the
+        // rows >= L of Q, K, V and dO, so their products vanish in the output MMAs; only the
+        // chunk that straddles L is clamped (p could overflow there), and causal chunks are
+        // masked element by element.
+        for (int c = 0; c < ((p.dbg & 1) ? 0 : nchunk); ++c) {
           const int col0 = hh * half + c * 16;
           uint32_t sv[16], dv[16], wp[8], wd[8];
           tmem_ld_x16(R0 + col0, sv);
           tmem_ld_x16(R1 + col0, dv);
           tmem_ld_wait();
+          const bool fast = !p.causal && col0 + 16 <= p.L;
           if (type_a) {
             // row = query gr, columns = keys
-            const int kmax = (gr < p.L) ? (p.causal ? min(p.L, gr + 1) : p.L) : 0;
+            if (fast) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float ds[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const float pe = (col0 + j + e < kmax)
-                                     ? ex2(fmaf(__uint_as_float(sv[j + e]), c2, -lse_r)) : 0.f;
-                ds[e] = pe * (__uint_as_float(dv[j + e]) - del_r);
+              for (int j = 0; j < 16; j += 2) {
+                const float p0 = ex2(fmaf(__uint_as_float(sv[j]), c2, -lse_r));
+                const float p1 = ex2(fmaf(__uint_as_float(sv[j + 1]), c2, -lse_r));
+                wd[j >> 1] = pack_bf16(p0 * (__uint_as_float(dv[j]) - del_r),
+                                       p1 * (__uint_as_float(dv[j + 1]) - del_r));
               }
-              wd[j >> 1] = pack_bf16(ds[0], ds[1]);
+            } else {
+              const int kmax = (gr < p.L) ? (p.causal ? min(p.L, gr + 1) : p.L) : 0;
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float ds[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const float pe = (col0 + j + e < kmax)
+                                       ? ex2(fmaf(__uint_as_float(sv[j + e]), c2, -lse_r)) : 0.f;
+                  ds[e] = pe * (__uint_as_float(dv[j + e]) - del_r);
+                }
+                wd[j >> 1] = pack_bf16(ds[0], ds[1]);
+              }
             }
             tmem_st_x8(R1 + hh * half + c * 8, wd);
           } else {
-            // row = key gr, columns = queries: lse / delta per column (smem broadcast)
-            const int qmin = p.causal ? gr : 0;   // visible iff qmin <= query < L
-            const bool krow = gr < p.L;
+            // row = key gr, columns = queries: lse / delta per column (16-byte smem broadcasts)
+            float lq[16], dq[16];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              float pe[2], ds[2];
+            for (int j = 0; j < 16; j += 4) {
+              const float4 a = *reinterpret_cast<const float4*>(&sLse[col0 + j]);
+              const float4 b = *reinterpret_cast<const float4*>(&sDelta[col0 + j]);
+              lq[j] = a.x; lq[j + 1] = a.y; lq[j + 2] = a.z; lq[j + 3] = a.w;
+              dq[j] = b.x; dq[j + 1] = b.y; dq[j + 2] = b.z; dq[j + 3] = b.w;
+            }
+            if (fast) {
 #pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int qi = col0 + j + e;
-                const bool ok = krow && qi < p.L && qi >= qmin;
-                pe[e] = ok ? ex2(fmaf(__uint_as_float(sv[j + e]), c2, -sLse[qi & 255])) : 0.f;
-                ds[e] = pe[e] * (__uint_as_float(dv[j + e]) - sDelta[qi & 255]);
+              for (int j = 0; j < 16; j += 2) {
+                const float p0 = ex2(fmaf(__uint_as_float(sv[j]), c2, -lq[j]));
+                const float p1 = ex2(fmaf(__uint_as_float(sv[j + 1]), c2, -lq[j + 1]));
+                wp[j >> 1] = pack_bf16(p0, p1);
+                wd[j >> 1] = pack_bf16(p0 * (__uint_as_float(dv[j]) - dq[j]),
+                                       p1 * (__uint_as_float(dv[j + 1]) - dq[j + 1]));
               }
-              wp[j >> 1] = pack_bf16(pe[0], pe[1]);
-              wd[j >> 1] = pack_bf16(ds[0], ds[1]);
+            } else {
+              const int qmin = p.causal ? gr : 0;   // visible iff qmin <= query < L
+              const bool krow = gr < p.L;
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float pe[2], ds[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int qi = col0 + j + e;
+                  const bool ok = krow && qi < p.L && qi >= qmin;
+                  pe[e] = ok ? ex2(fmaf(__uint_as_float(sv[j + e]), c2, -lq[j + e])) : 0.f;
+                  ds[e] = pe[e] * (__uint_as_float(dv[j + e]) - dq[j + e]);
+                }
+                wp[j >> 1] = pack_bf16(pe[0], pe[1]);
+                wd[j >> 1] = pack_bf16(ds[0], ds[1]);
+              }
             }
             tmem_st_x8(R0 + hh * half + c * 8, wp);
             tmem_st_x8(R1 + hh * half + c * 8, wd);
@@ -498,7 +576,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(acc_free));
-          if (gr < p.L) {
+          if (gr < p.L && !(p.dbg & 8)) {
             uint4* dst = reinterpret_cast<uint4*>(
                 p.dqkv + (size_t)(tok0 + gr * p.sl) * p.ld_dqkv + h * HD + hh * 32);
 #pragma unroll
@@ -518,7 +596,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(acc_free));
-          if (gr < p.L) {
+          if (gr < p.L && !(p.dbg & 8)) {
             const float sc = hh == 0 ? 1.0f : 0.125f;
             uint4* dst = reinterpret_cast<uint4*>(
                 p.dqkv + (size_t)(tok0 + gr * p.sl) * p.ld_dqkv + (hh == 0 ? 2 * D : D) + h * HD);
@@ -602,6 +680,8 @@ int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const 
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); p.ld_dqkv = ld_dqkv;
   p.N = N; p.L = L; p.H = H; p.LK = (L + 31) / 32 * 32; p.NT = (L + 127) / 128;
   p.sn = sn; p.sl = sl; p.causal = causal;
+  static const int dbg = getenv("LLC_ATTN_DBG") ? atoi(getenv("LLC_ATTN_DBG")) : 0;
+  p.dbg = dbg;
   static bool configured = false;
   if (!configured) {
     LLC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

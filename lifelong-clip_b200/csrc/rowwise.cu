@@ -210,33 +210,50 @@ lora_rowdot_kernel(__nv_bfloat16* X, int ld_x, int T, int C, int r, const float*
   __syncthreads();
   const int gw = blockIdx.x * (kSideThreads / 32) + warp;
   const int nw = gridDim.x * (kSideThreads / 32);
-  for (int t = gw; t < T; t += nw) {
-    const uint4* xr = reinterpret_cast<const uint4*>(X + (size_t)t * ld_x);
-    float d[R];
+  constexpr int U = 4;  // rows per iteration: every staged factor word is used U times
+  for (int t0 = gw * U; t0 < T; t0 += nw * U) {
+    float d[U][R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) d[j] = 0.f;
-#pragma unroll 3
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < R; ++j) d[u][j] = 0.f;
     for (int v = lane; v < nvec; v += 32) {
-      const uint4 pk = xr[v];
-      const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+      uint4 pk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        pk[u] = make_uint4(0, 0, 0, 0);
+        if (t0 + u < T) pk[u] = reinterpret_cast<const uint4*>(X + (size_t)(t0 + u) * ld_x)[v];
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16(pw[e]);
+        float m0[R], m1[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          d[j] += f.x * sM[((2 * e) * R + j) * nvec + v] + f.y * sM[((2 * e + 1) * R + j) * nvec + v];
+        for (int j = 0; j < R; ++j) {
+          m0[j] = sM[((2 * e) * R + j) * nvec + v];
+          m1[j] = sM[((2 * e + 1) * R + j) * nvec + v];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t w = e == 0 ? pk[u].x : e == 1 ? pk[u].y : e == 2 ? pk[u].z : pk[u].w;
+          const float2 f = unpack_bf16(w);
+#pragma unroll
+          for (int j = 0; j < R; ++j) d[u][j] += f.x * m0[j] + f.y * m1[j];
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < R; ++j) d[j] = warp_sum(d[j]);
-    if (lane < LLC_LORA_PAD / 2) {
-      float a = 0.f, b = 0.f;
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        if (j == 2 * lane) a = d[j];
-        if (j == 2 * lane + 1) b = d[j];
+      for (int j = 0; j < R; ++j) d[u][j] = warp_sum(d[u][j]);
+      if (lane < LLC_LORA_PAD / 2 && t0 + u < T) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (j == 2 * lane) a = d[u][j];
+          if (j == 2 * lane + 1) b = d[u][j];
+        }
+        reinterpret_cast<uint32_t*>(X + (size_t)(t0 + u) * ld_x + C)[lane] = pack_bf16(a, b);
       }
-      reinterpret_cast<uint32_t*>(X + (size_t)t * ld_x + C)[lane] = pack_bf16(a, b);
     }
   }
 }
@@ -540,7 +557,7 @@ extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float
   if (Mrd != nullptr) {
     const size_t smem = (size_t)C * R * sizeof(float);
     LLC_REQUIRE(smem <= 160 * 1024, "llc_lora_side: C=%d too wide for the staged factor", C);
-    const int grid = min((T + 7) / 8, 4 * llc_num_sms());
+    const int grid = min((T + 31) / 32, 4 * llc_num_sms());
     LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 0, 2.0 * T * C * r, 2.0 * T * C, st);
     if (R == 4) {
       static bool cfg4 = false;
@@ -567,7 +584,7 @@ extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float
   }
   if (w != nullptr) {
     const int groups = (C + kSideGroup - 1) / kSideGroup;
-    int gx = llc_lora_side_max_partials() / groups;
+    int gx = llc_lora_side_max_partials() / groups;   // ~4 CTAs per SM over all column groups
     const int by_rows = (T + 31) / 32;  // at least ~4 rows per warp
     if (gx > by_rows) gx = by_rows;
     if (gx < 1) gx = 1;

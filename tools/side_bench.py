@@ -1,0 +1,37 @@
+"""LoRA side kernels + LN timing at the step's shapes (dev tool)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from lifelong_clip_b200 import ops
+T = 50432
+def timeit(f, n=10):
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+for C in (768, 2304):
+    X = torch.randn(T, C + 64, device="cuda").to(torch.bfloat16)
+    Mrd = torch.randn(C, 4, device="cuda") * 0.05
+    w = torch.randn(T, 832, device="cuda").to(torch.bfloat16)
+    partial = torch.empty(ops.lora_side_max_partials() * C * 8, device="cuda")
+    out = torch.empty(C, 4, device="cuda")
+    us = timeit(lambda: ops.lora_side(X, T, C, 4, Mrd=Mrd, rd_sc=4, rd_sj=1, rd_scale=0.25))
+    print(f"rowdot C={C}: {us:7.1f} us  {T*C*2/us/1e3:7.1f} GB/s")
+    n = [0]
+    def cs(): n[0] = ops.lora_side(X, T, C, 4, w=w[:, 768:], ld_w=832, partial=partial)
+    us = timeit(cs)
+    print(f"colsum C={C}: {us:7.1f} us  {T*C*2/us/1e3:7.1f} GB/s  partials {n[0]}")
+    us = timeit(lambda: ops.lora_colsum_finish(partial, n[0], C, 4, 1.0, out, 4, 1))
+    print(f"finish C={C}: {us:7.1f} us")
+# rowdot as a skinny GEMM on the tensor cores: u[T,16] = X[T,C] . F[16,C]^T written into X's pad
+for C in (768, 2304):
+    X = torch.randn(T, C + 64, device="cuda").to(torch.bfloat16)
+    F = torch.zeros(16, C, device="cuda", dtype=torch.bfloat16); F[:4] = torch.randn(4, C, device="cuda") * 0.05
+    out = X[:, C:C + 16]
+    us = timeit(lambda: ops.gemm_tn(X, F, T, 16, C, out))
+    ref = X[:4096, :C].float() @ F.float().T
+    err = float((out[:4096].float() - ref).norm() / ref.norm())
+    print(f"rowdot-as-GEMM C={C}: {us:7.1f} us  {T*C*2/us/1e3:7.1f} GB/s  rel {err:.2e}")
