@@ -211,3 +211,44 @@ class LoRAClipTrainer:
         num = torch.bincount(cls, minlength=self.n_tasks).float().cpu()[:self.n_tasks]
         ok = torch.bincount(cls[y == pred], minlength=self.n_tasks).float().cpu()[:self.n_tasks]
         return num, ok
+
+
+class DevicePrefetcher:
+    """Wraps the reference's DataLoader (pin_memory=True): the host->device copy of batch i+1 is
+    issued on a side stream while batch i trains, so `online_step` receives device images.
+    Yields `(images_on_device, labels_on_host, idx)` - labels stay on the host because the class
+    bookkeeping of online_step (methods/_trainer.py:404-416) is host-side list logic; their 2 KB
+    device copy is made inside online_train.
+
+        for images, labels, idx in DevicePrefetcher(train_dataloader, device):
+            loss, acc = trainer.online_step(images, labels, idx)
+    """
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+
+    def _stage(self, batch):
+        images, labels = batch[0], batch[1]
+        rest = tuple(batch[2:])
+        with torch.cuda.stream(self.stream):
+            dev = images.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return dev, labels, rest, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            dev, labels, rest, ev = nxt
+            try:
+                nxt = self._stage(next(it))      # copy of the NEXT batch overlaps this step
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            dev.record_stream(torch.cuda.current_stream(self.device))
+            yield (dev, labels) + rest

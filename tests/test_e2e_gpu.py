@@ -243,6 +243,15 @@ def test_trainer_online_step_interface_and_learning():
     got_local = ops.label_remap(labels.cuda(), tr._class_lut(tr.exposed_classes)).cpu().numpy()
     np.testing.assert_array_equal(got_local, want_local)
     assert losses[-1] < losses[0] - 1e-4, losses
+    # the prefetching loader wrapper hands device images to the same interface
+    from lifelong_clip_b200.trainer import DevicePrefetcher
+    pinned = [(images.pin_memory(), labels, torch.arange(8)) for _ in range(3)]
+    seen = 0
+    for im, lb, ids in DevicePrefetcher(pinned, "cuda:0"):
+        assert im.is_cuda and not lb.is_cuda
+        loss2, _ = tr.online_step(im, lb, ids)
+        seen += 1
+    assert seen == 3 and loss2 < losses[0]
     tr.online_after_task(0)
     res = tr.online_evaluate([(images, labels)])
     assert set(res) == {"avg_loss", "avg_acc", "cls_acc", "task_acc", "confusion_matrix"}
