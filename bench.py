@@ -221,7 +221,8 @@ def run_ours(args):
     g = torch.Generator().manual_seed(1)
     model.set_text_features(names, torch.randn(C, E, generator=g))
     trainer = LoRAClipTrainer(model, names, n_classes=C, n_tasks=5, lr=1e-3, online_iter=1,
-                              visible_classes="all", sharded_input=True)
+                              visible_classes="all", sharded_input=True,
+                              use_cuda_graph=not args.no_graph)
     trainer.online_before_task(0)
 
     # synthetic stream: a pool of distinct pinned host batches (each 154 MB fp32 at B=256, i.e.
@@ -266,7 +267,9 @@ def run_ours(args):
         trainer.fused_step(dev_x[i % 2], dev_y[i % 2], gB, sync=False)
     e1.record()
     barrier()
-    launches = ops.launch_count() - l0
+    launches = ops.launch_count() - l0     # eager llc_* launches (AdamW, and everything w/o graph)
+    if trainer.use_cuda_graph:             # + the kernel nodes of every graph replay
+        launches += trainer.graph_kernels * args.steps
     ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.stop() if sampler else None
     value = gB / (ms_dev * 1e-3)
@@ -280,12 +283,14 @@ def run_ours(args):
         for i in range(n):
             yield host_x[i % n_pool], host_y[i % n_pool], idx
 
-    for images, labels, ids in DevicePrefetcher(host_loader(max(2, args.warmup // 2)), dev):
-        trainer.online_step(images, labels, ids)
-    barrier()
-    e0.record()
+    # one continuous loop in steady state (as a long run is): W untimed steps, then exactly K
+    # timed ones; every timed step's H2D copy is issued and completes inside the timed region
     last = None
-    for images, labels, ids in DevicePrefetcher(host_loader(args.steps), dev):
+    for i, (images, labels, ids) in enumerate(
+            DevicePrefetcher(host_loader(args.warmup + args.steps), dev)):
+        if i == args.warmup:
+            barrier()
+            e0.record()
         last = trainer.online_step(images, labels, ids)
     e1.record()
     barrier()
@@ -295,12 +300,14 @@ def run_ours(args):
     d2h = 8
 
     # ---------------------------------------------------------------- per-kernel pass (roofline)
+    trainer.use_cuda_graph = False          # per-launch events need eager launches
     ops.prof_enable(True)
     for i in range(args.prof_steps):
         trainer.fused_step(dev_x[i % 2], dev_y[i % 2], gB, sync=False)
     torch.cuda.synchronize()
     recs = ops.prof_read()
     ops.prof_enable(False)
+    trainer.use_cuda_graph = not args.no_graph
     by_kind = {}
     for kind, m, n, k, ms, fl, by in recs:
         d = by_kind.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
@@ -354,7 +361,8 @@ def run_ours(args):
                    "batch_per_gpu": B, "global_batch": gB, "classes": C, "tokens": (S // p) ** 2 + 1,
                    "parallelism": f"dp{world}", "weights": "random-init",
                    "l2": "inputs larger than L2 (154 MB images per step; activations 1 GB/layer)",
-                   "loss": "CE on probabilities (reference double softmax)"},
+                   "loss": "CE on probabilities (reference double softmax)",
+                   "cuda_graph": not args.no_graph},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -387,6 +395,7 @@ def main():
     ap.add_argument("--prof-steps", type=int, default=2)
     ap.add_argument("--dump-prof", default=None, help="write per-launch records (json) here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -85,9 +85,9 @@ class VitEngine:
         """Call after writing lora_flat outside torch's version tracking (llc_adamw)."""
         self._lora_version = None
 
-    def _refresh_lora(self):
+    def _refresh_lora(self, force: bool = False):
         ver = sum(p._version for p in self.lora_params)
-        if ver != self._lora_version:
+        if force or ver != self._lora_version:
             K.check(K.load().llc_vit_refresh_lora(C.byref(self.cfg), C.byref(self.weights),
                                                   K.stream_ptr()), "llc_vit_refresh_lora")
             self._lora_version = ver
@@ -106,7 +106,7 @@ class VitEngine:
         self.dx = torch.empty(N * self.L, self.D, device=self.device) if training else None
         self.arena_key = key
 
-    def forward(self, images: torch.Tensor, training: bool):
+    def forward(self, images: torch.Tensor, training: bool, force_refresh: bool = False):
         if images.device != self.device or images.dtype != torch.float32:
             images = images.to(device=self.device, dtype=torch.float32)
         images = images.contiguous()
@@ -115,7 +115,7 @@ class VitEngine:
             raise RuntimeError(f"expected [N, 3, {self.cfg.image_size}, {self.cfg.image_size}] "
                                f"images, got {tuple(images.shape)}")
         self._ensure_arena(N, training)
-        self._refresh_lora()
+        self._refresh_lora(force_refresh)   # force: CUDA-graph capture must always contain it
         mode = int(self.arena_key[1])
         xf = C.c_void_p()
         K.check(K.load().llc_vit_forward(C.byref(self.cfg), C.byref(self.weights),

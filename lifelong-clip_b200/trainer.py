@@ -30,7 +30,7 @@ class LoRAClipTrainer:
                  online_iter=1, visible_classes='batch', memory=None, memory_provider=None,
                  memory_batchsize=0, memory_size=0, train_transform=None, test_transform=None,
                  use_amp=True, topk=1, double_softmax=True, device=None, rank=None,
-                 world_size=None, sharded_input=False):
+                 world_size=None, sharded_input=False, use_cuda_graph=True):
         self.custom_clip = model
         self.model = model
         self.device = device or model.model.visual.proj.device
@@ -55,6 +55,12 @@ class LoRAClipTrainer:
         # style; utils/online_sampler.py:33-48 has the num_replicas/rank plumbing); False: every
         # rank sees the global batch (the reference's single DataLoader) and slices rank::world.
         self.sharded_input = sharded_input
+        # forward + head + backward (~330 launches) are captured once per (batch, class list) and
+        # replayed: the step is then 6 host operations instead of ~350 (matters at 32 images / GPU)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._graph_key = None
+        self.graph_kernels = 0
         self.optimizer = None
         self._lut = torch.full((self.n_classes,), -1, dtype=torch.int64, device=self.device)
         self._lut_src = None
@@ -159,16 +165,52 @@ class LoRAClipTrainer:
         loss_sum, n_correct = self.fused_step(x, y_local, B)
         return loss_sum, n_correct / B
 
-    def fused_step(self, x, y_local, global_batch, sync=True):
-        """forward + loss + backward + gradient all-reduce + AdamW, all on the device."""
+    def _step_body(self, x, y_local, global_batch, force_refresh=False):
+        """forward + loss + backward; leaves LoRA grads in eng.grad_flat and (loss_sum, n_correct)
+        of this shard in self._scal. All llc_* launches on the current stream."""
         m = self.custom_clip
         eng = m.model.visual.engine()
-        eng.forward(x, training=True)
+        eng.forward(x, training=True, force_refresh=force_refresh)
         head = eng.head(m._text_all, m.model.logit_scale_exp(),
                         cls_idx=m._cls_idx, add_mask=m._add_mask, labels=y_local,
                         double_softmax=self.double_softmax, inv_batch=1.0 / global_batch)
         eng.backward_from_head(head)
         ops.loss_acc(head.loss_rows, head.pred, y_local, self._scal)
+        return head
+
+    def _graph_step(self, x, y_local, global_batch):
+        m = self.custom_clip
+        key = (tuple(x.shape), x.dtype, global_batch, m._cls_idx.data_ptr(), m._cls_idx.numel(),
+               None if m._add_mask is None else m._add_mask.data_ptr(), m._text_all.data_ptr(),
+               m.model.logit_scale_exp(), self.double_softmax)
+        if key != self._graph_key:
+            self._graph = None
+            self._gx = torch.empty_like(x)
+            self._gy = torch.empty_like(y_local)
+            self._gx.copy_(x); self._gy.copy_(y_local)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):      # warm-up: arena, smem attributes, allocator pool
+                self._step_body(self._gx, self._gy, global_batch, force_refresh=True)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                self._ghead = self._step_body(self._gx, self._gy, global_batch, force_refresh=True)
+            self.graph_kernels = ops.launch_count() - n0   # libllc kernel nodes per replay
+            self._graph, self._graph_key = g, key
+        self._gx.copy_(x, non_blocking=True)
+        self._gy.copy_(y_local, non_blocking=True)
+        self._graph.replay()
+        return self._ghead
+
+    def fused_step(self, x, y_local, global_batch, sync=True):
+        """forward + loss + backward + gradient all-reduce + AdamW, all on the device."""
+        eng = self.custom_clip.model.visual.engine()
+        if self.use_cuda_graph:
+            head = self._graph_step(x, y_local, global_batch)
+        else:
+            head = self._step_body(x, y_local, global_batch)
         dp.allreduce_step(eng.grad_flat, self._scal, self.world)
         self.optimizer.step()
         self.last_head = head
