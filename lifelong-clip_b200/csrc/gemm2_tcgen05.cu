@@ -7,7 +7,7 @@
 // fetches 32 KB through TMA for 2 x 128 x 256 x 64 MACs of its own - half the L2->SM bytes per
 // FLOP of the single-CTA 128 x 256 kernel, which measured L2-feed-bound (profiles/).
 //
-//   warp 0      TMA producer (one lane per CTA): 6-stage ring; both CTAs complete bytes on the
+//   warp 0      TMA producer (one lane per CTA): 5-stage ring; both CTAs complete bytes on the
 //               LEADER's full barrier
 //   warp 1      MMA issuer (leader CTA, one lane); commits multicast to both CTAs' barriers
 //   warps 2..9  epilogue (gemm_epilogue.cuh): two warps per TMEM lane quarter, 128 columns each
@@ -21,7 +21,7 @@ namespace {
 constexpr int BM = 256;       // per pair; 128 rows per CTA
 constexpr int BN = 256;
 constexpr int BK = 64;        // 128 B swizzle row
-constexpr int kStages = 6;
+constexpr int kStages = 5;
 constexpr int kPrefetchKb = 8;  // A blocks requested into L2 this many k-blocks ahead of the ring
 constexpr int kABytes = 128 * BK * 2;
 constexpr int kBBytes = 128 * BK * 2;
@@ -36,6 +36,7 @@ constexpr int kTmemCols = 512;
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
              int M, int N, int K, EpiParams ep, int dbg) {
   // dbg (LLC_GEMM_DBG, development only): 1 = epilogue does no work, 2 = producer issues no TMA,
   // 4 = no MMA is issued, 8 = no L2 prefetch, 32 = producer does not wait for free slots,
@@ -178,13 +179,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(smem_u32(&tfull_bar[buf]), bphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * BN + hh * (BN / 2) + ((uint32_t)(q * 32) << 16);
-      if (!(dbg & 1)) epi_warp_tile<MODE, BN / 2 / 32>(ep, t_addr, tile_s, row0, col0, M, N, lane);
+      if (!(dbg & 1)) {
+        if (MODE == EPI_F32)
+          epi_warp_tile<MODE, BN / 2 / 32>(ep, t_addr, tile_s, row0, col0, M, N, lane);
+        else
+          epi_warp_tile_tma<MODE, BN / 2 / 32>(ep, &tmO, &tmO2, t_addr, tile_s, row0, col0, M, N,
+                                               lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(te_leader + buf * 8);
     }
   }
 
+  if (MODE != EPI_F32 && warp >= 2 && lane == 0) tma_store_wait<0>();  // bulk stores landed
   // no CTA may exit (or free TMEM) while its peer can still signal its barriers / read its smem
   __syncwarp();
   tc_fence_before();
@@ -196,8 +204,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 template <int MODE>
-int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
-                 const EpiParams& ep, cudaStream_t stream) {
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                 const CUtensorMap& tmO2, int M, int N, int K, const EpiParams& ep,
+                 cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     LLC_CUDA(cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -211,7 +220,9 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, i
                  2.0 * ((double)M * K + (double)N * K) + (double)M * N * (ep.out_fp32 ? 4 : 2),
                  stream);
   static const int dbg = getenv("LLC_GEMM_DBG") ? atoi(getenv("LLC_GEMM_DBG")) : 0;
-  gemm2_kernel<MODE><<<grid, kThreads, kSmem, stream>>>(tmA, tmB, M, N, K, ep, dbg);
+  EpiParams ep2 = ep;
+  ep2.dbg = dbg;
+  gemm2_kernel<MODE><<<grid, kThreads, kSmem, stream>>>(tmA, tmB, tmO, tmO2, M, N, K, ep2, dbg);
   LLC_PROF_END(stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("gemm2_kernel");
@@ -236,10 +247,27 @@ int llc_gemm2_launch(const void* A, int lda, const void* B, int ldb, int M, int 
   rc = llc_encode_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N,
                           (uint64_t)ldb * 2, BK, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  switch (epi_mode_of(ep)) {
-    case EPI_GELU: return launch_gemm2<EPI_GELU>(tmA, tmB, M, N, K, ep, stream);
-    case EPI_DGELU: return launch_gemm2<EPI_DGELU>(tmA, tmB, M, N, K, ep, stream);
-    case EPI_F32: return launch_gemm2<EPI_F32>(tmA, tmB, M, N, K, ep, stream);
-    default: return launch_gemm2<EPI_BF16>(tmA, tmB, M, N, K, ep, stream);
+  // bf16 outputs leave through TMA stores: [32 rows x 64 columns] boxes, 128 B swizzle
+  CUtensorMap tmO = tmA, tmO2 = tmA;
+  const int mode = epi_mode_of(ep);
+  if (mode != EPI_F32) {
+    if (ep.out != nullptr) {
+      rc = llc_encode_tmap_2d(&tmO, ep.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N,
+                              (uint64_t)M, (uint64_t)ep.ld_out * 2, 64, 32,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    if (mode == EPI_GELU) {
+      rc = llc_encode_tmap_2d(&tmO2, ep.out2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N,
+                              (uint64_t)M, (uint64_t)ep.ld_out2 * 2, 64, 32,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+  }
+  switch (mode) {
+    case EPI_GELU: return launch_gemm2<EPI_GELU>(tmA, tmB, tmO, tmO2, M, N, K, ep, stream);
+    case EPI_DGELU: return launch_gemm2<EPI_DGELU>(tmA, tmB, tmO, tmO2, M, N, K, ep, stream);
+    case EPI_F32: return launch_gemm2<EPI_F32>(tmA, tmB, tmO, tmO2, M, N, K, ep, stream);
+    default: return launch_gemm2<EPI_BF16>(tmA, tmB, tmO, tmO2, M, N, K, ep, stream);
   }
 }

@@ -31,9 +31,10 @@ struct EpiParams {
   int out_fp32;
   __nv_bfloat16* out2;
   int ld_out2;
+  int dbg;  // development only (LLC_GEMM_DBG): 256 = no global stores, 512 = no TMEM loads
 };
 
-constexpr int kEpiWarpBytes = 4096;  // two 2 KB bf16 tiles, or one 4 KB fp32 tile
+constexpr int kEpiWarpBytes = 8192;  // TMA-store tiles (see epi_warp_tile_tma) / one 4 KB fp32 tile
 
 // QuickGELU x*sigmoid(1.702x) with sigmoid(y) = 0.5 + 0.5 tanh(y/2): one MUFU op per element
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -107,6 +108,7 @@ __device__ __forceinline__ void epi_prefetch(EpiPre<MODE>& p, const EpiParams& e
   }
 }
 
+#define g_dbg_nostore (ep_dbg_flags & 256)
 // packed bf16 row (32 columns = 4 x 16 B) of this thread -> staging tile
 __device__ __forceinline__ void stage_row_bf16(uint8_t* tile, int lane, const uint32_t (&pk)[16]) {
 #pragma unroll
@@ -116,13 +118,14 @@ __device__ __forceinline__ void stage_row_bf16(uint8_t* tile, int lane, const ui
 }
 // staging tile -> global, 4 lanes per row, 8 rows per instruction
 __device__ __forceinline__ void store_tile_bf16(const uint8_t* tile, __nv_bfloat16* out, int ld,
-                                                int row0, int col, int M, int N, int lane) {
+                                                int row0, int col, int M, int N, int lane,
+                                                int ep_dbg_flags) {
   const int cc = col + (lane & 3) * 8;
 #pragma unroll
   for (int pass = 0; pass < 4; ++pass) {
     const int rr = pass * 8 + (lane >> 2), row = row0 + rr;
     const uint4 v = *reinterpret_cast<const uint4*>(tile + bf_tile_off(rr, lane & 3));
-    if (row < M && cc < N) *reinterpret_cast<uint4*>(out + (size_t)row * ld + cc) = v;
+    if (row < M && cc < N && !(g_dbg_nostore)) *reinterpret_cast<uint4*>(out + (size_t)row * ld + cc) = v;
   }
 }
 
@@ -195,12 +198,12 @@ __device__ __forceinline__ void epi_chunk(const EpiPre<MODE>& p, const EpiParams
     }
     stage_row_bf16(t1, lane, pk);
     __syncwarp();
-    if (out != nullptr) store_tile_bf16(t0, out, ep.ld_out, row0, col, M, N, lane);
-    store_tile_bf16(t1, ep.out2, ep.ld_out2, row0, col, M, N, lane);
+    if (out != nullptr) store_tile_bf16(t0, out, ep.ld_out, row0, col, M, N, lane, ep.dbg);
+    store_tile_bf16(t1, ep.out2, ep.ld_out2, row0, col, M, N, lane, ep.dbg);
   } else {
     stage_row_bf16(t0, lane, pk);
     __syncwarp();
-    store_tile_bf16(t0, out, ep.ld_out, row0, col, M, N, lane);
+    store_tile_bf16(t0, out, ep.ld_out, row0, col, M, N, lane, ep.dbg);
   }
   __syncwarp();  // tiles are rewritten by the next chunk
 }
@@ -256,10 +259,118 @@ __device__ __forceinline__ void epi_warp_tile(const EpiParams& ep, uint32_t t_ad
   for (int c = 0; c < NCH; ++c) {
     if (c + 1 < NCH) epi_prefetch<MODE>(nxt, ep, row0, col0 + (c + 1) * 32, M, N, lane);
     uint32_t acc[32];
-    tmem_ld_32x32(t_addr + c * 32, acc);
-    tmem_ld_wait();
+    if (!(ep.dbg & 512)) {
+      tmem_ld_32x32(t_addr + c * 32, acc);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0x3f800000u + j + lane;
+    }
     epi_chunk<MODE>(cur, ep, acc, tile, row0, col0 + c * 32, M, N, lane);
     if (c + 1 < NCH) cur = nxt;
+  }
+}
+
+
+// ---- bf16 modes with TMA stores (CTA-pair kernel) ------------------------------------------------
+// Register-side math as above, but the packed rows of TWO chunks (64 columns = one full 128 B
+// line per row) are staged in a [32 x 128 B] tile in TMA's SWIZZLE_128B pattern and written with
+// one cp.async.bulk.tensor store per warp: no LDS, no per-lane global stores (the 16 B STG path
+// cost 30-70 us per GEMM in LSU wavefronts and write transactions, profiles/), full-line writes,
+// row tail clipped by the tensor map. Per warp 8 KB: BF16 double-buffers the tile, GELU holds the
+// z and g tiles, DGELU one tile + a 2 KB scratch that turns the coalesced aux load into rows.
+__device__ __forceinline__ uint32_t line_tile_off(int row, int c16) {
+  return (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4));
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_rows_bf16(const EpiPre<MODE>& p, const uint32_t (&acc)[32],
+                                              uint8_t* scratch, int lane, uint32_t (&pk)[16],
+                                              uint32_t (&pg)[16]) {
+  float v[32];
+  if (MODE == EPI_DGELU) {
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass)
+      *reinterpret_cast<uint4*>(scratch + bf_tile_off(pass * 8 + (lane >> 2), lane & 3)) =
+          p.aux[pass];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 zq = *reinterpret_cast<const uint4*>(scratch + bf_tile_off(lane, c));
+      const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 z = unpack_bf16(zw[e]);
+        v[8 * c + 2 * e] = __uint_as_float(acc[8 * c + 2 * e]) * quick_gelu_grad_fast(z.x);
+        v[8 * c + 2 * e + 1] = __uint_as_float(acc[8 * c + 2 * e + 1]) * quick_gelu_grad_fast(z.y);
+      }
+    }
+    __syncwarp();  // scratch is rewritten by the next chunk
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] = __uint_as_float(acc[4 * j]) + p.bias[j].x;
+      v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + p.bias[j].y;
+      v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + p.bias[j].z;
+      v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + p.bias[j].w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  if (MODE == EPI_GELU) {
+    // activation of the bf16-ROUNDED pre-activation (what backward will see)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 z = unpack_bf16(pk[i]);
+      pg[i] = pack_bf16(quick_gelu_fast(z.x), quick_gelu_fast(z.y));
+    }
+  }
+}
+
+// one warp, NCH (even) chunks of 32 columns, 32 rows; wtile = this warp's 8 KB
+template <int MODE, int NCH>
+__device__ __forceinline__ void epi_warp_tile_tma(const EpiParams& ep, const CUtensorMap* tmO,
+                                                  const CUtensorMap* tmO2, uint32_t t_addr,
+                                                  uint8_t* wtile, int row0, int col0, int M, int N,
+                                                  int lane) {
+  EpiPre<MODE> cur, nxt;
+  epi_prefetch<MODE>(cur, ep, row0, col0, M, N, lane);
+#pragma unroll
+  for (int g = 0; g < NCH / 2; ++g) {
+    uint8_t* tA = (MODE == EPI_BF16) ? wtile + (g & 1) * 4096 : wtile;
+    uint8_t* tB = wtile + 4096;   // GELU: g tile; DGELU: aux scratch
+    // the tile(s) about to be rewritten must have been read by their previous TMA store
+    if (lane == 0) {
+      if (MODE == EPI_BF16) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+    }
+    __syncwarp();
+#pragma unroll
+    for (int hc = 0; hc < 2; ++hc) {
+      const int c = 2 * g + hc;
+      if (c + 1 < NCH) epi_prefetch<MODE>(nxt, ep, row0, col0 + (c + 1) * 32, M, N, lane);
+      uint32_t acc[32], pk[16], pg[16];
+      tmem_ld_32x32(t_addr + c * 32, acc);
+      tmem_ld_wait();
+      epi_rows_bf16<MODE>(cur, acc, tB, lane, pk, pg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (MODE != EPI_GELU || ep.out != nullptr)
+          *reinterpret_cast<uint4*>(tA + line_tile_off(lane, hc * 4 + j)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        if (MODE == EPI_GELU)
+          *reinterpret_cast<uint4*>(tB + line_tile_off(lane, hc * 4 + j)) =
+              make_uint4(pg[4 * j], pg[4 * j + 1], pg[4 * j + 2], pg[4 * j + 3]);
+      }
+      if (c + 1 < NCH) cur = nxt;
+    }
+    fence_proxy_async_smem();   // generic-proxy tile writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+      if (MODE != EPI_GELU || ep.out != nullptr)
+        tma_store_2d(tmO, smem_u32(tA), col0 + g * 64, row0);
+      if (MODE == EPI_GELU) tma_store_2d(tmO2, smem_u32(tB), col0 + g * 64, row0);
+      tma_store_commit();
+    }
   }
 }
 
