@@ -127,6 +127,11 @@ int llc_pack_weight(const float* src, int rows, int cols, int transpose, void* d
 int llc_pack_lora_cols(const float* src, int rows, int r, int s_i, int s_j, float scale, void* dst,
                        int ld_dst, int col0, void* stream);
 
+/* dst bf16 [16, ld_dst]: row j < r = scale * src[j*s_j + c*s_c], rows r..15 zero: the [16, K]
+ * factor of a rank-r row product computed as a skinny GEMM (u = X . F^T) */
+int llc_pack_factor_rows(const float* src, int r, int cols, int s_j, int s_c, float scale, void* dst,
+                         int ld_dst, void* stream);
+
 /* ---- patch embedding front end (model.py:756-767) -------------------------------------------- */
 /* NCHW fp32 image -> bf16 patch rows [N*G*G, ld_out] (im2col of the stride-P conv, no bias);
  * columns >= 3*P*P are zero-filled (K padding to a multiple of 16) */
@@ -199,6 +204,9 @@ typedef struct llc_vit_layer {
   void* woT_aug;   /* [D, D+16]:  W_o^T  | A_o^T        */
   void* wfcT;      /* [D, mlp]                          */
   void* wprojT;    /* [mlp, D]                          */
+  /* rank-r row products as skinny GEMMs on the tensor cores: [16, K] bf16 factors (rows >= r 0) */
+  void* f_out_A;   /* [16, D]:  A_o            u_o  = o . A_o^T              (forward)  */
+  void* f_in_B;    /* [16, 3D]: s * B_in^T     du_in = s dqkv . B_in         (backward) */
   const float *bqkv, *bo, *bfc, *bproj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   /* live fp32 LoRA parameters and their gradient slots (views of the flat buffers) */
   const float *in_A, *in_B, *out_A, *out_B; /* [r,D] [3D,r] [r,D] [D,r] */

@@ -3,6 +3,8 @@
 // reductions, weight packing and the fused AdamW on the flat LoRA buffer.
 // All are one-warp-per-row, 16-byte vectorised, shuffle-reduced; no shared-memory round trips
 // except where a [C, r] factor is reused by every row.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -191,6 +193,12 @@ ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g
 //   colsum  P[c, j] = sum_t X[t, c] * w[t, j]              -> per-CTA partials, reduced in fixed
 //                                                             order by colsum_finish (deterministic)
 constexpr int kSideThreads = 256;
+}  // namespace
+// tensor-core path for the column sums (lora_tc.cu)
+bool llc_colsum_tc_eligible(const void* X, int ld_x, int T, int C, const void* w, int ld_w);
+int llc_colsum_tc(const void* X, int ld_x, int T, int C, int R, const void* w, int ld_w,
+                  float* partial, int* n_partials, cudaStream_t st);
+namespace {
 constexpr int kSideGroup = 256;  // columns per colsum CTA: one 16 B vector per lane
 
 template <int R>
@@ -391,6 +399,17 @@ __global__ void pack_lora_cols_kernel(const float* __restrict__ src, int rows, i
   dst[(size_t)i * ld_dst + col0 + j] = __float2bfloat16_rn(v);
 }
 
+// dst[j, c] = scale * src[j * s_j + c * s_c] for j < r, 0 for r <= j < 16 (bf16 [16, ld_dst])
+__global__ void pack_factor_rows_kernel(const float* __restrict__ src, int r, int cols, int s_j,
+                                        int s_c, float scale, __nv_bfloat16* __restrict__ dst,
+                                        int ld_dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= LLC_LORA_PAD * cols) return;
+  const int j = idx / cols, c = idx % cols;
+  const float v = (j < r) ? scale * src[(size_t)j * s_j + (size_t)c * s_c] : 0.f;
+  dst[(size_t)j * ld_dst + c] = __float2bfloat16_rn(v);
+}
+
 // ------------------------------------------------------------------------------------------------
 // im2col of the stride-P patch conv: out[(n*G+py)*G+px, c*P*P + i*P + j] = img[n,c,py*P+i,px*P+j]
 // (two pixels per thread: P is even, so a pair never straddles a patch). Columns
@@ -582,6 +601,9 @@ extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float
     LLC_COUNT_LAUNCH();
     LLC_LAUNCH_CHECK("lora_rowdot_kernel");
   }
+  static const bool cc_colsum = getenv("LLC_COLSUM_LEGACY") != nullptr;
+  if (w != nullptr && !cc_colsum && llc_colsum_tc_eligible(X, ld_x, T, C, w, ld_w))
+    return llc_colsum_tc(X, ld_x, T, C, R, w, ld_w, partial, n_partials, st);
   if (w != nullptr) {
     const int groups = (C + kSideGroup - 1) / kSideGroup;
     int gx = llc_lora_side_max_partials() / groups;   // ~4 CTAs per SM over all column groups
@@ -643,6 +665,18 @@ extern "C" int llc_pack_lora_cols(const float* src, int rows, int r, int s_i, in
       src, rows, r, s_i, s_j, scale, (__nv_bfloat16*)dst, ld_dst, col0);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("pack_lora_cols_kernel");
+  return 0;
+}
+
+extern "C" int llc_pack_factor_rows(const float* src, int r, int cols, int s_j, int s_c, float scale,
+                                    void* dst, int ld_dst, void* stream) {
+  LLC_REQUIRE(src && dst && r >= 1 && r <= LLC_LORA_PAD && cols > 0 && ld_dst >= cols,
+              "llc_pack_factor_rows: bad args");
+  const int n = LLC_LORA_PAD * cols;
+  pack_factor_rows_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      src, r, cols, s_j, s_c, scale, (__nv_bfloat16*)dst, ld_dst);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("pack_factor_rows_kernel");
   return 0;
 }
 

@@ -159,8 +159,9 @@ extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   RUN(llc_gemm_bf16_tn(b->h1, DA, w->wqkv_aug, DA, T, 3 * D, KA, &e, stream));
   RUN(llc_attn_fwd(b->qkv, QA, b->o, DA, b->lse, N, L, H, sn, sl, causal, stream));
   // u_o = o A_o^T into o's pad columns
-  RUN(llc_lora_side(b->o, DA, T, D, r, w->out_A, 1, D, 1.0f, nullptr, 0, nullptr, nullptr,
-                    stream));
+  e = llc_gemm_epi{};
+  e.out = reinterpret_cast<__nv_bfloat16*>(b->o) + D; e.ld_out = DA;
+  RUN(llc_gemm_bf16_tn(b->o, DA, w->f_out_A, D, T, LLC_LORA_PAD, D, &e, stream));
   // x_mid = x + o W_o^T + b_o + s (o A_o^T) B_o^T
   e = llc_gemm_epi{};
   e.bias = w->bo; e.resid = b->x_in; e.ld_resid = D; e.out = b->x_mid; e.ld_out = D;
@@ -218,7 +219,10 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   RUN(llc_attn_bwd(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
                    stream));
   // in-proj LoRA grads: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
-  RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, w->in_B, r, 1, sc, h1 + D, DA, s->partial, &np,
+  e = llc_gemm_epi{};
+  e.out = dqkv + 3 * D; e.ld_out = QA;
+  RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
+  RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, s->partial, &np,
                     stream));
   RUN(llc_lora_colsum_finish(s->partial, np, 3 * D, r, sc, w->g_in_B, r, 1, stream));
   RUN(llc_lora_side(b->h1, DA, T, D, r, nullptr, 0, 0, 0.f, dqkv + 3 * D, QA, s->partial, &np,
@@ -254,6 +258,9 @@ extern "C" int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weight
     RUN(llc_pack_lora_cols(y->out_B, D, r, r, 1, sc, y->wo_aug, DA, D, stream));
     RUN(llc_pack_lora_cols(y->in_A, D, r, 1, D, 1.0f, y->wqkvT_aug, QA, 3 * D, stream));
     RUN(llc_pack_lora_cols(y->out_A, D, r, 1, D, 1.0f, y->woT_aug, DA, D, stream));
+    // [16, K] factors of the skinny row-product GEMMs: rows j < r, zero rows above
+    RUN(llc_pack_factor_rows(y->out_A, r, D, D, 1, 1.0f, y->f_out_A, D, stream));
+    RUN(llc_pack_factor_rows(y->in_B, r, 3 * D, 1, r, sc, y->f_in_B, 3 * D, stream));
   }
   return 0;
 }

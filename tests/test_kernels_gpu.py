@@ -197,7 +197,8 @@ def test_attention_fwd_bwd(ops, N, L, H, causal, seq_first):
 
 
 # --------------------------------------------------------------------------------------- LoRA side
-@pytest.mark.parametrize("T,Cc", [(100, 128), (197 * 3, 768), (197 * 3, 2304)])
+@pytest.mark.parametrize("T,Cc", [(100, 128), (197 * 3, 768), (197 * 3, 2304), (5003, 768),
+                                  (6304, 2304), (1100, 128)])   # T >= 1024: tensor-core colsum
 def test_lora_side_rowdot_and_colsum(ops, T, Cc):
     r = 4
     X = bf16_randn(T, Cc + 16, seed=30)
