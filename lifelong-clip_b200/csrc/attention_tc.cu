@@ -296,21 +296,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, FwdParams p) {
 //   type A (query rows):  R0 = Q_t K^T, R1 = dO_t V^T  -> dS (bf16, into R1)   -> dQ_t = dS K
 //   type B (key rows):    R0 = K_t Q^T, R1 = V_t dO^T  -> P^T (R0), dS^T (R1)  -> dV_t = P^T dO,
 //                                                                                 dK_t = dS^T Q
-// R0/R1 = TMEM columns [0,256) / [256,512). 256 threads work on a phase: thread = (row, column
-// half). Each half writes its packed bf16 operands over columns of ITS OWN half that it has
-// already consumed (half 0 at [0, LK/4), half 1 at [LK/2, 3LK/4)), so no thread overwrites data
-// another thread still has to read; the MMA walks the two areas k-step by k-step. The second
-// operands (K, dO, Q as "[k][hd]" MN-major B) are the tiles exactly as TMA loaded them.
+// R0/R1 = TMEM columns [0,256) / [256,512); LK = L rounded up to 16 columns are used. 256 threads
+// work on a phase: thread = (row, column half; half 0 = columns [0, c0), half 1 = [c0, LK)). Each
+// half writes its packed bf16 operands over columns of ITS OWN half that it has already consumed
+// (words at [0, c0/2) and [c0, c0 + (LK-c0)/2)), so no thread overwrites data another thread
+// still has to read; the MMA walks the two areas k-step by k-step. The second operands (K, dO, Q
+// as "[k][hd]" MN-major B) are the tiles exactly as TMA loaded them. Q, K, V, dO of the next pair
+// land in a second smem stage while this pair computes (two stages fit up to LK = 208); outputs
+// leave through a 16 KB staging tile and TMA stores (rows >= L are clipped by the tensor map).
 struct BwdParams {
   const __nv_bfloat16* o;
   int ld_o;
   const float* lse;
-  __nv_bfloat16* dqkv;
-  int ld_dqkv;
-  int N, L, H, LK, NT, sn, sl, causal, dbg;
+  int N, L, H, LK, NT, c0, sn, sl, causal, nstages, mat_bytes, dbg;
 };
-constexpr int kBwdStage = 4 * kMatBytes;  // Q | K | V | dO
-constexpr int kBwdSmem = 1024 + kBwdStage + 2 * 256 * 4 + 256;
+constexpr int kStagingBytes = 128 * 128;
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -330,36 +330,52 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1,
+                                             int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// 16 B chunk c16 of row r in a [rows x 128 B] tile laid out in TMA's 128 B swizzle
+__device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
+  return (uint32_t)(row * 128 + ((c16 ^ (row & 7)) << 4));
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   BwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~(uintptr_t)1023);
-  float* sLse = reinterpret_cast<float*>(smem + kBwdStage);   // [256] lse * log2e per query
-  float* sDelta = sLse + 256;                                 // [256]
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
+                   const __grid_constant__ CUtensorMap tmD0, const __grid_constant__ CUtensorMap tmD1,
+                   const __grid_constant__ CUtensorMap tmOut, BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int LK = p.LK, NT = p.NT, c0 = p.c0, mat = p.mat_bytes;
+  const int stage_bytes = 4 * mat;
+  uint8_t* staging = smem + p.nstages * stage_bytes;
+  float* sLse = reinterpret_cast<float*>(staging + kStagingBytes);   // [256] lse * log2e
+  float* sDelta = sLse + 256;                                        // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
-  uint64_t* ld_full = bars;       // TMA landed Q,K,V,dO
-  uint64_t* ld_empty = bars + 1;  // every MMA of the pair retired
-  uint64_t* s_full = bars + 2;    // R0/R1 hold the phase's S-type products
-  uint64_t* p_ready = bars + 3;   // operands written back to TMEM (256 arrivals)
-  uint64_t* o_full = bars + 4;    // output accumulators complete
-  uint64_t* acc_free = bars + 5;  // accumulators drained (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* ld_full = bars;       // [2] TMA landed Q,K,V,dO of a pair
+  uint64_t* ld_empty = bars + 2;  // [2] every MMA of the pair retired
+  uint64_t* s_full = bars + 4;    // R0/R1 hold the phase's S-type products
+  uint64_t* p_ready = bars + 5;   // operands written back to TMEM (256 arrivals)
+  uint64_t* o_full = bars + 6;    // output accumulators complete
+  uint64_t* acc_free = bars + 7;  // accumulators drained (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int pairs = p.N * p.H;
   const int D = p.H * HD;
-  const int LK = p.LK, NT = p.NT, half = LK / 2;
-  const int out_b = (3 * LK / 4 + 31) & ~31;   // dV / dK accumulator columns inside R0 / R1
+  // dV / dK accumulator columns inside R0 / R1: past both operand areas
+  const int out_b = (c0 + (LK - c0) / 2 + 31) & ~31;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQKV);
-    tma_prefetch_desc(&tmDO);
-    mbar_init(smem_u32(ld_full), 1);
-    mbar_init(smem_u32(ld_empty), 1);
+    if (smem_u32(smem) & 1023) __trap();   // swizzled tiles need the 1024 B alignment asked for
+    tma_prefetch_desc(&tmQ0); tma_prefetch_desc(&tmQ1);
+    tma_prefetch_desc(&tmD0); tma_prefetch_desc(&tmD1);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&ld_full[i]), 1);
+      mbar_init(smem_u32(&ld_empty[i]), 1);
+    }
     mbar_init(smem_u32(s_full), 1);
     mbar_init(smem_u32(p_ready), 256);
     mbar_init(smem_u32(o_full), 1);
@@ -371,24 +387,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const uint32_t sQ = smem_u32(smem), sK = sQ + kMatBytes, sV = sQ + 2 * kMatBytes,
-                 sD = sQ + 3 * kMatBytes;
+  const uint32_t smem0 = smem_u32(smem);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     int it = 0;
     for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
+      const int st = it % p.nstages;
+      const uint32_t ph = (it / p.nstages) & 1;
       const int n = pr / p.H, h = pr % p.H;
-      mbar_wait(smem_u32(ld_empty), (it & 1) ^ 1);
+      mbar_wait(smem_u32(&ld_empty[st]), ph ^ 1);
       if (elect_one()) {
-        const uint32_t fb = smem_u32(ld_full);
-        mbar_expect_tx(fb, 4 * NT * kTileBytes);
-        for (int t = 0; t < NT; ++t) {
-          tma_load_3d(sQ + t * kTileBytes, &tmQKV, fb, h * HD, t * 128, n);
-          tma_load_3d(sK + t * kTileBytes, &tmQKV, fb, D + h * HD, t * 128, n);
-          tma_load_3d(sV + t * kTileBytes, &tmQKV, fb, 2 * D + h * HD, t * 128, n);
-          tma_load_3d(sD + t * kTileBytes, &tmDO, fb, h * HD, t * 128, n);
+        const uint32_t fb = smem_u32(&ld_full[st]);
+        const uint32_t base = smem0 + st * stage_bytes;
+        mbar_expect_tx(fb, 4 * mat);
+        for (int m = 0; m < 3; ++m) {   // Q, K, V: column blocks h*64 + {0, D, 2D}
+          tma_load_3d(base + m * mat, &tmQ0, fb, m * D + h * HD, 0, n);
+          if (NT > 1) tma_load_3d(base + m * mat + kTileBytes, &tmQ1, fb, m * D + h * HD, 128, n);
         }
+        tma_load_3d(base + 3 * mat, &tmD0, fb, h * HD, 0, n);
+        if (NT > 1) tma_load_3d(base + 3 * mat + kTileBytes, &tmD1, fb, h * HD, 128, n);
       }
       __syncwarp();
     }
@@ -397,9 +415,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint32_t idesc_s = umma_idesc_bf16(128, LK, 0, 0);
     const uint32_t idesc_o = umma_idesc_bf16(128, HD, 0, 1);
     const uint32_t R0 = tmem_base, R1 = tmem_base + 256;
+    const int ksteps = LK / 16, kh = c0 / 16;
     int it = 0, g = 0;
     for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
-      mbar_wait(smem_u32(ld_full), it & 1);
+      const int st = it % p.nstages;
+      const uint32_t sQ = smem0 + st * stage_bytes, sK = sQ + mat, sV = sQ + 2 * mat,
+                     sD = sQ + 3 * mat;
+      mbar_wait(smem_u32(&ld_full[st]), (it / p.nstages) & 1);
       tc_fence_after();
       for (int ph = 0; ph < 2 * NT; ++ph, ++g) {
         const bool type_a = ph < NT;
@@ -411,21 +433,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           const uint64_t b0 = umma_desc_k_sw128(type_a ? sK : sQ);
           const uint64_t a1 = umma_desc_k_sw128((type_a ? sD : sV) + t * kTileBytes);
           const uint64_t b1 = umma_desc_k_sw128(type_a ? sV : sD);
-          if (!(p.dbg & 4)) {
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_bf16(R0, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(R0, a0 + 2 * k, b0 + 2 * k, idesc_s, k != 0);
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_bf16(R1, a1 + 2 * k, b1 + 2 * k, idesc_s, k != 0);
-          }
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(R1, a1 + 2 * k, b1 + 2 * k, idesc_s, k != 0);
           umma_commit(smem_u32(s_full));
         }
         __syncwarp();
         mbar_wait(smem_u32(p_ready), g & 1);
         tc_fence_after();
         if (elect_one()) {
-          const int ksteps = LK / 16, kh = LK / 32;
-          for (int ks = 0; ks < ((p.dbg & 2) ? 0 : ksteps); ++ks) {
-            const uint32_t aoff = ks < kh ? ks * 8 : half + (ks - kh) * 8;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t aoff = ks < kh ? ks * 8 : c0 + (ks - kh) * 8;
             if (type_a) {   // dQ_t = dS K
               umma_bf16_ts(R0, R1 + aoff, umma_desc_mn_sw128(sK + ks * 2048, 8192, 1024), idesc_o,
                            ks != 0);
@@ -437,7 +456,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             }
           }
           umma_commit(smem_u32(o_full));
-          if (ph == 2 * NT - 1) umma_commit(smem_u32(ld_empty));
+          if (ph == 2 * NT - 1) umma_commit(smem_u32(&ld_empty[st]));
         }
         __syncwarp();
       }
@@ -447,38 +466,52 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const int q = warp & 3;             // TMEM lane quarter
     const int hh = (warp - 2) >> 2;     // column half
     const int r = q * 32 + lane;        // accumulator row within a phase
-    const int tid2 = (warp - 2) * 32 + lane;   // 0..255: the query this thread preprocesses
+    const int tid2 = (warp - 2) * 32 + lane;   // 0..255
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t R0 = tmem_base + lane_sel, R1 = tmem_base + 256 + lane_sel;
     const float c2 = 0.125f * kLog2e;
-    const int nchunk = half / 16;
+    const int col_base = hh ? c0 : 0;
+    const int nchunk = (hh ? LK - c0 : c0) / 16;
     int it = 0, g = 0;
     for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
+      const int st = it % p.nstages;
       const int n = pr / p.H, h = pr % p.H;
       const int tok0 = n * p.sn;
-      mbar_wait(smem_u32(ld_full), it & 1);
-      // delta and lse of query tid2 (dO row from the landed tile, O row from global)
+      const uint8_t* sDO = smem + st * stage_bytes + 3 * mat;
+      mbar_wait(smem_u32(&ld_full[st]), (it / p.nstages) & 1);
+      // delta_q = dO_q . O_q for the 32 queries of this warp: 8 lanes per row, 16 B each, the O
+      // rows read straight from global (coalesced), the dO rows from the landed tile
       {
-        float d = 0.f, l2 = 0.f;
-        if (tid2 < p.L && !(p.dbg & 16)) {
-          const uint8_t* drow = smem + 3 * kMatBytes + (tid2 >> 7) * kTileBytes + (tid2 & 127) * 128;
-          const uint4* orow = reinterpret_cast<const uint4*>(
-              p.o + (size_t)(tok0 + tid2 * p.sl) * p.ld_o + h * HD);
+        const int rb = (warp - 2) * 32;
+        uint4 ov[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 dv = *reinterpret_cast<const uint4*>(drow + ((c ^ (tid2 & 7)) << 4));
-            const uint4 ov = orow[c];
-            const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+        for (int ps = 0; ps < 8; ++ps) {
+          const int row = rb + ps * 4 + (lane >> 3);
+          ov[ps] = make_uint4(0, 0, 0, 0);
+          if (row < p.L)
+            ov[ps] = *reinterpret_cast<const uint4*>(
+                p.o + (size_t)(tok0 + row * p.sl) * p.ld_o + h * HD + (lane & 7) * 8);
+        }
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+          const int row = rb + ps * 4 + (lane >> 3);
+          float d = 0.f;
+          if (row < p.L) {
+            const uint4 dv = *reinterpret_cast<const uint4*>(sDO + sw128_off(row, lane & 7));
+            const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+            const uint32_t ow[4] = {ov[ps].x, ov[ps].y, ov[ps].z, ov[ps].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 a = unpack_bf16(dw[e]), b = unpack_bf16(ow[e]);
               d += a.x * b.x + a.y * b.y;
             }
           }
-          l2 = p.lse[(size_t)pr * p.L + tid2] * kLog2e;
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if ((lane & 7) == 0) sDelta[row] = d;
         }
-        sDelta[tid2] = d;
-        sLse[tid2] = l2;
+        sLse[tid2] = tid2 < p.L ? p.lse[(size_t)pr * p.L + tid2] * kLog2e : 0.f;
       }
       named_bar_sync(1, 256);
       for (int ph = 0; ph < 2 * NT; ++ph, ++g) {
@@ -490,17 +523,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const float lse_r = sLse[gr & 255], del_r = sDelta[gr & 255];
         // Out-of-range rows/columns need no masking in the non-causal case: TMA zero-filled the
         // rows >= L of Q, K, V and dO, so their products vanish in the output MMAs; only the
-        // chunk that straddles L is clamped (p could overflow there), and causal chunks are
+        // chunk that straddles L is masked (p could overflow there), and causal chunks are
         // masked element by element.
-        for (int c = 0; c < ((p.dbg & 1) ? 0 : nchunk); ++c) {
-          const int col0 = hh * half + c * 16;
-          uint32_t sv[16], dv[16], wp[8], wd[8];
-          tmem_ld_x16(R0 + col0, sv);
-          tmem_ld_x16(R1 + col0, dv);
-          tmem_ld_wait();
+        auto process = [&](const uint32_t (&sv)[16], const uint32_t (&dv)[16], int c) {
+          const int col0 = col_base + c * 16;
+          uint32_t wp[8], wd[8];
           const bool fast = !p.causal && col0 + 16 <= p.L;
           if (type_a) {
-            // row = query gr, columns = keys
             if (fast) {
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
@@ -523,9 +552,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 wd[j >> 1] = pack_bf16(ds[0], ds[1]);
               }
             }
-            tmem_st_x8(R1 + hh * half + c * 8, wd);
+            tmem_st_x8(R1 + col_base + c * 8, wd);
           } else {
-            // row = key gr, columns = queries: lse / delta per column (16-byte smem broadcasts)
             float lq[16], dq[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -560,14 +588,36 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 wd[j >> 1] = pack_bf16(ds[0], ds[1]);
               }
             }
-            tmem_st_x8(R0 + hh * half + c * 8, wp);
-            tmem_st_x8(R1 + hh * half + c * 8, wd);
+            tmem_st_x8(R0 + col_base + c * 8, wp);
+            tmem_st_x8(R1 + col_base + c * 8, wd);
+          }
+        };
+        if (!(p.dbg & 1)) {
+          // chunk c+1 is in flight from TMEM while chunk c is processed
+          uint32_t sA[16], dA[16], sB[16], dB[16];
+          tmem_ld_x16(R0 + col_base, sA);
+          tmem_ld_x16(R1 + col_base, dA);
+          for (int c = 0; c < nchunk; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nchunk) {
+              tmem_ld_x16(R0 + col_base + (c + 1) * 16, sB);
+              tmem_ld_x16(R1 + col_base + (c + 1) * 16, dB);
+            }
+            process(sA, dA, c);
+            if (c + 1 < nchunk) {
+              tmem_ld_wait();
+              if (c + 2 < nchunk) {
+                tmem_ld_x16(R0 + col_base + (c + 2) * 16, sA);
+                tmem_ld_x16(R1 + col_base + (c + 2) * 16, dA);
+              }
+              process(sB, dB, c + 1);
+            }
           }
         }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(p_ready));
-        // epilogue of the phase
+        // ---- epilogue of the phase: accumulators -> staging tile -> TMA store
         mbar_wait(smem_u32(o_full), g & 1);
         tc_fence_after();
         if (type_a) {
@@ -576,19 +626,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(acc_free));
-          if (gr < p.L && !(p.dbg & 8)) {
-            uint4* dst = reinterpret_cast<uint4*>(
-                p.dqkv + (size_t)(tok0 + gr * p.sl) * p.ld_dqkv + h * HD + hh * 32);
+          if (tid2 == 0) tma_store_wait_read<0>();   // staging no longer read by an older store
+          named_bar_sync(1, 256);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(
-                  pack_bf16(__uint_as_float(a[8 * j]) * 0.125f, __uint_as_float(a[8 * j + 1]) * 0.125f),
-                  pack_bf16(__uint_as_float(a[8 * j + 2]) * 0.125f, __uint_as_float(a[8 * j + 3]) * 0.125f),
-                  pack_bf16(__uint_as_float(a[8 * j + 4]) * 0.125f, __uint_as_float(a[8 * j + 5]) * 0.125f),
-                  pack_bf16(__uint_as_float(a[8 * j + 6]) * 0.125f, __uint_as_float(a[8 * j + 7]) * 0.125f));
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(staging + sw128_off(r, hh * 4 + j)) = make_uint4(
+                pack_bf16(__uint_as_float(a[8 * j]) * 0.125f, __uint_as_float(a[8 * j + 1]) * 0.125f),
+                pack_bf16(__uint_as_float(a[8 * j + 2]) * 0.125f, __uint_as_float(a[8 * j + 3]) * 0.125f),
+                pack_bf16(__uint_as_float(a[8 * j + 4]) * 0.125f, __uint_as_float(a[8 * j + 5]) * 0.125f),
+                pack_bf16(__uint_as_float(a[8 * j + 6]) * 0.125f, __uint_as_float(a[8 * j + 7]) * 0.125f));
+          fence_proxy_async_smem();
+          named_bar_sync(1, 256);
+          if (tid2 == 0 && !(p.dbg & 8)) {
+            tma_store_3d(&tmOut, smem_u32(staging), h * HD, t * 128, n);
+            tma_store_commit();
           }
         } else {
-          // half 0 stores dV (R0), half 1 stores dK (R1, scaled by hd^-0.5)
+          // half 0 holds dV (R0), half 1 holds dK (R1, scaled by hd^-0.5); the staging tile is
+          // used twice, dV first
           uint32_t a[32], b[32];
           const uint32_t src = (hh == 0 ? R0 : R1) + out_b;
           tmem_ld_32x32(src, a);
@@ -596,22 +651,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(acc_free));
-          if (gr < p.L && !(p.dbg & 8)) {
-            const float sc = hh == 0 ? 1.0f : 0.125f;
-            uint4* dst = reinterpret_cast<uint4*>(
-                p.dqkv + (size_t)(tok0 + gr * p.sl) * p.ld_dqkv + (hh == 0 ? 2 * D : D) + h * HD);
+          const float sc = hh == 0 ? 1.0f : 0.125f;
+          for (int pass = 0; pass < 2; ++pass) {
+            if (tid2 == 0) tma_store_wait_read<0>();
+            named_bar_sync(1, 256);
+            if (hh == pass) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dst[j] = make_uint4(
-                  pack_bf16(__uint_as_float(a[8 * j]) * sc, __uint_as_float(a[8 * j + 1]) * sc),
-                  pack_bf16(__uint_as_float(a[8 * j + 2]) * sc, __uint_as_float(a[8 * j + 3]) * sc),
-                  pack_bf16(__uint_as_float(a[8 * j + 4]) * sc, __uint_as_float(a[8 * j + 5]) * sc),
-                  pack_bf16(__uint_as_float(a[8 * j + 6]) * sc, __uint_as_float(a[8 * j + 7]) * sc));
-              dst[4 + j] = make_uint4(
-                  pack_bf16(__uint_as_float(b[8 * j]) * sc, __uint_as_float(b[8 * j + 1]) * sc),
-                  pack_bf16(__uint_as_float(b[8 * j + 2]) * sc, __uint_as_float(b[8 * j + 3]) * sc),
-                  pack_bf16(__uint_as_float(b[8 * j + 4]) * sc, __uint_as_float(b[8 * j + 5]) * sc),
-                  pack_bf16(__uint_as_float(b[8 * j + 6]) * sc, __uint_as_float(b[8 * j + 7]) * sc));
+              for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<uint4*>(staging + sw128_off(r, j)) = make_uint4(
+                    pack_bf16(__uint_as_float(a[8 * j]) * sc, __uint_as_float(a[8 * j + 1]) * sc),
+                    pack_bf16(__uint_as_float(a[8 * j + 2]) * sc, __uint_as_float(a[8 * j + 3]) * sc),
+                    pack_bf16(__uint_as_float(a[8 * j + 4]) * sc, __uint_as_float(a[8 * j + 5]) * sc),
+                    pack_bf16(__uint_as_float(a[8 * j + 6]) * sc, __uint_as_float(a[8 * j + 7]) * sc));
+                *reinterpret_cast<uint4*>(staging + sw128_off(r, 4 + j)) = make_uint4(
+                    pack_bf16(__uint_as_float(b[8 * j]) * sc, __uint_as_float(b[8 * j + 1]) * sc),
+                    pack_bf16(__uint_as_float(b[8 * j + 2]) * sc, __uint_as_float(b[8 * j + 3]) * sc),
+                    pack_bf16(__uint_as_float(b[8 * j + 4]) * sc, __uint_as_float(b[8 * j + 5]) * sc),
+                    pack_bf16(__uint_as_float(b[8 * j + 6]) * sc, __uint_as_float(b[8 * j + 7]) * sc));
+              }
+              fence_proxy_async_smem();
+            }
+            named_bar_sync(1, 256);
+            if (tid2 == 0 && !(p.dbg & 8)) {
+              tma_store_3d(&tmOut, smem_u32(staging), (pass == 0 ? 2 * D : D) + h * HD, t * 128, n);
+              tma_store_commit();
             }
           }
         }
@@ -619,6 +682,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       // sLse / sDelta are rewritten for the next pair only after every thread left the last phase
       named_bar_sync(1, 256);
     }
+    if (tid2 == 0) tma_store_wait<0>();
   }
 
   __syncwarp();
@@ -669,29 +733,45 @@ int llc_attn_fwd_tc(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, 
   return 0;
 }
 
+static int encode_tokens_map_rows(CUtensorMap* tm, const void* base, int cols, int ld, int L, int N,
+                                  int sn, int sl, int box_rows) {
+  return llc_encode_tmap_3d(tm, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)cols,
+                            (uint64_t)L, (uint64_t)N, (uint64_t)ld * 2 * sl, (uint64_t)ld * 2 * sn,
+                            HD, box_rows, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o, int ld_do,
                     const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H, int sn, int sl,
                     int causal, cudaStream_t st) {
-  CUtensorMap tq, td;
-  if (int rc = encode_tokens_map(&tq, qkv, 3 * H * HD, ld_qkv, L, N, sn, sl)) return rc;
-  if (int rc = encode_tokens_map(&td, d_o, H * HD, ld_do, L, N, sn, sl)) return rc;
   BwdParams p;
   p.o = reinterpret_cast<const __nv_bfloat16*>(o); p.ld_o = ld_o; p.lse = lse;
-  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); p.ld_dqkv = ld_dqkv;
-  p.N = N; p.L = L; p.H = H; p.LK = (L + 31) / 32 * 32; p.NT = (L + 127) / 128;
+  p.N = N; p.L = L; p.H = H; p.LK = (L + 15) / 16 * 16; p.NT = (L + 127) / 128;
+  p.c0 = (p.LK / 2 + 15) / 16 * 16;
   p.sn = sn; p.sl = sl; p.causal = causal;
+  p.mat_bytes = p.LK * 128;
+  if (p.mat_bytes < kTileBytes && p.NT == 1) p.mat_bytes = p.LK * 128;  // one box of LK rows
+  const int fixed = kStagingBytes + 2 * 256 * 4 + 256;
+  p.nstages = (2 * 4 * p.mat_bytes + fixed <= 227 * 1024) ? 2 : 1;
+  const int smem = p.nstages * 4 * p.mat_bytes + fixed;
   static const int dbg = getenv("LLC_ATTN_DBG") ? atoi(getenv("LLC_ATTN_DBG")) : 0;
   p.dbg = dbg;
-  static bool configured = false;
-  if (!configured) {
+  const int rows0 = p.NT > 1 ? 128 : p.LK, rows1 = p.NT > 1 ? p.LK - 128 : 16;
+  CUtensorMap q0, q1, d0, d1, to;
+  if (int rc = encode_tokens_map_rows(&q0, qkv, 3 * H * HD, ld_qkv, L, N, sn, sl, rows0)) return rc;
+  if (int rc = encode_tokens_map_rows(&q1, qkv, 3 * H * HD, ld_qkv, L, N, sn, sl, rows1)) return rc;
+  if (int rc = encode_tokens_map_rows(&d0, d_o, H * HD, ld_do, L, N, sn, sl, rows0)) return rc;
+  if (int rc = encode_tokens_map_rows(&d1, d_o, H * HD, ld_do, L, N, sn, sl, rows1)) return rc;
+  if (int rc = encode_tokens_map_rows(&to, dqkv, 3 * H * HD, ld_dqkv, L, N, sn, sl, 128)) return rc;
+  static int configured = 0;
+  if (configured < smem) {
     LLC_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kBwdSmem));
-    configured = true;
+                                  smem));
+    configured = smem;
   }
   const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
                  16.0 * N * H * (double)L * HD, st);
-  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmem, st>>>(tq, td, p);
+  attn_bwd_tc_kernel<<<grid, kThreads, smem, st>>>(q0, q1, d0, d1, to, p);
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("attn_bwd_tc_kernel");
