@@ -118,6 +118,15 @@ int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float* Mrd, int 
 int llc_lora_colsum_finish(const float* partial, int n_partials, int C, int r, float cs_scale,
                            float* out, int o_sc, int o_sj, void* stream);
 int llc_lora_side_max_partials(void);
+/* several finishes in one launch (one per LoRA tensor of a layer) */
+typedef struct llc_finish_job {
+  const float* partial;
+  int n_partials, C;
+  float scale;
+  float* out;
+  int o_sc, o_sj;
+} llc_finish_job;
+int llc_lora_colsum_finish_multi(const llc_finish_job* jobs, int n_jobs, int r, void* stream);
 
 /* ---- weight preparation (frozen backbone: done once; LoRA columns refreshed every step) ------ */
 /* dst bf16 [rows, ld_dst] <- src fp32 [rows, cols] (row-major) or its transpose */

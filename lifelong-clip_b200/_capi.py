@@ -68,6 +68,11 @@ class BlockBwdBufs(C.Structure):
     _fields_ = [(n, c_void) for n in ("dx", "dxb", "dz", "dh", "d_o", "dqkv", "partial")]
 
 
+class FinishJob(C.Structure):
+    _fields_ = [("partial", c_void), ("n_partials", c_int), ("C", c_int), ("scale", c_float),
+                ("out", c_void), ("o_sc", c_int), ("o_sj", c_int)]
+
+
 class ProfRec(C.Structure):
     _fields_ = [("kind", c_int), ("m", c_int), ("n", c_int), ("k", c_int), ("ms", c_float),
                 ("flops", C.c_double), ("bytes", C.c_double)]
@@ -99,6 +104,7 @@ SIGNATURES = {
     "llc_lora_colsum_finish": (c_int, [c_void, c_int, c_int, c_int, c_float, c_void, c_int, c_int,
                                        c_void]),
     "llc_lora_side_max_partials": (c_int, []),
+    "llc_lora_colsum_finish_multi": (c_int, [C.POINTER(FinishJob), c_int, c_int, c_void]),
     "llc_pack_weight": (c_int, [c_void, c_int, c_int, c_int, c_void, c_int, c_void]),
     "llc_pack_lora_cols": (c_int, [c_void, c_int, c_int, c_int, c_int, c_float, c_void, c_int,
                                    c_int, c_void]),

@@ -79,8 +79,17 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadK a) {
   // z = y @ proj
   float nrm = 0.f;
   for (int e = tid; e < a.E; e += kThreads) {
-    float acc = 0.f;
-    for (int k = 0; k < a.D; ++k) acc += sy[k] * __ldg(a.proj + (size_t)k * a.E + e);
+    // 8 independent partial sums: the proj column walk is a chain of L2 loads otherwise
+    float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 8 <= a.D; k += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        part[u] = fmaf(sy[k + u], __ldg(a.proj + (size_t)(k + u) * a.E + e), part[u]);
+    }
+    for (; k < a.D; ++k) part[0] = fmaf(sy[k], __ldg(a.proj + (size_t)k * a.E + e), part[0]);
+    const float acc = ((part[0] + part[1]) + (part[2] + part[3])) +
+                      ((part[4] + part[5]) + (part[6] + part[7]));
     sf[e] = acc;
     a.feat[(size_t)n * a.E + e] = acc;
     nrm += acc * acc;
@@ -195,11 +204,20 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
     // df = scale * dlogits @ T ; dz = (df - f (f.df)) / |z|
     float fd = 0.f, zz = 0.f;
     for (int e = tid; e < a.E; e += kThreads) {
-      float acc = 0.f;
-      for (int c = 0; c < a.C; ++c) {
-        const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
-        acc += sg[c] * __ldg(a.text + (size_t)row * a.E + e);
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
+      int c = 0;
+      for (; c + 4 <= a.C; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t row = a.cls_idx ? a.cls_idx[c + u] : (int64_t)(c + u);
+          part[u] = fmaf(sg[c + u], __ldg(a.text + (size_t)row * a.E + e), part[u]);
+        }
       }
+      for (; c < a.C; ++c) {
+        const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
+        part[0] = fmaf(sg[c], __ldg(a.text + (size_t)row * a.E + e), part[0]);
+      }
+      float acc = (part[0] + part[1]) + (part[2] + part[3]);
       acc *= a.logit_scale;
       sz[e] = acc;
       fd += acc * sf[e];

@@ -363,6 +363,37 @@ colsum_finish_kernel(const float* __restrict__ partial, int n_partials, int C, i
   }
 }
 
+constexpr int kMaxFinishJobs = 8;
+struct FinishArgs {
+  llc_finish_job j[kMaxFinishJobs];
+};
+// blockIdx.y = job; same fixed-order reduction as colsum_finish_kernel
+__global__ void __launch_bounds__(256)
+colsum_finish_multi_kernel(const __grid_constant__ FinishArgs a, int R, int r) {
+  __shared__ float red[8][32];
+  const llc_finish_job& jb = a.j[blockIdx.y];
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int n = jb.C * R;
+  for (int base = blockIdx.x * 32; base < n; base += gridDim.x * 32) {
+    const int i = base + o;
+    float s = 0.f;
+    if (i < n) {
+#pragma unroll 4
+      for (int p = sl; p < jb.n_partials; p += 8) s += jb.partial[(size_t)p * n + i];
+    }
+    red[sl][o] = s;
+    __syncthreads();
+    if (sl == 0 && i < n) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][o];
+      const int c = i / R, j = i % R;
+      if (j < r) jb.out[(size_t)c * jb.o_sc + (size_t)j * jb.o_sj] = t * jb.scale;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ src, int rows, int cols,
                                    int transpose, __nv_bfloat16* __restrict__ dst, int ld_dst) {
@@ -408,6 +439,66 @@ __global__ void pack_factor_rows_kernel(const float* __restrict__ src, int r, in
   const int j = idx / cols, c = idx % cols;
   const float v = (j < r) ? scale * src[(size_t)j * s_j + (size_t)c * s_c] : 0.f;
   dst[(size_t)j * ld_dst + c] = __float2bfloat16_rn(v);
+}
+
+// Per-step refresh of every LoRA-dependent operand of the tower in ONE launch (it used to be six
+// tiny kernels per layer): the 16 LoRA K-columns of the four augmented weights and the two
+// [16, K] row-product factors, for all layers. blockIdx.y = layer.
+struct RefreshLayer {
+  const float *in_A, *in_B, *out_A, *out_B;
+  __nv_bfloat16 *wqkv_aug, *wo_aug, *wqkvT_aug, *woT_aug, *f_out_A, *f_in_B;
+};
+constexpr int kMaxRefreshLayers = 32;
+struct RefreshArgs {
+  RefreshLayer l[kMaxRefreshLayers];
+};
+
+__global__ void __launch_bounds__(256)
+refresh_lora_kernel(const __grid_constant__ RefreshArgs args, int D, int r, float sc) {
+  const RefreshLayer& y = args.l[blockIdx.y];
+  const int DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;
+  const int P = LLC_LORA_PAD;
+  // task sizes (elements): [W_in | s B_in] 3D*16, [W_o | s B_o] D*16, [W_in^T | A_in^T] D*16,
+  // [W_o^T | A_o^T] D*16, F_oA 16*D, F_inB 16*3D
+  const int n0 = 3 * D * P, n1 = D * P, n2 = D * P, n3 = D * P, n4 = P * D, n5 = P * 3 * D;
+  const int total = n0 + n1 + n2 + n3 + n4 + n5;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int i = idx;
+    if (i < n0) {            // wqkv_aug[c, D + j] = s * in_B[c, j]
+      const int c = i / P, j = i % P;
+      y.wqkv_aug[(size_t)c * DA + D + j] = __float2bfloat16_rn(j < r ? sc * y.in_B[c * r + j] : 0.f);
+      continue;
+    }
+    i -= n0;
+    if (i < n1) {            // wo_aug[c, D + j] = s * out_B[c, j]
+      const int c = i / P, j = i % P;
+      y.wo_aug[(size_t)c * DA + D + j] = __float2bfloat16_rn(j < r ? sc * y.out_B[c * r + j] : 0.f);
+      continue;
+    }
+    i -= n1;
+    if (i < n2) {            // wqkvT_aug[c, 3D + j] = in_A[j, c]
+      const int c = i / P, j = i % P;
+      y.wqkvT_aug[(size_t)c * QA + 3 * D + j] = __float2bfloat16_rn(j < r ? y.in_A[j * D + c] : 0.f);
+      continue;
+    }
+    i -= n2;
+    if (i < n3) {            // woT_aug[c, D + j] = out_A[j, c]
+      const int c = i / P, j = i % P;
+      y.woT_aug[(size_t)c * DA + D + j] = __float2bfloat16_rn(j < r ? y.out_A[j * D + c] : 0.f);
+      continue;
+    }
+    i -= n3;
+    if (i < n4) {            // f_out_A[j, c] = out_A[j, c]
+      const int j = i / D, c = i % D;
+      y.f_out_A[(size_t)j * D + c] = __float2bfloat16_rn(j < r ? y.out_A[j * D + c] : 0.f);
+      continue;
+    }
+    i -= n4;
+    {                        // f_in_B[j, c] = s * in_B[c, j]
+      const int j = i / (3 * D), c = i % (3 * D);
+      y.f_in_B[(size_t)j * 3 * D + c] = __float2bfloat16_rn(j < r ? sc * y.in_B[c * r + j] : 0.f);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -644,6 +735,28 @@ extern "C" int llc_lora_colsum_finish(const float* partial, int n_partials, int 
   return 0;
 }
 
+extern "C" int llc_lora_colsum_finish_multi(const llc_finish_job* jobs, int n_jobs, int r,
+                                            void* stream) {
+  LLC_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= kMaxFinishJobs && r >= 1 && r <= kMaxR,
+              "llc_lora_colsum_finish_multi: bad args");
+  const int R = r <= 4 ? 4 : 8;
+  FinishArgs a;
+  int maxn = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    LLC_REQUIRE(jobs[i].partial && jobs[i].out && jobs[i].n_partials > 0 && jobs[i].C > 0,
+                "llc_lora_colsum_finish_multi: job %d incomplete", i);
+    a.j[i] = jobs[i];
+    if (jobs[i].C * R > maxn) maxn = jobs[i].C * R;
+  }
+  LLC_PROF_BEGIN(LLC_K_LORA_SIDE, n_jobs, maxn, 1, 0.0, 0.0, (cudaStream_t)stream);
+  colsum_finish_multi_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, (cudaStream_t)stream>>>(
+      a, R, r);
+  LLC_PROF_END((cudaStream_t)stream);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("colsum_finish_multi_kernel");
+  return 0;
+}
+
 extern "C" int llc_pack_weight(const float* src, int rows, int cols, int transpose, void* dst,
                                int ld_dst, void* stream) {
   LLC_REQUIRE(src && dst && rows > 0 && cols > 0 && ld_dst >= cols, "llc_pack_weight: bad args");
@@ -665,6 +778,27 @@ extern "C" int llc_pack_lora_cols(const float* src, int rows, int r, int s_i, in
       src, rows, r, s_i, s_j, scale, (__nv_bfloat16*)dst, ld_dst, col0);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("pack_lora_cols_kernel");
+  return 0;
+}
+
+int llc_refresh_lora_all(const llc_vit_layer* layers, int n_layers, int D, int r, float sc,
+                         cudaStream_t st) {
+  LLC_REQUIRE(n_layers >= 1 && n_layers <= kMaxRefreshLayers, "llc_vit_refresh_lora: %d layers (max %d)",
+              n_layers, kMaxRefreshLayers);
+  RefreshArgs a;
+  for (int i = 0; i < n_layers; ++i) {
+    const llc_vit_layer& y = layers[i];
+    LLC_REQUIRE(y.in_A && y.in_B && y.out_A && y.out_B && y.wqkv_aug && y.wo_aug && y.wqkvT_aug &&
+                    y.woT_aug && y.f_out_A && y.f_in_B,
+                "llc_vit_refresh_lora: layer %d has a null operand", i);
+    a.l[i] = RefreshLayer{y.in_A, y.in_B, y.out_A, y.out_B,
+                          (__nv_bfloat16*)y.wqkv_aug, (__nv_bfloat16*)y.wo_aug,
+                          (__nv_bfloat16*)y.wqkvT_aug, (__nv_bfloat16*)y.woT_aug,
+                          (__nv_bfloat16*)y.f_out_A, (__nv_bfloat16*)y.f_in_B};
+  }
+  refresh_lora_kernel<<<dim3(48, n_layers), 256, 0, st>>>(a, D, r, sc);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("refresh_lora_kernel");
   return 0;
 }
 

@@ -8,6 +8,10 @@
 
 namespace {
 
+}  // namespace
+int llc_refresh_lora_all(const llc_vit_layer* layers, int n_layers, int D, int r, float sc,
+                         cudaStream_t st);
+namespace {
 inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
 struct Dims {
@@ -67,7 +71,7 @@ Arena plan(const Dims& d, int training) {
     a.dh = take(T * d.D * 2);
     a.d_o = take(T * d.D * 2);
     a.dqkv = take(T * (3 * d.D + LLC_LORA_LD) * 2);
-    a.partial = take((size_t)llc_lora_side_max_partials() * 3 * d.D * 8 * 4);
+    a.partial = take((size_t)llc_lora_side_max_partials() * 3 * d.D * 2 * 4 * 4);  // 4 regions
   } else {
     a.dxb = a.dz = a.dh = a.d_o = a.dqkv = a.partial = 0;
   }
@@ -194,7 +198,6 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(b->o);
   __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(b->h1);
   __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(s->dqkv);
-  int np = 0;
   llc_gemm_epi e;
   // dz = (dx W_proj) o QuickGELU'(z)
   e = llc_gemm_epi{};
@@ -207,27 +210,37 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   // dx_mid = dx + LN2'(dh2); bf16 copy | du_o = s dx_mid B_o
   RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, w->out_B, r, sc,
                  stream));
-  // out-proj LoRA grads: dB_o = s dx_mid^T u_o ; dA_o = du_o^T o
-  RUN(llc_lora_side(s->dxb, DA, T, D, r, nullptr, 0, 0, 0.f, o + D, DA, s->partial, &np, stream));
-  RUN(llc_lora_colsum_finish(s->partial, np, D, r, sc, w->g_out_B, r, 1, stream));
-  RUN(llc_lora_side(b->o, DA, T, D, r, nullptr, 0, 0, 0.f, dxb + D, DA, s->partial, &np, stream));
-  RUN(llc_lora_colsum_finish(s->partial, np, D, r, 1.0f, w->g_out_A, 1, D, stream));
+  // LoRA weight gradients: four column sums, each into its own partial region, reduced by ONE
+  // finish launch at the end of the layer.
+  const size_t preg = (size_t)llc_lora_side_max_partials() * 3 * D * 2;   // floats per region
+  float* pr[4] = {s->partial, s->partial + preg, s->partial + 2 * preg, s->partial + 3 * preg};
+  int np4[4] = {0, 0, 0, 0};
+  // out-proj: dB_o = s dx_mid^T u_o ; dA_o = du_o^T o
+  RUN(llc_lora_side(s->dxb, DA, T, D, r, nullptr, 0, 0, 0.f, o + D, DA, pr[0], &np4[0], stream));
+  RUN(llc_lora_side(b->o, DA, T, D, r, nullptr, 0, 0, 0.f, dxb + D, DA, pr[1], &np4[1], stream));
   // d_o = dx_mid W_o + du_o A_o
   e = llc_gemm_epi{};
   e.out = s->d_o; e.ld_out = D;
   RUN(llc_gemm_bf16_tn(s->dxb, DA, w->woT_aug, DA, T, D, KA, &e, stream));
   RUN(llc_attn_bwd(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
                    stream));
-  // in-proj LoRA grads: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
+  // in-proj: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
   e = llc_gemm_epi{};
   e.out = dqkv + 3 * D; e.ld_out = QA;
   RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
-  RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, s->partial, &np,
+  RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, pr[2], &np4[2],
                     stream));
-  RUN(llc_lora_colsum_finish(s->partial, np, 3 * D, r, sc, w->g_in_B, r, 1, stream));
-  RUN(llc_lora_side(b->h1, DA, T, D, r, nullptr, 0, 0, 0.f, dqkv + 3 * D, QA, s->partial, &np,
+  RUN(llc_lora_side(b->h1, DA, T, D, r, nullptr, 0, 0, 0.f, dqkv + 3 * D, QA, pr[3], &np4[3],
                     stream));
-  RUN(llc_lora_colsum_finish(s->partial, np, D, r, 1.0f, w->g_in_A, 1, D, stream));
+  {
+    llc_finish_job jobs[4] = {
+        {pr[0], np4[0], D, sc, w->g_out_B, r, 1},
+        {pr[1], np4[1], D, 1.0f, w->g_out_A, 1, D},
+        {pr[2], np4[2], 3 * D, sc, w->g_in_B, r, 1},
+        {pr[3], np4[3], D, 1.0f, w->g_in_A, 1, D},
+    };
+    RUN(llc_lora_colsum_finish_multi(jobs, 4, r, stream));
+  }
   if (need_dx_in) {
     // dh1 = dqkv W_in + du A_in ; dx_in = dx_mid + LN1'(dh1)
     e = llc_gemm_epi{};
@@ -248,21 +261,8 @@ extern "C" int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weight
                                     void* stream) {
   RUN(check_cfg(cfg, "llc_vit_refresh_lora"));
   LLC_REQUIRE(w && w->layers, "llc_vit_refresh_lora: null weights");
-  const int D = cfg->width, r = cfg->lora_r;
-  const int DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;
-  const float sc = cfg->lora_scale;
-  for (int l = 0; l < cfg->layers; ++l) {
-    const llc_vit_layer* y = &w->layers[l];
-    // forward: [W_in | s B_in], [W_o | s B_o]; backward: [W_in^T | A_in^T], [W_o^T | A_o^T]
-    RUN(llc_pack_lora_cols(y->in_B, 3 * D, r, r, 1, sc, y->wqkv_aug, DA, D, stream));
-    RUN(llc_pack_lora_cols(y->out_B, D, r, r, 1, sc, y->wo_aug, DA, D, stream));
-    RUN(llc_pack_lora_cols(y->in_A, D, r, 1, D, 1.0f, y->wqkvT_aug, QA, 3 * D, stream));
-    RUN(llc_pack_lora_cols(y->out_A, D, r, 1, D, 1.0f, y->woT_aug, DA, D, stream));
-    // [16, K] factors of the skinny row-product GEMMs: rows j < r, zero rows above
-    RUN(llc_pack_factor_rows(y->out_A, r, D, D, 1, 1.0f, y->f_out_A, D, stream));
-    RUN(llc_pack_factor_rows(y->in_B, r, 3 * D, 1, r, sc, y->f_in_B, 3 * D, stream));
-  }
-  return 0;
+  return llc_refresh_lora_all(w->layers, cfg->layers, cfg->width, cfg->lora_r, cfg->lora_scale,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w,
