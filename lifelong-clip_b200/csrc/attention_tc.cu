@@ -96,6 +96,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, FwdParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -388,6 +389,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t smem0 = smem_u32(smem);
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -726,7 +728,7 @@ int llc_attn_fwd_tc(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, 
   const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_ATTN_FWD, N * H, L, 0, 4.0 * N * H * (double)L * L * HD,
                  8.0 * N * H * (double)L * HD, st);
-  attn_fwd_tc_kernel<<<grid, kThreads, kFwdSmem, st>>>(tm, p);
+  LLC_CUDA(llc_launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(kThreads), kFwdSmem, st, tm, p));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("attn_fwd_tc_kernel");
@@ -771,7 +773,8 @@ int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const 
   const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
                  16.0 * N * H * (double)L * HD, st);
-  attn_bwd_tc_kernel<<<grid, kThreads, smem, st>>>(q0, q1, d0, d1, to, p);
+  LLC_CUDA(llc_launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(kThreads), (size_t)smem, st, q0, q1, d0, d1,
+                          to, p));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("attn_bwd_tc_kernel");

@@ -1,5 +1,6 @@
 // Library plumbing: error slot, device check, TMA descriptor encoding, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -8,6 +9,7 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_llc_launches = 0;
+int g_llc_pdl = getenv("LLC_NO_PDL") == nullptr;
 
 void llc_set_error(const char* fmt, ...) {
   va_list ap;

@@ -86,6 +86,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();   // barrier inits and the TMEM allocation are visible to both CTAs
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -222,7 +223,8 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   static const int dbg = getenv("LLC_GEMM_DBG") ? atoi(getenv("LLC_GEMM_DBG")) : 0;
   EpiParams ep2 = ep;
   ep2.dbg = dbg;
-  gemm2_kernel<MODE><<<grid, kThreads, kSmem, stream>>>(tmA, tmB, tmO, tmO2, M, N, K, ep2, dbg);
+  LLC_CUDA(llc_launch_pdl(gemm2_kernel<MODE>, dim3(grid), dim3(kThreads), kSmem, stream, tmA, tmB, tmO,
+                          tmO2, M, N, K, ep2, dbg));
   LLC_PROF_END(stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("gemm2_kernel");

@@ -28,7 +28,7 @@ constexpr int kEpiPad = 33;  // 32x32 fp32 transpose tile, padded against bank c
 
 template <int BN>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 10);  // BN = 32: skinny, HBM-bound
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -151,6 +151,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -280,7 +281,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, in
   LLC_PROF_BEGIN(LLC_K_GEMM, M, N, K, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + (double)M * N * (ep.out_fp32 ? 4 : 2),
                  stream);
-  gemm_tn_kernel<BN><<<grid, kThreads, C::kSmem, stream>>>(tmA, tmB, M, N, K, ep);
+  LLC_CUDA(llc_launch_pdl(gemm_tn_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmem, stream, tmA, tmB, M,
+                          N, K, ep));
   LLC_PROF_END(stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("gemm_tn_kernel");
@@ -327,7 +329,8 @@ extern "C" int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
   // leave most SMs without a tile.
   const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
   const bool use256 = (N % 256 == 0) && tiles256 >= llc_num_sms();
-  const int BN = use256 ? 256 : 128;
+  const bool use32 = N <= 32;   // rank-r row products (N = 16): stream A at HBM rate
+  const int BN = use256 ? 256 : (use32 ? 32 : 128);
 
   CUtensorMap tmA, tmB;
   int rc = llc_encode_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K,
@@ -337,6 +340,7 @@ extern "C" int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
                           (uint64_t)ldb * 2, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use32) return launch_gemm<32>(tmA, tmB, M, N, K, ep, st);
   return use256 ? launch_gemm<256>(tmA, tmB, M, N, K, ep, st)
                 : launch_gemm<128>(tmA, tmB, M, N, K, ep, st);
 }

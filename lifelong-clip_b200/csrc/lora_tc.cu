@@ -52,6 +52,7 @@ lora_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();
 
   if (warp == 0) {
     int stage = 0;
@@ -169,8 +170,8 @@ int llc_colsum_tc(const void* X, int ld_x, int T, int C, int R, const void* w, i
     configured = true;
   }
   LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 2, 2.0 * T * C * 16, 2.0 * T * C, st);
-  lora_colsum_tc_kernel<<<dim3(mtiles, splits), kThreads, kSmem, st>>>(
-      tm, reinterpret_cast<const __nv_bfloat16*>(w), ld_w, T, C, R, per, partial);
+  LLC_CUDA(llc_launch_pdl(lora_colsum_tc_kernel, dim3(mtiles, splits), dim3(kThreads), kSmem, st, tm,
+                          reinterpret_cast<const __nv_bfloat16*>(w), ld_w, T, C, R, per, partial));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("lora_colsum_tc_kernel");

@@ -23,6 +23,7 @@ ln_fwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
+  pdl_wait();
   if (row >= T) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld_x);
   float4 v[NV];
@@ -94,6 +95,7 @@ ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
+  pdl_wait();
   if (row >= T) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld_x);
   const uint2* dyr = reinterpret_cast<const uint2*>(dy + (size_t)row * ld_dy);
@@ -620,8 +622,8 @@ extern "C" int llc_ln_fwd(const float* x, int ld_x, const float* gamma, const fl
   if (T == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   LLC_PROF_BEGIN(LLC_K_LN_FWD, T, D, 0, 0.0, 6.0 * T * D, st);
-  DISPATCH_NV(D, (ln_fwd_kernel<NV><<<(T + 7) / 8, 256, 0, st>>>(
-                     x, ld_x, gamma, beta, T, (__nv_bfloat16*)y, ld_y, lora_A, r)));
+  DISPATCH_NV(D, (llc_launch_pdl(ln_fwd_kernel<NV>, dim3((T + 7) / 8), dim3(256), 0, st, x, ld_x,
+                                 gamma, beta, T, (__nv_bfloat16*)y, ld_y, lora_A, r)));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("ln_fwd_kernel");
@@ -642,9 +644,9 @@ extern "C" int llc_ln_bwd(const float* x, int ld_x, const float* gamma, const vo
   cudaStream_t st = (cudaStream_t)stream;
   LLC_PROF_BEGIN(LLC_K_LN_BWD, T, D, 0, 0.0,
                  (double)T * D * (4 + 2 + (dx_in ? 4 : 0) + 4 + (dxb ? 2 : 0)), st);
-  DISPATCH_NV(D, (ln_bwd_kernel<NV><<<(T + 7) / 8, 256, 0, st>>>(
-                     x, ld_x, gamma, (const __nv_bfloat16*)dy, ld_dy, dx_in, dx_out, T,
-                     (__nv_bfloat16*)dxb, ld_dxb, lora_B, r, scale)));
+  DISPATCH_NV(D, (llc_launch_pdl(ln_bwd_kernel<NV>, dim3((T + 7) / 8), dim3(256), 0, st, x, ld_x,
+                                 gamma, (const __nv_bfloat16*)dy, ld_dy, dx_in, dx_out, T,
+                                 (__nv_bfloat16*)dxb, ld_dxb, lora_B, r, scale)));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("ln_bwd_kernel");
