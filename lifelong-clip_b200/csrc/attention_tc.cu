@@ -172,7 +172,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, FwdParams p) {
         const uint32_t tp = it & 1;
         const int n = pr / p.H, h = pr % p.H;
         const int kmax = p.causal ? min(p.L, row + 1) : p.L;   // keys [0, kmax) are visible
-        mbar_wait(smem_u32(&s_full[t]), tp);
+        mbar_wait_relaxed(smem_u32(&s_full[t]), tp);
         tc_fence_after();
         // pass 1: row maximum. Chunks that lie entirely below kmax take the predicate-free
         // path; the TMEM load of chunk c+1 is in flight while chunk c is reduced.
@@ -251,7 +251,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, FwdParams p) {
           p.lse[(size_t)pr * p.L + row] = m * 0.125f + logf(l);
         const float inv = 1.0f / l;
         // epilogue: O row (64 fp32) -> bf16 -> one 128 B row segment per thread
-        mbar_wait(smem_u32(&o_full[t]), tp);
+        mbar_wait_relaxed(smem_u32(&o_full[t]), tp);
         tc_fence_after();
         uint32_t o0[32], o1[32];
         tmem_ld_32x32(treg + 128, o0);
@@ -520,7 +520,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_consta
         const bool type_a = ph < NT;
         const int t = type_a ? ph : ph - NT;
         const int gr = t * 128 + r;     // global row: query (A) or key (B) index
-        mbar_wait(smem_u32(s_full), g & 1);
+        mbar_wait_relaxed(smem_u32(s_full), g & 1);
         tc_fence_after();
         const float lse_r = sLse[gr & 255], del_r = sDelta[gr & 255];
         // Out-of-range rows/columns need no masking in the non-causal case: TMA zero-filled the
@@ -620,7 +620,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_consta
         tc_fence_before();
         mbar_arrive(smem_u32(p_ready));
         // ---- epilogue of the phase: accumulators -> staging tile -> TMA store
-        mbar_wait(smem_u32(o_full), g & 1);
+        mbar_wait_relaxed(smem_u32(o_full), g & 1);
         tc_fence_after();
         if (type_a) {
           uint32_t a[32];

@@ -188,6 +188,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Wait for warps that expect to wait LONG (epilogue / element-wise warps parked until a whole
+// tile's MMAs retire): back off with nanosleep between polls instead of spinning - the spinning
+// warps compete for issue slots with the single-thread MMA/TMA issuers and burn power on a
+// power-capped part.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if ((++spins & 0x3ffu) == 0) {
+      unsigned long long t = llc_globaltimer();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) {
+        printf("llc: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -177,7 +177,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           epi_l2_prefetch<MODE, BN / 2 / 32>(ep, (nt / tiles_n) * BM + (int)rank * 128 + q * 32,
                                              (nt % tiles_n) * BN + hh * (BN / 2), M, lane);
       }
-      mbar_wait(smem_u32(&tfull_bar[buf]), bphase);
+      mbar_wait_relaxed(smem_u32(&tfull_bar[buf]), bphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * BN + hh * (BN / 2) + ((uint32_t)(q * 32) << 16);
       if (!(dbg & 1)) {

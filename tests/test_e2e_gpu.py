@@ -143,6 +143,62 @@ def test_fused_trainer_step_matches_fp64_oracle(cfg, n, c, gather):
     assert rel(head.feat.cpu(), want["feat"]) < TOL
 
 
+def test_vit_l14_shapes_two_layers():
+    """BASELINE config 3 geometry (ViT-L/14: width 1024, 16 heads, 257 tokens, embed 768) at two
+    layers: the 257-token attention runs on the mma.sync kernels, everything else as ViT-B/16."""
+    cfg = vo.VitCfg(image_size=224, patch=14, width=1024, layers=2, heads=16, embed_dim=768)
+    n, c, seed = 3, 200, 41
+    w = vo.synth_weights(cfg, seed)
+    images, labels = synth_inputs(cfg, n, c, seed + 1)
+    text = vo.synth_text_features(c, cfg.embed_dim, seed + 2)
+    want = vo.online_step_oracle(images, labels, w, text, cfg)
+    m = build_model(cfg, w)
+    eng = m.model.visual.engine()
+    eng.forward(torch.from_numpy(images).cuda(), training=True)
+    head = eng.head(torch.from_numpy(text).cuda(), 1.0 / 0.07,
+                    labels=torch.from_numpy(labels).cuda())
+    eng.backward_from_head(head)
+    torch.cuda.synchronize()
+    names = [k for k in w if "lora" in k]
+    grads = {k: g.cpu().numpy() for k, g in zip(names, eng.lora_grad_views)}
+    check_step(head.probs.cpu().numpy(), float(head.loss_rows.sum()), head.pred.cpu().numpy(),
+               grads, want, cfg)
+
+
+def test_inference_1000_classes_masked_logits():
+    """BASELINE config 5 shape of the head: eval (no grad), 1000 cached class text embeddings,
+    both class-restriction variants: gather of the seen classes (methods/adapter_clip.py:129-130)
+    and the additive -inf mask (methods/mvp_clip.py:113-118). Predictions bit-exact where the
+    oracle's top-2 gap exceeds the bf16 noise floor."""
+    cfg = vo.VitCfg(image_size=64, patch=16, width=768, layers=2, heads=12, embed_dim=512)
+    n, c, seed = 48, 1000, 51
+    w = vo.synth_weights(cfg, seed)
+    images, _ = synth_inputs(cfg, n, c, seed + 1)
+    text = vo.synth_text_features(c, cfg.embed_dim, seed + 2)
+    m = build_model(cfg, w)
+    eng = m.model.visual.engine()
+    wd = vo.to_torch(w, torch.float64, lora_grad=False)
+    feat = vo.vit_forward(torch.from_numpy(images).double(), wd, cfg)
+    seen = np.sort(np.random.default_rng(seed).choice(c, size=300, replace=False))
+    mask = np.full((c,), -np.inf); mask[seen] = 0.0
+    with torch.no_grad():
+        eng.forward(torch.from_numpy(images).cuda(), training=False)
+        h_all = eng.head(torch.from_numpy(text).cuda(), 1.0 / 0.07)
+        h_gat = eng.head(torch.from_numpy(text).cuda(), 1.0 / 0.07,
+                         cls_idx=torch.from_numpy(seen).cuda())
+        h_msk = eng.head(torch.from_numpy(text).cuda(), 1.0 / 0.07,
+                         add_mask=torch.from_numpy(mask).float().cuda())
+    torch.cuda.synchronize()
+    for h, idx, msk in ((h_all, None, None), (h_gat, torch.from_numpy(seen), None),
+                        (h_msk, None, torch.from_numpy(mask))):
+        probs, _, _ = vo.head_forward(feat, torch.from_numpy(text).double(), 1.0 / 0.07, idx, msk)
+        assert rel(h.probs, probs) < TOL
+        srt = torch.sort(probs, dim=-1).values
+        safe = ((srt[:, -1] - srt[:, -2]) > 0.05 * srt[:, -1]).numpy()
+        np.testing.assert_array_equal(h.pred.cpu().numpy()[safe], probs.argmax(-1).numpy()[safe])
+    assert float(h_msk.probs[:, np.setdiff1d(np.arange(c), seen)].abs().max()) == 0.0
+
+
 def test_block_module_is_dropin_on_seq_first_layout():
     """ResidualAttentionBlock_LoRA on the reference's [L, N, D] layout, autograd through x and the
     four LoRA tensors, against oracle.block_forward (model.py:233-236, :400-415)."""
