@@ -17,6 +17,9 @@ bool llc_attn_tc_eligible(int L);
 int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o, int ld_do,
                     const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H, int sn, int sl,
                     int causal, cudaStream_t st);
+int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
+                     int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
+                     int sn, int sl, int causal, cudaStream_t st);
 int llc_attn_fwd_tc(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L, int H,
                     int sn, int sl, int causal, cudaStream_t st);
 
@@ -543,6 +546,10 @@ extern "C" int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o
   LLC_REQUIRE((((uintptr_t)o | (uintptr_t)d_o) & 15) == 0 && ((uintptr_t)dqkv & 3) == 0,
               "llc_attn_bwd: misaligned pointer");
   static const bool legacy = getenv("LLC_ATTN_LEGACY") != nullptr;
+  static const bool v2 = getenv("LLC_ATTN_BWD2") != nullptr;   // previous two-orientation kernel
+  if (!legacy && !v2 && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
+    return llc_attn_bwd_tc3(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
+                            tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream);
   if (!legacy && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
     return llc_attn_bwd_tc(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
                            tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream);
