@@ -52,6 +52,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull_bar = bars + 2 * kStages;    // [2]        one per CTA (multicast commit)
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]     leader only: both CTAs' epilogues
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* epi_bar = bars + 2 * kStages + 5;     // [2 per epilogue warp] residual tiles landed
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -79,6 +80,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(smem_u32(&tfull_bar[b]), 1);
       mbar_init(smem_u32(&tempty_bar[b]), 2 * kEpiWarps);
     }
+    for (int b = 0; b < 2 * kEpiWarps; ++b) mbar_init(smem_u32(&epi_bar[b]), 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc_cg2<kTmemCols>(smem_u32(tmem_slot));
@@ -165,6 +167,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int hh = ew >> 2;    // column half
     uint8_t* tile_s = smem_epi + ew * kEpiWarpBytes;
     const uint32_t te_leader = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    uint64_t* my_bar = epi_bar + 2 * ew;
+    EpiF32State f32st;
+    f32st.ph[0] = f32st.ph[1] = 0;
+    const bool f32_resid = MODE == EPI_F32 && ep.resid != nullptr;
+    if (f32_resid && pair < num_tiles && lane == 0)   // residual tiles of the first output tile
+      epi_f32_prime(&tmO2, tile_s, my_bar, (pair / tiles_n) * BM + (int)rank * 128 + q * 32,
+                    (pair % tiles_n) * BN + hh * (BN / 2));
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int buf = it & 1;
@@ -181,9 +190,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * BN + hh * (BN / 2) + ((uint32_t)(q * 32) << 16);
       if (!(dbg & 1)) {
-        if (MODE == EPI_F32)
-          epi_warp_tile<MODE, BN / 2 / 32>(ep, t_addr, tile_s, row0, col0, M, N, lane);
-        else
+        if (MODE == EPI_F32) {
+          epi_warp_tile_f32_tma<BN / 2 / 32>(ep, &tmO, &tmO2, t_addr, tile_s, my_bar, f32st, row0,
+                                             col0, N, lane);
+          const int nt = tile + num_pairs;
+          if (f32_resid && nt < num_tiles && lane == 0)
+            epi_f32_prime(&tmO2, tile_s, my_bar, (nt / tiles_n) * BM + (int)rank * 128 + q * 32,
+                          (nt % tiles_n) * BN + hh * (BN / 2));
+        } else
           epi_warp_tile_tma<MODE, BN / 2 / 32>(ep, &tmO, &tmO2, t_addr, tile_s, row0, col0, M, N,
                                                lane);
       }
@@ -193,7 +207,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
-  if (MODE != EPI_F32 && warp >= 2 && lane == 0) tma_store_wait<0>();  // bulk stores landed
+  if (warp >= 2 && lane == 0) tma_store_wait<0>();  // bulk stores landed
   // no CTA may exit (or free TMEM) while its peer can still signal its barriers / read its smem
   __syncwarp();
   tc_fence_before();
@@ -252,7 +266,19 @@ int llc_gemm2_launch(const void* A, int lda, const void* B, int ldb, int M, int 
   // bf16 outputs leave through TMA stores: [32 rows x 64 columns] boxes, 128 B swizzle
   CUtensorMap tmO = tmA, tmO2 = tmA;
   const int mode = epi_mode_of(ep);
-  if (mode != EPI_F32) {
+  if (mode == EPI_F32) {
+    // fp32 out (tmO) and residual (tmO2): [32 rows x 32 columns] boxes = 128 B lines
+    rc = llc_encode_tmap_2d(&tmO, ep.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N,
+                            (uint64_t)M, (uint64_t)ep.ld_out * 4, 32, 32,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (ep.resid != nullptr) {
+      rc = llc_encode_tmap_2d(&tmO2, ep.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N,
+                              (uint64_t)M, (uint64_t)ep.ld_resid * 4, 32, 32,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+  } else {
     if (ep.out != nullptr) {
       rc = llc_encode_tmap_2d(&tmO, ep.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N,
                               (uint64_t)M, (uint64_t)ep.ld_out * 2, 64, 32,

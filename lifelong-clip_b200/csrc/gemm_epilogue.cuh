@@ -374,6 +374,80 @@ __device__ __forceinline__ void epi_warp_tile_tma(const EpiParams& ep, const CUt
   }
 }
 
+
+// ---- fp32 residual epilogue with TMA in both directions (CTA-pair kernel) -------------------------
+// out = fp32(acc + bias + resid). Per 32-column chunk the residual rows arrive by TMA in a
+// [32 x 128 B] swizzled tile, each thread adds its accumulator row IN PLACE (row-per-thread, 8 x
+// 16 B, conflict-free), and the tile leaves by TMA store: full 128 B lines both ways, no per-lane
+// global access (the LSU version cost ~35 us per GEMM, profiles/). Two tiles per warp alternate;
+// the loads of a tile's first two chunks are issued one tile ahead, the other two as soon as the
+// stores of the first two have read their tiles (their rows were requested into L2 a tile ago).
+struct EpiF32State {
+  uint32_t ph[2];
+};
+__device__ __forceinline__ void epi_f32_load(const CUtensorMap* tmR, uint8_t* tile, uint64_t* mb,
+                                             int col, int row) {
+  mbar_expect_tx(smem_u32(mb), 4096);
+  tma_load_2d(smem_u32(tile), tmR, smem_u32(mb), col, row);
+}
+// issue the residual loads of chunks 0 and 1 of the tile at (row0, col0); lane 0 only
+__device__ __forceinline__ void epi_f32_prime(const CUtensorMap* tmR, uint8_t* wtile, uint64_t* mb,
+                                              int row0, int col0) {
+  tma_store_wait_read<0>();   // both tiles have been read by their stores
+  epi_f32_load(tmR, wtile, mb, col0, row0);
+  epi_f32_load(tmR, wtile + 4096, mb + 1, col0 + 32, row0);
+}
+
+template <int NCH>
+__device__ __forceinline__ void epi_warp_tile_f32_tma(const EpiParams& ep, const CUtensorMap* tmO,
+                                                      const CUtensorMap* tmR, uint32_t t_addr,
+                                                      uint8_t* wtile, uint64_t* mb, EpiF32State& st,
+                                                      int row0, int col0, int N, int lane) {
+  const bool has_resid = ep.resid != nullptr;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int b = c & 1;
+    uint8_t* T = wtile + b * 4096;
+    float4 bias[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bias[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.bias != nullptr && col0 + c * 32 + 4 * j < N)
+        bias[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + c * 32 + 4 * j));
+    }
+    uint32_t acc[32];
+    tmem_ld_32x32(t_addr + c * 32, acc);
+    if (has_resid) {
+      mbar_wait(smem_u32(mb + b), st.ph[b]);
+      st.ph[b] ^= 1;
+    } else {
+      if (lane == 0) tma_store_wait_read<1>();   // the store two chunks ago has read this tile
+      __syncwarp();
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4* p = reinterpret_cast<float4*>(T + f32_tile_off(lane, j));
+      float4 v = has_resid ? *p : make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x += __uint_as_float(acc[4 * j]) + bias[j].x;
+      v.y += __uint_as_float(acc[4 * j + 1]) + bias[j].y;
+      v.z += __uint_as_float(acc[4 * j + 2]) + bias[j].z;
+      v.w += __uint_as_float(acc[4 * j + 3]) + bias[j].w;
+      *p = v;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmO, smem_u32(T), col0 + c * 32, row0);
+      tma_store_commit();
+      if (has_resid && c + 2 < NCH) {
+        tma_store_wait_read<0>();
+        epi_f32_load(tmR, T, mb + b, col0 + (c + 2) * 32, row0);
+      }
+    }
+  }
+}
+
 inline int epi_mode_of(const EpiParams& ep) {
   if (ep.act == 1) return EPI_GELU;
   if (ep.act == 2) return EPI_DGELU;
