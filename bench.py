@@ -310,17 +310,33 @@ def run_ours(args):
     trainer.use_cuda_graph = not args.no_graph
     by_kind = {}
     for kind, m, n, k, ms, fl, by in recs:
+        if kind == "gemm" and n < 256:
+            kind = "gemm_skinny"   # rank-r row products (N = 16): HBM-bound gemm_tn_kernel<32>
         d = by_kind.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
         d["launches"] += 1; d["ms"] += ms; d["flops"] += fl; d["bytes"] += by
     peaks = load_peaks()
     gemm = by_kind.get("gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
     total_ms = sum(d["ms"] for d in by_kind.values()) or 1.0
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (forward
+    # launches of one block inside this same bench command; profiles/r01_ncu_gemm2_in_step.csv)
+    traffic = None
+    try:
+        import csv
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm2_in_step.csv")) as f:
+            rows = list(csv.DictReader(f))
+        tot = [(float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"])) * 1e6
+               for r in rows]
+        traffic = sum(tot) / len(tot)
+    except Exception:
+        traffic = None
     roof = None
     if gemm["launches"]:
         achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm2_kernel (tcgen05 cta_group::2 / TMEM; all GEMM launches of the step)",
+        roof = {"bound": "tensor", "kernel": "gemm2_kernel (tcgen05 cta_group::2 / TMEM): the 8 dense contractions of every block, forward and backward",
                 "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16"], "traffic": None,
+                "frac": achieved / peaks["bf16"], "traffic": traffic,
+                "traffic_note": "mean dram read+write bytes per launch, ncu --set full, 8 forward "
+                                "launches inside this bench (profiles/r01_ncu_gemm2_in_step.csv)",
                 "peak_source": peaks["source"] + ", burst",
                 "flop_per_launch": gemm["flops"] / gemm["launches"],
                 "us_per_launch": gemm["ms"] * 1e3 / gemm["launches"],
