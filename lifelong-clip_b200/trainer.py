@@ -61,6 +61,8 @@ class LoRAClipTrainer:
         self._graph = None
         self._graph_key = None
         self.graph_kernels = 0
+        self._graph_hits = 0
+        self._graph_churn = 0
         self.optimizer = None
         self._lut = torch.full((self.n_classes,), -1, dtype=torch.int64, device=self.device)
         self._lut_src = None
@@ -148,8 +150,9 @@ class LoRAClipTrainer:
                     train_class_list.append(i)
                     train_class_name_list.append(
                         self.exposed_classes_names[self.exposed_classes.index(i)])
-            x = torch.cat([x, memory_images], dim=0)
-            y = torch.cat([y, memory_labels], dim=0)
+            # stream images may already sit on the device (DevicePrefetcher); labels stay on host
+            x = torch.cat([x, memory_images.to(x.device, non_blocking=True)], dim=0)
+            y = torch.cat([y.cpu(), memory_labels.cpu()], dim=0)
         B = y.shape[0]
         # data-parallel shard of the combined stream+replay batch
         if self.world > 1:
@@ -184,6 +187,19 @@ class LoRAClipTrainer:
                None if m._add_mask is None else m._add_mask.data_ptr(), m._text_all.data_ptr(),
                m.model.logit_scale_exp(), self.double_softmax)
         if key != self._graph_key:
+            # a capture costs tens of ms: worth it only when the (batch, class list) signature is
+            # stable (visible_classes='all', one change per task). If it keeps changing
+            # (visible_classes='batch'), fall back to eager launches for good.
+            if self._graph is not None and self._graph_hits < 2:
+                self._graph_churn += 1
+                if self._graph_churn >= 4:
+                    self.use_cuda_graph = False
+                    self._graph = None
+                    self._graph_key = None
+                    return self._step_body(x, y_local, global_batch)
+            else:
+                self._graph_churn = 0
+            self._graph_hits = 0
             self._graph = None
             self._gx = torch.empty_like(x)
             self._gy = torch.empty_like(y_local)
@@ -202,6 +218,7 @@ class LoRAClipTrainer:
         self._gx.copy_(x, non_blocking=True)
         self._gy.copy_(y_local, non_blocking=True)
         self._graph.replay()
+        self._graph_hits += 1
         return self._ghead
 
     def fused_step(self, x, y_local, global_batch, sync=True):

@@ -313,6 +313,47 @@ def test_trainer_online_step_interface_and_learning():
     assert set(res) == {"avg_loss", "avg_acc", "cls_acc", "task_acc", "confusion_matrix"}
 
 
+def test_trainer_replay_concat_and_batch_visible_classes():
+    """Replay path of online_train (methods/adapter_clip.py:65-73: the memory batch is concatenated
+    to the stream batch, unseen replay classes join the visible list) with device-resident stream
+    images and host-resident replay images; visible_classes='batch' changes the class list every
+    step, which must quietly drop the CUDA-graph path instead of re-capturing forever."""
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+    cfg = vo.VIT_TINY
+    c = 10
+    m = build_model(cfg, vo.synth_weights(cfg, 3))
+    names = [f"class{i}" for i in range(c)]
+    m.set_text_features(names, torch.from_numpy(vo.synth_text_features(c, cfg.embed_dim, 4)))
+    rng = np.random.default_rng(1)
+
+    class FakeMemory:            # the two members online_train touches (utils/memory.py)
+        filled = 0
+        def __len__(self): return self.filled
+        def add_new_class(self, cls_list): self.cls = list(cls_list)
+
+    def provider():
+        while True:
+            yield (torch.from_numpy(rng.standard_normal((4, 3, 32, 32)).astype(np.float32)),
+                   torch.tensor([1, 1, 3, 5]))
+
+    tr = LoRAClipTrainer(m, names, n_classes=c, n_tasks=2, lr=1e-3, visible_classes="batch",
+                         memory=FakeMemory(), memory_provider=provider(), memory_batchsize=4)
+    tr.online_before_task(0)
+    # replay memory only ever holds classes the stream has shown: expose 1, 3, 5 first
+    first = torch.tensor([1, 3, 5, 1, 3, 5])
+    tr.online_step(torch.from_numpy(rng.standard_normal((6, 3, 32, 32)).astype(np.float32)).cuda(),
+                   first, torch.arange(6))
+    tr.memory.filled = 4
+    for step in range(8):
+        labels = torch.from_numpy(rng.integers(0, c, size=(6,)))
+        images = torch.from_numpy(rng.standard_normal((6, 3, 32, 32)).astype(np.float32)).cuda()
+        loss, acc = tr.online_step(images, labels, torch.arange(6))
+        assert np.isfinite(loss) and 0.0 <= acc <= 1.0
+        assert tr.last_head.args.N == 10                      # 6 stream + 4 replay samples
+        assert {1, 3, 5} <= set(tr.batch_exposed_classes)     # replay classes became visible
+    assert tr.use_cuda_graph is False                         # churned signatures -> eager
+
+
 def test_no_cpu_fallback():
     """A CPU tensor / CPU module must fail loudly: the product path has no eager fallback."""
     from lifelong_clip_b200 import ops
