@@ -373,7 +373,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(args), "model": args.model,
+        "config": {"workload": workload_name(args),
                    "batch_per_gpu": B, "global_batch": gB, "classes": C, "tokens": (S // p) ** 2 + 1,
                    "parallelism": f"dp{world}", "weights": "random-init",
                    "l2": "inputs larger than L2 (154 MB images per step; activations 1 GB/layer)",

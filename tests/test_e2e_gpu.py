@@ -143,6 +143,28 @@ def test_fused_trainer_step_matches_fp64_oracle(cfg, n, c, gather):
     assert rel(head.feat.cpu(), want["feat"]) < TOL
 
 
+@pytest.mark.parametrize("n", [1, 2])
+def test_single_image_batches(n):
+    """Smallest batches (one sample: the 3-D token maps degenerate to one slice)."""
+    cfg = vo.VitCfg(image_size=64, patch=16, width=256, layers=2, heads=4, embed_dim=128)
+    c, seed = 5, 61
+    w = vo.synth_weights(cfg, seed)
+    images, labels = synth_inputs(cfg, n, c, seed + 1)
+    text = vo.synth_text_features(c, cfg.embed_dim, seed + 2)
+    want = vo.online_step_oracle(images, labels, w, text, cfg)
+    m = build_model(cfg, w)
+    eng = m.model.visual.engine()
+    eng.forward(torch.from_numpy(images).cuda(), training=True)
+    head = eng.head(torch.from_numpy(text).cuda(), 1.0 / 0.07,
+                    labels=torch.from_numpy(labels).cuda())
+    eng.backward_from_head(head)
+    torch.cuda.synchronize()
+    names = [k for k in w if "lora" in k]
+    grads = {k: g.cpu().numpy() for k, g in zip(names, eng.lora_grad_views)}
+    check_step(head.probs.cpu().numpy(), float(head.loss_rows.sum()), head.pred.cpu().numpy(),
+               grads, want, cfg, tol=2e-2)   # 17 tokens x 1-2 images: almost no averaging
+
+
 def test_vit_l14_shapes_two_layers():
     """BASELINE config 3 geometry (ViT-L/14: width 1024, 16 heads, 257 tokens, embed 768) at two
     layers: the 257-token attention runs on the mma.sync kernels, everything else as ViT-B/16."""
