@@ -216,6 +216,7 @@ typedef struct llc_vit_layer {
   /* rank-r row products as skinny GEMMs on the tensor cores: [16, K] bf16 factors (rows >= r 0) */
   void* f_out_A;   /* [16, D]:  A_o            u_o  = o . A_o^T              (forward)  */
   void* f_in_B;    /* [16, 3D]: s * B_in^T     du_in = s dqkv . B_in         (backward) */
+  void* f_out_B;   /* [16, D]:  s * B_o^T      du_o  = s dx_mid . B_o        (backward) */
   const float *bqkv, *bo, *bfc, *bproj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   /* live fp32 LoRA parameters and their gradient slots (views of the flat buffers) */
   const float *in_A, *in_B, *out_A, *out_B; /* [r,D] [3D,r] [r,D] [D,r] */

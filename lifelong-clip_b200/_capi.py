@@ -50,7 +50,7 @@ class VitCfg(C.Structure):
 class VitLayer(C.Structure):
     _fields_ = [(n, c_void) for n in (
         "wqkv_aug", "wo_aug", "wfc", "wproj", "wqkvT_aug", "woT_aug", "wfcT", "wprojT",
-        "f_out_A", "f_in_B", "bqkv", "bo", "bfc", "bproj", "ln1_g", "ln1_b", "ln2_g", "ln2_b",
+        "f_out_A", "f_in_B", "f_out_B", "bqkv", "bo", "bfc", "bproj", "ln1_g", "ln1_b", "ln2_g", "ln2_b",
         "in_A", "in_B", "out_A", "out_B", "g_in_A", "g_in_B", "g_out_A", "g_out_B")]
 
 

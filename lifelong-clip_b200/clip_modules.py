@@ -133,13 +133,14 @@ class PackedLayer:
         self.wprojT = ops.pack_weight(f32(blk.mlp.c_proj.weight), _bf16(M, D, dev), True)
         self.f_out_A = _bf16(16, D, dev)       # refreshed from the live LoRA factors every step
         self.f_in_B = _bf16(16, 3 * D, dev)
+        self.f_out_B = _bf16(16, D, dev)
         self.small = [f32(p) for p in (a.in_proj_bias, a.out_proj.bias, blk.mlp.c_fc.bias,
                                        blk.mlp.c_proj.bias, blk.ln_1.weight, blk.ln_1.bias,
                                        blk.ln_2.weight, blk.ln_2.bias)]
 
     def fill(self, s: K.VitLayer, lora, grads):
         for n in ("wqkv_aug", "wo_aug", "wfc", "wproj", "wqkvT_aug", "woT_aug", "wfcT", "wprojT",
-                  "f_out_A", "f_in_B"):
+                  "f_out_A", "f_in_B", "f_out_B"):
             setattr(s, n, getattr(self, n).data_ptr())
         for n, t in zip(("bqkv", "bo", "bfc", "bproj", "ln1_g", "ln1_b", "ln2_g", "ln2_b"),
                         self.small):

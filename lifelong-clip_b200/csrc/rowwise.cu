@@ -87,7 +87,7 @@ ln_fwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g
 //   xh = (x-mean)*rstd, g = dy*gamma, dx = rstd*(g - mean(g) - xh*mean(g*xh))
 // out = dx_in + dx -> fp32 (+ bf16 copy, + du = scale * out . B appended at column D of the copy)
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NV <= 6 ? 3 : 2)
 ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ dy, int ld_dy, const float* dx_in, float* dx_out,
               int T, __nv_bfloat16* __restrict__ dxb, int ld_dxb,
@@ -448,7 +448,7 @@ __global__ void pack_factor_rows_kernel(const float* __restrict__ src, int r, in
 // [16, K] row-product factors, for all layers. blockIdx.y = layer.
 struct RefreshLayer {
   const float *in_A, *in_B, *out_A, *out_B;
-  __nv_bfloat16 *wqkv_aug, *wo_aug, *wqkvT_aug, *woT_aug, *f_out_A, *f_in_B;
+  __nv_bfloat16 *wqkv_aug, *wo_aug, *wqkvT_aug, *woT_aug, *f_out_A, *f_in_B, *f_out_B;
 };
 constexpr int kMaxRefreshLayers = 32;
 struct RefreshArgs {
@@ -463,7 +463,8 @@ refresh_lora_kernel(const __grid_constant__ RefreshArgs args, int D, int r, floa
   // task sizes (elements): [W_in | s B_in] 3D*16, [W_o | s B_o] D*16, [W_in^T | A_in^T] D*16,
   // [W_o^T | A_o^T] D*16, F_oA 16*D, F_inB 16*3D
   const int n0 = 3 * D * P, n1 = D * P, n2 = D * P, n3 = D * P, n4 = P * D, n5 = P * 3 * D;
-  const int total = n0 + n1 + n2 + n3 + n4 + n5;
+  const int n6 = P * D;
+  const int total = n0 + n1 + n2 + n3 + n4 + n5 + n6;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     int i = idx;
     if (i < n0) {            // wqkv_aug[c, D + j] = s * in_B[c, j]
@@ -496,9 +497,15 @@ refresh_lora_kernel(const __grid_constant__ RefreshArgs args, int D, int r, floa
       continue;
     }
     i -= n4;
-    {                        // f_in_B[j, c] = s * in_B[c, j]
+    if (i < n5) {            // f_in_B[j, c] = s * in_B[c, j]
       const int j = i / (3 * D), c = i % (3 * D);
       y.f_in_B[(size_t)j * 3 * D + c] = __float2bfloat16_rn(j < r ? sc * y.in_B[c * r + j] : 0.f);
+      continue;
+    }
+    i -= n5;
+    {                        // f_out_B[j, c] = s * out_B[c, j]
+      const int j = i / D, c = i % D;
+      y.f_out_B[(size_t)j * D + c] = __float2bfloat16_rn(j < r ? sc * y.out_B[c * r + j] : 0.f);
     }
   }
 }
@@ -791,12 +798,13 @@ int llc_refresh_lora_all(const llc_vit_layer* layers, int n_layers, int D, int r
   for (int i = 0; i < n_layers; ++i) {
     const llc_vit_layer& y = layers[i];
     LLC_REQUIRE(y.in_A && y.in_B && y.out_A && y.out_B && y.wqkv_aug && y.wo_aug && y.wqkvT_aug &&
-                    y.woT_aug && y.f_out_A && y.f_in_B,
+                    y.woT_aug && y.f_out_A && y.f_in_B && y.f_out_B,
                 "llc_vit_refresh_lora: layer %d has a null operand", i);
     a.l[i] = RefreshLayer{y.in_A, y.in_B, y.out_A, y.out_B,
                           (__nv_bfloat16*)y.wqkv_aug, (__nv_bfloat16*)y.wo_aug,
                           (__nv_bfloat16*)y.wqkvT_aug, (__nv_bfloat16*)y.woT_aug,
-                          (__nv_bfloat16*)y.f_out_A, (__nv_bfloat16*)y.f_in_B};
+                          (__nv_bfloat16*)y.f_out_A, (__nv_bfloat16*)y.f_in_B,
+                          (__nv_bfloat16*)y.f_out_B};
   }
   refresh_lora_kernel<<<dim3(48, n_layers), 256, 0, st>>>(a, D, r, sc);
   LLC_COUNT_LAUNCH();

@@ -208,8 +208,13 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   e.out = s->dh; e.ld_out = D;
   RUN(llc_gemm_bf16_tn(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
   // dx_mid = dx + LN2'(dh2); bf16 copy | du_o = s dx_mid B_o
-  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, w->out_B, r, sc,
+  // (the row product du_o = s dx_mid B_o runs as a skinny GEMM on the tensor cores: fused into the
+  // LayerNorm kernel it cost 52 us per launch in L1 traffic for the factor, profiles/)
+  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
                  stream));
+  e = llc_gemm_epi{};
+  e.out = dxb + D; e.ld_out = DA;
+  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->f_out_B, D, T, LLC_LORA_PAD, D, &e, stream));
   // LoRA weight gradients: four column sums, each into its own partial region, reduced by ONE
   // finish launch at the end of the layer.
   const size_t preg = (size_t)llc_lora_side_max_partials() * 3 * D * 2;   // floats per region

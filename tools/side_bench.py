@@ -35,3 +35,14 @@ for C in (768, 2304):
     ref = X[:4096, :C].float() @ F.float().T
     err = float((out[:4096].float() - ref).norm() / ref.norm())
     print(f"rowdot-as-GEMM C={C}: {us:7.1f} us  {T*C*2/us/1e3:7.1f} GB/s  rel {err:.2e}")
+# LayerNorm forward / backward at the step's shape
+D = 768
+x = torch.randn(T, D, device="cuda"); g = torch.ones(D, device="cuda"); b = torch.zeros(D, device="cuda")
+A = torch.randn(4, D, device="cuda") * 0.05; Bm = torch.randn(D, 4, device="cuda") * 0.05
+y = torch.empty(T, D + 64, device="cuda", dtype=torch.bfloat16)
+us = timeit(lambda: ops.ln_fwd(x, g, b, y, lora_A=A, r=4)); print(f"ln_fwd: {us:7.1f} us  {T*D*6/us/1e3:7.1f} GB/s")
+dy = torch.randn(T, D, device="cuda").to(torch.bfloat16); dxin = torch.randn(T, D, device="cuda"); dxo = torch.empty(T, D, device="cuda")
+us = timeit(lambda: ops.ln_bwd(x, g, dy, dxin, dxo, dxb=y, lora_B=Bm, r=4, scale=0.25)); print(f"ln_bwd: {us:7.1f} us  {T*D*16/us/1e3:7.1f} GB/s")
+y2 = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
+us = timeit(lambda: ops.ln_fwd(x, g, b, y2)); print(f"ln_fwd (no lora): {us:7.1f} us  {T*D*6/us/1e3:7.1f} GB/s")
+us = timeit(lambda: ops.ln_bwd(x, g, dy, dxin, dxo, dxb=y)); print(f"ln_bwd (no lora): {us:7.1f} us  {T*D*16/us/1e3:7.1f} GB/s")
