@@ -352,6 +352,22 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap*
       "l"(m), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_cg2_hint(uint32_t dst, const CUtensorMap* m,
+                                                     uint32_t bar_cluster, int c0, int c1,
+                                                     uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(m), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, uint32_t src, int c0, int c1,
+                                                  uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(m),
+      "r"(src), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),

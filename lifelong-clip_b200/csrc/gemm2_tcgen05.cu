@@ -118,8 +118,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (rank == 0) mbar_arrive(fb_local);
           } else {
             if (rank == 0) mbar_expect_tx(fb_local, 2 * kStageBytes);
-            tma_load_2d_cg2(sa, &tmA, fb_leader, kb * BK, m0);
-            tma_load_2d_cg2(sa + kABytes, &tmB, fb_leader, kb * BK, n0);
+            if (dbg & 2048) {
+              tma_load_2d_cg2(sa, &tmA, fb_leader, kb * BK, m0);
+              tma_load_2d_cg2(sa + kABytes, &tmB, fb_leader, kb * BK, n0);
+            } else {
+              // operands are re-read by the other n-/m-tiles within microseconds: keep them in L2
+              // ahead of the single-use output / residual streams
+              tma_load_2d_cg2_hint(sa, &tmA, fb_leader, kb * BK, m0, kEvictLast);
+              tma_load_2d_cg2_hint(sa + kABytes, &tmB, fb_leader, kb * BK, n0, kEvictLast);
+            }
           }
         }
         __syncwarp();

@@ -367,8 +367,8 @@ __device__ __forceinline__ void epi_warp_tile_tma(const EpiParams& ep, const CUt
     __syncwarp();
     if (lane == 0) {
       if (MODE != EPI_GELU || ep.out != nullptr)
-        tma_store_2d(tmO, smem_u32(tA), col0 + g * 64, row0);
-      if (MODE == EPI_GELU) tma_store_2d(tmO2, smem_u32(tB), col0 + g * 64, row0);
+        tma_store_2d_hint(tmO, smem_u32(tA), col0 + g * 64, row0, kEvictFirst);
+      if (MODE == EPI_GELU) tma_store_2d_hint(tmO2, smem_u32(tB), col0 + g * 64, row0, kEvictFirst);
       tma_store_commit();
     }
   }
@@ -388,7 +388,7 @@ struct EpiF32State {
 __device__ __forceinline__ void epi_f32_load(const CUtensorMap* tmR, uint8_t* tile, uint64_t* mb,
                                              int col, int row) {
   mbar_expect_tx(smem_u32(mb), 4096);
-  tma_load_2d(smem_u32(tile), tmR, smem_u32(mb), col, row);
+  tma_load_2d_hint(smem_u32(tile), tmR, smem_u32(mb), col, row, kEvictFirst);
 }
 // issue the residual loads of chunks 0 and 1 of the tile at (row0, col0); lane 0 only
 __device__ __forceinline__ void epi_f32_prime(const CUtensorMap* tmR, uint8_t* wtile, uint64_t* mb,
@@ -438,7 +438,7 @@ __device__ __forceinline__ void epi_warp_tile_f32_tma(const EpiParams& ep, const
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tmO, smem_u32(T), col0 + c * 32, row0);
+      tma_store_2d_hint(tmO, smem_u32(T), col0 + c * 32, row0, kEvictFirst);
       tma_store_commit();
       if (has_resid && c + 2 < NCH) {
         tma_store_wait_read<0>();
