@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libllc.so")
+LIB_PATH = os.environ.get("LLC_LIB") or os.path.join(_HERE, "libllc.so")  # LLC_LIB: dev A/B builds
 
 LORA_PAD = 16   # K columns appended for the rank-r factors
 LORA_LD = 64    # row-pitch growth of an augmented buffer (keeps rows 128 B aligned)

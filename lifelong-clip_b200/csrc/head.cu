@@ -54,218 +54,297 @@ struct HeadK {
   int skip_logit_grad;
 };
 
-// smem: y[D] | f[E] | p[C] | red[32]
+// Both head kernels are written for kS samples per CTA (the two fat loops read every proj / text
+// element once for the kS samples). Measured at N = 256: kS = 1 is fastest (97 / 122 us fwd / bwd
+// against 189 / 126 us at kS = 4): with 64 CTAs the work no longer covers the machine and the
+// loops are latency-, not L2-bandwidth-bound.
+constexpr int kS = 1;
+
+// smem: y[kS][D] | f[kS][E] | p[kS][C] | red[32]
 __global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadK a) {
   extern __shared__ float sm[];
   float* sy = sm;
-  float* sf = sy + a.D;
-  float* sp = sf + a.E;
-  float* red = sp + a.C;
+  float* sf = sy + kS * a.D;
+  float* sp = sf + kS * a.E;
+  float* red = sp + kS * a.C;
   __shared__ int s_arg;
-  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* xr = a.x + (size_t)n * a.cls_stride * a.ld_x;
+  const int n0 = blockIdx.x * kS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ln_post
-  float s = 0.f;
-  for (int k = tid; k < a.D; k += kThreads) { sy[k] = xr[k]; s += sy[k]; }
-  const float mean = block_sum(s, red) / a.D;
-  float q = 0.f;
-  for (int k = tid; k < a.D; k += kThreads) { const float d = sy[k] - mean; q += d * d; }
-  const float rstd = rsqrtf(block_sum(q, red) / a.D + kLnEps);
-  for (int k = tid; k < a.D; k += kThreads)
-    sy[k] = (sy[k] - mean) * rstd * a.ln_g[k] + a.ln_b[k];
+  // ln_post of each sample's CLS row
+  for (int sI = 0; sI < kS; ++sI) {
+    const int n = min(n0 + sI, a.N - 1);     // tail samples recompute the last one (not stored)
+    const float* xr = a.x + (size_t)n * a.cls_stride * a.ld_x;
+    float* y = sy + sI * a.D;
+    float s = 0.f;
+    for (int k = tid; k < a.D; k += kThreads) { y[k] = xr[k]; s += y[k]; }
+    const float mean = block_sum(s, red) / a.D;
+    float q = 0.f;
+    for (int k = tid; k < a.D; k += kThreads) { const float d = y[k] - mean; q += d * d; }
+    const float rstd = rsqrtf(block_sum(q, red) / a.D + kLnEps);
+    for (int k = tid; k < a.D; k += kThreads) y[k] = (y[k] - mean) * rstd * a.ln_g[k] + a.ln_b[k];
+  }
   __syncthreads();
 
-  // z = y @ proj
-  float nrm = 0.f;
-  for (int e = tid; e < a.E; e += kThreads) {
-    // 8 independent partial sums: the proj column walk is a chain of L2 loads otherwise
-    float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int k = 0;
-    for (; k + 8 <= a.D; k += 8) {
+  // z = y @ proj for the kS samples at once
+  float nrm[kS];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        part[u] = fmaf(sy[k + u], __ldg(a.proj + (size_t)(k + u) * a.E + e), part[u]);
-    }
-    for (; k < a.D; ++k) part[0] = fmaf(sy[k], __ldg(a.proj + (size_t)k * a.E + e), part[0]);
-    const float acc = ((part[0] + part[1]) + (part[2] + part[3])) +
-                      ((part[4] + part[5]) + (part[6] + part[7]));
-    sf[e] = acc;
-    a.feat[(size_t)n * a.E + e] = acc;
-    nrm += acc * acc;
-  }
-  const float inv_norm = 1.0f / sqrtf(block_sum(nrm, red));
+  for (int sI = 0; sI < kS; ++sI) nrm[sI] = 0.f;
   for (int e = tid; e < a.E; e += kThreads) {
-    sf[e] *= inv_norm;
-    a.fnorm[(size_t)n * a.E + e] = sf[e];
+    float acc[kS][2];
+#pragma unroll
+    for (int sI = 0; sI < kS; ++sI) acc[sI][0] = acc[sI][1] = 0.f;
+    int k = 0;
+    for (; k + 2 <= a.D; k += 2) {
+      const float p0 = __ldg(a.proj + (size_t)k * a.E + e);
+      const float p1 = __ldg(a.proj + (size_t)(k + 1) * a.E + e);
+#pragma unroll
+      for (int sI = 0; sI < kS; ++sI) {
+        acc[sI][0] = fmaf(sy[sI * a.D + k], p0, acc[sI][0]);
+        acc[sI][1] = fmaf(sy[sI * a.D + k + 1], p1, acc[sI][1]);
+      }
+    }
+    for (; k < a.D; ++k) {
+      const float p0 = __ldg(a.proj + (size_t)k * a.E + e);
+#pragma unroll
+      for (int sI = 0; sI < kS; ++sI) acc[sI][0] = fmaf(sy[sI * a.D + k], p0, acc[sI][0]);
+    }
+#pragma unroll
+    for (int sI = 0; sI < kS; ++sI) {
+      const float v = acc[sI][0] + acc[sI][1];
+      sf[sI * a.E + e] = v;
+      if (n0 + sI < a.N) a.feat[(size_t)(n0 + sI) * a.E + e] = v;
+      nrm[sI] += v * v;
+    }
+  }
+#pragma unroll
+  for (int sI = 0; sI < kS; ++sI) {
+    const float inv_norm = 1.0f / sqrtf(block_sum(nrm[sI], red));
+    for (int e = tid; e < a.E; e += kThreads) {
+      const float v = sf[sI * a.E + e] * inv_norm;
+      sf[sI * a.E + e] = v;
+      if (n0 + sI < a.N) a.fnorm[(size_t)(n0 + sI) * a.E + e] = v;
+    }
   }
   __syncthreads();
 
-  // logits: one warp per class, lanes stride the embedding
+  // logits: one warp per class, lanes stride the embedding, kS samples per text row read
   for (int c = warp; c < a.C; c += kThreads / 32) {
     const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
     const float* tr = a.text + (size_t)row * a.E;
-    float acc = 0.f;
-    for (int e = lane; e < a.E; e += 32) acc += sf[e] * __ldg(tr + e);
-    acc = warp_sum(acc) * a.logit_scale;
-    if (a.add_mask) acc += a.add_mask[c];
-    if (lane == 0) {
-      sp[c] = acc;
-      a.logits[(size_t)n * a.C + c] = acc;
+    float acc[kS];
+#pragma unroll
+    for (int sI = 0; sI < kS; ++sI) acc[sI] = 0.f;
+    for (int e = lane; e < a.E; e += 32) {
+      const float t = __ldg(tr + e);
+#pragma unroll
+      for (int sI = 0; sI < kS; ++sI) acc[sI] = fmaf(sf[sI * a.E + e], t, acc[sI]);
+    }
+#pragma unroll
+    for (int sI = 0; sI < kS; ++sI) {
+      float v = warp_sum(acc[sI]) * a.logit_scale;
+      if (a.add_mask) v += a.add_mask[c];
+      if (lane == 0) {
+        sp[sI * a.C + c] = v;
+        if (n0 + sI < a.N) a.logits[(size_t)(n0 + sI) * a.C + c] = v;
+      }
     }
   }
   __syncthreads();
 
-  // softmax
-  float m = -INFINITY;
-  for (int c = tid; c < a.C; c += kThreads) m = fmaxf(m, sp[c]);
-  m = block_max(m, red);
-  float z = 0.f;
-  for (int c = tid; c < a.C; c += kThreads) z += __expf(sp[c] - m);
-  z = block_sum(z, red);
-  const float logz = m + logf(z);
-  float pm = -1.f;
-  for (int c = tid; c < a.C; c += kThreads) {
-    const float p = __expf(sp[c] - m) / z;
-    const float lg = sp[c];
-    sp[c] = p;
-    a.probs[(size_t)n * a.C + c] = p;
-    pm = fmaxf(pm, p);
-    (void)lg;
-  }
-  pm = block_max(pm, red);
-  // argmax: lowest index among the maxima
-  if (tid == 0) s_arg = 0x7fffffff;
-  __syncthreads();
-  for (int c = tid; c < a.C; c += kThreads)
-    if (sp[c] == pm) atomicMin(&s_arg, c);
-  __syncthreads();
-  if (tid == 0 && a.pred) a.pred[n] = (int64_t)s_arg;
-
-  if (a.labels && a.loss_rows) {
-    const int64_t yv = a.labels[n];
-    float loss;
-    if (a.double_softmax) {
-      // CE on probabilities: -p_y + log sum_j exp(p_j)
-      float z2 = 0.f;
-      for (int c = tid; c < a.C; c += kThreads) z2 += __expf(sp[c]);
-      z2 = block_sum(z2, red);
-      const float py = (yv >= 0 && yv < a.C) ? sp[yv] : 0.f;
-      loss = -py + logf(z2);
-    } else {
-      const float ly = (yv >= 0 && yv < a.C) ? a.logits[(size_t)n * a.C + yv] : 0.f;
-      loss = -(ly - logz);
+  for (int sI = 0; sI < kS; ++sI) {
+    const int n = n0 + sI;
+    if (n >= a.N) break;               // uniform across the block
+    float* p_ = sp + sI * a.C;
+    // softmax
+    float m = -INFINITY;
+    for (int c = tid; c < a.C; c += kThreads) m = fmaxf(m, p_[c]);
+    m = block_max(m, red);
+    float z = 0.f;
+    for (int c = tid; c < a.C; c += kThreads) z += __expf(p_[c] - m);
+    z = block_sum(z, red);
+    const float logz = m + logf(z);
+    float pm = -1.f;
+    for (int c = tid; c < a.C; c += kThreads) {
+      const float p = __expf(p_[c] - m) / z;
+      p_[c] = p;
+      a.probs[(size_t)n * a.C + c] = p;
+      pm = fmaxf(pm, p);
     }
-    if (tid == 0) a.loss_rows[n] = loss * a.inv_batch;
+    pm = block_max(pm, red);
+    // argmax: lowest index among the maxima
+    if (tid == 0) s_arg = 0x7fffffff;
+    __syncthreads();
+    for (int c = tid; c < a.C; c += kThreads)
+      if (p_[c] == pm) atomicMin(&s_arg, c);
+    __syncthreads();
+    if (tid == 0 && a.pred) a.pred[n] = (int64_t)s_arg;
+
+    if (a.labels && a.loss_rows) {
+      const int64_t yv = a.labels[n];
+      float loss;
+      if (a.double_softmax) {
+        // CE on probabilities: -p_y + log sum_j exp(p_j)
+        float z2 = 0.f;
+        for (int c = tid; c < a.C; c += kThreads) z2 += __expf(p_[c]);
+        z2 = block_sum(z2, red);
+        const float py = (yv >= 0 && yv < a.C) ? p_[yv] : 0.f;
+        loss = -py + logf(z2);
+      } else {
+        const float ly = (yv >= 0 && yv < a.C) ? a.logits[(size_t)n * a.C + yv] : 0.f;
+        loss = -(ly - logz);
+      }
+      if (tid == 0) a.loss_rows[n] = loss * a.inv_batch;
+    }
+    __syncthreads();
   }
 }
 
-// smem: g[C] | f[E] | z[E](df then dz) | dy[D] | xh[D] | red[32]
+// smem: g[kS][C] | f[kS][E] | z[kS][E](df then dz) | dy[kS][D] | xh[kS][D] | red[32]
 __global__ void __launch_bounds__(kThreads)
 head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
                 float* __restrict__ dx, int ld_dx) {
   extern __shared__ float sm[];
   float* sg = sm;
-  float* sf = sg + a.C;
-  float* sz = sf + a.E;
-  float* sdy = sz + a.E;
-  float* sxh = sdy + a.D;
-  float* red = sxh + a.D;
-  const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* pr = a.probs + (size_t)n * a.C;
+  float* sf = sg + kS * a.C;
+  float* sz = sf + kS * a.E;
+  float* sdy = sz + kS * a.E;
+  float* sxh = sdy + kS * a.D;
+  float* red = sxh + kS * a.D;
+  const int n0 = blockIdx.x * kS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (!a.skip_logit_grad) {
-    // dL/dlogits
-    if (d_probs == nullptr && !a.double_softmax) {
-      const int64_t yv = a.labels[n];
-      for (int c = tid; c < a.C; c += kThreads)
-        sg[c] = (pr[c] - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
-    } else {
-      if (d_probs != nullptr) {
-        for (int c = tid; c < a.C; c += kThreads)
-          sg[c] = d_probs[(size_t)n * a.C + c] * loss_scale;
-      } else {
+    // dL/dlogits of each sample
+    for (int sI = 0; sI < kS; ++sI) {
+      const int n = min(n0 + sI, a.N - 1);
+      const float* pr = a.probs + (size_t)n * a.C;
+      float* g = sg + sI * a.C;
+      if (d_probs == nullptr && !a.double_softmax) {
         const int64_t yv = a.labels[n];
-        float z2 = 0.f;
-        for (int c = tid; c < a.C; c += kThreads) z2 += __expf(pr[c]);
-        z2 = block_sum(z2, red);
         for (int c = tid; c < a.C; c += kThreads)
-          sg[c] = (__expf(pr[c]) / z2 - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
+          g[c] = (pr[c] - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
+      } else {
+        if (d_probs != nullptr) {
+          for (int c = tid; c < a.C; c += kThreads) g[c] = d_probs[(size_t)n * a.C + c] * loss_scale;
+        } else {
+          const int64_t yv = a.labels[n];
+          float z2 = 0.f;
+          for (int c = tid; c < a.C; c += kThreads) z2 += __expf(pr[c]);
+          z2 = block_sum(z2, red);
+          for (int c = tid; c < a.C; c += kThreads)
+            g[c] = (__expf(pr[c]) / z2 - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
+        }
+        __syncthreads();
+        float dot = 0.f;
+        for (int c = tid; c < a.C; c += kThreads) dot += g[c] * pr[c];
+        dot = block_sum(dot, red);
+        for (int c = tid; c < a.C; c += kThreads) g[c] = pr[c] * (g[c] - dot);
       }
-      __syncthreads();
-      float dot = 0.f;
-      for (int c = tid; c < a.C; c += kThreads) dot += sg[c] * pr[c];
-      dot = block_sum(dot, red);
-      for (int c = tid; c < a.C; c += kThreads) sg[c] = pr[c] * (sg[c] - dot);
+      for (int e = tid; e < a.E; e += kThreads) sf[sI * a.E + e] = a.fnorm[(size_t)n * a.E + e];
     }
-    for (int e = tid; e < a.E; e += kThreads) sf[e] = a.fnorm[(size_t)n * a.E + e];
     __syncthreads();
 
-    // df = scale * dlogits @ T ; dz = (df - f (f.df)) / |z|
-    float fd = 0.f, zz = 0.f;
-    for (int e = tid; e < a.E; e += kThreads) {
-      float part[4] = {0.f, 0.f, 0.f, 0.f};
-      int c = 0;
-      for (; c + 4 <= a.C; c += 4) {
+    // df = scale * dlogits @ T for the kS samples per text element read
+    float fd[kS], zz[kS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int64_t row = a.cls_idx ? a.cls_idx[c + u] : (int64_t)(c + u);
-          part[u] = fmaf(sg[c + u], __ldg(a.text + (size_t)row * a.E + e), part[u]);
+    for (int sI = 0; sI < kS; ++sI) fd[sI] = zz[sI] = 0.f;
+    for (int e = tid; e < a.E; e += kThreads) {
+      float acc[kS][2];
+#pragma unroll
+      for (int sI = 0; sI < kS; ++sI) acc[sI][0] = acc[sI][1] = 0.f;
+      int c = 0;
+      for (; c + 2 <= a.C; c += 2) {
+        const int64_t r0 = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
+        const int64_t r1 = a.cls_idx ? a.cls_idx[c + 1] : (int64_t)(c + 1);
+        const float t0 = __ldg(a.text + (size_t)r0 * a.E + e);
+        const float t1 = __ldg(a.text + (size_t)r1 * a.E + e);
+#pragma unroll
+        for (int sI = 0; sI < kS; ++sI) {
+          acc[sI][0] = fmaf(sg[sI * a.C + c], t0, acc[sI][0]);
+          acc[sI][1] = fmaf(sg[sI * a.C + c + 1], t1, acc[sI][1]);
         }
       }
       for (; c < a.C; ++c) {
-        const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
-        part[0] = fmaf(sg[c], __ldg(a.text + (size_t)row * a.E + e), part[0]);
+        const int64_t r0 = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
+        const float t0 = __ldg(a.text + (size_t)r0 * a.E + e);
+#pragma unroll
+        for (int sI = 0; sI < kS; ++sI) acc[sI][0] = fmaf(sg[sI * a.C + c], t0, acc[sI][0]);
       }
-      float acc = (part[0] + part[1]) + (part[2] + part[3]);
-      acc *= a.logit_scale;
-      sz[e] = acc;
-      fd += acc * sf[e];
-      const float zf = a.feat[(size_t)n * a.E + e];
-      zz += zf * zf;
+#pragma unroll
+      for (int sI = 0; sI < kS; ++sI) {
+        const int n = min(n0 + sI, a.N - 1);
+        const float v = (acc[sI][0] + acc[sI][1]) * a.logit_scale;
+        sz[sI * a.E + e] = v;
+        fd[sI] += v * sf[sI * a.E + e];
+        const float zf = a.feat[(size_t)n * a.E + e];
+        zz[sI] += zf * zf;
+      }
     }
-    fd = block_sum(fd, red);
-    zz = block_sum(zz, red);
-    const float inv_norm = 1.0f / sqrtf(zz);
-    for (int e = tid; e < a.E; e += kThreads) {
-      float v = (sz[e] - sf[e] * fd) * inv_norm;
-      if (a.d_feat) v += a.d_feat[(size_t)n * a.E + e] * loss_scale;
-      sz[e] = v;
+    // dz = (df - f (f.df)) / |z|
+#pragma unroll
+    for (int sI = 0; sI < kS; ++sI) {
+      const int n = min(n0 + sI, a.N - 1);
+      const float fds = block_sum(fd[sI], red);
+      const float inv_norm = 1.0f / sqrtf(block_sum(zz[sI], red));
+      for (int e = tid; e < a.E; e += kThreads) {
+        float v = (sz[sI * a.E + e] - sf[sI * a.E + e] * fds) * inv_norm;
+        if (a.d_feat) v += a.d_feat[(size_t)n * a.E + e] * loss_scale;
+        sz[sI * a.E + e] = v;
+      }
     }
   } else {
-    for (int e = tid; e < a.E; e += kThreads) sz[e] = a.d_feat[(size_t)n * a.E + e] * loss_scale;
+    for (int sI = 0; sI < kS; ++sI) {
+      const int n = min(n0 + sI, a.N - 1);
+      for (int e = tid; e < a.E; e += kThreads)
+        sz[sI * a.E + e] = a.d_feat[(size_t)n * a.E + e] * loss_scale;
+    }
   }
   __syncthreads();
 
-  // dy = dz @ proj^T : one warp per k
+  // dy = dz @ proj^T : one warp per k, every proj row read once for the kS samples
   for (int k = warp; k < a.D; k += kThreads / 32) {
     const float* prow = a.proj + (size_t)k * a.E;
-    float acc = 0.f;
-    for (int e = lane; e < a.E; e += 32) acc += sz[e] * __ldg(prow + e);
-    acc = warp_sum(acc);
-    if (lane == 0) sdy[k] = acc;
+    float acc[kS];
+#pragma unroll
+    for (int sI = 0; sI < kS; ++sI) acc[sI] = 0.f;
+    for (int e = lane; e < a.E; e += 32) {
+      const float pv = __ldg(prow + e);
+#pragma unroll
+      for (int sI = 0; sI < kS; ++sI) acc[sI] = fmaf(sz[sI * a.E + e], pv, acc[sI]);
+    }
+#pragma unroll
+    for (int sI = 0; sI < kS; ++sI) {
+      const float v = warp_sum(acc[sI]);
+      if (lane == 0) sdy[sI * a.D + k] = v;
+    }
   }
+  __syncthreads();
   // ln_post backward (input gradient only)
-  const float* xr = a.x + (size_t)n * a.cls_stride * a.ld_x;
-  float s = 0.f;
-  for (int k = tid; k < a.D; k += kThreads) { sxh[k] = xr[k]; s += sxh[k]; }
-  const float mean = block_sum(s, red) / a.D;
-  float q = 0.f;
-  for (int k = tid; k < a.D; k += kThreads) { const float d = sxh[k] - mean; q += d * d; }
-  const float rstd = rsqrtf(block_sum(q, red) / a.D + kLnEps);
-  float c1 = 0.f, c2 = 0.f;
-  for (int k = tid; k < a.D; k += kThreads) {
-    const float xh = (sxh[k] - mean) * rstd;
-    const float g = sdy[k] * a.ln_g[k];
-    sxh[k] = xh;
-    sdy[k] = g;
-    c1 += g;
-    c2 += g * xh;
+  for (int sI = 0; sI < kS; ++sI) {
+    const int n = n0 + sI;
+    if (n >= a.N) break;
+    const float* xr = a.x + (size_t)n * a.cls_stride * a.ld_x;
+    float* xh_ = sxh + sI * a.D;
+    float* dy_ = sdy + sI * a.D;
+    float s = 0.f;
+    for (int k = tid; k < a.D; k += kThreads) { xh_[k] = xr[k]; s += xh_[k]; }
+    const float mean = block_sum(s, red) / a.D;
+    float q = 0.f;
+    for (int k = tid; k < a.D; k += kThreads) { const float d = xh_[k] - mean; q += d * d; }
+    const float rstd = rsqrtf(block_sum(q, red) / a.D + kLnEps);
+    float c1 = 0.f, c2 = 0.f;
+    for (int k = tid; k < a.D; k += kThreads) {
+      const float xh = (xh_[k] - mean) * rstd;
+      const float g = dy_[k] * a.ln_g[k];
+      xh_[k] = xh;
+      dy_[k] = g;
+      c1 += g;
+      c2 += g * xh;
+    }
+    c1 = block_sum(c1, red) / a.D;
+    c2 = block_sum(c2, red) / a.D;
+    float* dr = dx + (size_t)n * a.cls_stride * ld_dx;
+    for (int k = tid; k < a.D; k += kThreads) dr[k] = rstd * (dy_[k] - c1 - xh_[k] * c2);
   }
-  c1 = block_sum(c1, red) / a.D;
-  c2 = block_sum(c2, red) / a.D;
-  float* dr = dx + (size_t)n * a.cls_stride * ld_dx;
-  for (int k = tid; k < a.D; k += kThreads) dr[k] = rstd * (sdy[k] - c1 - sxh[k] * c2);
 }
 
 __global__ void label_remap_kernel(const int64_t* __restrict__ y, const int64_t* __restrict__ lut,
@@ -310,14 +389,14 @@ int to_k(const llc_head_args* a, HeadK* k, const char* who) {
 extern "C" int llc_head_fwd(const llc_head_args* a, void* stream) {
   HeadK k;
   if (int rc = to_k(a, &k, "llc_head_fwd")) return rc;
-  const size_t smem = (size_t)(a->D + a->E + a->C + 32) * sizeof(float);
+  const size_t smem = (size_t)(kS * (a->D + a->E + a->C) + 32) * sizeof(float);
   LLC_REQUIRE(smem <= 200 * 1024, "llc_head_fwd: D+E+C too large for one CTA");
   if (smem > 48 * 1024)
     LLC_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   LLC_PROF_BEGIN(LLC_K_HEAD, a->N, a->C, 0, 2.0 * a->N * ((double)a->D * a->E + (double)a->E * a->C),
                  4.0 * a->N * (a->D + 2 * a->E + 2 * a->C), (cudaStream_t)stream);
-  head_fwd_kernel<<<a->N, kThreads, smem, (cudaStream_t)stream>>>(k);
+  head_fwd_kernel<<<(a->N + kS - 1) / kS, kThreads, smem, (cudaStream_t)stream>>>(k);
   LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("head_fwd_kernel");
@@ -332,15 +411,15 @@ extern "C" int llc_head_bwd(const llc_head_args* a, const float* d_probs, float 
   LLC_REQUIRE(d_probs || a->labels || (a->skip_logit_grad && a->d_feat),
               "llc_head_bwd: need d_probs, labels or d_feat");
   LLC_REQUIRE(!a->skip_logit_grad || a->d_feat, "llc_head_bwd: skip_logit_grad needs d_feat");
-  const size_t smem = (size_t)(a->C + 2 * a->E + 2 * a->D + 32) * sizeof(float);
+  const size_t smem = (size_t)(kS * (a->C + 2 * a->E + 2 * a->D) + 32) * sizeof(float);
   LLC_REQUIRE(smem <= 200 * 1024, "llc_head_bwd: sizes too large for one CTA");
   if (smem > 48 * 1024)
     LLC_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   LLC_PROF_BEGIN(LLC_K_HEAD, a->N, a->C, 1, 2.0 * a->N * ((double)a->D * a->E + (double)a->E * a->C),
                  4.0 * a->N * (2 * a->D + 2 * a->E + a->C), (cudaStream_t)stream);
-  head_bwd_kernel<<<a->N, kThreads, smem, (cudaStream_t)stream>>>(k, d_probs, loss_scale, dx,
-                                                                  ld_dx);
+  head_bwd_kernel<<<(a->N + kS - 1) / kS, kThreads, smem, (cudaStream_t)stream>>>(
+      k, d_probs, loss_scale, dx, ld_dx);
   LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("head_bwd_kernel");
