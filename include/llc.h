@@ -266,6 +266,7 @@ typedef struct llc_block_bwd_bufs {
   void* d_o;     /* [T, D] bf16 scratch                                            */
   void* dqkv;    /* [T, 3D+16] bf16 scratch                                        */
   float* partial;/* llc_lora_side partials: max_partials * 3D * r floats           */
+  float* delta;  /* [N * heads * L] fp32 scratch: rowsum(dO o O) of the attention backward */
 } llc_block_bwd_bufs;
 int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
                        const llc_block_bwd_bufs* s, int N, int L, int tok_stride_n,

@@ -65,7 +65,8 @@ class BlockBufs(C.Structure):
 
 
 class BlockBwdBufs(C.Structure):
-    _fields_ = [(n, c_void) for n in ("dx", "dxb", "dz", "dh", "d_o", "dqkv", "partial")]
+    _fields_ = [(n, c_void) for n in (
+        "dx", "dxb", "dz", "dh", "d_o", "dqkv", "partial", "delta")]
 
 
 class FinishJob(C.Structure):

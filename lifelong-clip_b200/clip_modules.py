@@ -199,7 +199,8 @@ class _BlockFn(torch.autograd.Function):
         scratch = dict(
             dx=dx, dxb=_bf16(T, D + PAD, dev), dz=_bf16(T, M, dev), dh=_bf16(T, D, dev),
             d_o=_bf16(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
-            partial=torch.empty(ops.lora_side_max_partials() * 3 * D * 8, device=dev))
+            partial=torch.empty(ops.lora_side_max_partials() * 3 * D * 8, device=dev),
+            delta=torch.empty(N * blk.n_head * L, device=dev))
         for k, v in scratch.items():
             setattr(s, k, v.data_ptr())
         lib = K.load()

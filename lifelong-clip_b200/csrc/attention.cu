@@ -17,6 +17,10 @@ bool llc_attn_tc_eligible(int L);
 int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o, int ld_do,
                     const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H, int sn, int sl,
                     int causal, cudaStream_t st);
+int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
+                     int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
+                     int sn, int sl, int causal, float* delta_ws, cudaStream_t st);
+int llc_attn_bwd_tc4_smem(int L);
 int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
                      int sn, int sl, int causal, cudaStream_t st);
@@ -536,9 +540,11 @@ extern "C" int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, floa
                                  (cudaStream_t)stream)));
 }
 
-extern "C" int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
-                            int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L,
-                            int H, int tok_stride_n, int tok_stride_l, int causal, void* stream) {
+// llc_attn_bwd with caller-provided scratch for delta = rowsum(dO o O) ([N*H*L] floats; nullptr:
+// library-owned scratch, which cannot grow under stream capture)
+int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
+                    int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
+                    int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, void* stream) {
   if (int rc = check_common(qkv, ld_qkv, N, L, H, "llc_attn_bwd")) return rc;
   LLC_REQUIRE(o && d_o && lse && dqkv, "llc_attn_bwd: null pointer");
   LLC_REQUIRE(ld_o % 8 == 0 && ld_do % 8 == 0 && ld_dqkv % 2 == 0 && ld_dqkv >= 3 * H * HD,
@@ -547,6 +553,11 @@ extern "C" int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o
               "llc_attn_bwd: misaligned pointer");
   static const bool legacy = getenv("LLC_ATTN_LEGACY") != nullptr;
   static const bool v2 = getenv("LLC_ATTN_BWD2") != nullptr;   // previous two-orientation kernel
+  static const bool v3 = getenv("LLC_ATTN_BWD3") != nullptr;   // previous block-structured kernel
+  if (!legacy && !v2 && !v3 && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 &&
+      ((uintptr_t)dqkv & 15) == 0 && llc_attn_bwd_tc4_smem(L) <= 227 * 1024)
+    return llc_attn_bwd_tc4(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
+                            tok_stride_n, tok_stride_l, causal, delta_ws, (cudaStream_t)stream);
   if (!legacy && !v2 && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
     return llc_attn_bwd_tc3(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
                             tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream);
@@ -557,4 +568,11 @@ extern "C" int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o
                                  (const __nv_bfloat16*)d_o, ld_do, lse, (__nv_bfloat16*)dqkv,
                                  ld_dqkv, N, L, H, tok_stride_n, tok_stride_l, causal,
                                  (cudaStream_t)stream)));
+}
+
+extern "C" int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
+                            int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L,
+                            int H, int tok_stride_n, int tok_stride_l, int causal, void* stream) {
+  return llc_attn_bwd_ws(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
+                         tok_stride_n, tok_stride_l, causal, nullptr, stream);
 }

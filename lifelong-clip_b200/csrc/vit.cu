@@ -6,6 +6,10 @@
 // the sequence is CUDA-graph capturable.
 #include "common.cuh"
 
+int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
+                    int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
+                    int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, void* stream);
+
 namespace {
 
 }  // namespace
@@ -41,7 +45,7 @@ struct Arena {
   size_t patches, patch_out, x /*[layers+1]*/, x_stride;
   size_t h1, qkv, lse, o, x_mid, z, layer_stride;  // per-layer block (training) or shared
   size_t h2, g;
-  size_t dxb, dz, dh, d_o, dqkv, partial;  // backward scratch
+  size_t dxb, dz, dh, d_o, dqkv, partial, delta;  // backward scratch
   size_t total;
 };
 
@@ -72,8 +76,9 @@ Arena plan(const Dims& d, int training) {
     a.d_o = take(T * d.D * 2);
     a.dqkv = take(T * (3 * d.D + LLC_LORA_LD) * 2);
     a.partial = take((size_t)llc_lora_side_max_partials() * 3 * d.D * 2 * 4 * 4);  // 4 regions
+    a.delta = take((size_t)d.N * d.H * d.L * 4);   // rowsum(dO o O) for the attention backward
   } else {
-    a.dxb = a.dz = a.dh = a.d_o = a.dqkv = a.partial = 0;
+    a.dxb = a.dz = a.dh = a.d_o = a.dqkv = a.partial = a.delta = 0;
   }
   a.total = off;
   return a;
@@ -227,8 +232,8 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   e = llc_gemm_epi{};
   e.out = s->d_o; e.ld_out = D;
   RUN(llc_gemm_bf16_tn(s->dxb, DA, w->woT_aug, DA, T, D, KA, &e, stream));
-  RUN(llc_attn_bwd(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
-                   stream));
+  RUN(llc_attn_bwd_ws(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
+                      s->delta, stream));
   // in-proj: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
   e = llc_gemm_epi{};
   e.out = dqkv + 3 * D; e.ld_out = QA;
@@ -311,6 +316,7 @@ extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w
   s.d_o = base + a.d_o;
   s.dqkv = base + a.dqkv;
   s.partial = reinterpret_cast<float*>(base + a.partial);
+  s.delta = reinterpret_cast<float*>(base + a.delta);
   RUN(llc_cast_bf16(dx_final, s.dxb, d.T, d.D, d.D + LLC_LORA_LD, stream));
   llc_block_bufs b;
   for (int l = d.layers - 1; l >= 0; --l) {
