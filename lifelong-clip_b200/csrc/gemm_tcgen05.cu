@@ -125,7 +125,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * C::kStages + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   const int tiles_m = (M + BM - 1) / BM;
@@ -155,51 +155,56 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM;
-        const int n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+    // (warp-uniform control flow, one elected lane issues: a divergent `if (lane == 0)` makes
+    // ptxas wrap every TMA / MMA operand in a register->uniform-register waterfall loop)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM;
+      const int n0 = (tile % tiles_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, C::kStageBytes);
           const uint32_t sa = smem_u32(smem_ab + stage * C::kStageBytes);
           tma_load_2d(sa, &tmA, fb, kb * BK, m0);
           tma_load_2d(sa + C::kABytes, &tmB, fb, kb * BK, n0);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t bphase = (it >> 1) & 1;
-        mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1);  // epilogue drained this accumulator
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1);  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem_ab + stage * C::kStageBytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + C::kABytes);
           const int ksteps = min(BK / 16, (K - kb * BK) / 16);
-          for (int k = 0; k < ksteps; ++k) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (start address is in 16 B units)
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (k < ksteps) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(smem_u32(&empty_bar[stage]));  // smem slot reusable once these MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) umma_commit(smem_u32(&tfull_bar[buf]));  // accumulator complete
         }
-        umma_commit(smem_u32(&tfull_bar[buf]));  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
