@@ -118,6 +118,16 @@ int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float* Mrd, int 
 int llc_lora_colsum_finish(const float* partial, int n_partials, int C, int r, float cs_scale,
                            float* out, int o_sc, int o_sj, void* stream);
 int llc_lora_side_max_partials(void);
+/* Fused form for the two reductions of a LoRA projection's backward that read the same X
+ * (bf16 [T, ld_x], C columns), ONE pass over X on the tensor cores:
+ *   partial[p][c][j] = sum over CTA p's tokens of X[t,c] * w[t,j], j < r   (-> colsum_finish)
+ *   U[t, 0..16)      = sum_c X[t,c] * F[j,c]   bf16, F = packed factors bf16 [16, ld_f]
+ * (dB = s g^T u and du = s g B of lora.py:838-839,1072-1074 under autograd). Needs
+ * C % 128 == 0, C <= 2304, T >= 1024, 16 B aligned pointers and pitches % 8 == 0; returns
+ * LLC_ERR_ARG otherwise (the caller then uses llc_lora_side + a skinny GEMM). */
+int llc_lora_side_fused(const void* X, int ld_x, int T, int C, int r, const void* w, int ld_w,
+                        const void* F, int ld_f, void* U, int ld_u, float* partial,
+                        int* n_partials, void* stream);
 /* several finishes in one launch (one per LoRA tensor of a layer) */
 typedef struct llc_finish_job {
   const float* partial;

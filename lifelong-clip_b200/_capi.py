@@ -105,6 +105,8 @@ SIGNATURES = {
     "llc_lora_colsum_finish": (c_int, [c_void, c_int, c_int, c_int, c_float, c_void, c_int, c_int,
                                        c_void]),
     "llc_lora_side_max_partials": (c_int, []),
+    "llc_lora_side_fused": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_int, c_void,
+                                    c_int, c_void, c_int, c_void, C.POINTER(c_int), c_void]),
     "llc_lora_colsum_finish_multi": (c_int, [C.POINTER(FinishJob), c_int, c_int, c_void]),
     "llc_pack_weight": (c_int, [c_void, c_int, c_int, c_int, c_void, c_int, c_void]),
     "llc_pack_lora_cols": (c_int, [c_void, c_int, c_int, c_int, c_int, c_float, c_void, c_int,

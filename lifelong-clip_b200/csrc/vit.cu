@@ -6,6 +6,11 @@
 // the sequence is CUDA-graph capturable.
 #include "common.cuh"
 
+bool llc_lora_fused_eligible(const void* X, int ld_x, int T, int C, int R, const void* w, int ld_w,
+                             const void* F, int ld_f, const void* U, int ld_u);
+int llc_lora_fused_tc(const void* X, int ld_x, int T, int C, int R, const void* w, int ld_w,
+                      const void* F, int ld_f, void* U, int ld_u, float* partial, int* n_partials,
+                      cudaStream_t st);
 int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                     int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
                     int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, void* stream);
@@ -217,16 +222,24 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   // LayerNorm kernel it cost 52 us per launch in L1 traffic for the factor, profiles/)
   RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
                  stream));
-  e = llc_gemm_epi{};
-  e.out = dxb + D; e.ld_out = DA;
-  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->f_out_B, D, T, LLC_LORA_PAD, D, &e, stream));
   // LoRA weight gradients: four column sums, each into its own partial region, reduced by ONE
   // finish launch at the end of the layer.
   const size_t preg = (size_t)llc_lora_side_max_partials() * 3 * D * 2;   // floats per region
   float* pr[4] = {s->partial, s->partial + preg, s->partial + 2 * preg, s->partial + 3 * preg};
   int np4[4] = {0, 0, 0, 0};
-  // out-proj: dB_o = s dx_mid^T u_o ; dA_o = du_o^T o
-  RUN(llc_lora_side(s->dxb, DA, T, D, r, nullptr, 0, 0, 0.f, o + D, DA, pr[0], &np4[0], stream));
+  cudaStream_t cst = (cudaStream_t)stream;
+  // out-proj: du_o = s dx_mid B_o (-> dxb pad cols) and dB_o = s dx_mid^T u_o read the same
+  // dx_mid: one fused pass when the shape allows, else a skinny GEMM plus a column-sum launch
+  if (llc_lora_fused_eligible(s->dxb, DA, T, D, r, o + D, DA, w->f_out_B, D, dxb + D, DA)) {
+    RUN(llc_lora_fused_tc(s->dxb, DA, T, D, r, o + D, DA, w->f_out_B, D, dxb + D, DA, pr[0],
+                          &np4[0], cst));
+  } else {
+    e = llc_gemm_epi{};
+    e.out = dxb + D; e.ld_out = DA;
+    RUN(llc_gemm_bf16_tn(s->dxb, DA, w->f_out_B, D, T, LLC_LORA_PAD, D, &e, stream));
+    RUN(llc_lora_side(s->dxb, DA, T, D, r, nullptr, 0, 0, 0.f, o + D, DA, pr[0], &np4[0], stream));
+  }
+  // dA_o = du_o^T o
   RUN(llc_lora_side(b->o, DA, T, D, r, nullptr, 0, 0, 0.f, dxb + D, DA, pr[1], &np4[1], stream));
   // d_o = dx_mid W_o + du_o A_o
   e = llc_gemm_epi{};
@@ -235,11 +248,17 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   RUN(llc_attn_bwd_ws(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
                       s->delta, stream));
   // in-proj: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
-  e = llc_gemm_epi{};
-  e.out = dqkv + 3 * D; e.ld_out = QA;
-  RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
-  RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, pr[2], &np4[2],
-                    stream));
+  if (llc_lora_fused_eligible(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D,
+                              QA)) {
+    RUN(llc_lora_fused_tc(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D, QA,
+                          pr[2], &np4[2], cst));
+  } else {
+    e = llc_gemm_epi{};
+    e.out = dqkv + 3 * D; e.ld_out = QA;
+    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
+    RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, pr[2], &np4[2],
+                      stream));
+  }
   RUN(llc_lora_side(b->h1, DA, T, D, r, nullptr, 0, 0, 0.f, dqkv + 3 * D, QA, pr[3], &np4[3],
                     stream));
   {

@@ -112,6 +112,17 @@ def lora_side(X, T, Cc, r, Mrd=None, rd_sc=0, rd_sj=0, rd_scale=1.0, w=None, ld_
     return n.value
 
 
+def lora_side_fused(X, T, Cc, r, w, ld_w, F, U, partial):
+    """One pass over X: column sums with w into `partial`, row products with the packed factors
+    F [16, C] into U [T, 16]. Returns the number of partial slices."""
+    n = C.c_int(0)
+    K.check(_lib().llc_lora_side_fused(X.data_ptr(), X.stride(0), T, Cc, r, w.data_ptr(), ld_w,
+                                       F.data_ptr(), F.stride(0), U.data_ptr(), U.stride(0),
+                                       partial.data_ptr(), C.byref(n), _s()),
+            "llc_lora_side_fused")
+    return n.value
+
+
 def lora_colsum_finish(partial, n_partials, Cc, r, scale, out, o_sc, o_sj):
     K.check(_lib().llc_lora_colsum_finish(partial.data_ptr(), n_partials, Cc, r, float(scale),
                                           out.data_ptr(), o_sc, o_sj, _s()),

@@ -220,6 +220,29 @@ def test_lora_side_rowdot_and_colsum(ops, T, Cc):
     assert rel(outT, want.T) < 1e-5
 
 
+@pytest.mark.parametrize("T,Cc", [(1024, 128), (3000, 768), (197 * 40, 2304), (6304 + 5, 768)])
+def test_lora_side_fused(ops, T, Cc):
+    """Fused column sums + row products (one pass over X) against fp64."""
+    r = 8
+    X = bf16_randn(T, Cc + 64, seed=33)
+    w = bf16_randn(T, 24, seed=34)
+    F = (torch.randn(16, Cc, device="cuda") * 0.05).to(torch.bfloat16)
+    F[r:] = 0
+    X[:, Cc:] = 7.0      # the pad columns receive U and must not be read as data
+    partial = torch.empty(ops.lora_side_max_partials() * Cc * 8, device="cuda")
+    U = X[:, Cc:]
+    n = ops.lora_side_fused(X, T, Cc, r, w, 24, F, U, partial)
+    out = torch.empty(Cc, r, device="cuda")
+    ops.lora_colsum_finish(partial, n, Cc, r, 0.5, out, r, 1)
+    torch.cuda.synchronize()
+    Xd = X[:, :Cc].double()
+    want_u = Xd @ F.double().T
+    assert rel(U[:, :16].float(), want_u) < 4e-3
+    assert float(U[:, r:16].abs().max()) == 0.0
+    assert float((X[:, Cc + 16:] - 7.0).abs().max()) == 0.0
+    assert rel(out, 0.5 * Xd.T @ w[:, :r].double()) < 1e-5
+
+
 # -------------------------------------------------------------------------------------- front end
 def test_pack_weight_and_lora_cols(ops):
     W = torch.randn(96, 160, device="cuda")
