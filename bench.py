@@ -308,6 +308,15 @@ def run_ours(args):
     recs = ops.prof_read()
     ops.prof_enable(False)
     trainer.use_cuda_graph = not args.no_graph
+    # per (kind, m, n, k) launch statistics of the instrumented steps
+    agg = {}
+    for kind, m, n, k, ms, fl, by in recs:
+        d = agg.setdefault((kind, m, n, k), [0, 0.0])
+        d[0] += 1; d[1] += ms
+    by_shape = [{"kind": kk[0], "m": kk[1], "n": kk[2], "k": kk[3],
+                 "launches_per_step": v[0] / args.prof_steps, "us_per_launch": 1e3 * v[1] / v[0],
+                 "ms_per_step": v[1] / args.prof_steps} for kk, v in agg.items()]
+    by_shape.sort(key=lambda r: -r["ms_per_step"])
     by_kind = {}
     for kind, m, n, k, ms, fl, by in recs:
         if kind == "gemm" and n < 256:
@@ -352,7 +361,7 @@ def run_ours(args):
     if args.dump_prof and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.dump_prof)), exist_ok=True)
         with open(args.dump_prof, "w") as f:
-            json.dump({"records": recs, "by_kind": breakdown}, f)
+            json.dump({"by_shape": by_shape, "by_kind": breakdown, "records": recs}, f)
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1)
     cpu = None

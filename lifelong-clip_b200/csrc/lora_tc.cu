@@ -153,26 +153,27 @@ lora_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat
 // column tiles; the [128 tokens x 128 columns] tile (two 64-column TMA boxes) feeds
 //   8 MMAs with the tile as MN-major A (M = columns), w rows as MN-major B  -> TMEM cols 16 ct..
 //   8 MMAs with the tile as K-major  A (M = tokens),  F block as K-major B  -> U accumulator
+// (the factor rows of a tile's columns are loaded with it: 4 KB from L2 next to 32 KB from HBM).
 // The column-sum accumulators (C / 128 x 16 TMEM columns, <= 288) live for the whole kernel and
 // go out as one partial per CTA; U (2 x 16 columns, double-buffered) leaves after every slab.
 constexpr int kFXTile = 2 * 128 * 128;     // 128 tokens x two 64-column atoms
+constexpr int kFFTile = 2 * 16 * 128;      // the 16 factor rows of the same 128 columns
+constexpr int kFStage = kFXTile + kFFTile;
 constexpr int kFWTile = 128 * 128;         // w rows of a slab, 32 B used per 128 B row
-constexpr int kFStages = 3;
+constexpr int kFStages = 5;
 constexpr uint32_t kFUCol = 288;           // U accumulators behind the column sums
 
 __global__ void __launch_bounds__(kThreads, 1)
-lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ w,
-                     int ld_w, const __nv_bfloat16* __restrict__ F, int ld_f,
-                     __nv_bfloat16* __restrict__ U, int ld_u, int T, int C, int R,
-                     float* __restrict__ partial) {
+lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF,
+                     const __nv_bfloat16* __restrict__ w, int ld_w, __nv_bfloat16* __restrict__ U,
+                     int ld_u, int T, int C, int R, float* __restrict__ partial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
   const int nct = C / 128;
-  uint8_t* sF = smem;                                   // C / 64 blocks of [16 rows x 128 B]
-  uint8_t* sW = sF + (C / 64) * 2048;                   // 2 slabs
-  uint8_t* sX = sW + 2 * kFWTile;                       // kFStages tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + kFStages * kFXTile);
+  uint8_t* sW = smem;                                   // w rows of 2 slabs
+  uint8_t* sX = sW + 2 * kFWTile;                       // kFStages x (X tile | factor block)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + kFStages * kFStage);
   uint64_t* full_bar = bars;                  // [kFStages] X tile landed
   uint64_t* empty_bar = bars + kFStages;      // [kFStages] its MMAs retired
   uint64_t* w_full = bars + 2 * kFStages;     // [2] w rows of a slab landed (128 loader threads)
@@ -186,6 +187,7 @@ lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat1
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmF);
     for (int s = 0; s < kFStages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -199,16 +201,6 @@ lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat1
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
   pdl_wait();
-  // the row factors, once per CTA: 16 B pieces into K-major 128 B-swizzled [16 x 64] blocks
-  {
-    const int ppr = C / 8;                     // pieces per factor row
-    for (int i = threadIdx.x; i < 16 * ppr; i += kThreads) {
-      const int j = i / ppr, cp = i - j * ppr;
-      const uint4 v = *reinterpret_cast<const uint4*>(F + (size_t)j * ld_f + cp * 8);
-      *reinterpret_cast<uint4*>(sF + (cp >> 3) * 2048 + j * 128 + (((cp & 7) ^ (j & 7)) << 4)) = v;
-    }
-    fence_proxy_async_smem();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -222,10 +214,13 @@ lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat1
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          const uint32_t sa = smem_u32(sX + stage * kFXTile);
-          mbar_expect_tx(fb, kFXTile);
+          const uint32_t sa = smem_u32(sX + stage * kFStage);
+          mbar_expect_tx(fb, kFStage);
           tma_load_2d(sa, &tmX, fb, ct * 128, slab * 128);
           tma_load_2d(sa + 128 * 128, &tmX, fb, ct * 128 + 64, slab * 128);
+          // the factor rows of these columns ride along (72 KB in all: L2-resident)
+          tma_load_2d(sa + kFXTile, &tmF, fb, ct * 128, 0);
+          tma_load_2d(sa + kFXTile + 16 * 128, &tmF, fb, ct * 128 + 64, 0);
         }
         __syncwarp();
         if (++stage == kFStages) { stage = 0; phase ^= 1; }
@@ -247,7 +242,7 @@ lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat1
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(sX + stage * kFXTile);
+          const uint32_t sa = smem_u32(sX + stage * kFStage);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)     // K = the slab's tokens
             umma_bf16(tmem_base + ct * 16, umma_desc_mn_sw128(sa + ks * 2048, 128 * 128, 1024),
@@ -257,7 +252,7 @@ lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat1
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4)
               umma_bf16(tmem_base + kFUCol + wb * 16, umma_desc_k_sw128(sa + a * 128 * 128) + 2 * k4,
-                        umma_desc_k_sw128(smem_u32(sF) + (ct * 2 + a) * 2048) + 2 * k4, idesc_r,
+                        umma_desc_k_sw128(sa + kFXTile + a * 2048) + 2 * k4, idesc_r,
                         (ct | a | k4) != 0);
           umma_commit(smem_u32(&empty_bar[stage]));
           if (ct == nct - 1) umma_commit(smem_u32(&u_done[wb]));
@@ -365,9 +360,13 @@ int llc_lora_fused_tc(const void* X, int ld_x, int T, int C, int R, const void* 
                                   (uint64_t)T, (uint64_t)ld_x * 2, 64, 128,
                                   CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
+  CUtensorMap tf;
+  if (int rc = llc_encode_tmap_2d(&tf, F, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)C, 16,
+                                  (uint64_t)ld_f * 2, 64, 16, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
   const int nslabs = (T + 127) / 128;
   const int grid = nslabs < llc_num_sms() ? nslabs : llc_num_sms();
-  const int smem = 1024 + (C / 64) * 2048 + 2 * kFWTile + kFStages * kFXTile + 256;
+  const int smem = 1024 + 2 * kFWTile + kFStages * kFStage + 256;
   static int configured = 0;
   if (configured < smem) {
     LLC_CUDA(cudaFuncSetAttribute(lora_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -375,9 +374,8 @@ int llc_lora_fused_tc(const void* X, int ld_x, int T, int C, int R, const void* 
     configured = smem;
   }
   LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 3, 4.0 * T * C * 16, 2.0 * T * C, st);
-  LLC_CUDA(llc_launch_pdl(lora_fused_tc_kernel, dim3(grid), dim3(kThreads), (size_t)smem, st, tm,
+  LLC_CUDA(llc_launch_pdl(lora_fused_tc_kernel, dim3(grid), dim3(kThreads), (size_t)smem, st, tm, tf,
                           reinterpret_cast<const __nv_bfloat16*>(w), ld_w,
-                          reinterpret_cast<const __nv_bfloat16*>(F), ld_f,
                           reinterpret_cast<__nv_bfloat16*>(U), ld_u, T, C, R, partial));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();

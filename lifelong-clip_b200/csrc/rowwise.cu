@@ -370,9 +370,11 @@ struct FinishArgs {
   llc_finish_job j[kMaxFinishJobs];
 };
 // blockIdx.y = job; same fixed-order reduction as colsum_finish_kernel
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 colsum_finish_multi_kernel(const __grid_constant__ FinishArgs a, int R, int r) {
-  __shared__ float red[8][32];
+  // 32 slices of the partial list per output element: with one partial per SM (the fused
+  // tensor-core pass) every thread has <= 5 independent loads, one global round trip
+  __shared__ float red[32][32];
   const llc_finish_job& jb = a.j[blockIdx.y];
   const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int n = jb.C * R;
@@ -380,15 +382,15 @@ colsum_finish_multi_kernel(const __grid_constant__ FinishArgs a, int R, int r) {
     const int i = base + o;
     float s = 0.f;
     if (i < n) {
-#pragma unroll 4
-      for (int p = sl; p < jb.n_partials; p += 8) s += jb.partial[(size_t)p * n + i];
+#pragma unroll 8
+      for (int p = sl; p < jb.n_partials; p += 32) s += jb.partial[(size_t)p * n + i];
     }
     red[sl][o] = s;
     __syncthreads();
     if (sl == 0 && i < n) {
       float t = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t += red[k][o];
+      for (int k = 0; k < 32; ++k) t += red[k][o];
       const int c = i / R, j = i % R;
       if (j < r) jb.out[(size_t)c * jb.o_sc + (size_t)j * jb.o_sj] = t * jb.scale;
     }
@@ -758,7 +760,7 @@ extern "C" int llc_lora_colsum_finish_multi(const llc_finish_job* jobs, int n_jo
     if (jobs[i].C * R > maxn) maxn = jobs[i].C * R;
   }
   LLC_PROF_BEGIN(LLC_K_LORA_SIDE, n_jobs, maxn, 1, 0.0, 0.0, (cudaStream_t)stream);
-  colsum_finish_multi_kernel<<<dim3((maxn + 31) / 32, n_jobs), 256, 0, (cudaStream_t)stream>>>(
+  colsum_finish_multi_kernel<<<dim3((maxn + 31) / 32, n_jobs), 1024, 0, (cudaStream_t)stream>>>(
       a, R, r);
   LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
