@@ -24,6 +24,8 @@ int llc_attn_bwd_tc4_smem(int L);
 int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
                      int sn, int sl, int causal, cudaStream_t st);
+int llc_attn_fwd_tc2(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L,
+                     int H, int sn, int sl, int causal, cudaStream_t st);
 int llc_attn_fwd_tc(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L, int H,
                     int sn, int sl, int causal, cudaStream_t st);
 
@@ -532,6 +534,10 @@ extern "C" int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, floa
   // sequences up to 256 tokens run on the tensor cores through TMEM; LLC_ATTN_LEGACY=1 keeps the
   // mma.sync kernels (development A/B only)
   static const bool legacy = getenv("LLC_ATTN_LEGACY") != nullptr;
+  static const bool v1 = getenv("LLC_ATTN_FWD1") != nullptr;   // previous lock-step kernel
+  if (!legacy && !v1 && llc_attn_tc_eligible(L))
+    return llc_attn_fwd_tc2(qkv, ld_qkv, o, ld_o, lse, N, L, H, tok_stride_n, tok_stride_l, causal,
+                            (cudaStream_t)stream);
   if (!legacy && llc_attn_tc_eligible(L))
     return llc_attn_fwd_tc(qkv, ld_qkv, o, ld_o, lse, N, L, H, tok_stride_n, tok_stride_l, causal,
                            (cudaStream_t)stream);
