@@ -527,50 +527,37 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
 }
 
 // delta[(n H + h) L + l] = sum_d dO[tok, h, d] * O[tok, h, d], tok = n sn + l sl. Eight lanes per
-// (token, head): one 16 B piece of each row, three shuffles.
+// (token, head): one 16 B piece of each row, three shuffles. blockIdx.y = sample; HC = H as a
+// compile-time constant (0: runtime) keeps the index arithmetic off the XU pipe.
+template <int HC>
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int ld_o, const __nv_bfloat16* __restrict__ d_o,
-                  int ld_do, float* __restrict__ delta, int N, int L, int H, int sn, int sl) {
+                  int ld_do, float* __restrict__ delta, int L, int Hrt, int sn, int sl) {
   pdl_wait();
+  const int H = HC ? HC : Hrt;
   const int piece = threadIdx.x & 7;
-  const size_t total = (size_t)N * L * H;
-  const size_t stride = (size_t)gridDim.x * (blockDim.x >> 3);
-  for (size_t idx = (size_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
-       idx < total + stride; idx += 2 * stride) {    // two independent items per trip
-    float d[2];
+  const int item = blockIdx.x * 32 + (threadIdx.x >> 3);     // (l, h) of this sample
+  const int n = blockIdx.y;
+  float d = 0.f;
+  int l = 0, h = 0;
+  const bool ok = item < L * H;
+  if (ok) {
+    l = item / H;
+    h = item - l * H;
+    const size_t tok = (size_t)n * sn + (size_t)l * sl;
+    const uint4 ov = *reinterpret_cast<const uint4*>(o + tok * ld_o + h * HD + piece * 8);
+    const uint4 dv = *reinterpret_cast<const uint4*>(d_o + tok * ld_do + h * HD + piece * 8);
+    const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const size_t i = idx + k * stride;
-      d[k] = 0.f;
-      if (i < total) {
-        const int h = (int)(i % H);
-        const size_t nl = i / H;
-        const int l = (int)(nl % L), n = (int)(nl / L);
-        const size_t tok = (size_t)n * sn + (size_t)l * sl;
-        const uint4 ov = *reinterpret_cast<const uint4*>(o + tok * ld_o + h * HD + piece * 8);
-        const uint4 dv = *reinterpret_cast<const uint4*>(d_o + tok * ld_do + h * HD + piece * 8);
-        const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 a = unpack_bf16(dw[e]), b = unpack_bf16(ow[e]);
-          d[k] += a.x * b.x + a.y * b.y;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      d[k] += __shfl_xor_sync(0xffffffffu, d[k], 1);
-      d[k] += __shfl_xor_sync(0xffffffffu, d[k], 2);
-      d[k] += __shfl_xor_sync(0xffffffffu, d[k], 4);
-      const size_t i = idx + k * stride;
-      if (piece == 0 && i < total) {
-        const int h = (int)(i % H);
-        const size_t nl = i / H;
-        const int l = (int)(nl % L), n = (int)(nl / L);
-        delta[((size_t)n * H + h) * L + l] = d[k];
-      }
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = unpack_bf16(dw[e]), b = unpack_bf16(ow[e]);
+      d += a.x * b.x + a.y * b.y;
     }
   }
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  d += __shfl_xor_sync(0xffffffffu, d, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 4);
+  if (ok && piece == 0) delta[((size_t)n * H + h) * L + l] = d;
 }
 
 int encode_rows(CUtensorMap* tm, const void* base, int cols, int ld, int L, int N, int sn, int sl,
@@ -640,14 +627,18 @@ int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const
   LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
                  16.0 * N * H * (double)L * HD, st);
   {
-    const size_t items = need;   // (token, head) items, 8 lanes each, 2 per loop trip
-    long long blocks = (long long)((items + 63) / 64);
-    const long long cap = (long long)llc_num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    LLC_CUDA(llc_launch_pdl(attn_delta_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st,
-                            reinterpret_cast<const __nv_bfloat16*>(o), ld_o,
-                            reinterpret_cast<const __nv_bfloat16*>(d_o), ld_do, delta_ws, N, L, H, sn,
-                            sl));
+    const dim3 dgrid((unsigned)((L * H + 31) / 32), (unsigned)N);
+    const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
+    const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(d_o);
+    if (H == 12)
+      LLC_CUDA(llc_launch_pdl(attn_delta_kernel<12>, dgrid, dim3(256), (size_t)0, st, ob, ld_o, db,
+                              ld_do, delta_ws, L, H, sn, sl));
+    else if (H == 16)
+      LLC_CUDA(llc_launch_pdl(attn_delta_kernel<16>, dgrid, dim3(256), (size_t)0, st, ob, ld_o, db,
+                              ld_do, delta_ws, L, H, sn, sl));
+    else
+      LLC_CUDA(llc_launch_pdl(attn_delta_kernel<0>, dgrid, dim3(256), (size_t)0, st, ob, ld_o, db,
+                              ld_do, delta_ws, L, H, sn, sl));
     LLC_COUNT_LAUNCH();
     LLC_LAUNCH_CHECK("attn_delta_kernel");
   }

@@ -266,6 +266,7 @@ __device__ __forceinline__ void tma_store_wait() {
 // createpolicy-encoded L2 hints (same constants CUTLASS uses for SM90+ TMA)
 static constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 static constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+static constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tc_fence_before() {

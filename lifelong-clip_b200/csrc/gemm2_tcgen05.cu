@@ -244,6 +244,9 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   static const int dbg = getenv("LLC_GEMM_DBG") ? atoi(getenv("LLC_GEMM_DBG")) : 0;
   EpiParams ep2 = ep;
   ep2.dbg = dbg;
+  // a bf16 output that fits L2 (dh, d_o: 77 MB) is read again by the next kernel(s): let it stay
+  static const bool nokeep = getenv("LLC_GEMM_NOKEEP") != nullptr;
+  ep2.keep_out = (!nokeep && !ep.out_fp32 && (double)M * N * 2.0 <= 100e6) ? 1 : 0;
   LLC_CUDA(llc_launch_pdl(gemm2_kernel<MODE>, dim3(grid), dim3(kThreads), kSmem, stream, tmA, tmB, tmO,
                           tmO2, M, N, K, ep2, dbg));
   LLC_PROF_END(stream);

@@ -32,6 +32,7 @@ struct EpiParams {
   __nv_bfloat16* out2;
   int ld_out2;
   int dbg;  // development only (LLC_GEMM_DBG): 256 = no global stores, 512 = no TMEM loads
+  int keep_out;  // the bf16 output is small enough to stay in L2 for its consumer: no evict-first
 };
 
 constexpr int kEpiWarpBytes = 8192;  // TMA-store tiles (see epi_warp_tile_tma) / one 4 KB fp32 tile
@@ -367,7 +368,8 @@ __device__ __forceinline__ void epi_warp_tile_tma(const EpiParams& ep, const CUt
     __syncwarp();
     if (lane == 0) {
       if (MODE != EPI_GELU || ep.out != nullptr)
-        tma_store_2d_hint(tmO, smem_u32(tA), col0 + g * 64, row0, kEvictFirst);
+        tma_store_2d_hint(tmO, smem_u32(tA), col0 + g * 64, row0,
+                          ep.keep_out ? kEvictNormal : kEvictFirst);
       if (MODE == EPI_GELU) tma_store_2d_hint(tmO2, smem_u32(tB), col0 + g * 64, row0, kEvictFirst);
       tma_store_commit();
     }

@@ -323,6 +323,7 @@ extern "C" int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
   ep.out = e->out; ep.ld_out = e->ld_out; ep.out_fp32 = e->out_fp32;
   ep.out2 = reinterpret_cast<__nv_bfloat16*>(e->out2); ep.ld_out2 = e->ld_out2;
   ep.dbg = 0;
+  ep.keep_out = 0;
 
   // production shapes: 256 x 256 tiles on CTA pairs (gemm2_tcgen05.cu); LLC_GEMM_1CTA=1 forces
   // the single-CTA kernel below (debugging / A-B comparison)
