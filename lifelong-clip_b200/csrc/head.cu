@@ -8,6 +8,8 @@
 //   additive seen-class mask (methods/mvp_clip.py:113-118)
 // and the analytic backward down to the CLS rows of the residual stream (proj, ln_post frozen).
 // Also the integer label remap (methods/adapter_clip.py:75-76) and the per-step loss/acc scalars.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -52,6 +54,7 @@ struct HeadK {
   int64_t* pred;
   const float* d_feat;
   int skip_logit_grad;
+  int rot;   // bit 0: rotate the proj row order per CTA, bit 1: the text row order (LLC_HEAD_ROT)
 };
 
 // Both head kernels are written for kS samples per CTA (the two fat loops read every proj / text
@@ -93,17 +96,26 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadK a) {
     float acc[kS][2];
 #pragma unroll
     for (int sI = 0; sI < kS; ++sI) acc[sI][0] = acc[sI][1] = 0.f;
-    int k = 0;
-    for (; k + 2 <= a.D; k += 2) {
+    // Every CTA walks the proj rows from its own starting row: in lock step all CTAs would ask
+    // the same L2 lines at the same time (one slice serving 256 requesters per line).
+    const int k0 = (a.rot & 1) ? ((int)((blockIdx.x * 6u) % (unsigned)a.D) & ~1) : 0;
+    int i = 0;
+#pragma unroll 4
+    for (; i + 2 <= a.D; i += 2) {
+      int k = i + k0;
+      if (k >= a.D) k -= a.D;            // D even or the tail loop below takes the odd row
+      const int k1 = (k + 1 < a.D) ? k + 1 : 0;
       const float p0 = __ldg(a.proj + (size_t)k * a.E + e);
-      const float p1 = __ldg(a.proj + (size_t)(k + 1) * a.E + e);
+      const float p1 = __ldg(a.proj + (size_t)k1 * a.E + e);
 #pragma unroll
       for (int sI = 0; sI < kS; ++sI) {
         acc[sI][0] = fmaf(sy[sI * a.D + k], p0, acc[sI][0]);
-        acc[sI][1] = fmaf(sy[sI * a.D + k + 1], p1, acc[sI][1]);
+        acc[sI][1] = fmaf(sy[sI * a.D + k1], p1, acc[sI][1]);
       }
     }
-    for (; k < a.D; ++k) {
+    for (; i < a.D; ++i) {
+      int k = i + k0;
+      if (k >= a.D) k -= a.D;
       const float p0 = __ldg(a.proj + (size_t)k * a.E + e);
 #pragma unroll
       for (int sI = 0; sI < kS; ++sI) acc[sI][0] = fmaf(sy[sI * a.D + k], p0, acc[sI][0]);
@@ -128,7 +140,10 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadK a) {
   __syncthreads();
 
   // logits: one warp per class, lanes stride the embedding, kS samples per text row read
-  for (int c = warp; c < a.C; c += kThreads / 32) {
+  const int c0 = (a.rot & 2) ? (int)((blockIdx.x * 3u) % (unsigned)a.C) : 0;   // as for proj
+  for (int ci = warp; ci < a.C; ci += kThreads / 32) {
+    int c = ci + c0;
+    if (c >= a.C) c -= a.C;
     const int64_t row = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
     const float* tr = a.text + (size_t)row * a.E;
     float acc[kS];
@@ -251,19 +266,26 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
       float acc[kS][2];
 #pragma unroll
       for (int sI = 0; sI < kS; ++sI) acc[sI][0] = acc[sI][1] = 0.f;
-      int c = 0;
-      for (; c + 2 <= a.C; c += 2) {
+      const int cs0 = (a.rot & 2) ? (int)((blockIdx.x * 3u) % (unsigned)a.C) : 0;
+      int i = 0;
+#pragma unroll 4
+      for (; i + 2 <= a.C; i += 2) {
+        int c = i + cs0;
+        if (c >= a.C) c -= a.C;
+        const int c1 = (c + 1 < a.C) ? c + 1 : 0;
         const int64_t r0 = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
-        const int64_t r1 = a.cls_idx ? a.cls_idx[c + 1] : (int64_t)(c + 1);
+        const int64_t r1 = a.cls_idx ? a.cls_idx[c1] : (int64_t)c1;
         const float t0 = __ldg(a.text + (size_t)r0 * a.E + e);
         const float t1 = __ldg(a.text + (size_t)r1 * a.E + e);
 #pragma unroll
         for (int sI = 0; sI < kS; ++sI) {
           acc[sI][0] = fmaf(sg[sI * a.C + c], t0, acc[sI][0]);
-          acc[sI][1] = fmaf(sg[sI * a.C + c + 1], t1, acc[sI][1]);
+          acc[sI][1] = fmaf(sg[sI * a.C + c1], t1, acc[sI][1]);
         }
       }
-      for (; c < a.C; ++c) {
+      for (; i < a.C; ++i) {
+        int c = i + cs0;
+        if (c >= a.C) c -= a.C;
         const int64_t r0 = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
         const float t0 = __ldg(a.text + (size_t)r0 * a.E + e);
 #pragma unroll
@@ -300,8 +322,12 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
   }
   __syncthreads();
 
-  // dy = dz @ proj^T : one warp per k, every proj row read once for the kS samples
-  for (int k = warp; k < a.D; k += kThreads / 32) {
+  // dy = dz @ proj^T : one warp per k, every proj row read once for the kS samples (rows
+  // rotated per CTA, see head_fwd_kernel)
+  const int kr0 = (a.rot & 1) ? (int)((blockIdx.x * 6u) % (unsigned)a.D) : 0;
+  for (int ki = warp; ki < a.D; ki += kThreads / 32) {
+    int k = ki + kr0;
+    if (k >= a.D) k -= a.D;
     const float* prow = a.proj + (size_t)k * a.E;
     float acc[kS];
 #pragma unroll
@@ -381,6 +407,8 @@ int to_k(const llc_head_args* a, HeadK* k, const char* who) {
   k->feat = a->feat; k->fnorm = a->fnorm; k->logits = a->logits; k->probs = a->probs;
   k->loss_rows = a->loss_rows; k->pred = a->pred;
   k->d_feat = a->d_feat; k->skip_logit_grad = a->skip_logit_grad;
+  static const int rot = getenv("LLC_HEAD_ROT") ? atoi(getenv("LLC_HEAD_ROT")) : 1;
+  k->rot = rot;
   return 0;
 }
 
