@@ -196,6 +196,43 @@ def test_attention_fwd_bwd(ops, N, L, H, causal, seq_first):
     _attn_case(ops, N, L, H, causal, seq_first, seed=20 + L)
 
 
+@pytest.mark.parametrize("N,L,H,causal,seq_first", [
+    # more (sample, head) pairs than SMs: every persistent CTA walks several pairs (operand
+    # prefetch across pairs, barrier parities, accumulator hand-offs)
+    (40, 197, 12, False, False), (64, 50, 12, True, True), (30, 160, 12, False, False),
+    # tile / unit boundaries: 64, 128 exactly, one row past, a 16-wide tail unit, and the
+    # lengths whose operands no longer fit the unit-pipelined backward's shared memory
+    (3, 64, 2, False, False), (2, 128, 4, False, True), (2, 129, 4, True, False),
+    (2, 145, 4, False, False), (2, 250, 4, False, True), (150, 256, 1, False, False)])
+def test_attention_many_pairs_and_boundaries(ops, N, L, H, causal, seq_first):
+    _attn_case(ops, N, L, H, causal, seq_first, seed=70 + L)
+
+
+def test_attention_bwd_under_graph_capture(ops):
+    """The plain C-ABI backward owns its delta scratch: after one eager call of the shape it can be
+    captured into a CUDA graph and replayed (the captured launch must not allocate)."""
+    N, L, H = 4, 197, 12
+    D = H * 64
+    qkv = bf16_randn(N * L, 3 * D + 16, seed=90)
+    o = torch.zeros(N * L, D + 16, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(N * H * L, device="cuda")
+    ops.attn_fwd(qkv, o, lse, N, L, H, L, 1, False)
+    d_o = bf16_randn(N * L, D, seed=91)
+    want = torch.zeros(N * L, 3 * D + 16, device="cuda", dtype=torch.bfloat16)
+    ops.attn_bwd(qkv, o, d_o, lse, want, N, L, H, L, 1, False)      # eager: sizes the scratch
+    torch.cuda.synchronize()
+    got = torch.zeros_like(want)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            ops.attn_bwd(qkv, o, d_o, lse, got, N, L, H, L, 1, False)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(got[:, :3 * D], want[:, :3 * D])
+
+
 # --------------------------------------------------------------------------------------- LoRA side
 @pytest.mark.parametrize("T,Cc", [(100, 128), (197 * 3, 768), (197 * 3, 2304), (5003, 768),
                                   (6304, 2304), (1100, 128)])   # T >= 1024: tensor-core colsum
