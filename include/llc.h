@@ -247,6 +247,16 @@ int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w, const floa
 /* dx_final fp32 [N*L, D] (the head's gradient; consumed/overwritten) -> LoRA grads in w->layers */
 int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N, void* arena,
                      float* dx_final, void* stream);
+/* The same two calls when the consumer reads only the class-token rows of x_final (the tower's
+ * own output, ln_post(x[:, 0, :]) @ proj, model.py:782-785): the last block then runs its
+ * attention for one query per (sample, head) and its out-proj / LN2 / MLP on N rows instead of
+ * N*L. llc_vit_forward_cls leaves the other rows of x_final undefined; llc_vit_backward_cls reads
+ * only rows n*L of dx_final (the other rows need not be initialised). Results on the CLS rows and
+ * all LoRA gradients are identical to the full calls. */
+int llc_vit_forward_cls(const llc_vit_cfg* cfg, const llc_vit_weights* w, const float* images,
+                        int N, void* arena, int training, float** x_final, void* stream);
+int llc_vit_backward_cls(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N, void* arena,
+                         float* dx_final, void* stream);
 /* dst bf16 [T, ld_dst] <- src fp32 [T, D] (contiguous rows) */
 int llc_cast_bf16(const float* src, void* dst, int T, int D, int ld_dst, void* stream);
 /* refresh the LoRA columns of the augmented weights from the live parameters */

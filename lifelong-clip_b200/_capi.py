@@ -127,6 +127,10 @@ SIGNATURES = {
                                 c_int, C.POINTER(c_void), c_void]),
     "llc_vit_backward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitWeights), c_int, c_void, c_void,
                                  c_void]),
+    "llc_vit_forward_cls": (c_int, [C.POINTER(VitCfg), C.POINTER(VitWeights), c_void, c_int, c_void,
+                                    c_int, C.POINTER(c_void), c_void]),
+    "llc_vit_backward_cls": (c_int, [C.POINTER(VitCfg), C.POINTER(VitWeights), c_int, c_void,
+                                     c_void, c_void]),
     "llc_cast_bf16": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void]),
     "llc_vit_refresh_lora": (c_int, [C.POINTER(VitCfg), C.POINTER(VitWeights), c_void]),
     "llc_block_forward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitLayer), C.POINTER(BlockBufs),

@@ -11,6 +11,10 @@ bool llc_lora_fused_eligible(const void* X, int ld_x, int T, int C, int R, const
 int llc_lora_fused_tc(const void* X, int ld_x, int T, int C, int R, const void* w, int ld_w,
                       const void* F, int ld_f, void* U, int ld_u, float* partial, int* n_partials,
                       cudaStream_t st);
+int llc_attn_cls_fwd(const void* qkv, int ld_qkv, void* o_cls, int ld_o, float* p_cls, int N, int L,
+                     int H, int sn, int sl, cudaStream_t st);
+int llc_attn_cls_bwd(const void* qkv, int ld_qkv, const float* p_cls, const void* d_o_cls, int ld_do,
+                     void* dqkv, int ld_dqkv, int N, int L, int H, int sn, int sl, cudaStream_t st);
 int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                     int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
                     int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, void* stream);
@@ -51,6 +55,8 @@ struct Arena {
   size_t h1, qkv, lse, o, x_mid, z, layer_stride;  // per-layer block (training) or shared
   size_t h2, g;
   size_t dxb, dz, dh, d_o, dqkv, partial, delta;  // backward scratch
+  // compact buffers of the class-token-only last block (rows = samples), llc_vit_*_cls
+  size_t c_o, c_p, c_xmid, c_h2, c_z, c_g, c_dx, c_dxb, c_dz, c_dh, c_do;
   size_t total;
 };
 
@@ -84,6 +90,21 @@ Arena plan(const Dims& d, int training) {
     a.delta = take((size_t)d.N * d.H * d.L * 4);   // rowsum(dO o O) for the attention backward
   } else {
     a.dxb = a.dz = a.dh = a.d_o = a.dqkv = a.partial = a.delta = 0;
+  }
+  a.c_o = take((size_t)d.N * (d.D + LLC_LORA_LD) * 2);
+  a.c_p = take((size_t)d.N * d.H * d.L * 4);
+  a.c_xmid = take((size_t)d.N * d.D * 4);
+  a.c_h2 = take((size_t)d.N * d.D * 2);
+  a.c_z = take((size_t)d.N * d.M * 2);
+  a.c_g = take((size_t)d.N * d.M * 2);
+  if (training) {
+    a.c_dx = take((size_t)d.N * d.D * 4);
+    a.c_dxb = take((size_t)d.N * (d.D + LLC_LORA_LD) * 2);
+    a.c_dz = take((size_t)d.N * d.M * 2);
+    a.c_dh = take((size_t)d.N * d.D * 2);
+    a.c_do = take((size_t)d.N * d.D * 2);
+  } else {
+    a.c_dx = a.c_dxb = a.c_dz = a.c_dh = a.c_do = 0;
   }
   a.total = off;
   return a;
@@ -286,6 +307,170 @@ extern "C" size_t llc_vit_arena_bytes(const llc_vit_cfg* cfg, int N, int trainin
   return plan(make_dims(cfg, N), training).total;
 }
 
+namespace {
+// ------------------------------------------------------------------------------------------------
+// Class-token-only last block. The tower returns ln_post(x[:, 0, :]) @ proj (reference
+// models/clip/model.py:782-785): of the last block's output only the CLS rows are ever read, and
+// on the way back only they carry a gradient. LN1, the qkv GEMM (K and V of every token) and the
+// in-projection's backward stay full size; attention runs for one query per (sample, head), and
+// out-proj, LN2 and the MLP shrink from N*L rows to N rows. Identical results on the CLS rows.
+struct ClsBufs {
+  __nv_bfloat16 *o, *h2, *z, *g, *dxb, *dz, *dh, *d_o;
+  float *p, *x_mid, *dx;
+};
+
+ClsBufs fill_cls(const Arena& a, uint8_t* base) {
+  ClsBufs c;
+  c.o = reinterpret_cast<__nv_bfloat16*>(base + a.c_o);
+  c.p = reinterpret_cast<float*>(base + a.c_p);
+  c.x_mid = reinterpret_cast<float*>(base + a.c_xmid);
+  c.h2 = reinterpret_cast<__nv_bfloat16*>(base + a.c_h2);
+  c.z = reinterpret_cast<__nv_bfloat16*>(base + a.c_z);
+  c.g = reinterpret_cast<__nv_bfloat16*>(base + a.c_g);
+  c.dx = reinterpret_cast<float*>(base + a.c_dx);
+  c.dxb = reinterpret_cast<__nv_bfloat16*>(base + a.c_dxb);
+  c.dz = reinterpret_cast<__nv_bfloat16*>(base + a.c_dz);
+  c.dh = reinterpret_cast<__nv_bfloat16*>(base + a.c_dh);
+  c.d_o = reinterpret_cast<__nv_bfloat16*>(base + a.c_do);
+  return c;
+}
+
+// dst[n, :] = src[n * row_stride, :] (fp32) and its bf16 copy (pitch ld_b)
+__global__ void gather_cls_rows_kernel(const float* __restrict__ src, size_t row_stride, int N, int D,
+                                       float* __restrict__ dst, __nv_bfloat16* __restrict__ dstb,
+                                       int ld_b) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float v = src[(size_t)n * row_stride + c];
+    dst[(size_t)n * D + c] = v;
+    dstb[(size_t)n * ld_b + c] = __float2bfloat16_rn(v);
+  }
+}
+// dx[n * row_stride, :] += add[n, :]; bf16 copy refreshed
+__global__ void add_cls_rows_kernel(float* __restrict__ dx, size_t row_stride, int N, int D,
+                                    const float* __restrict__ add, __nv_bfloat16* __restrict__ dxb,
+                                    size_t row_stride_b) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float v = dx[(size_t)n * row_stride + c] + add[(size_t)n * D + c];
+    dx[(size_t)n * row_stride + c] = v;
+    dxb[(size_t)n * row_stride_b + c] = __float2bfloat16_rn(v);
+  }
+}
+
+int block_forward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
+                      const ClsBufs& c, int N, int L, void* stream) {
+  const int D = cfg->width, M = cfg->mlp_dim, H = cfg->heads, r = cfg->lora_r;
+  const int T = N * L, DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;
+  const int KA = D + LLC_LORA_PAD;
+  cudaStream_t st = (cudaStream_t)stream;
+  llc_gemm_epi e;
+  // full size: x -> ln_1 -> h1 | u ; qkv of every token (K, V)
+  RUN(llc_ln_fwd(b->x_in, D, w->ln1_g, w->ln1_b, T, D, b->h1, DA, w->in_A, r, stream));
+  e = llc_gemm_epi{};
+  e.bias = w->bqkv; e.out = b->qkv; e.ld_out = QA;
+  RUN(llc_gemm_bf16_tn(b->h1, DA, w->wqkv_aug, DA, T, 3 * D, KA, &e, stream));
+  // one query per (sample, head)
+  RUN(llc_attn_cls_fwd(b->qkv, QA, c.o, DA, c.p, N, L, H, L, 1, st));
+  e = llc_gemm_epi{};
+  e.out = c.o + D; e.ld_out = DA;
+  RUN(llc_gemm_bf16_tn(c.o, DA, w->f_out_A, D, N, LLC_LORA_PAD, D, &e, stream));
+  // x_mid[cls] = x[cls] + o W_o^T + b_o + s (o A_o^T) B_o^T : N rows, residual rows L*D apart
+  e = llc_gemm_epi{};
+  e.bias = w->bo; e.resid = b->x_in; e.ld_resid = L * D; e.out = c.x_mid; e.ld_out = D;
+  e.out_fp32 = 1;
+  RUN(llc_gemm_bf16_tn(c.o, DA, w->wo_aug, DA, N, D, KA, &e, stream));
+  RUN(llc_ln_fwd(c.x_mid, D, w->ln2_g, w->ln2_b, N, D, c.h2, D, nullptr, 0, stream));
+  e = llc_gemm_epi{};
+  e.bias = w->bfc; e.act = 1; e.out = c.z; e.ld_out = M; e.out2 = c.g; e.ld_out2 = M;
+  RUN(llc_gemm_bf16_tn(c.h2, D, w->wfc, D, N, M, D, &e, stream));
+  // x_out[cls rows of the full buffer] = x_mid + g W_proj^T + b
+  e = llc_gemm_epi{};
+  e.bias = w->bproj; e.resid = c.x_mid; e.ld_resid = D; e.out = b->x_out; e.ld_out = L * D;
+  e.out_fp32 = 1;
+  RUN(llc_gemm_bf16_tn(c.g, M, w->wproj, M, N, D, M, &e, stream));
+  return 0;
+}
+
+int block_backward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
+                       const ClsBufs& c, const llc_block_bwd_bufs* s, int N, int L, int need_dx_in,
+                       void* stream) {
+  const int D = cfg->width, M = cfg->mlp_dim, H = cfg->heads, r = cfg->lora_r;
+  const float sc = cfg->lora_scale;
+  const int T = N * L, DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;
+  const int KA = D + LLC_LORA_PAD, KQ = 3 * D + LLC_LORA_PAD;
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(b->h1);
+  __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(s->dqkv);
+  __nv_bfloat16* dxb_full = reinterpret_cast<__nv_bfloat16*>(s->dxb);
+  llc_gemm_epi e;
+  // the head's gradient sits in the CLS rows of the full buffer
+  gather_cls_rows_kernel<<<N, 256, 0, st>>>(s->dx, (size_t)L * D, N, D, c.dx, c.dxb, DA);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("gather_cls_rows_kernel");
+  // MLP backward on N rows
+  e = llc_gemm_epi{};
+  e.act = 2; e.aux = c.z; e.ld_aux = M; e.out = c.dz; e.ld_out = M;
+  RUN(llc_gemm_bf16_tn(c.dxb, DA, w->wprojT, D, N, M, D, &e, stream));
+  e = llc_gemm_epi{};
+  e.out = c.dh; e.ld_out = D;
+  RUN(llc_gemm_bf16_tn(c.dz, M, w->wfcT, M, N, D, M, &e, stream));
+  RUN(llc_ln_bwd(c.x_mid, D, w->ln2_g, c.dh, D, c.dx, c.dx, N, D, c.dxb, DA, nullptr, 0, 0.f,
+                 stream));
+  // out-proj LoRA: du_o = s dx_mid B_o, dB_o = s dx_mid^T u_o, dA_o = du_o^T o   (N rows)
+  const size_t preg = (size_t)llc_lora_side_max_partials() * 3 * D * 2;   // floats per region
+  float* pr[4] = {s->partial, s->partial + preg, s->partial + 2 * preg, s->partial + 3 * preg};
+  int np4[4] = {0, 0, 0, 0};
+  e = llc_gemm_epi{};
+  e.out = c.dxb + D; e.ld_out = DA;
+  RUN(llc_gemm_bf16_tn(c.dxb, DA, w->f_out_B, D, N, LLC_LORA_PAD, D, &e, stream));
+  RUN(llc_lora_side(c.dxb, DA, N, D, r, nullptr, 0, 0, 0.f, c.o + D, DA, pr[0], &np4[0], stream));
+  RUN(llc_lora_side(c.o, DA, N, D, r, nullptr, 0, 0, 0.f, c.dxb + D, DA, pr[1], &np4[1], stream));
+  // d_o = dx_mid W_o + du_o A_o ; attention backward of the CLS query -> dqkv of every token
+  e = llc_gemm_epi{};
+  e.out = c.d_o; e.ld_out = D;
+  RUN(llc_gemm_bf16_tn(c.dxb, DA, w->woT_aug, DA, N, D, KA, &e, stream));
+  RUN(llc_attn_cls_bwd(b->qkv, QA, c.p, c.d_o, D, s->dqkv, QA, N, L, H, L, 1, st));
+  // in-projection: full size again
+  if (llc_lora_fused_eligible(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D,
+                              QA)) {
+    RUN(llc_lora_fused_tc(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D, QA,
+                          pr[2], &np4[2], st));
+  } else {
+    e = llc_gemm_epi{};
+    e.out = dqkv + 3 * D; e.ld_out = QA;
+    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
+    RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, pr[2], &np4[2],
+                      stream));
+  }
+  RUN(llc_lora_side(b->h1, DA, T, D, r, nullptr, 0, 0, 0.f, dqkv + 3 * D, QA, pr[3], &np4[3],
+                    stream));
+  {
+    llc_finish_job jobs[4] = {
+        {pr[0], np4[0], D, sc, w->g_out_B, r, 1},
+        {pr[1], np4[1], D, 1.0f, w->g_out_A, 1, D},
+        {pr[2], np4[2], 3 * D, sc, w->g_in_B, r, 1},
+        {pr[3], np4[3], D, 1.0f, w->g_in_A, 1, D},
+    };
+    RUN(llc_lora_colsum_finish_multi(jobs, 4, r, stream));
+  }
+  if (need_dx_in) {
+    // dx_in = LN1'(dh1) for every token; the residual path adds dx_mid on the CLS rows only
+    e = llc_gemm_epi{};
+    e.out = s->dh; e.ld_out = D;
+    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->wqkvT_aug, QA, T, D, KQ, &e, stream));
+    RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, nullptr, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
+                   stream));
+    add_cls_rows_kernel<<<N, 256, 0, st>>>(s->dx, (size_t)L * D, N, D, c.dx, dxb_full,
+                                           (size_t)L * DA);
+    LLC_COUNT_LAUNCH();
+    LLC_LAUNCH_CHECK("add_cls_rows_kernel");
+  }
+  return 0;
+}
+
+}  // namespace
+
 extern "C" int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weights* w,
                                     void* stream) {
   RUN(check_cfg(cfg, "llc_vit_refresh_lora"));
@@ -294,9 +479,9 @@ extern "C" int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weight
                               (cudaStream_t)stream);
 }
 
-extern "C" int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w,
-                               const float* images, int N, void* arena, int training,
-                               float** x_final, void* stream) {
+static int vit_forward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, const float* images,
+                            int N, void* arena, int training, float** x_final, void* stream,
+                            bool cls_only) {
   RUN(check_cfg(cfg, "llc_vit_forward"));
   LLC_REQUIRE(w && w->layers && images && arena && N > 0, "llc_vit_forward: bad args");
   const Dims d = make_dims(cfg, N);
@@ -314,14 +499,29 @@ extern "C" int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w,
   llc_block_bufs b;
   for (int l = 0; l < d.layers; ++l) {
     fill_bufs(d, a, base, l, training, &b);
-    RUN(llc_block_forward(cfg, &w->layers[l], &b, N, d.L, d.L, 1, 0, stream));
+    if (cls_only && l == d.layers - 1)
+      RUN(block_forward_cls(cfg, &w->layers[l], &b, fill_cls(a, base), N, d.L, stream));
+    else
+      RUN(llc_block_forward(cfg, &w->layers[l], &b, N, d.L, d.L, 1, 0, stream));
   }
   if (x_final) *x_final = b.x_out;
   return 0;
 }
 
-extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N,
-                                void* arena, float* dx_final, void* stream) {
+extern "C" int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w,
+                               const float* images, int N, void* arena, int training,
+                               float** x_final, void* stream) {
+  return vit_forward_impl(cfg, w, images, N, arena, training, x_final, stream, false);
+}
+
+extern "C" int llc_vit_forward_cls(const llc_vit_cfg* cfg, const llc_vit_weights* w,
+                                   const float* images, int N, void* arena, int training,
+                                   float** x_final, void* stream) {
+  return vit_forward_impl(cfg, w, images, N, arena, training, x_final, stream, true);
+}
+
+static int vit_backward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N, void* arena,
+                             float* dx_final, void* stream, bool cls_only) {
   RUN(check_cfg(cfg, "llc_vit_backward"));
   LLC_REQUIRE(w && w->layers && arena && dx_final && N > 0, "llc_vit_backward: bad args");
   const Dims d = make_dims(cfg, N);
@@ -336,11 +536,24 @@ extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w
   s.dqkv = base + a.dqkv;
   s.partial = reinterpret_cast<float*>(base + a.partial);
   s.delta = reinterpret_cast<float*>(base + a.delta);
-  RUN(llc_cast_bf16(dx_final, s.dxb, d.T, d.D, d.D + LLC_LORA_LD, stream));
+  if (!cls_only) RUN(llc_cast_bf16(dx_final, s.dxb, d.T, d.D, d.D + LLC_LORA_LD, stream));
   llc_block_bufs b;
   for (int l = d.layers - 1; l >= 0; --l) {
     fill_bufs(d, a, base, l, 1, &b);
-    RUN(llc_block_backward(cfg, &w->layers[l], &b, &s, N, d.L, d.L, 1, 0, l > 0, stream));
+    if (cls_only && l == d.layers - 1)
+      RUN(block_backward_cls(cfg, &w->layers[l], &b, fill_cls(a, base), &s, N, d.L, l > 0, stream));
+    else
+      RUN(llc_block_backward(cfg, &w->layers[l], &b, &s, N, d.L, d.L, 1, 0, l > 0, stream));
   }
   return 0;
+}
+
+extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N,
+                                void* arena, float* dx_final, void* stream) {
+  return vit_backward_impl(cfg, w, N, arena, dx_final, stream, false);
+}
+
+extern "C" int llc_vit_backward_cls(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N,
+                                    void* arena, float* dx_final, void* stream) {
+  return vit_backward_impl(cfg, w, N, arena, dx_final, stream, true);
 }

@@ -7,6 +7,8 @@ on), and the activation arena sized by llc_vit_arena_bytes. All compute is llc_*
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import torch
@@ -118,9 +120,12 @@ class VitEngine:
         self._refresh_lora(force_refresh)   # force: CUDA-graph capture must always contain it
         mode = int(self.arena_key[1])
         xf = C.c_void_p()
-        K.check(K.load().llc_vit_forward(C.byref(self.cfg), C.byref(self.weights),
-                                         images.data_ptr(), N, self.arena.data_ptr(), mode,
-                                         C.byref(xf), K.stream_ptr()), "llc_vit_forward")
+        # every consumer of this engine reads only the class-token rows (ln_post(x[:, 0]) @ proj):
+        # the last block runs class-token-only unless LLC_FULL_LAST_BLOCK is set (A/B, tests)
+        self._cls_only = os.environ.get("LLC_FULL_LAST_BLOCK") is None
+        fwd = K.load().llc_vit_forward_cls if self._cls_only else K.load().llc_vit_forward
+        K.check(fwd(C.byref(self.cfg), C.byref(self.weights), images.data_ptr(), N,
+                    self.arena.data_ptr(), mode, C.byref(xf), K.stream_ptr()), "llc_vit_forward")
         off = xf.value - self.arena.data_ptr()
         T = N * self.L
         self.x_final = self.arena[off:off + T * self.D * 4].view(torch.float32).view(T, self.D)
@@ -143,9 +148,15 @@ class VitEngine:
 
     # ------------------------------------------------------------------------------------------
     def _vit_backward(self):
-        K.check(K.load().llc_vit_backward(C.byref(self.cfg), C.byref(self.weights), self.N,
-                                          self.arena.data_ptr(), self.dx.data_ptr(),
-                                          K.stream_ptr()), "llc_vit_backward")
+        bwd = K.load().llc_vit_backward_cls if self._cls_only else K.load().llc_vit_backward
+        K.check(bwd(C.byref(self.cfg), C.byref(self.weights), self.N, self.arena.data_ptr(),
+                    self.dx.data_ptr(), K.stream_ptr()), "llc_vit_backward")
+
+    def _clear_dx(self):
+        # the full backward consumes dx for every token (zero except the CLS rows the head
+        # writes); the class-token-only backward reads just those rows
+        if not self._cls_only:
+            self.dx.zero_()
 
     def _check_trainable(self):
         if self.dx is None or not getattr(self, "_trained_arena", False):
@@ -158,7 +169,7 @@ class VitEngine:
         h.keep = h.keep + (d_feat,)
         h.args.d_feat = d_feat.data_ptr()
         h.args.skip_logit_grad = 1
-        self.dx.zero_()
+        self._clear_dx()
         h.backward(self.dx)
         self._vit_backward()
 
@@ -170,7 +181,7 @@ class VitEngine:
             head.keep = head.keep + (d_feat,)
             head.args.d_feat = d_feat.data_ptr()
         head.args.skip_logit_grad = 0
-        self.dx.zero_()
+        self._clear_dx()
         head.backward(self.dx, d_probs, loss_scale)
         self._vit_backward()
 

@@ -143,6 +143,47 @@ def test_fused_trainer_step_matches_fp64_oracle(cfg, n, c, gather):
     assert rel(head.feat.cpu(), want["feat"]) < TOL
 
 
+@pytest.mark.parametrize("cfg,n", [
+    (vo.VitCfg(image_size=64, patch=16, width=768, layers=2, heads=12, embed_dim=512), 9),
+    (vo.VitCfg(image_size=28, patch=14, width=128, layers=1, heads=2, embed_dim=64), 3)])
+def test_class_token_only_last_block_equals_full(cfg, n, monkeypatch):
+    """llc_vit_forward_cls / llc_vit_backward_cls (the last block computed for the class-token rows
+    only) against the full-size last block: same features, probabilities and LoRA gradients (the
+    two paths differ only in the rounding of the last block's attention probabilities, which
+    stay fp32 on the one-query path), and both within the parity policy of the fp64 oracle."""
+    c, seed = 10, 77
+    w = vo.synth_weights(cfg, seed)
+    images, _ = synth_inputs(cfg, n, c, seed + 1)
+    text = vo.synth_text_features(c, cfg.embed_dim, seed + 2)
+    labels = np.random.default_rng(seed + 3).integers(0, c, size=(n,)).astype(np.int64)
+    want = vo.online_step_oracle(images, labels, w, text, cfg)
+    names = [k for k in w if "lora" in k]
+
+    def run(full):
+        if full:
+            monkeypatch.setenv("LLC_FULL_LAST_BLOCK", "1")
+        else:
+            monkeypatch.delenv("LLC_FULL_LAST_BLOCK", raising=False)
+        m = build_model(cfg, w)
+        eng = m.model.visual.engine()
+        eng.forward(torch.from_numpy(images).cuda(), training=True)
+        head = eng.head(torch.from_numpy(text).cuda(), 1.0 / 0.07,
+                        labels=torch.from_numpy(labels).cuda())
+        eng.backward_from_head(head)
+        torch.cuda.synchronize()
+        assert eng._cls_only == (not full)
+        grads = {k: g.cpu().numpy().copy() for k, g in zip(names, eng.lora_grad_views)}
+        return head.feat.cpu().numpy().copy(), head.probs.cpu().numpy().copy(), grads, head
+
+    f_cls, p_cls, g_cls, h_cls = run(False)
+    f_full, p_full, g_full, _ = run(True)
+    assert rel(f_cls, f_full) < 3e-3
+    assert rel(p_cls, p_full) < 3e-3
+    flat = lambda g: np.concatenate([np.asarray(g[k], np.float64).ravel() for k in names])
+    assert rel(flat(g_cls), flat(g_full)) < 5e-3
+    check_step(p_cls, float(h_cls.loss_rows.sum()), h_cls.pred.cpu().numpy(), g_cls, want, cfg)
+
+
 @pytest.mark.parametrize("n", [1, 2])
 def test_single_image_batches(n):
     """Smallest batches (one sample: the 3-D token maps degenerate to one slice)."""
