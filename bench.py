@@ -404,7 +404,9 @@ def run_ours(args):
                    "parallelism": f"dp{world}", "weights": "random-init",
                    "l2": "inputs larger than L2 (154 MB images per step; activations 1 GB/layer)",
                    "loss": "CE on probabilities (reference double softmax)",
-                   "cuda_graph": not args.no_graph},
+                   "cuda_graph": not args.no_graph,
+                   "last_block": ("class-token rows only (llc_vit_forward_cls: identical outputs)"
+                                  if os.environ.get("LLC_FULL_LAST_BLOCK") is None else "full")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
