@@ -29,21 +29,34 @@ __device__ __forceinline__ float block_max_128(float v, float* red) {
   __syncthreads();
   return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
 }
-// dot of one 64-element bf16 row (128 B, 16 B aligned) with a 64-float vector in shared memory
-__device__ __forceinline__ float row_dot(const __nv_bfloat16* row, const float* v) {
-  float acc = 0.f;
+// out[k] = row_k . v for the keys of one (sample, head): one warp per key, lane l owns head dims
+// 2l, 2l+1 (one coalesced 128 B row per warp load), four keys in flight per warp
+__device__ __forceinline__ void rows_dot(const __nv_bfloat16* base, size_t row_stride, int L,
+                                         float v0, float v1, float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int U = 8;     // keys in flight per warp
+  for (int k0 = warp * U; k0 < L; k0 += 4 * U) {
+    float acc[U];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(row + c * 8);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack_bf16(w[e]);
-      acc = fmaf(f.x, v[c * 8 + 2 * e], acc);
-      acc = fmaf(f.y, v[c * 8 + 2 * e + 1], acc);
+    for (int i = 0; i < U; ++i) {
+      acc[i] = 0.f;
+      if (k0 + i < L) {
+        const float2 f = unpack_bf16(
+            *reinterpret_cast<const uint32_t*>(base + (size_t)(k0 + i) * row_stride + 2 * lane));
+        acc[i] = f.x * v0 + f.y * v1;
+      }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < U; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    // every lane holds all U sums: lane i stores the i-th
+    float mine = acc[0];
+#pragma unroll
+    for (int i = 1; i < U; ++i) mine = lane == i ? acc[i] : mine;
+    if (lane < U && k0 + lane < L) out[k0 + lane] = mine;
   }
-  return acc;
 }
 
 // smem: q[64] | red[4] | p[L]
@@ -60,12 +73,11 @@ attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, __nv_bflo
   const size_t tok0 = (size_t)n * sn;
   if (tid < HD) q[tid] = 0.125f * __bfloat162float(qkv[tok0 * ld_qkv + h * HD + tid]);
   __syncthreads();
+  rows_dot(qkv + tok0 * ld_qkv + D + h * HD, (size_t)sl * ld_qkv, L, q[2 * (tid & 31)],
+           q[2 * (tid & 31) + 1], p);
+  __syncthreads();
   float m = -INFINITY;
-  for (int k = tid; k < L; k += kThreads) {
-    const float s = row_dot(qkv + (tok0 + (size_t)k * sl) * ld_qkv + D + h * HD, q);
-    p[k] = s;
-    m = fmaxf(m, s);
-  }
+  for (int k = tid; k < L; k += kThreads) m = fmaxf(m, p[k]);
   m = block_max_128(m, red);
   float z = 0.f;
   for (int k = tid; k < L; k += kThreads) {
@@ -85,6 +97,7 @@ attn_cls_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, __nv_bflo
   // warps own every fourth key
   const int d2 = (tid & 31) * 2, kq = tid >> 5;
   float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
   for (int k = kq; k < L; k += 4) {
     const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(
         qkv + (tok0 + (size_t)k * sl) * ld_qkv + 2 * D + h * HD + d2));
@@ -121,40 +134,35 @@ attn_cls_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, const flo
     go[tid] = __bfloat162float(d_o_cls[(size_t)n * ld_do + h * HD + tid]);
   }
   __syncthreads();
+  rows_dot(qkv + tok0 * ld_qkv + 2 * D + h * HD, (size_t)sl * ld_qkv, L, go[2 * (tid & 31)],
+           go[2 * (tid & 31) + 1], ds);
+  __syncthreads();
   float dl = 0.f;
   for (int k = tid; k < L; k += kThreads) {
     const float pk = p_cls[(size_t)blockIdx.x * L + k];
-    const float dp = row_dot(qkv + (tok0 + (size_t)k * sl) * ld_qkv + 2 * D + h * HD, go);
     p[k] = pk;
-    ds[k] = dp;
-    dl = fmaf(pk, dp, dl);
+    dl = fmaf(pk, ds[k], dl);
   }
   dl = block_sum_128(dl, red);
   for (int k = tid; k < L; k += kThreads) ds[k] = p[k] * (ds[k] - dl);
   __syncthreads();
-  // dK_k = dS_k q (q already carries 1/8), dV_k = P_k dO, dQ_k = 0 for k > 0: thread-per-key rows
-  for (int k = tid; k < L; k += kThreads) {
-    __nv_bfloat16* row = dqkv + (tok0 + (size_t)k * sl) * ld_dqkv + h * HD;
-    const float dsk = ds[k], pk = p[k];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint4 uk, uv;
-      uk.x = pack_bf16(dsk * q[c * 8], dsk * q[c * 8 + 1]);
-      uk.y = pack_bf16(dsk * q[c * 8 + 2], dsk * q[c * 8 + 3]);
-      uk.z = pack_bf16(dsk * q[c * 8 + 4], dsk * q[c * 8 + 5]);
-      uk.w = pack_bf16(dsk * q[c * 8 + 6], dsk * q[c * 8 + 7]);
-      uv.x = pack_bf16(pk * go[c * 8], pk * go[c * 8 + 1]);
-      uv.y = pack_bf16(pk * go[c * 8 + 2], pk * go[c * 8 + 3]);
-      uv.z = pack_bf16(pk * go[c * 8 + 4], pk * go[c * 8 + 5]);
-      uv.w = pack_bf16(pk * go[c * 8 + 6], pk * go[c * 8 + 7]);
-      *reinterpret_cast<uint4*>(row + D + c * 8) = uk;
-      *reinterpret_cast<uint4*>(row + 2 * D + c * 8) = uv;
-      if (k > 0) *reinterpret_cast<uint4*>(row + c * 8) = make_uint4(0, 0, 0, 0);
+  // dK_k = dS_k q (q already carries 1/8), dV_k = P_k dO, dQ_k = 0 for k > 0: one warp per key,
+  // lane l writes head dims 2l, 2l+1 (coalesced 128 B rows)
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const float q0 = q[2 * lane], q1 = q[2 * lane + 1], g0 = go[2 * lane], g1 = go[2 * lane + 1];
+    for (int k = warp; k < L; k += 4) {
+      __nv_bfloat16* row = dqkv + (tok0 + (size_t)k * sl) * ld_dqkv + h * HD + 2 * lane;
+      const float dsk = ds[k], pk = p[k];
+      *reinterpret_cast<uint32_t*>(row + D) = pack_bf16(dsk * q0, dsk * q1);
+      *reinterpret_cast<uint32_t*>(row + 2 * D) = pack_bf16(pk * g0, pk * g1);
+      if (k > 0) *reinterpret_cast<uint32_t*>(row) = 0u;
     }
   }
   // dq[d] = sum_k dS_k K[k, d] / 8
   const int d2 = (tid & 31) * 2, kq = tid >> 5;
   float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
   for (int k = kq; k < L; k += 4) {
     const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(
         qkv + (tok0 + (size_t)k * sl) * ld_qkv + D + h * HD + d2));
