@@ -19,7 +19,7 @@ int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const 
                     int causal, cudaStream_t st);
 int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
-                     int sn, int sl, int causal, float* delta_ws, cudaStream_t st);
+                     int sn, int sl, int causal, float* delta_ws, int delta_ready, cudaStream_t st);
 int llc_attn_bwd_tc4_smem(int L);
 int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
@@ -546,11 +546,18 @@ extern "C" int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, floa
                                  (cudaStream_t)stream)));
 }
 
+// true when llc_attn_bwd_ws runs the unit-pipelined kernel for this L (the one that reads delta)
+bool llc_attn_bwd_uses_delta(int L) {
+  static const bool other = getenv("LLC_ATTN_LEGACY") || getenv("LLC_ATTN_BWD2") || getenv("LLC_ATTN_BWD3");
+  return !other && llc_attn_tc_eligible(L) && llc_attn_bwd_tc4_smem(L) <= 227 * 1024;
+}
+
 // llc_attn_bwd with caller-provided scratch for delta = rowsum(dO o O) ([N*H*L] floats; nullptr:
 // library-owned scratch, which cannot grow under stream capture)
 int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                     int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
-                    int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, void* stream) {
+                    int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, int delta_ready,
+                    void* stream) {
   if (int rc = check_common(qkv, ld_qkv, N, L, H, "llc_attn_bwd")) return rc;
   LLC_REQUIRE(o && d_o && lse && dqkv, "llc_attn_bwd: null pointer");
   LLC_REQUIRE(ld_o % 8 == 0 && ld_do % 8 == 0 && ld_dqkv % 2 == 0 && ld_dqkv >= 3 * H * HD,
@@ -563,7 +570,8 @@ int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const 
   if (!legacy && !v2 && !v3 && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 &&
       ((uintptr_t)dqkv & 15) == 0 && llc_attn_bwd_tc4_smem(L) <= 227 * 1024)
     return llc_attn_bwd_tc4(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
-                            tok_stride_n, tok_stride_l, causal, delta_ws, (cudaStream_t)stream);
+                            tok_stride_n, tok_stride_l, causal, delta_ws, delta_ready,
+                            (cudaStream_t)stream);
   if (!legacy && !v2 && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
     return llc_attn_bwd_tc3(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
                             tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream);
@@ -580,5 +588,5 @@ extern "C" int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o
                             int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L,
                             int H, int tok_stride_n, int tok_stride_l, int causal, void* stream) {
   return llc_attn_bwd_ws(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
-                         tok_stride_n, tok_stride_l, causal, nullptr, stream);
+                         tok_stride_n, tok_stride_l, causal, nullptr, 0, stream);
 }

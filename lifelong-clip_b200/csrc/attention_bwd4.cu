@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
 
 struct Bwd4Params {
   const float* lse;     // [N*H, L] log-sum-exp of the scaled scores (natural log)
-  const float* delta;   // [N*H, L] rowsum(dO o O), from attn_delta_kernel
+  const float* delta;   // [tokens, H] rowsum(dO o O) per (token, head)
   int N, L, H, LK, NT, NU, sn, sl, causal, mat_bytes, dbg;
 };
 
@@ -459,10 +459,12 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
     float pl0 = 0.f, pl1 = 0.f, pd0 = 0.f, pd1 = 0.f;
     auto prepare_load = [&](int pr) {
       const size_t base = (size_t)pr * p.L;
+      const int n = pr / p.H, h = pr % p.H;
+      const size_t tok = (size_t)n * p.sn;
       pl0 = tid3 < p.L ? p.lse[base + tid3] : 0.f;
-      pd0 = tid3 < p.L ? p.delta[base + tid3] : 0.f;
+      pd0 = tid3 < p.L ? p.delta[(tok + (size_t)tid3 * p.sl) * p.H + h] : 0.f;
       pl1 = tid3 + 128 < p.L ? p.lse[base + tid3 + 128] : 0.f;
-      pd1 = tid3 + 128 < p.L ? p.delta[base + tid3 + 128] : 0.f;
+      pd1 = tid3 + 128 < p.L ? p.delta[(tok + (size_t)(tid3 + 128) * p.sl) * p.H + h] : 0.f;
     };
     auto prepare_store = [&](int i) {
       float* ls_p = sLse + (i & 1) * 256;
@@ -526,7 +528,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
 #undef TR
 }
 
-// delta[(n H + h) L + l] = sum_d dO[tok, h, d] * O[tok, h, d], tok = n sn + l sl. Eight lanes per
+// delta[tok H + h] = sum_d dO[tok, h, d] * O[tok, h, d], tok = n sn + l sl. Eight lanes per
 // (token, head): one 16 B piece of each row, three shuffles. blockIdx.y = sample; HC = H as a
 // compile-time constant (0: runtime) keeps the index arithmetic off the XU pipe.
 template <int HC>
@@ -557,7 +559,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, int ld_o, const __nv_bflo
   d += __shfl_xor_sync(0xffffffffu, d, 1);
   d += __shfl_xor_sync(0xffffffffu, d, 2);
   d += __shfl_xor_sync(0xffffffffu, d, 4);
-  if (ok && piece == 0) delta[((size_t)n * H + h) * L + l] = d;
+  if (ok && piece == 0) delta[((size_t)n * sn + (size_t)l * sl) * H + h] = d;
 }
 
 int encode_rows(CUtensorMap* tm, const void* base, int cols, int ld, int L, int N, int sn, int sl,
@@ -583,7 +585,8 @@ static size_t g_delta_ws_floats = 0;
 
 int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
-                     int sn, int sl, int causal, float* delta_ws, cudaStream_t st) {
+                     int sn, int sl, int causal, float* delta_ws, int delta_ready, cudaStream_t st) {
+  // delta_ready: the caller already filled delta_ws[token * H + head] (llc_colsum_tc_delta)
   const size_t need = (size_t)N * H * L;
   if (!delta_ws) {
     if (g_delta_ws_floats < need) {
@@ -626,7 +629,7 @@ int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const
   const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
                  16.0 * N * H * (double)L * HD, st);
-  {
+  if (!(delta_ready && delta_ws)) {
     const dim3 dgrid((unsigned)((L * H + 31) / 32), (unsigned)N);
     const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(o);
     const __nv_bfloat16* db = reinterpret_cast<const __nv_bfloat16*>(d_o);

@@ -6,6 +6,10 @@
 // 8-stage ring, and tcgen05.mma consumes them AS THEY LIE: X tiles are the MN-major A operand
 // (M = columns), the 16-wide w rows are the MN-major B operand. The per-slice results go out as
 // partials that llc_lora_colsum_finish adds in a fixed order (bit-deterministic).
+// Optional rider (dA_o of the attention block, X = the attention output O): the same O tiles are
+// also what delta = rowsum(dO o O) of the attention backward needs, so the kernel can TMA-load the
+// matching dO tiles next to them and two warps form delta[token, head] from shared memory - the
+// separate delta pass (its own read of O from HBM) disappears.
 #include "common.cuh"
 
 namespace {
@@ -13,15 +17,17 @@ namespace {
 constexpr int kKB = 64;                      // tokens per k-block
 constexpr int kATile = 2 * kKB * 128;        // two 64-column atoms
 constexpr int kBTile = kKB * 128;            // w rows, 32 B used per 128 B row
-constexpr int kStage = kATile + kBTile;
-constexpr int kStages = 8;
+constexpr int kDTile = 2 * kKB * 128;        // dO tile of the delta rider (same shape as A)
+constexpr int kStage = kATile + kBTile + kDTile;
+constexpr int kStages = 5;
 constexpr int kSmem = 1024 + kStages * kStage + 256;
-constexpr int kThreads = 6 * 32;             // TMA, MMA, 4 x (w loader + epilogue)
+constexpr int kThreads = 6 * 32;             // TMA, MMA, 2 x w loader, 2 x delta (all 4: epilogue)
 
 __global__ void __launch_bounds__(kThreads, 1)
-lora_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ w,
-                      int ld_w, int T, int C, int R, int tok_per_split,
-                      float* __restrict__ partial) {
+lora_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
+                      const __nv_bfloat16* __restrict__ w, int ld_w, int T, int C, int R,
+                      int tok_per_split, float* __restrict__ partial, float* __restrict__ delta,
+                      int delta_ld) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -41,8 +47,8 @@ lora_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1 + 128);   // TMA issuer + every loader thread
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), 1 + 64);    // TMA issuer + every loader thread
+      mbar_init(smem_u32(&empty_bar[s]), delta ? 3 : 1);   // MMA commit (+ the two delta warps)
     }
     mbar_init(smem_u32(done_bar), 1);
     mbar_fence_init();
@@ -62,9 +68,13 @@ lora_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat
       if (elect_one()) {
         const uint32_t fb = smem_u32(&full_bar[stage]);
         const uint32_t sa = smem_u32(smem + stage * kStage);
-        mbar_expect_tx(fb, kATile);
+        mbar_expect_tx(fb, delta ? kATile + kDTile : kATile);
         tma_load_2d(sa, &tmX, fb, c0, t_begin + kb * kKB);
         tma_load_2d(sa + kKB * 128, &tmX, fb, c0 + 64, t_begin + kb * kKB);
+        if (delta) {
+          tma_load_2d(sa + kATile + kBTile, &tmD, fb, c0, t_begin + kb * kKB);
+          tma_load_2d(sa + kATile + kBTile + kKB * 128, &tmD, fb, c0 + 64, t_begin + kb * kKB);
+        }
       }
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -90,27 +100,64 @@ lora_colsum_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else {
-    // w loader: warp i stages token rows [16 i, 16 i + 16) of every k-block (two 16 B pieces per
-    // row, TMA's 128 B swizzle pattern so the tile reads as an MN-major operand)
-    const int wi = warp - 2;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-      const int row = wi * 16 + (lane >> 1), piece = lane & 1;
-      const int t = t_begin + kb * kKB + row;
-      // asynchronous 16 B copy (zero-filled past the slice end); its completion arrives on the
-      // stage's full barrier, so the loader never waits for a load
-      const uint32_t dst = smem_u32(smem + stage * kStage + kATile + row * 128 +
-                                    ((piece ^ (row & 7)) << 4));
-      const __nv_bfloat16* src = w + (size_t)(t < t_end ? t : t_begin) * ld_w + piece * 8;
-      const uint32_t nbytes = t < t_end ? 16u : 0u;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes)
-                   : "memory");
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
-                       smem_u32(&full_bar[stage]))
-                   : "memory");
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    if (warp < 4) {
+      // w loader: warps 2, 3 stage the 64 token rows of every k-block (thread = row, two 16 B
+      // pieces, TMA's 128 B swizzle pattern so the tile reads as an MN-major operand)
+      const int row = (warp - 2) * 32 + lane;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const int t = t_begin + kb * kKB + row;
+        // asynchronous 16 B copies (zero-filled past the slice end); their completion arrives on
+        // the stage's full barrier, so the loader never waits for a load
+        const __nv_bfloat16* src = w + (size_t)(t < t_end ? t : t_begin) * ld_w;
+        const uint32_t nbytes = t < t_end ? 16u : 0u;
+        const uint32_t dst = smem_u32(smem + stage * kStage + kATile + row * 128);
+#pragma unroll
+        for (int piece = 0; piece < 2; ++piece)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                           dst + ((piece ^ (row & 7)) << 4)),
+                       "l"(src + piece * 8), "r"(nbytes)
+                       : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                         smem_u32(&full_bar[stage]))
+                     : "memory");
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (delta) {
+      // delta rider: warps 4, 5, thread = token row of the k-block, both heads of the column tile:
+      // delta[t, head] = sum over the head's 64 columns of O[t, c] * dO[t, c], from the landed tiles
+      const int row = (warp - 4) * 32 + lane;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        const uint8_t* sO = smem + stage * kStage;
+        const uint8_t* sD = sO + kATile + kBTile;
+        const int t = t_begin + kb * kKB + row;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          float d = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t off = (uint32_t)(a * kKB * 128 + row * 128 + ((c ^ (row & 7)) << 4));
+            const uint4 ov = *reinterpret_cast<const uint4*>(sO + off);
+            const uint4 dv = *reinterpret_cast<const uint4*>(sD + off);
+            const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16(ow[e]), y = unpack_bf16(dw[e]);
+              d = fmaf(x.x, y.x, d);
+              d = fmaf(x.y, y.y, d);
+            }
+          }
+          if (t < t_end) delta[(size_t)t * delta_ld + (c0 >> 6) + a] = d;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));   // this warp is done reading
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
     }
     // epilogue: accumulator row = column c0 + 32 q + lane of X
     float* out = partial + ((size_t)blockIdx.y * C + c0) * R;
@@ -389,13 +436,22 @@ bool llc_colsum_tc_eligible(const void* X, int ld_x, int T, int C, const void* w
          ((uintptr_t)X & 15) == 0 && ((uintptr_t)w & 15) == 0;
 }
 
-int llc_colsum_tc(const void* X, int ld_x, int T, int C, int R, const void* w, int ld_w,
-                  float* partial, int* n_partials, cudaStream_t st) {
-  CUtensorMap tm;
+// d_o / delta: optional rider (see the header comment): delta[t * delta_ld + c / 64] =
+// sum over head c / 64 of X[t, c] * d_o[t, c]; requires C % 128 == 0 (it always is here)
+int llc_colsum_tc_delta(const void* X, int ld_x, int T, int C, int R, const void* w, int ld_w,
+                        float* partial, int* n_partials, const void* d_o, int ld_do, float* delta,
+                        int delta_ld, cudaStream_t st) {
+  CUtensorMap tm, td;
   if (int rc = llc_encode_tmap_2d(&tm, X, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)C,
                                   (uint64_t)T, (uint64_t)ld_x * 2, 64, kKB,
                                   CU_TENSOR_MAP_SWIZZLE_128B))
     return rc;
+  td = tm;
+  if (delta != nullptr)
+    if (int rc = llc_encode_tmap_2d(&td, d_o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)C,
+                                    (uint64_t)T, (uint64_t)ld_do * 2, 64, kKB,
+                                    CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
   const int mtiles = C / 128;
   int splits = llc_num_sms() / mtiles;
   if (splits < 1) splits = 1;
@@ -408,14 +464,22 @@ int llc_colsum_tc(const void* X, int ld_x, int T, int C, int R, const void* w, i
                                   kSmem));
     configured = true;
   }
-  LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 2, 2.0 * T * C * 16, 2.0 * T * C, st);
+  LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, delta ? 4 : 2, 2.0 * T * C * 16,
+                 (delta ? 4.0 : 2.0) * T * C, st);
   LLC_CUDA(llc_launch_pdl(lora_colsum_tc_kernel, dim3(mtiles, splits), dim3(kThreads), kSmem, st, tm,
-                          reinterpret_cast<const __nv_bfloat16*>(w), ld_w, T, C, R, per, partial));
+                          td, reinterpret_cast<const __nv_bfloat16*>(w), ld_w, T, C, R, per, partial,
+                          delta, delta_ld));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("lora_colsum_tc_kernel");
   *n_partials = splits;
   return 0;
+}
+
+int llc_colsum_tc(const void* X, int ld_x, int T, int C, int R, const void* w, int ld_w,
+                  float* partial, int* n_partials, cudaStream_t st) {
+  return llc_colsum_tc_delta(X, ld_x, T, C, R, w, ld_w, partial, n_partials, nullptr, 0, nullptr, 0,
+                             st);
 }
 
 extern "C" int llc_lora_side_fused(const void* X, int ld_x, int T, int C, int r, const void* w,

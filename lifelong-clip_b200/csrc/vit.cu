@@ -17,7 +17,13 @@ int llc_attn_cls_bwd(const void* qkv, int ld_qkv, const float* p_cls, const void
                      void* dqkv, int ld_dqkv, int N, int L, int H, int sn, int sl, cudaStream_t st);
 int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                     int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
-                    int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, void* stream);
+                    int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, int delta_ready,
+                    void* stream);
+bool llc_colsum_tc_eligible(const void* X, int ld_x, int T, int C, const void* w, int ld_w);
+int llc_colsum_tc_delta(const void* X, int ld_x, int T, int C, int R, const void* w, int ld_w,
+                        float* partial, int* n_partials, const void* d_o, int ld_do, float* delta,
+                        int delta_ld, cudaStream_t st);
+bool llc_attn_bwd_uses_delta(int L);
 
 namespace {
 
@@ -260,14 +266,23 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
     RUN(llc_gemm_bf16_tn(s->dxb, DA, w->f_out_B, D, T, LLC_LORA_PAD, D, &e, stream));
     RUN(llc_lora_side(s->dxb, DA, T, D, r, nullptr, 0, 0, 0.f, o + D, DA, pr[0], &np4[0], stream));
   }
-  // dA_o = du_o^T o
-  RUN(llc_lora_side(b->o, DA, T, D, r, nullptr, 0, 0, 0.f, dxb + D, DA, pr[1], &np4[1], stream));
   // d_o = dx_mid W_o + du_o A_o
   e = llc_gemm_epi{};
   e.out = s->d_o; e.ld_out = D;
   RUN(llc_gemm_bf16_tn(s->dxb, DA, w->woT_aug, DA, T, D, KA, &e, stream));
+  // dA_o = du_o^T o. The same pass over O also forms delta = rowsum(dO o O) for the attention
+  // backward (from the O tiles it streams anyway and the L2-hot dO), when the shapes allow
+  int delta_ready = 0;
+  if (s->delta && D == H * 64 && llc_attn_bwd_uses_delta(L) &&
+      llc_colsum_tc_eligible(b->o, DA, T, D, dxb + D, DA)) {
+    RUN(llc_colsum_tc_delta(b->o, DA, T, D, r, dxb + D, DA, pr[1], &np4[1], s->d_o, D, s->delta, H,
+                            cst));
+    delta_ready = 1;
+  } else {
+    RUN(llc_lora_side(b->o, DA, T, D, r, nullptr, 0, 0, 0.f, dxb + D, DA, pr[1], &np4[1], stream));
+  }
   RUN(llc_attn_bwd_ws(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
-                      s->delta, stream));
+                      s->delta, delta_ready, stream));
   // in-proj: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
   if (llc_lora_fused_eligible(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D,
                               QA)) {
