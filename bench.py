@@ -53,13 +53,14 @@ def train_flops_per_image(model: str) -> float:
 
 def executed_flops_per_image(model: str) -> float:
     """What the step actually executes: the last block runs class-token-only (out-proj, MLP and
-    the attention query side on 1 of L rows; the qkv GEMM, K/V and the in-projection backward stay
-    full size), see llc_vit_forward_cls. Everything else as train_flops_per_image."""
+    the Q projection on 1 of L rows; K, V and their backward stay full size), see
+    llc_vit_forward_cls. Everything else as train_flops_per_image."""
     S, p, D, layers, H, E = MODELS[model]
     L, m, r, hd = (S // p) ** 2 + 1, 4 * D, 4, 64
     full = train_flops_per_image(model)
-    # per image, last block: rows L -> 1 on out-proj + MLP (fwd and bwd), attention L*L -> L
-    lin_tail = 2 * (L - 1) * (D * D + 2 * D * m)
+    # per image, last block: rows L -> 1 on out-proj + MLP + the Q third of the in-projection (fwd
+    # and bwd), attention L*L -> L
+    lin_tail = 2 * (L - 1) * (D * D + 2 * D * m + D * D)
     attn_tail = 2 * 2 * H * (L - 1) * L * hd
     lora_tail = 2 * (L - 1) * (D * r + r * D)
     saved = (lin_tail + attn_tail + lora_tail) + (lin_tail + 2 * attn_tail + 2 * lora_tail)

@@ -380,11 +380,17 @@ int block_forward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_
   const int KA = D + LLC_LORA_PAD;
   cudaStream_t st = (cudaStream_t)stream;
   llc_gemm_epi e;
-  // full size: x -> ln_1 -> h1 | u ; qkv of every token (K, V)
+  // full size: x -> ln_1 -> h1 | u ; K and V of every token (output features D .. 3D), Q of the
+  // class tokens only (rows L apart)
   RUN(llc_ln_fwd(b->x_in, D, w->ln1_g, w->ln1_b, T, D, b->h1, DA, w->in_A, r, stream));
+  __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(b->qkv);
+  const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(w->wqkv_aug);
   e = llc_gemm_epi{};
-  e.bias = w->bqkv; e.out = b->qkv; e.ld_out = QA;
-  RUN(llc_gemm_bf16_tn(b->h1, DA, w->wqkv_aug, DA, T, 3 * D, KA, &e, stream));
+  e.bias = w->bqkv + D; e.out = qkv + D; e.ld_out = QA;
+  RUN(llc_gemm_bf16_tn(b->h1, DA, wqkv + (size_t)D * DA, DA, T, 2 * D, KA, &e, stream));
+  e = llc_gemm_epi{};
+  e.bias = w->bqkv; e.out = qkv; e.ld_out = L * QA;
+  RUN(llc_gemm_bf16_tn(b->h1, L * DA, wqkv, DA, N, D, KA, &e, stream));
   // one query per (sample, head)
   RUN(llc_attn_cls_fwd(b->qkv, QA, c.o, DA, c.p, N, L, H, L, 1, st));
   e = llc_gemm_epi{};
@@ -470,10 +476,16 @@ int block_backward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc
     RUN(llc_lora_colsum_finish_multi(jobs, 4, r, stream));
   }
   if (need_dx_in) {
-    // dx_in = LN1'(dh1) for every token; the residual path adds dx_mid on the CLS rows only
+    // dx_in = LN1'(dh1) for every token; the residual path adds dx_mid on the CLS rows only.
+    // dQ is zero outside the class-token rows: the full-size GEMM contracts over K, V and the
+    // LoRA columns only (K range D .. 3D+16), the class-token rows are redone over all of K
+    const __nv_bfloat16* wT = reinterpret_cast<const __nv_bfloat16*>(w->wqkvT_aug);
     e = llc_gemm_epi{};
     e.out = s->dh; e.ld_out = D;
-    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->wqkvT_aug, QA, T, D, KQ, &e, stream));
+    RUN(llc_gemm_bf16_tn(dqkv + D, QA, wT + D, QA, T, D, KQ - D, &e, stream));
+    e = llc_gemm_epi{};
+    e.out = s->dh; e.ld_out = L * D;
+    RUN(llc_gemm_bf16_tn(s->dqkv, L * QA, w->wqkvT_aug, QA, N, D, KQ, &e, stream));
     RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, nullptr, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
                    stream));
     add_cls_rows_kernel<<<N, 256, 0, st>>>(s->dx, (size_t)L * D, N, D, c.dx, dxb_full,
