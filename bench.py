@@ -189,12 +189,22 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "classes": args.classes},
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+def workload_config(args, world: int) -> dict:
+    """The workload both arms report (BASELINE.json configs[1] on `world` GPUs, weak scaling)."""
+    S, p = MODELS[args.model][0], MODELS[args.model][1]
+    return {"workload": workload_name(args), "batch_per_gpu": args.batch,
+            "global_batch": args.batch * world, "classes": args.classes,
+            "tokens": (S // p) ** 2 + 1, "parallelism": f"dp{world}", "weights": "random-init",
+            "l2": "inputs larger than L2 (154 MB images per step; activations 1 GB/layer)",
+            "loss": "CE on probabilities (reference double softmax)"}
 
 
 def workload_name(args) -> str:
@@ -400,11 +410,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(args),
-                   "batch_per_gpu": B, "global_batch": gB, "classes": C, "tokens": (S // p) ** 2 + 1,
-                   "parallelism": f"dp{world}", "weights": "random-init",
-                   "l2": "inputs larger than L2 (154 MB images per step; activations 1 GB/layer)",
-                   "loss": "CE on probabilities (reference double softmax)",
+        "config": {**workload_config(args, world),
                    "cuda_graph": not args.no_graph,
                    "last_block": ("class-token rows only (llc_vit_forward_cls: identical outputs)"
                                   if os.environ.get("LLC_FULL_LAST_BLOCK") is None else "full")},
