@@ -335,7 +335,10 @@ extern "C" int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
   // leave most SMs without a tile.
   const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
   const bool use256 = (N % 256 == 0) && tiles256 >= llc_num_sms();
-  const bool use32 = N <= 32;   // rank-r row products (N = 16): stream A at HBM rate
+  // N <= 32: rank-r row products (N = 16), stream A at HBM rate. M <= 512 (the class-token-only
+  // last block: M = images): 32-wide tiles spread the few rows over 4x more CTAs
+  static const bool small_m32 = getenv("LLC_GEMM_SMALLM_BN128") == nullptr;
+  const bool use32 = N <= 32 || (small_m32 && M <= 512 && N % 32 == 0 && !use256);
   const int BN = use256 ? 256 : (use32 ? 32 : 128);
 
   CUtensorMap tmA, tmB;
