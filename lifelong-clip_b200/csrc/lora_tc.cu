@@ -488,6 +488,7 @@ extern "C" int llc_lora_side_fused(const void* X, int ld_x, int T, int C, int r,
   LLC_REQUIRE(X && w && F && U && partial && n_partials, "llc_lora_side_fused: null pointer");
   LLC_REQUIRE(llc_lora_fused_eligible(X, ld_x, T, C, r, w, ld_w, F, ld_f, U, ld_u),
               "llc_lora_side_fused: unsupported shape/alignment (T=%d C=%d r=%d)", T, C, r);
-  return llc_lora_fused_tc(X, ld_x, T, C, r, w, ld_w, F, ld_f, U, ld_u, partial, n_partials,
-                           (cudaStream_t)stream);
+  // partial slices use the padded rank llc_lora_colsum_finish expects (4 or 8 columns)
+  return llc_lora_fused_tc(X, ld_x, T, C, r <= 4 ? 4 : 8, w, ld_w, F, ld_f, U, ld_u, partial,
+                           n_partials, (cudaStream_t)stream);
 }

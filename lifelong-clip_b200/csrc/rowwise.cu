@@ -372,26 +372,34 @@ struct FinishArgs {
 // blockIdx.y = job; same fixed-order reduction as colsum_finish_kernel
 __global__ void __launch_bounds__(1024)
 colsum_finish_multi_kernel(const __grid_constant__ FinishArgs a, int R, int r) {
-  // 32 slices of the partial list per output element: with one partial per SM (the fused
-  // tensor-core pass) every thread has <= 5 independent loads, one global round trip
-  __shared__ float red[32][32];
+  // 32 slices of the partial list per output element (with one partial per SM from the fused
+  // tensor-core pass every thread has <= 5 independent loads, one global round trip), four
+  // consecutive elements per thread (16 B loads): a block reduces 128 elements
+  __shared__ float4 red[32][32];
   const llc_finish_job& jb = a.j[blockIdx.y];
   const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int n = jb.C * R;
-  for (int base = blockIdx.x * 32; base < n; base += gridDim.x * 32) {
-    const int i = base + o;
-    float s = 0.f;
+  const int n = jb.C * R;                      // multiple of 4 (checked by the launcher)
+  for (int base = blockIdx.x * 128; base < n; base += gridDim.x * 128) {
+    const int i = base + 4 * o;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n) {
 #pragma unroll 8
-      for (int p = sl; p < jb.n_partials; p += 32) s += jb.partial[(size_t)p * n + i];
+      for (int p = sl; p < jb.n_partials; p += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(jb.partial + (size_t)p * n + i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
     }
     red[sl][o] = s;
     __syncthreads();
-    if (sl == 0 && i < n) {
+    if (sl < 4 && i < n) {        // warp sl finishes component sl of every element group
       float t = 0.f;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) t += red[k][o];
-      const int c = i / R, j = i % R;
+      for (int k = 0; k < 32; ++k) {
+        const float4 v = red[k][o];
+        t += sl == 0 ? v.x : sl == 1 ? v.y : sl == 2 ? v.z : v.w;
+      }
+      const int e = i + sl;
+      const int c = e / R, j = e % R;
       if (j < r) jb.out[(size_t)c * jb.o_sc + (size_t)j * jb.o_sj] = t * jb.scale;
     }
     __syncthreads();
@@ -781,7 +789,10 @@ extern "C" int llc_lora_colsum_finish_multi(const llc_finish_job* jobs, int n_jo
     if (jobs[i].C * R > maxn) maxn = jobs[i].C * R;
   }
   LLC_PROF_BEGIN(LLC_K_LORA_SIDE, n_jobs, maxn, 1, 0.0, 0.0, (cudaStream_t)stream);
-  colsum_finish_multi_kernel<<<dim3((maxn + 31) / 32, n_jobs), 1024, 0, (cudaStream_t)stream>>>(
+  for (int i = 0; i < n_jobs; ++i)
+    LLC_REQUIRE(((uintptr_t)jobs[i].partial & 15) == 0,
+                "llc_lora_colsum_finish_multi: job %d partials must be 16-byte aligned", i);
+  colsum_finish_multi_kernel<<<dim3((maxn + 127) / 128, n_jobs), 1024, 0, (cudaStream_t)stream>>>(
       a, R, r);
   LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();

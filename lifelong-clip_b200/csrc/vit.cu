@@ -258,7 +258,7 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   // out-proj: du_o = s dx_mid B_o (-> dxb pad cols) and dB_o = s dx_mid^T u_o read the same
   // dx_mid: one fused pass when the shape allows, else a skinny GEMM plus a column-sum launch
   if (llc_lora_fused_eligible(s->dxb, DA, T, D, r, o + D, DA, w->f_out_B, D, dxb + D, DA)) {
-    RUN(llc_lora_fused_tc(s->dxb, DA, T, D, r, o + D, DA, w->f_out_B, D, dxb + D, DA, pr[0],
+    RUN(llc_lora_fused_tc(s->dxb, DA, T, D, r <= 4 ? 4 : 8, o + D, DA, w->f_out_B, D, dxb + D, DA, pr[0],
                           &np4[0], cst));
   } else {
     e = llc_gemm_epi{};
@@ -275,7 +275,7 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   int delta_ready = 0;
   if (s->delta && D == H * 64 && llc_attn_bwd_uses_delta(L) &&
       llc_colsum_tc_eligible(b->o, DA, T, D, dxb + D, DA)) {
-    RUN(llc_colsum_tc_delta(b->o, DA, T, D, r, dxb + D, DA, pr[1], &np4[1], s->d_o, D, s->delta, H,
+    RUN(llc_colsum_tc_delta(b->o, DA, T, D, r <= 4 ? 4 : 8, dxb + D, DA, pr[1], &np4[1], s->d_o, D, s->delta, H,
                             cst));
     delta_ready = 1;
   } else {
@@ -286,7 +286,7 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   // in-proj: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
   if (llc_lora_fused_eligible(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D,
                               QA)) {
-    RUN(llc_lora_fused_tc(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D, QA,
+    RUN(llc_lora_fused_tc(s->dqkv, QA, T, 3 * D, r <= 4 ? 4 : 8, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D, QA,
                           pr[2], &np4[2], cst));
   } else {
     e = llc_gemm_epi{};
@@ -455,7 +455,7 @@ int block_backward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc
   // in-projection: full size again
   if (llc_lora_fused_eligible(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D,
                               QA)) {
-    RUN(llc_lora_fused_tc(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D, QA,
+    RUN(llc_lora_fused_tc(s->dqkv, QA, T, 3 * D, r <= 4 ? 4 : 8, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D, QA,
                           pr[2], &np4[2], st));
   } else {
     e = llc_gemm_epi{};

@@ -257,10 +257,10 @@ def test_lora_side_rowdot_and_colsum(ops, T, Cc):
     assert rel(outT, want.T) < 1e-5
 
 
-@pytest.mark.parametrize("T,Cc", [(1024, 128), (3000, 768), (197 * 40, 2304), (6304 + 5, 768)])
-def test_lora_side_fused(ops, T, Cc):
+@pytest.mark.parametrize("T,Cc,r", [(1024, 128, 8), (3000, 768, 4), (197 * 40, 2304, 8),
+                                    (6304 + 5, 768, 3)])
+def test_lora_side_fused(ops, T, Cc, r):
     """Fused column sums + row products (one pass over X) against fp64."""
-    r = 8
     X = bf16_randn(T, Cc + 64, seed=33)
     w = bf16_randn(T, 24, seed=34)
     F = (torch.randn(16, Cc, device="cuda") * 0.05).to(torch.bfloat16)
