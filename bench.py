@@ -367,12 +367,18 @@ def run_ours(args):
     roof = None
     if gemm["launches"]:
         achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+        # the launches are timed inside instrumented steps that follow the timed region directly
+        # (a long, power-capped run): the denominator is the SUSTAINED measured cuBLAS figure; the
+        # burst figure (a kernel timed alone on a cool part) is reported next to it
+        peak = peaks["bf16_sustained"] or peaks["bf16"]
         roof = {"bound": "tensor", "kernel": "gemm2_kernel (tcgen05 cta_group::2 / TMEM): the 8 dense contractions of every block, forward and backward",
-                "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16"], "traffic": traffic,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_burst": peaks["bf16"], "frac_of_burst_peak": achieved / peaks["bf16"],
                 "traffic_note": "mean dram read+write bytes per launch, ncu --set full, 8 forward "
                                 "launches inside this bench (profiles/r01_ncu_gemm2_in_step.csv)",
-                "peak_source": peaks["source"] + ", burst",
+                "peak_source": peaks["source"] + (", sustained (kernel timed inside a long step)"
+                                                  if peaks["bf16_sustained"] else ", burst"),
                 "flop_per_launch": gemm["flops"] / gemm["launches"],
                 "us_per_launch": gemm["ms"] * 1e3 / gemm["launches"],
                 "launches_per_step": gemm["launches"] / args.prof_steps,
