@@ -10,7 +10,8 @@
  *
  * Conventions
  *  - extern "C", plain pointers + sizes; every device pointer is owned by the caller (PyTorch's
- *    caching allocator); the library retains nothing past the call.
+ *    caching allocator); the library retains nothing past the call and allocates no device
+ *    memory of its own (scratch is passed in).
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and never
  *    synchronise the device; all are CUDA-graph capturable.
  *  - return 0 on success; <0 = argument/shape error found before launch; >0 = cudaError_t.
@@ -101,9 +102,11 @@ int llc_ln_bwd(const float* x, int ld_x, const float* gamma, const void* dy, int
  * [N*H*L] saved for backward. hd must be 64. */
 int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L, int H,
                  int tok_stride_n, int tok_stride_l, int causal, void* stream);
+/* delta: caller-owned scratch of N*H*L floats (rowsum(dO o O), formed by a pre-pass); the library
+ * keeps no buffer of its own */
 int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o, int ld_do,
                  const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H, int tok_stride_n,
-                 int tok_stride_l, int causal, void* stream);
+                 int tok_stride_l, int causal, float* delta, void* stream);
 
 /* ---- LoRA side reductions (lora.py:838-839,1072-1074 and their autograd) ---------------------
  * One pass over X bf16 [T, ld_x] (C columns):
@@ -188,18 +191,62 @@ typedef struct llc_head_args {
   float* probs;          /* [N, C] */
   float* loss_rows;      /* [N] per-sample loss (already * inv_batch) */
   int64_t* pred;         /* [N] argmax (lowest index among ties) */
+  /* text side (peft_encoder='both', model.py:941-956) */
+  const int64_t* row_idx;/* [N] row of sample n in x / dx, or NULL (then n*cls_stride): the EOT
+                            token of every prompt, text.argmax(-1) of model.py:953-954 */
+  const float* d_fnorm;  /* backward only: [N, E] gradient w.r.t. the NORMALISED features (used
+                            with skip_logit_grad; chained through f = z/|z| in the kernel) */
+  float* dlogits;        /* backward only: [N, C] dL/dlogits written out, or NULL */
 } llc_head_args;
 int llc_head_fwd(const llc_head_args* a, void* stream);
 /* d_probs (may be NULL: then the analytic gradient of the fused loss is used, scaled by
  * loss_scale) -> d_x rows of the CLS tokens: fp32 [T, ld_dx] (other rows untouched) */
 int llc_head_bwd(const llc_head_args* a, const float* d_probs, float loss_scale, float* dx,
                  int ld_dx, void* stream);
+/* d_text[c, e] = scale * sum_n dlogits[n, c] * fnorm[n, e] ([C, E] fp32): gradient of the logit
+ * product (model.py:972) w.r.t. the normalised text features when the text tower is trainable */
+int llc_head_dtext(const float* dlogits, const float* fnorm, int N, int C, int E, float scale,
+                   float* d_text, void* stream);
 /* y_local[i] = lut[y_global[i]] (methods/adapter_clip.py:75-76; -1 when the class is unseen) */
 int llc_label_remap(const int64_t* y_global, const int64_t* lut, int lut_size, int64_t* y_local,
                     int n, void* stream);
 /* per-step scalars: out[0] = sum(loss_rows), out[1] = #(pred == labels) */
 int llc_loss_acc(const float* loss_rows, const int64_t* pred, const int64_t* labels, int n,
                  float* out2, void* stream);
+
+/* ---- evaluation tail (methods/adapter_clip.py:132-176, methods/_trainer.py:519-534) ---------- */
+/* counts [22] (uint64): counts[b] += #(y // n_tasks == b), counts[11 + b] += #(... and y == pred)
+ * for the reference's ten bins b < 10; bins past ten (where the reference raises IndexError) land
+ * in slot 10. cm [n_classes * n_classes] (uint64, may be NULL): cm[y * n_classes + pred] += 1. */
+int llc_eval_accum(const int64_t* y, const int64_t* pred, int n, int n_tasks, int n_classes,
+                   unsigned long long* cm, unsigned long long* counts, void* stream);
+/* y = scale * x / |x| per row (model.py:966-969): fp32 [N, ld_y] and/or bf16 [N, ld_yb] (the
+ * operand of the tensor-core logit GEMM) */
+int llc_l2norm_rows(const float* x, int ld_x, int N, int E, float scale, float* y, int ld_y,
+                    void* y_bf16, int ld_yb, void* stream);
+/* probs = softmax(logits + add_mask) per row, pred = argmax (lowest index among ties);
+ * models/adapter_clip.py:99, methods/adapter_clip.py:149; probs / pred / add_mask may be NULL */
+int llc_softmax_argmax(const float* logits, int ld, int N, int C, const float* add_mask,
+                       float* probs, int ld_p, int64_t* pred, void* stream);
+
+/* ---- GPU input transform (methods/_trainer.py:236-247): Resize((S,S)) -> RandomCrop(S, padding)
+ *      -> RandomHorizontalFlip -> Normalize(mean, std) on the raw batch, one pass ------------- */
+typedef struct llc_img_transform {
+  const void* src;        /* raw batch [N, 3, h, w]: uint8 0..255 (src_u8 = 1) or fp32 0..1 */
+  int src_u8, h, w;
+  int out_size;           /* S (even, >= h and w: bilinear up-sampling, align_corners=False) */
+  int pad;                /* RandomCrop padding (zeros); 0 = no crop */
+  int crop_i, crop_j;     /* crop offset inside the padded frame, 0..2*pad */
+  int flip;               /* horizontal flip of the whole batch */
+  const int* dyn_params;  /* device int[3] {crop_i, crop_j, flip} overriding the three fields
+                             above (so a captured CUDA graph replays with new draws), or NULL */
+  float mean[3], std[3];
+} llc_img_transform;
+/* fp32 NCHW [N, 3, S, S] (what train_transform / test_transform return) */
+int llc_transform_images(const llc_img_transform* t, int N, float* out, void* stream);
+/* bf16 im2col rows of the stride-P patch conv [N*G*G, ld_out] (as llc_patchify) */
+int llc_transform_patchify(const llc_img_transform* t, int N, int P, void* out, int ld_out,
+                           void* stream);
 
 /* ---- fused AdamW on the flat LoRA buffer (utils/train_utils.py:27-28, torch.optim.AdamW) ----- */
 int llc_adamw(float* p, const float* g, float* m, float* v, int n, float lr, float beta1,
@@ -257,6 +304,11 @@ int llc_vit_forward_cls(const llc_vit_cfg* cfg, const llc_vit_weights* w, const 
                         int N, void* arena, int training, float** x_final, void* stream);
 int llc_vit_backward_cls(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N, void* arena,
                          float* dx_final, void* stream);
+/* llc_vit_forward[_cls] with the input transform fused in front of the patch embedding: the raw
+ * batch described by `tx` replaces the fp32 images */
+int llc_vit_forward_tx(const llc_vit_cfg* cfg, const llc_vit_weights* w,
+                       const llc_img_transform* tx, int N, void* arena, int training, int cls_only,
+                       float** x_final, void* stream);
 /* dst bf16 [T, ld_dst] <- src fp32 [T, D] (contiguous rows) */
 int llc_cast_bf16(const float* src, void* dst, int T, int D, int ld_dst, void* stream);
 /* refresh the LoRA columns of the augmented weights from the live parameters */
@@ -291,6 +343,33 @@ typedef struct llc_block_bwd_bufs {
 int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
                        const llc_block_bwd_bufs* s, int N, int L, int tok_stride_n,
                        int tok_stride_l, int causal, int need_dx_in, void* stream);
+
+/* lora.MultiheadAttention.forward(x, x, x, need_weights=False) (lora.py:454-702 -> :732-1082) as
+ * its own call: b->x_in = x fp32 [T, D] -> b->x_out fp32 [T, D]; h1 / qkv / lse / o are saved for
+ * the backward. llc_mha_backward: s->dx = gradient of the output (fp32, read only) -> LoRA
+ * gradients and, if need_dx_in, s->dh = gradient of x (bf16 [T, D]). */
+int llc_mha_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b, int N,
+                    int L, int tok_stride_n, int tok_stride_l, int causal, void* stream);
+int llc_mha_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
+                     const llc_block_bwd_bufs* s, int N, int L, int tok_stride_n, int tok_stride_l,
+                     int causal, int need_dx_in, void* stream);
+
+/* ---- text tower with LoRA (CLIP.encode_text model.py:941-956, causal mask :926-932;
+ *      peft_encoder='both' of scripts/lora_clip.sh) ------------------------------------------- */
+typedef struct llc_text_weights {
+  const float* tok_emb;  /* [vocab, D] fp32 (token_embedding.weight, frozen) */
+  const float* pos_emb;  /* [context, D] fp32 (positional_embedding, frozen) */
+  const llc_vit_layer* layers;
+  int vocab, context;
+} llc_text_weights;
+/* cfg: width / layers / heads / mlp_dim / lora_* of the text transformer (patch geometry unused
+ * but must be valid). tokens int64 [C, context] -> x_final fp32 [C*context, D] inside the arena;
+ * ln_final + EOT gather + text_projection are llc_head_fwd with row_idx. */
+size_t llc_text_arena_bytes(const llc_vit_cfg* cfg, int context, int C, int training);
+int llc_text_forward(const llc_vit_cfg* cfg, const llc_text_weights* w, const int64_t* tokens,
+                     int C, void* arena, int training, float** x_final, void* stream);
+int llc_text_backward(const llc_vit_cfg* cfg, const llc_text_weights* w, int C, void* arena,
+                      float* dx_final, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ class HeadArgs(C.Structure):
         ("double_softmax", c_int), ("inv_batch", c_float),
         ("feat", c_void), ("fnorm", c_void), ("logits", c_void), ("probs", c_void),
         ("loss_rows", c_void), ("pred", c_void),
+        ("row_idx", c_void), ("d_fnorm", c_void), ("dlogits", c_void),
     ]
 
 
@@ -57,6 +58,18 @@ class VitLayer(C.Structure):
 class VitWeights(C.Structure):
     _fields_ = [("wpatch", c_void), ("class_emb", c_void), ("pos_emb", c_void),
                 ("ln_pre_g", c_void), ("ln_pre_b", c_void), ("layers", C.POINTER(VitLayer))]
+
+
+class TextWeights(C.Structure):
+    _fields_ = [("tok_emb", c_void), ("pos_emb", c_void), ("layers", C.POINTER(VitLayer)),
+                ("vocab", c_int), ("context", c_int)]
+
+
+class ImgTransform(C.Structure):
+    _fields_ = [("src", c_void), ("src_u8", c_int), ("h", c_int), ("w", c_int),
+                ("out_size", c_int), ("pad", c_int), ("crop_i", c_int), ("crop_j", c_int),
+                ("flip", c_int), ("dyn_params", c_void), ("mean", c_float * 3),
+                ("std", c_float * 3)]
 
 
 class BlockBufs(C.Structure):
@@ -99,7 +112,7 @@ SIGNATURES = {
     "llc_attn_fwd": (c_int, [c_void, c_int, c_void, c_int, c_void, c_int, c_int, c_int, c_int,
                              c_int, c_int, c_void]),
     "llc_attn_bwd": (c_int, [c_void, c_int, c_void, c_int, c_void, c_int, c_void, c_void, c_int,
-                             c_int, c_int, c_int, c_int, c_int, c_int, c_void]),
+                             c_int, c_int, c_int, c_int, c_int, c_int, c_void, c_void]),
     "llc_lora_side": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_int, c_int, c_float,
                               c_void, c_int, c_void, C.POINTER(c_int), c_void]),
     "llc_lora_colsum_finish": (c_int, [c_void, c_int, c_int, c_int, c_float, c_void, c_int, c_int,
@@ -118,6 +131,28 @@ SIGNATURES = {
                                  c_int, c_void, c_void]),
     "llc_head_fwd": (c_int, [C.POINTER(HeadArgs), c_void]),
     "llc_head_bwd": (c_int, [C.POINTER(HeadArgs), c_void, c_float, c_void, c_int, c_void]),
+    "llc_head_dtext": (c_int, [c_void, c_void, c_int, c_int, c_int, c_float, c_void, c_void]),
+    "llc_eval_accum": (c_int, [c_void, c_void, c_int, c_int, c_int, c_void, c_void, c_void]),
+    "llc_l2norm_rows": (c_int, [c_void, c_int, c_int, c_int, c_float, c_void, c_int, c_void, c_int,
+                                c_void]),
+    "llc_softmax_argmax": (c_int, [c_void, c_int, c_int, c_int, c_void, c_void, c_int, c_void,
+                                   c_void]),
+    "llc_transform_images": (c_int, [C.POINTER(ImgTransform), c_int, c_void, c_void]),
+    "llc_transform_patchify": (c_int, [C.POINTER(ImgTransform), c_int, c_int, c_void, c_int,
+                                       c_void]),
+    "llc_vit_forward_tx": (c_int, [C.POINTER(VitCfg), C.POINTER(VitWeights),
+                                   C.POINTER(ImgTransform), c_int, c_void, c_int, c_int,
+                                   C.POINTER(c_void), c_void]),
+    "llc_mha_forward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitLayer), C.POINTER(BlockBufs),
+                                c_int, c_int, c_int, c_int, c_int, c_void]),
+    "llc_mha_backward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitLayer), C.POINTER(BlockBufs),
+                                 C.POINTER(BlockBwdBufs), c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_void]),
+    "llc_text_arena_bytes": (C.c_size_t, [C.POINTER(VitCfg), c_int, c_int, c_int]),
+    "llc_text_forward": (c_int, [C.POINTER(VitCfg), C.POINTER(TextWeights), c_void, c_int, c_void,
+                                 c_int, C.POINTER(c_void), c_void]),
+    "llc_text_backward": (c_int, [C.POINTER(VitCfg), C.POINTER(TextWeights), c_int, c_void,
+                                  c_void, c_void]),
     "llc_label_remap": (c_int, [c_void, c_void, c_int, c_void, c_int, c_void]),
     "llc_loss_acc": (c_int, [c_void, c_void, c_void, c_int, c_void, c_void]),
     "llc_adamw": (c_int, [c_void, c_void, c_void, c_void, c_int, c_float, c_float, c_float,

@@ -1,21 +1,32 @@
-"""Model wrapper mirroring the reference's models/adapter_clip.AdapterCLIP (peft_method='lora').
+"""Model wrapper mirroring the reference's models/adapter_clip.AdapterCLIP (peft_method='lora') and
+the parts of models/clip/model.CLIP it drives.
 
 forward(image, text_tokens=None) -> (probs [N, C], image_features [N, E], text_features [C, E])
-exactly as models/adapter_clip.py:94-100, with the class restriction of
-methods/adapter_clip.py:53-61,84 realised as a gather of cached, L2-normalised class text features
-(with peft_encoder='image' the text tower is frozen and dropout-free, so its output is a pure
-function of the class list: SURVEY.md §8a row a14). The text tower itself and the BPE tokenizer are
-the "next" row N1 and are not part of this package: text features are supplied by the caller
-through set_text_features().
+exactly as models/adapter_clip.py:94-100.
+
+Text side, by `peft_encoder`:
+  'image'  the text tower is frozen and dropout-free, so its output is a pure function of the class
+           list: class text features are cached — either supplied by the
+           caller (set_text_features) or computed ONCE per class by this package's text tower
+           (vanilla blocks on the same kernels) — and the class restriction of
+           methods/adapter_clip.py:53-61,84 is a gather index into the cache;
+  'both'   (what scripts/lora_clip.sh sets) the text tower carries LoRA and is recomputed every
+           step for the visible classes (CLIP.encode_text, models/clip/model.py:941-956), with
+           gradients to its 48 LoRA tensors through the logit product.
+The BPE vocabulary file of OpenAI CLIP is not part of this repository: labels_tokenize() uses the
+tokenizer given to set_tokenizer() (any callable list[str] -> int64 [C, 77]); SyntheticTokenizer
+is the deterministic stand-in used by the synthetic benchmarks.
 """
 from __future__ import annotations
 
 import math
+import zlib
 
 import torch
 import torch.nn as nn
 
-from .clip_modules import VisualTransformer
+from . import ops
+from .clip_modules import LayerNorm, Transformer, VisualTransformer
 
 # model_name -> (image_resolution, patch, width, layers, embed_dim); heads = width // 64
 # (reference models/clip/model.py:1008-1017,1036,1040 derive the same numbers from a checkpoint)
@@ -24,27 +35,127 @@ VISION_CONFIGS = {
     "ViT-B/32": (224, 32, 768, 12, 512),
     "ViT-L/14": (224, 14, 1024, 24, 768),
 }
+# model_name -> (context_length, vocab_size, transformer_width, transformer_heads, layers)
+TEXT_CONFIGS = {
+    "ViT-B/16": (77, 49408, 512, 8, 12),
+    "ViT-B/32": (77, 49408, 512, 8, 12),
+    "ViT-L/14": (77, 49408, 768, 12, 12),
+}
 
 
-class VisionCLIP(nn.Module):
-    """The part of models/clip/model.CLIP this path needs: `.visual`, `.logit_scale`, `.dtype`,
-    encode_image (model.py:934-939) and the cosine-logit forward (model.py:958-975) against
-    cached text features."""
+class SyntheticTokenizer:
+    """Deterministic stand-in for the BPE tokenizer: [SOT, k ids in [1, 40000), EOT, 0...], the
+    EOT id (vocab-1) being the arg-max of every row as model.py:953-954 requires."""
+
+    def __init__(self, context_length=77, vocab_size=49408, words=5):
+        self.ctx, self.vocab, self.words = context_length, vocab_size, words
+
+    def __call__(self, texts):
+        out = torch.zeros(len(texts), self.ctx, dtype=torch.int64)
+        hi = min(40000, self.vocab - 2)
+        for i, t in enumerate(texts):
+            h = zlib.crc32(t.encode("utf-8"))
+            ids = []
+            for k in range(self.words):
+                h = (h * 1103515245 + 12345) & 0x7fffffff
+                ids.append(1 + h % (hi - 1))
+            row = [self.vocab - 2] + ids + [self.vocab - 1]
+            out[i, :len(row)] = torch.tensor(row)
+        return out
+
+
+class _TextSide:
+    """engine() provider of the text tower for FlatAdamW / the trainer (mirrors
+    VisualTransformer.engine())."""
+
+    def __init__(self, clip):
+        self.clip = clip
+
+    def engine(self):
+        return self.clip.text_engine()
+
+
+class CLIP(nn.Module):
+    """models/clip/model.CLIP (:790-975): `.visual`, the text transformer with its embeddings,
+    `.logit_scale`, `.dtype`, encode_image, encode_text and the cosine-logit forward. The text
+    tower is optional (text_config=None): with cached text features it is never run."""
 
     def __init__(self, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size,
-                 design_details):
+                 context_length=None, vocab_size=None, transformer_width=None,
+                 transformer_heads=None, transformer_layers=None, design_details=None):
         super().__init__()
+        design_details = design_details or {}
         self.design_details = design_details
         self.visual = VisualTransformer(input_resolution=image_resolution,
                                         patch_size=vision_patch_size, width=vision_width,
                                         layers=vision_layers, heads=vision_width // 64,
                                         output_dim=embed_dim, modal='image',
                                         design_details=design_details)
+        self.context_length = context_length
+        self.has_text = transformer_layers is not None and transformer_layers > 0
+        if self.has_text:
+            self.transformer = Transformer(width=transformer_width, layers=transformer_layers,
+                                           heads=transformer_heads,
+                                           attn_mask=self.build_attention_mask(), modal='text',
+                                           design_details=design_details)
+            self.vocab_size = vocab_size
+            self.token_embedding = nn.Embedding(vocab_size, transformer_width)
+            self.positional_embedding = nn.Parameter(torch.empty(context_length,
+                                                                 transformer_width))
+            self.ln_final = LayerNorm(transformer_width)
+            self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
+            self._init_text(transformer_width, transformer_layers)
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))  # model.py:845
+        self._text_engine = None
+
+    def _init_text(self, width, layers):
+        """model.py:852-885 initialize_parameters (text side)."""
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        proj_std = (width ** -0.5) * ((2 * layers) ** -0.5)
+        attn_std = width ** -0.5
+        fc_std = (2 * width) ** -0.5
+        for block in self.transformer.resblocks:
+            nn.init.normal_(block.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(block.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(block.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(block.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(self.text_projection, std=width ** -0.5)
+
+    def build_attention_mask(self):
+        """model.py:926-932."""
+        mask = torch.empty(self.context_length, self.context_length)
+        mask.fill_(float("-inf"))
+        mask.triu_(1)
+        return mask
+
+    def _apply(self, fn, *a, **k):
+        self._text_engine = None
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._text_engine = None
+        return super()._load_from_state_dict(*a, **k)
 
     @property
     def dtype(self):
         return self.visual.conv1.weight.dtype
+
+    def text_engine(self):
+        from .engine import TextEngine
+        if not self.has_text:
+            raise RuntimeError("this CLIP was built without a text tower (text_config=None)")
+        if self._text_engine is None:
+            self._text_engine = TextEngine(self)
+        return self._text_engine
+
+    def text_side(self):
+        return _TextSide(self)
+
+    def text_lora_params(self):
+        if not self.has_text:
+            return ()
+        return tuple(p for b in self.transformer.resblocks for p in b.lora_params())
 
     def logit_scale_exp(self) -> float:
         """exp(logit_scale) as a host float, read back from the device only when the (frozen)
@@ -57,23 +168,100 @@ class VisionCLIP(nn.Module):
     def encode_image(self, image):
         return self.visual(image.type(self.dtype))
 
+    def encode_text(self, text):
+        """model.py:941-956: text int64 [C, ctx] -> [C, E] (before normalisation)."""
+        lora = self.text_lora_params()
+        return _TextFn.apply(self, text, *lora)
+
+    def forward(self, image, text):
+        """model.py:958-975."""
+        if image is None:
+            return self.encode_text(text)
+        if text is None:
+            return self.encode_image(image)
+        image_features = self.encode_image(image)
+        text_features = self.encode_text(text)
+        image_features = image_features / image_features.norm(dim=-1, keepdim=True)
+        text_features = text_features / text_features.norm(dim=-1, keepdim=True)
+        logits_per_image = self.logit_scale.exp() * image_features @ text_features.t()
+        return logits_per_image, logits_per_image.t(), image_features, text_features
+
+
+VisionCLIP = CLIP   # round-1 name
+
+
+def eot_rows(tokens: torch.Tensor) -> torch.Tensor:
+    """Row of every prompt's EOT token in the flattened [C*ctx] token axis (model.py:953-954:
+    x[arange, text.argmax(-1)])."""
+    Cn, ctx = tokens.shape
+    return (torch.arange(Cn, device=tokens.device) * ctx + tokens.argmax(dim=-1)).contiguous()
+
+
+def _text_requires_grad(model: CLIP, lora) -> bool:
+    return any(p.requires_grad for p in lora)
+
+
+class _TextFn(torch.autograd.Function):
+    """tokens -> text features [C, E] = ln_final(x)[eot] @ text_projection (llc_text_forward)."""
+
+    @staticmethod
+    def forward(ctx, model, tokens, *lora):
+        need_grad = any(ctx.needs_input_grad)
+        eng = model.text_engine()
+        tokens = tokens.to(eng.device).contiguous()
+        head = eng.forward(tokens, eot_rows(tokens), training=need_grad)
+        ctx.eng, ctx.head, ctx.lora, ctx.need_grad = eng, head, lora, need_grad
+        return head.feat.clone()
+
+    @staticmethod
+    def backward(ctx, d_feat):
+        if not ctx.need_grad:
+            raise RuntimeError("text forward ran without grad")
+        eng, h = ctx.eng, ctx.head
+        d_feat = d_feat.detach().float().contiguous()
+        eng._check_trainable()
+        h.keep = h.keep + (d_feat,)
+        h.args.d_feat = d_feat.data_ptr()
+        h.args.d_fnorm = None
+        h.args.skip_logit_grad = 1
+        eng.dx.zero_()
+        h.backward(eng.dx)
+        import ctypes as C
+        from . import _capi as K
+        K.check(K.load().llc_text_backward(C.byref(eng.cfg), C.byref(eng.weights), eng.N,
+                                           eng.arena.data_ptr(), eng.dx.data_ptr(),
+                                           K.stream_ptr()), "llc_text_backward")
+        return (None, None) + tuple(g.clone() if p.requires_grad else None
+                                    for g, p in zip(eng.lora_grad_views, ctx.lora))
+
 
 class _ProbsFn(torch.autograd.Function):
-    """images -> (probs, normalised image features) with the tower + head kernels."""
+    """images (+ text tokens when the text tower trains) -> (probs, normalised image features,
+    pred, normalised text features) with the tower + head kernels."""
 
     @staticmethod
-    def forward(ctx, model, images, text, cls_idx, add_mask, *lora):
+    def forward(ctx, model, images, text, cls_idx, add_mask, tokens, n_vis, *lora):
         need_grad = any(ctx.needs_input_grad)
+        lora_v, lora_t = lora[:n_vis], lora[n_vis:]
         eng = model.visual.engine()
+        teng = thead = None
+        if tokens is not None:       # trainable text tower: recomputed for the visible classes
+            teng = model.text_engine()
+            thead = teng.forward(tokens, eot_rows(tokens),
+                                 training=need_grad and _text_requires_grad(model, lora_t))
+            text, cls_idx = thead.fnorm, None
         eng.forward(images, training=need_grad)
-        head = eng.head(text, model.logit_scale_exp(), cls_idx=cls_idx,
-                        add_mask=add_mask)
-        ctx.eng, ctx.head, ctx.lora, ctx.need_grad = eng, head, lora, need_grad
+        head = eng.head(text, model.logit_scale_exp(), cls_idx=cls_idx, add_mask=add_mask,
+                        want_dlogits=teng is not None)
+        ctx.eng, ctx.teng, ctx.head, ctx.thead = eng, teng, head, thead
+        ctx.lora_v, ctx.lora_t, ctx.need_grad = lora_v, lora_t, need_grad
+        ctx.scale = model.logit_scale_exp()
         ctx.mark_non_differentiable(head.pred)
-        return head.probs, head.fnorm, head.pred
+        tf = text if cls_idx is None else text.index_select(0, cls_idx)
+        return head.probs, head.fnorm, head.pred, tf.detach().clone()
 
     @staticmethod
-    def backward(ctx, d_probs, d_fnorm, _):
+    def backward(ctx, d_probs, d_fnorm, _, d_text):
         if not ctx.need_grad:
             raise RuntimeError("forward ran without grad")
         head = ctx.head
@@ -87,43 +275,90 @@ class _ProbsFn(torch.autograd.Function):
         dp = d_probs.detach().float().contiguous() if d_probs is not None else \
             torch.zeros_like(head.probs)
         ctx.eng.backward_from_head(head, d_probs=dp, d_feat=d_feat)
-        return (None,) * 5 + tuple(g.clone() if p.requires_grad else None
-                                   for g, p in zip(ctx.eng.lora_grad_views, ctx.lora))
+        g_v = tuple(g.clone() if p.requires_grad else None
+                    for g, p in zip(ctx.eng.lora_grad_views, ctx.lora_v))
+        g_t = (None,) * len(ctx.lora_t)
+        if ctx.teng is not None and ctx.teng._trained_arena and \
+                any(p.requires_grad for p in ctx.lora_t):
+            d_t = ops.head_dtext(head.dlogits, head.fnorm, ctx.scale)
+            if d_text is not None and bool((d_text != 0).any()):
+                d_t = d_t + d_text.detach().float()
+            ctx.teng.backward(d_t.contiguous())
+            g_t = tuple(g.clone() if p.requires_grad else None
+                        for g, p in zip(ctx.teng.lora_grad_views, ctx.lora_t))
+        return (None,) * 7 + g_v + g_t
 
 
 class AdapterCLIP(nn.Module):
     """models/adapter_clip.py:14-104."""
 
     def __init__(self, model_name="ViT-B/16", peft_method='lora', peft_encoder='image',
-                 device=None, vision_config=None):
+                 device=None, vision_config=None, text_config=None):
         super().__init__()
         if peft_method != 'lora':
             raise NotImplementedError("lifelong_clip_b200 implements the lora-clip method only")
-        if peft_encoder != 'image':
-            raise NotImplementedError(
-                "peft_encoder='both'/'text' needs the LoRA text tower (SURVEY.md §8f N1, not "
-                "built yet); this path runs peft_encoder='image' with cached text features")
+        if peft_encoder not in ('image', 'both'):
+            raise NotImplementedError("peft_encoder must be 'image' (cached text features) or "
+                                      "'both' (LoRA text tower recomputed every step)")
         self.device = device
+        self.peft_encoder = peft_encoder
         design_details = {'method': peft_method, 'peft_encoder': peft_encoder, 'ffn_num': 64,
                           'lora_alpha': 1, 'lora_r': 4}  # models/adapter_clip.py:24-30
         res, patch, width, layers, embed = vision_config or VISION_CONFIGS[model_name]
-        self.model = VisionCLIP(embed, res, layers, width, patch, design_details)
+        if text_config is None and peft_encoder == 'both':
+            text_config = TEXT_CONFIGS[model_name]
+        tc = text_config or (None,) * 5
+        self.model = CLIP(embed, res, layers, width, patch, tc[0], tc[1], tc[2], tc[3], tc[4],
+                          design_details)
         if device is not None:
             self.model.to(device)
         self.text_tokens = None
         self.current_class_names = []
         self.dtype = self.model.dtype
         self.prompt_template = "a bad photo of a {}."
+        self._tokenizer = None
         self._text_names: list[str] = []
-        self._text_all = None      # [C_all, E] normalised, device
-        self._cls_idx = None       # int64 [C] visible rows
+        self._name_to_row = {}
+        self._text_all = None      # [C_all, E] normalised, device (cached path)
+        self._cls_idx = None       # int64 [C] visible rows of the cache
         self._cls_key = None
+        self._tok_cache = {}       # class name -> int64 [ctx] (host)
+        self._tokens = None        # int64 [C, ctx] on the device ('both')
         self._add_mask = None
 
-    # ---- cached text features ----------------------------------------------------------------
+    # ---- text side ---------------------------------------------------------------------------
+    def set_tokenizer(self, fn):
+        """fn(list[str]) -> int64 [C, context_length] (e.g. OpenAI CLIP's SimpleTokenizer driven
+        as models/adapter_clip.py:55-70 does; SyntheticTokenizer for synthetic runs)."""
+        self._tokenizer = fn
+        self._tok_cache = {}
+
+    def labels_tokenize(self, labels, context_length: int = 77):
+        """models/adapter_clip.py:39-74: prompt template + tokenizer -> int64 [C, ctx] on the
+        model's device."""
+        if self._tokenizer is None:
+            raise RuntimeError("no tokenizer: call set_tokenizer() (the BPE vocabulary of OpenAI "
+                               "CLIP is not shipped), or provide cached class text features with "
+                               "set_text_features()")
+        if isinstance(labels, str):
+            labels = [labels]
+        missing = [c for c in labels if c not in self._tok_cache]
+        if missing:
+            toks = self._tokenizer([self.prompt_template.format(c) for c in missing])
+            toks = torch.as_tensor(toks, dtype=torch.int64)
+            if toks.dim() != 2 or toks.shape[1] != context_length:
+                raise RuntimeError(f"tokenizer must return [C, {context_length}] ids")
+            for c, row in zip(missing, toks):
+                self._tok_cache[c] = row.clone()
+        out = torch.stack([self._tok_cache[c] for c in labels])
+        return out.to(self.model.visual.proj.device)
+
     def set_text_features(self, class_names, features: torch.Tensor):
         """Cache one feature row per class name (model.py:941-956 output); rows are L2-normalised
-        here as model.py:968-969 does every step."""
+        here as model.py:968-969 does every step. peft_encoder='image' only."""
+        if self.peft_encoder != 'image':
+            raise RuntimeError("peft_encoder='both' recomputes the text features every step; "
+                               "there is nothing to cache")
         feats = features.detach().float()
         feats = feats / feats.norm(dim=-1, keepdim=True)
         dev = self.model.visual.proj.device
@@ -132,16 +367,40 @@ class AdapterCLIP(nn.Module):
         self._name_to_row = {n: i for i, n in enumerate(self._text_names)}
         self._cls_idx = None
 
-    def labels_tokenize(self, labels, context_length: int = 77):
-        raise NotImplementedError("BPE tokenisation belongs to the text side (SURVEY.md §8f N1); "
-                                  "provide class text features with set_text_features()")
+    def _cache_missing(self, classnames):
+        """peft_encoder='image' without caller-supplied features: run the frozen text tower once
+        for the classes not seen before and append their normalised features to the cache."""
+        missing = [c for c in classnames if c not in self._name_to_row]
+        if not missing:
+            return
+        if not self.model.has_text:
+            raise RuntimeError(f"no text features cached for {missing[:3]}...: call "
+                               "set_text_features(), or build AdapterCLIP with text_config and "
+                               "set_tokenizer()")
+        with torch.no_grad():
+            z = self.model.encode_text(self.labels_tokenize(missing))
+            z = z / z.norm(dim=-1, keepdim=True)
+        base = len(self._text_names)
+        self._text_all = z if self._text_all is None else torch.cat([self._text_all, z])
+        for i, c in enumerate(missing):
+            self._name_to_row[c] = base + i
+        self._text_names += missing
+        self._cls_idx = None
 
     def set_token(self, classnames):
-        """models/adapter_clip.py:102-104: select the classes visible to forward(). Here it
-        builds the gather index into the cached text features instead of re-tokenising."""
-        if self._text_all is None:
-            raise RuntimeError("call set_text_features() before set_token()")
+        """models/adapter_clip.py:102-104: select the classes visible to forward(). 'image': the
+        gather index into the cached text features (no per-step tokenisation); 'both': the token
+        matrix of the visible classes (tokenised once per class name)."""
         key = tuple(classnames)
+        if self.peft_encoder == 'both':
+            if self._tokens is None or key != self._cls_key:
+                self._tokens = self.labels_tokenize(list(classnames)).contiguous()
+                self._cls_key = key
+            self.text_tokens = self._tokens
+            return
+        if self._text_all is None and not self.model.has_text:
+            raise RuntimeError("call set_text_features() before set_token()")
+        self._cache_missing(classnames)
         if self._cls_idx is None or key != self._cls_key:   # unchanged list: no H2D, no alloc
             rows = [self._name_to_row[c] for c in classnames]
             self._cls_idx = torch.tensor(rows, dtype=torch.int64, device=self._text_all.device)
@@ -150,8 +409,8 @@ class AdapterCLIP(nn.Module):
 
     def set_additive_mask(self, mask):
         """methods/mvp_clip.py:113-118 variant: logits + mask (0 for seen, -inf for unseen)."""
-        self._add_mask = None if mask is None else mask.detach().float().to(
-            self._text_all.device).contiguous()
+        dev = self.model.visual.proj.device
+        self._add_mask = None if mask is None else mask.detach().float().to(dev).contiguous()
 
     def update_class_names(self, new_class_names):
         """models/adapter_clip.py:81-92 (bookkeeping only; returns None like the reference)."""
@@ -169,9 +428,16 @@ class AdapterCLIP(nn.Module):
     def forward(self, image, text_tokens=None):
         if text_tokens is None:
             text_tokens = self.text_tokens
-        if text_tokens is None or self._text_all is None:
-            raise RuntimeError("no visible classes: call set_text_features() and set_token()")
+        if text_tokens is None:
+            raise RuntimeError("no visible classes: call set_token() (and set_text_features() or "
+                               "set_tokenizer()) first")
         vis = self.model.visual
-        probs, fnorm, _ = _ProbsFn.apply(self.model, image, self._text_all, text_tokens,
-                                         self._add_mask, *vis.lora_params())
-        return probs, fnorm, self._text_all[text_tokens]
+        lv = vis.lora_params()
+        if self.peft_encoder == 'both':
+            lt = self.model.text_lora_params()
+            probs, fnorm, _, tf = _ProbsFn.apply(self.model, image, None, None, self._add_mask,
+                                                 text_tokens, len(lv), *lv, *lt)
+        else:
+            probs, fnorm, _, tf = _ProbsFn.apply(self.model, image, self._text_all, text_tokens,
+                                                 self._add_mask, None, len(lv), *lv)
+        return probs, fnorm, tf

@@ -51,15 +51,77 @@ class QuickGELU(nn.Module):
         return x * torch.sigmoid(1.702 * x)
 
 
+class _LoraLinearFn(torch.autograd.Function):
+    """y = x W^T + b + s (x A^T) B^T (lora.py:162-173) on libllc: the rank-r update rides as 16
+    extra K columns of the same tcgen05 GEMM; backward gives dx and the two LoRA gradients, the
+    frozen weight/bias get none."""
+
+    @staticmethod
+    def forward(ctx, lin, x, A, B):
+        dev = x.device
+        if dev.type != "cuda":
+            raise RuntimeError("lifelong_clip_b200 modules compute on CUDA (sm_100a) only; "
+                               "move the module and its input to the GPU (no CPU fallback)")
+        I, O, r, s = lin.in_features, lin.out_features, lin.r, lin.scaling
+        x2 = x.detach().float().contiguous().view(-1, I)
+        T = x2.shape[0]
+        xb = _bf16(T, I + PAD, dev)
+        ops.cast_bf16(x2, xb)
+        f32 = lambda p: p.detach().float().contiguous()
+        A32, B32 = f32(A), f32(B)
+        ops.lora_side(xb, T, I, r, Mrd=A32, rd_sc=1, rd_sj=I, rd_scale=1.0)      # u = x A^T
+        w_aug = ops.pack_weight(f32(lin.weight), _bf16(O, I + PAD, dev))
+        ops.pack_lora_cols(B32, O, r, r, 1, s, w_aug, I)                          # | s B
+        y = torch.empty(T, O, device=dev)
+        ops.gemm_tn(xb, w_aug, T, O, I + K.LORA_PAD, y,
+                    bias=f32(lin.bias) if lin.bias is not None else None)
+        ctx.lin, ctx.xb, ctx.A32, ctx.B32, ctx.shape = lin, xb, A32, B32, x.shape
+        return y.view(*x.shape[:-1], O)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lin, xb, A32, B32 = ctx.lin, ctx.xb, ctx.A32, ctx.B32
+        I, O, r, s = lin.in_features, lin.out_features, lin.r, lin.scaling
+        dev = dy.device
+        d2 = dy.detach().float().contiguous().view(-1, O)
+        T = d2.shape[0]
+        db = _bf16(T, O + PAD, dev)
+        ops.cast_bf16(d2, db)
+        part = torch.empty(ops.lora_side_max_partials() * max(I, O) * 8, device=dev)
+        # du = s dy B (-> pad columns of db); dB = s dy^T u
+        n1 = ops.lora_side(db, T, O, r, Mrd=B32, rd_sc=r, rd_sj=1, rd_scale=s,
+                           w=xb[:, I:], ld_w=xb.stride(0), partial=part)
+        gB = torch.empty(O, r, device=dev)
+        ops.lora_colsum_finish(part, n1, O, r, s, gB, r, 1)
+        # dA = du^T x
+        n2 = ops.lora_side(xb, T, I, r, w=db[:, O:], ld_w=db.stride(0), partial=part)
+        gA = torch.empty(r, I, device=dev)
+        ops.lora_colsum_finish(part, n2, I, r, 1.0, gA, 1, I)
+        gx = None
+        if ctx.needs_input_grad[1]:
+            # dx = dy W + du A : one GEMM over K = O + 16 against [W^T | A^T]
+            wT = ops.pack_weight(lin.weight.detach().float().contiguous(),
+                                 _bf16(I, O + PAD, dev), True)
+            ops.pack_lora_cols(A32, I, r, 1, I, 1.0, wT, O)
+            gx = torch.empty(T, I, device=dev)
+            ops.gemm_tn(db, wT, T, I, O + K.LORA_PAD, gx)
+            gx = gx.view(ctx.shape)
+        return None, gx, gA, gB
+
+
 class Linear(nn.Linear):
-    """lora.py:100-139 LoRA dense layer: parameter container for out_proj (weight, bias, lora_A
-    kaiming-uniform(a=sqrt 5), lora_B zeros, scaling = alpha / r)."""
+    """lora.py:100-173 LoRA dense layer (out_proj of the LoRA attention): weight, bias, lora_A
+    kaiming-uniform(a=sqrt 5), lora_B zeros, scaling = alpha / r; forward adds the rank-r update.
+    Inside a block the layer is only a parameter container (the projection is fused into
+    llc_block_forward); called on its own it runs _LoraLinearFn."""
 
     def __init__(self, in_features, out_features, r=0, lora_alpha=1, lora_dropout=0.,
                  fan_in_fan_out=False, merge_weights=True, **kwargs):
         super().__init__(in_features, out_features, **kwargs)
         if lora_dropout != 0.:
             raise NotImplementedError("LoRA dropout is 0 on the reference path (lora.py:376)")
+        if fan_in_fan_out:
+            raise NotImplementedError("fan_in_fan_out is never set on the reference path")
         self.r, self.lora_alpha, self.merged, self.merge_weights = r, lora_alpha, False, merge_weights
         self.fan_in_fan_out = fan_in_fan_out
         if r > 0:
@@ -70,11 +132,90 @@ class Linear(nn.Linear):
             nn.init.kaiming_uniform_(self.lora_A, a=math.sqrt(5))
             nn.init.zeros_(self.lora_B)
 
+    def train(self, mode: bool = True):
+        """lora.py:141-160 merges W += s B A in eval mode when merge_weights is set; the reference
+        constructs out_proj with merge_weights=False (lora.py:430-435), the only supported use."""
+        if self.merge_weights and self.r > 0 and not mode:
+            raise NotImplementedError("merge_weights=True (weight merging in eval mode) is not "
+                                      "used on the reference path")
+        return super().train(mode)
+
+    def forward(self, x: torch.Tensor):
+        if self.r > 0 and not self.merged:
+            return _LoraLinearFn.apply(self, x, self.lora_A, self.lora_B)
+        raise NotImplementedError("LoRA rank 0 / merged weights: use nn.Linear")
+
+
+class _MhaFn(torch.autograd.Function):
+    """lora.MultiheadAttention.forward(x, x, x) through llc_mha_forward / llc_mha_backward on the
+    reference's [L, N, D] layout (token strides (1, N))."""
+
+    @staticmethod
+    def forward(ctx, attn, x, causal, *lora):
+        L, N, D = x.shape
+        T, dev = L * N, x.device
+        if dev.type != "cuda":
+            raise RuntimeError("lifelong_clip_b200 modules compute on CUDA (sm_100a) only; "
+                               "move the module and its input to the GPU (no CPU fallback)")
+        bufs = dict(x_in=x.detach().float().contiguous().view(T, D), h1=_bf16(T, D + PAD, dev),
+                    qkv=_bf16(T, 3 * D + PAD, dev),
+                    lse=torch.empty(N * attn.num_heads * L, device=dev), o=_bf16(T, D + PAD, dev),
+                    x_out=torch.empty(T, D, device=dev))
+        b = K.BlockBufs()
+        for k, v in bufs.items():
+            setattr(b, k, K.ptr(v))
+        layer = attn._layer_struct(lora, [None] * 4)
+        attn._refresh_lora(layer)
+        K.check(K.load().llc_mha_forward(C.byref(attn._cfg), C.byref(layer), C.byref(b), N, L, 1,
+                                         N, int(causal), K.stream_ptr()), "llc_mha_forward")
+        ctx.attn, ctx.bufs, ctx.shape, ctx.causal, ctx.lora = attn, bufs, (L, N, D), causal, lora
+        return bufs["x_out"].view(L, N, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        attn, bufs, (L, N, D) = ctx.attn, ctx.bufs, ctx.shape
+        T, dev = L * N, dy.device
+        grads = [torch.zeros_like(p, dtype=torch.float32) for p in ctx.lora]
+        scratch = dict(
+            dx=dy.detach().float().contiguous().view(T, D), dxb=_bf16(T, D + PAD, dev),
+            dh=_bf16(T, D, dev), d_o=_bf16(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
+            partial=torch.empty(ops.lora_side_max_partials() * 3 * D * 8, device=dev),
+            delta=torch.empty(N * attn.num_heads * L, device=dev))
+        s = K.BlockBwdBufs()
+        for k, v in scratch.items():
+            setattr(s, k, v.data_ptr())
+        b = K.BlockBufs()
+        for k, v in bufs.items():
+            setattr(b, k, K.ptr(v))
+        layer = attn._layer_struct(ctx.lora, grads)
+        need_dx = bool(ctx.needs_input_grad[1])
+        K.check(K.load().llc_mha_backward(C.byref(attn._cfg), C.byref(layer), C.byref(b),
+                                          C.byref(s), N, L, 1, N, int(ctx.causal), int(need_dx),
+                                          K.stream_ptr()), "llc_mha_backward")
+        gx = scratch["dh"].float().view(L, N, D) if need_dx else None
+        return (None, gx, None) + tuple(g.to(p.dtype) if p.requires_grad else None
+                                        for g, p in zip(grads, ctx.lora))
+
+
+def _causal_flag(attn_mask, L: int) -> int:
+    """None -> 0; the text tower's additive -inf upper triangle (model.py:926-932) -> 1."""
+    if attn_mask is None:
+        return 0
+    want = torch.full((L, L), float("-inf")).triu(1)
+    m = attn_mask.detach().float().cpu()
+    if tuple(m.shape) == (L, L) and torch.equal(m, want):
+        return 1
+    if m.dim() == 2 and m.shape[0] >= L and torch.equal(m[:L, :L], want):
+        return 1   # a mask built for the full context, applied to a shorter sequence
+    raise NotImplementedError("only attn_mask=None or the causal mask is supported")
+
 
 class MultiheadAttention(nn.Module):
     """lora.py:371-452: in_proj_weight/bias + one rank-r (A [r,D], B [3D,r]) pair shared by q,k,v
-    (both xavier-uniform), out_proj = LoRA Linear. Parameter container; the math
-    (lora.py:825-840,950,1002-1074) runs inside llc_block_forward."""
+    (both xavier-uniform), out_proj = LoRA Linear. forward (lora.py:454-702) supports what the
+    reference's blocks call: self-attention on [L, N, D], need_weights=False, attn_mask None or
+    causal. Inside ResidualAttentionBlock_LoRA.forward the same math runs fused in
+    llc_block_forward."""
 
     def __init__(self, embed_dim, num_heads, dropout=0., bias=True, add_bias_kv=False,
                  add_zero_attn=False, kdim=None, vdim=None, lora_alpha: int = 1, r: int = 0):
@@ -102,6 +243,52 @@ class MultiheadAttention(nn.Module):
         nn.init.constant_(self.out_proj.bias, 0.)
         nn.init.xavier_uniform_(self.in_proj_weight_lora_A)
         nn.init.xavier_uniform_(self.in_proj_weight_lora_B)
+        self._packed = None
+        self._cfg = _cfg_struct(embed_dim, num_heads, embed_dim * 4, r, lora_alpha / r)
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def lora_params(self):
+        return (self.in_proj_weight_lora_A, self.in_proj_weight_lora_B, self.out_proj.lora_A,
+                self.out_proj.lora_B)
+
+    def _layer_struct(self, lora, grads) -> K.VitLayer:
+        if self._packed is None:
+            self._packed = PackedLayer(self, None)
+        s = K.VitLayer()
+        self._packed.fill(s, lora, grads)
+        return s
+
+    def _refresh_lora(self, s: K.VitLayer):
+        w = K.VitWeights()
+        w.layers = (K.VitLayer * 1)(s)
+        K.check(K.load().llc_vit_refresh_lora(C.byref(self._cfg), C.byref(w), K.stream_ptr()),
+                "llc_vit_refresh_lora")
+
+    def forward(self, query, key=None, value=None, key_padding_mask=None, need_weights=True,
+                attn_mask=None, average_attn_weights=True, is_causal=False):
+        if key is None:
+            key = query
+        if value is None:
+            value = query
+        if key is not query or value is not query:
+            raise NotImplementedError("only self-attention (q is k is v), the call of "
+                                      "model.py:226-231, is implemented")
+        if need_weights or key_padding_mask is not None:
+            raise NotImplementedError("need_weights=True / key_padding_mask: the reference's "
+                                      "blocks call with need_weights=False (model.py:230)")
+        if query.dim() != 3 or query.shape[-1] != self.embed_dim:
+            raise RuntimeError(f"expected [L, N, {self.embed_dim}], got {tuple(query.shape)}")
+        causal = 1 if (is_causal and attn_mask is None) else _causal_flag(attn_mask,
+                                                                          query.shape[0])
+        out = _MhaFn.apply(self, query, causal, *self.lora_params())
+        return out, None
 
 
 LORA_NAMES = ("attn.in_proj_weight_lora_A", "attn.in_proj_weight_lora_B",
@@ -116,35 +303,43 @@ class PackedLayer:
     """Prepared operands of one block: frozen weights as bf16 K-major matrices (forward and
     transposed for the activation-gradient GEMMs), 16 spare K columns for the LoRA factors."""
 
-    def __init__(self, blk: "ResidualAttentionBlock_LoRA"):
-        a = blk.attn
-        D, M, dev = blk.d_model, blk.mlp.c_fc.out_features, a.in_proj_weight.device
+    def __init__(self, attn: "MultiheadAttention", blk=None):
+        """attn: the block's attention module; blk: the block (None: attention-only packing for
+        MultiheadAttention.forward, the MLP / LayerNorm slots then stay empty)."""
+        a = attn
+        D, dev = a.embed_dim, a.in_proj_weight.device
         if dev.type != "cuda":
             raise RuntimeError("lifelong_clip_b200 modules compute on CUDA (sm_100a) only; "
                                "move the module to the GPU first (no CPU fallback)")
         f32 = lambda p: p.detach().float().contiguous()
         self.wqkv_aug = ops.pack_weight(f32(a.in_proj_weight), _bf16(3 * D, D + PAD, dev))
         self.wo_aug = ops.pack_weight(f32(a.out_proj.weight), _bf16(D, D + PAD, dev))
-        self.wfc = ops.pack_weight(f32(blk.mlp.c_fc.weight), _bf16(M, D, dev))
-        self.wproj = ops.pack_weight(f32(blk.mlp.c_proj.weight), _bf16(D, M, dev))
         self.wqkvT_aug = ops.pack_weight(f32(a.in_proj_weight), _bf16(D, 3 * D + PAD, dev), True)
         self.woT_aug = ops.pack_weight(f32(a.out_proj.weight), _bf16(D, D + PAD, dev), True)
-        self.wfcT = ops.pack_weight(f32(blk.mlp.c_fc.weight), _bf16(D, M, dev), True)
-        self.wprojT = ops.pack_weight(f32(blk.mlp.c_proj.weight), _bf16(M, D, dev), True)
+        self.wfc = self.wproj = self.wfcT = self.wprojT = None
+        if blk is not None:
+            M = blk.mlp.c_fc.out_features
+            self.wfc = ops.pack_weight(f32(blk.mlp.c_fc.weight), _bf16(M, D, dev))
+            self.wproj = ops.pack_weight(f32(blk.mlp.c_proj.weight), _bf16(D, M, dev))
+            self.wfcT = ops.pack_weight(f32(blk.mlp.c_fc.weight), _bf16(D, M, dev), True)
+            self.wprojT = ops.pack_weight(f32(blk.mlp.c_proj.weight), _bf16(M, D, dev), True)
         self.f_out_A = _bf16(16, D, dev)       # refreshed from the live LoRA factors every step
         self.f_in_B = _bf16(16, 3 * D, dev)
         self.f_out_B = _bf16(16, D, dev)
-        self.small = [f32(p) for p in (a.in_proj_bias, a.out_proj.bias, blk.mlp.c_fc.bias,
-                                       blk.mlp.c_proj.bias, blk.ln_1.weight, blk.ln_1.bias,
-                                       blk.ln_2.weight, blk.ln_2.bias)]
+        if blk is not None:
+            self.small = [f32(p) for p in (a.in_proj_bias, a.out_proj.bias, blk.mlp.c_fc.bias,
+                                           blk.mlp.c_proj.bias, blk.ln_1.weight, blk.ln_1.bias,
+                                           blk.ln_2.weight, blk.ln_2.bias)]
+        else:
+            self.small = [f32(a.in_proj_bias), f32(a.out_proj.bias)] + [None] * 6
 
     def fill(self, s: K.VitLayer, lora, grads):
         for n in ("wqkv_aug", "wo_aug", "wfc", "wproj", "wqkvT_aug", "woT_aug", "wfcT", "wprojT",
                   "f_out_A", "f_in_B", "f_out_B"):
-            setattr(s, n, getattr(self, n).data_ptr())
+            setattr(s, n, K.ptr(getattr(self, n)))
         for n, t in zip(("bqkv", "bo", "bfc", "bproj", "ln1_g", "ln1_b", "ln2_g", "ln2_b"),
                         self.small):
-            setattr(s, n, t.data_ptr())
+            setattr(s, n, K.ptr(t))
         for n, t in zip(("in_A", "in_B", "out_A", "out_B"), lora):
             setattr(s, n, t.data_ptr())
         for n, t in zip(("g_in_A", "g_in_B", "g_out_A", "g_out_B"), grads):
@@ -218,16 +413,39 @@ class _BlockFn(torch.autograd.Function):
                                   for g, p in zip(grads, ctx.lora))
 
 
-class ResidualAttentionBlock_LoRA(nn.Module):
-    """model.py:400-415 (on top of :209-236): x + attn(ln_1(x)); x + mlp(ln_2(x)) on [L, N, D]."""
+class FrozenMultiheadAttention(nn.Module):
+    """Parameter container with nn.MultiheadAttention's state_dict keys (in_proj_weight,
+    in_proj_bias, out_proj.weight, out_proj.bias) for the vanilla block (model.py:217). The LoRA
+    slots are zero buffers (not Parameters, not in the state_dict), so the same kernels compute
+    exactly x W^T + b."""
 
-    def __init__(self, d_model: int, n_head: int, attn_mask: torch.Tensor = None,
-                 design_details: dict = {}):
+    def __init__(self, embed_dim, num_heads, r=4):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.r = embed_dim, num_heads, r
+        self.head_dim = embed_dim // num_heads
+        self.batch_first, self.dropout = False, 0.
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)       # keys out_proj.weight / .bias
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.out_proj.bias, 0.)
+        for n, shape in (("_z_in_A", (r, embed_dim)), ("_z_in_B", (3 * embed_dim, r)),
+                         ("_z_out_A", (r, embed_dim)), ("_z_out_B", (embed_dim, r))):
+            self.register_buffer(n, torch.zeros(shape), persistent=False)
+
+    def lora_params(self):
+        return (self._z_in_A, self._z_in_B, self._z_out_A, self._z_out_B)
+
+
+class ResidualAttentionBlock(nn.Module):
+    """model.py:209-236: x + attn(ln_1(x)); x + mlp(ln_2(x)) on [L, N, D], frozen (no weight
+    gradients are ever computed on this path; the input gradient is)."""
+
+    def __init__(self, d_model: int, n_head: int, attn_mask: torch.Tensor = None):
         super().__init__()
         self.d_model, self.n_head = d_model, n_head
-        self.lora_alpha = design_details.get('lora_alpha', 1)
-        self.lora_r = design_details.get('lora_r', 4)
-        self.attn = MultiheadAttention(d_model, n_head, lora_alpha=self.lora_alpha, r=self.lora_r)
+        self.lora_alpha, self.lora_r = 1, 4      # zero factors: see FrozenMultiheadAttention
+        self.attn = FrozenMultiheadAttention(d_model, n_head, r=self.lora_r)
         self.ln_1 = LayerNorm(d_model)
         self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d_model, d_model * 4)),
                                               ("gelu", QuickGELU()),
@@ -243,6 +461,8 @@ class ResidualAttentionBlock_LoRA(nn.Module):
         """Call after modifying frozen weights in place (load_state_dict and .to()/.cuda() do it
         automatically)."""
         self._packed = None
+        if hasattr(self.attn, "_packed"):
+            self.attn._packed = None
 
     def _apply(self, fn, *a, **k):
         self._packed = None
@@ -254,13 +474,11 @@ class ResidualAttentionBlock_LoRA(nn.Module):
 
     def packed(self) -> PackedLayer:
         if self._packed is None:
-            self._packed = PackedLayer(self)
+            self._packed = PackedLayer(self.attn, self)
         return self._packed
 
     def lora_params(self):
-        a = self.attn
-        return (a.in_proj_weight_lora_A, a.in_proj_weight_lora_B, a.out_proj.lora_A,
-                a.out_proj.lora_B)
+        return self.attn.lora_params()
 
     def _layer_struct(self, lora, grads) -> K.VitLayer:
         s = K.VitLayer()
@@ -279,16 +497,17 @@ class ResidualAttentionBlock_LoRA(nn.Module):
                 "llc_vit_refresh_lora")
 
     def _causal_flag(self, L: int) -> int:
-        m = self.attn_mask
-        if m is None:
-            return 0
-        want = torch.full((L, L), float("-inf")).triu(1)
-        if tuple(m.shape) == (L, L) and torch.equal(m.detach().float().cpu(), want):
-            return 1  # the text tower's mask (model.py:926-932)
-        raise NotImplementedError("only attn_mask=None or the causal mask is supported")
+        return _causal_flag(self.attn_mask, L)
 
     def attention(self, x: torch.Tensor):
-        raise NotImplementedError("attention() is fused into forward(); call the block")
+        """model.py:226-231: self.attn(x, x, x, need_weights=False, attn_mask=self.attn_mask)[0]."""
+        if isinstance(self.attn, MultiheadAttention):
+            return self.attn(x, x, x, need_weights=False, attn_mask=self.attn_mask)[0]
+        # vanilla block: the same kernels with zero LoRA factors
+        if getattr(self, "_plain_mha", None) is None:
+            self._plain_mha = _PlainMha(self.attn)
+        return _MhaFn.apply(self._plain_mha, x, self._causal_flag(x.shape[0]),
+                            *self.attn.lora_params())
 
     def forward(self, x: torch.Tensor):
         if x.dim() != 3 or x.shape[-1] != self.d_model:
@@ -296,9 +515,44 @@ class ResidualAttentionBlock_LoRA(nn.Module):
         return _BlockFn.apply(self, x, *self.lora_params())
 
 
+class _PlainMha:
+    """Adapter giving a FrozenMultiheadAttention the packing interface _MhaFn expects."""
+
+    def __init__(self, attn: FrozenMultiheadAttention):
+        self.attn, self.num_heads = attn, attn.num_heads
+        self._cfg = _cfg_struct(attn.embed_dim, attn.num_heads, attn.embed_dim * 4, attn.r,
+                                1.0 / attn.r)
+        self._packed = None
+        self._key = None
+
+    def _layer_struct(self, lora, grads):
+        key = (self.attn.in_proj_weight.data_ptr(), self.attn.in_proj_weight._version)
+        if self._packed is None or key != self._key:
+            self._packed, self._key = PackedLayer(self.attn, None), key
+        s = K.VitLayer()
+        self._packed.fill(s, lora, grads)
+        return s
+
+    _refresh_lora = MultiheadAttention._refresh_lora
+
+
+class ResidualAttentionBlock_LoRA(ResidualAttentionBlock):
+    """model.py:400-415: the vanilla block with lora.MultiheadAttention as `attn`."""
+
+    def __init__(self, d_model: int, n_head: int, attn_mask: torch.Tensor = None,
+                 design_details: dict = {}):
+        super().__init__(d_model, n_head, attn_mask)
+        self.lora_alpha = design_details.get('lora_alpha', 1)
+        self.lora_r = design_details.get('lora_r', 4)
+        self.attn = MultiheadAttention(d_model, n_head, lora_alpha=self.lora_alpha, r=self.lora_r)
+        self._cfg = _cfg_struct(d_model, n_head, d_model * 4, self.lora_r,
+                                self.lora_alpha / self.lora_r)
+
+
 class Transformer(nn.Module):
-    """model.py:639-686. Only the 'lora' (both/this modality) flavour holds trainable blocks on
-    this path; other methods of the reference are out of scope."""
+    """model.py:639-686: LoRA blocks when method='lora' and peft_encoder covers this modality,
+    vanilla (frozen) blocks otherwise. The adapter / MoE / prefix flavours belong to other methods
+    of the reference (out of scope)."""
 
     def __init__(self, width: int, layers: int, heads: int, attn_mask: torch.Tensor = None,
                  design_details: dict = {}, modal='text'):
@@ -306,13 +560,17 @@ class Transformer(nn.Module):
         self.width, self.layers = width, layers
         res_type = design_details.get('method', 'vanilla')
         peft_flag = design_details.get('peft_encoder', 'none') in ['both', modal]
-        if not (res_type == 'lora' and peft_flag):
+        if res_type in ('moe', 'adapter', 'prefix_prompt') and peft_flag:
             raise NotImplementedError(
-                f"method={res_type!r} on modal={modal!r}: only LoRA blocks are built by "
-                "lifelong_clip_b200 (the image tower of scripts/lora_clip.sh)")
-        self.resblocks = nn.Sequential(*[
-            ResidualAttentionBlock_LoRA(width, heads, attn_mask, design_details)
-            for _ in range(layers)])
+                f"method={res_type!r}: only the LoRA and vanilla blocks are built by "
+                "lifelong_clip_b200 (scripts/lora_clip.sh)")
+        if res_type == 'lora' and peft_flag:
+            self.resblocks = nn.Sequential(*[
+                ResidualAttentionBlock_LoRA(width, heads, attn_mask, design_details)
+                for _ in range(layers)])
+        else:
+            self.resblocks = nn.Sequential(*[
+                ResidualAttentionBlock(width, heads, attn_mask) for _ in range(layers)])
 
     def forward(self, x: torch.Tensor):
         return self.resblocks(x)

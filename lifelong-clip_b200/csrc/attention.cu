@@ -12,11 +12,8 @@
 
 #include "common.cuh"
 
-// tcgen05/TMEM path (attention_tc.cu)
-bool llc_attn_tc_eligible(int L);
-int llc_attn_bwd_tc(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o, int ld_do,
-                    const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H, int sn, int sl,
-                    int causal, cudaStream_t st);
+// tcgen05/TMEM path (attention_fwd2.cu, attention_bwd4.cu, attention_bwd3.cu)
+static bool llc_attn_tc_eligible(int L) { return L <= 256; }
 int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
                      int sn, int sl, int causal, float* delta_ws, int delta_ready, cudaStream_t st);
@@ -26,8 +23,6 @@ int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const
                      int sn, int sl, int causal, cudaStream_t st);
 int llc_attn_fwd_tc2(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L,
                      int H, int sn, int sl, int causal, cudaStream_t st);
-int llc_attn_fwd_tc(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L, int H,
-                    int sn, int sl, int causal, cudaStream_t st);
 
 namespace {
 
@@ -465,12 +460,7 @@ template <int LP>
 int launch_fwd(const __nv_bfloat16* qkv, int ld_qkv, __nv_bfloat16* o, int ld_o, float* lse, int N,
                int L, int H, int sn, int sl, int causal, cudaStream_t st) {
   constexpr int smem = 3 * LP * 128;
-  static bool configured = false;
-  if (!configured) {
-    LLC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  smem));
-    configured = true;
-  }
+  LLC_CONFIGURE_SMEM(attn_fwd_kernel<LP>, smem);
   LLC_PROF_BEGIN(LLC_K_ATTN_FWD, N * H, L, 0, 4.0 * N * H * (double)L * L * HD,
                  8.0 * N * H * (double)L * HD, st);
   attn_fwd_kernel<LP><<<N * H, kWarps * 32, smem, st>>>(qkv, ld_qkv, o, ld_o, lse, L, H, sn, sl,
@@ -486,12 +476,7 @@ int launch_bwd(const __nv_bfloat16* qkv, int ld_qkv, const __nv_bfloat16* o, int
                const __nv_bfloat16* d_o, int ld_do, const float* lse, __nv_bfloat16* dqkv,
                int ld_dqkv, int N, int L, int H, int sn, int sl, int causal, cudaStream_t st) {
   constexpr int smem = 4 * LP * 128 + 2 * LP * 4;
-  static bool configured = false;
-  if (!configured) {
-    LLC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  smem));
-    configured = true;
-  }
+  LLC_CONFIGURE_SMEM(attn_bwd_kernel<LP>, smem);
   LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
                  16.0 * N * H * (double)L * HD, st);
   attn_bwd_kernel<LP><<<N * H, kWarps * 32, smem, st>>>(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse,
@@ -533,14 +518,10 @@ extern "C" int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, floa
               "llc_attn_fwd: bad output");
   // sequences up to 256 tokens run on the tensor cores through TMEM; LLC_ATTN_LEGACY=1 keeps the
   // mma.sync kernels (development A/B only)
-  static const bool legacy = getenv("LLC_ATTN_LEGACY") != nullptr;
-  static const bool v1 = getenv("LLC_ATTN_FWD1") != nullptr;   // previous lock-step kernel
-  if (!legacy && !v1 && llc_attn_tc_eligible(L))
+  static const bool legacy = llc_dev_env("LLC_ATTN_LEGACY") != nullptr;
+  if (!legacy && llc_attn_tc_eligible(L))
     return llc_attn_fwd_tc2(qkv, ld_qkv, o, ld_o, lse, N, L, H, tok_stride_n, tok_stride_l, causal,
                             (cudaStream_t)stream);
-  if (!legacy && llc_attn_tc_eligible(L))
-    return llc_attn_fwd_tc(qkv, ld_qkv, o, ld_o, lse, N, L, H, tok_stride_n, tok_stride_l, causal,
-                           (cudaStream_t)stream);
   DISPATCH_LP(L, (launch_fwd<LP>((const __nv_bfloat16*)qkv, ld_qkv, (__nv_bfloat16*)o, ld_o, lse,
                                  N, L, H, tok_stride_n, tok_stride_l, causal,
                                  (cudaStream_t)stream)));
@@ -548,12 +529,12 @@ extern "C" int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, floa
 
 // true when llc_attn_bwd_ws runs the unit-pipelined kernel for this L (the one that reads delta)
 bool llc_attn_bwd_uses_delta(int L) {
-  static const bool other = getenv("LLC_ATTN_LEGACY") || getenv("LLC_ATTN_BWD2") || getenv("LLC_ATTN_BWD3");
+  static const bool other = llc_dev_env("LLC_ATTN_LEGACY") || llc_dev_env("LLC_ATTN_BWD3");
   return !other && llc_attn_tc_eligible(L) && llc_attn_bwd_tc4_smem(L) <= 227 * 1024;
 }
 
-// llc_attn_bwd with caller-provided scratch for delta = rowsum(dO o O) ([N*H*L] floats; nullptr:
-// library-owned scratch, which cannot grow under stream capture)
+// llc_attn_bwd with the state of the caller-provided delta = rowsum(dO o O) scratch ([N*H*L]
+// floats) made explicit: delta_ready = 1 when the caller already filled it (llc_colsum_tc_delta)
 int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                     int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
                     int tok_stride_n, int tok_stride_l, int causal, float* delta_ws, int delta_ready,
@@ -564,20 +545,16 @@ int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const 
               "llc_attn_bwd: bad leading dimension");
   LLC_REQUIRE((((uintptr_t)o | (uintptr_t)d_o) & 15) == 0 && ((uintptr_t)dqkv & 3) == 0,
               "llc_attn_bwd: misaligned pointer");
-  static const bool legacy = getenv("LLC_ATTN_LEGACY") != nullptr;
-  static const bool v2 = getenv("LLC_ATTN_BWD2") != nullptr;   // previous two-orientation kernel
-  static const bool v3 = getenv("LLC_ATTN_BWD3") != nullptr;   // previous block-structured kernel
-  if (!legacy && !v2 && !v3 && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 &&
+  static const bool legacy = llc_dev_env("LLC_ATTN_LEGACY") != nullptr;
+  static const bool v3 = llc_dev_env("LLC_ATTN_BWD3") != nullptr;   // block-structured kernel (A/B)
+  if (!legacy && !v3 && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 &&
       ((uintptr_t)dqkv & 15) == 0 && llc_attn_bwd_tc4_smem(L) <= 227 * 1024)
     return llc_attn_bwd_tc4(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
                             tok_stride_n, tok_stride_l, causal, delta_ws, delta_ready,
                             (cudaStream_t)stream);
-  if (!legacy && !v2 && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
+  if (!legacy && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
     return llc_attn_bwd_tc3(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
                             tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream);
-  if (!legacy && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
-    return llc_attn_bwd_tc(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
-                           tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream);
   DISPATCH_LP(L, (launch_bwd<LP>((const __nv_bfloat16*)qkv, ld_qkv, (const __nv_bfloat16*)o, ld_o,
                                  (const __nv_bfloat16*)d_o, ld_do, lse, (__nv_bfloat16*)dqkv,
                                  ld_dqkv, N, L, H, tok_stride_n, tok_stride_l, causal,
@@ -586,7 +563,9 @@ int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const 
 
 extern "C" int llc_attn_bwd(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                             int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L,
-                            int H, int tok_stride_n, int tok_stride_l, int causal, void* stream) {
+                            int H, int tok_stride_n, int tok_stride_l, int causal, float* delta,
+                            void* stream) {
+  LLC_REQUIRE(delta, "llc_attn_bwd: delta scratch ([N*H*L] floats) is required");
   return llc_attn_bwd_ws(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
-                         tok_stride_n, tok_stride_l, causal, nullptr, 0, stream);
+                         tok_stride_n, tok_stride_l, causal, delta, 0, stream);
 }

@@ -444,7 +444,7 @@ int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const
   p.N = N; p.L = L; p.H = H; p.LK = (L + 15) / 16 * 16; p.NT = (L + 127) / 128;
   p.sn = sn; p.sl = sl; p.causal = causal;
   p.mat_bytes = p.LK * 128;
-  static const int dbg = getenv("LLC_ATTN_DBG") ? atoi(getenv("LLC_ATTN_DBG")) : 0;
+  static const int dbg = llc_dev_env("LLC_ATTN_DBG") ? atoi(llc_dev_env("LLC_ATTN_DBG")) : 0;
   p.dbg = dbg;
   const int smem = 4 * p.mat_bytes + 2 * kPTileBytes + kStagingBytes + 2 * 256 * 4 + 256;
   const int rows0 = p.NT > 1 ? 128 : p.LK, rows1 = p.NT > 1 ? p.LK - 128 : 16;
@@ -454,12 +454,7 @@ int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const
   if (int rc = encode_rows(&d0, d_o, H * HD, ld_do, L, N, sn, sl, rows0)) return rc;
   if (int rc = encode_rows(&d1, d_o, H * HD, ld_do, L, N, sn, sl, rows1)) return rc;
   if (int rc = encode_rows(&to, dqkv, 3 * H * HD, ld_dqkv, L, N, sn, sl, 128)) return rc;
-  static int configured = 0;
-  if (configured < smem) {
-    LLC_CUDA(cudaFuncSetAttribute(attn_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  smem));
-    configured = smem;
-  }
+  LLC_CONFIGURE_SMEM(attn_bwd3_kernel, smem);
   const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
                  16.0 * N * H * (double)L * HD, st);

@@ -578,32 +578,11 @@ int llc_attn_bwd_tc4_smem(int L) {
   return 4 * LK * 128 + 4 * kTileBytes + kStagingBytes + 4 * 256 * 4 + 1024;
 }
 
-// Scratch for delta when the caller passes none (the plain C-ABI entry): grown on demand, one
-// per process (the library drives one stream per device). It cannot grow under stream capture.
-static float* g_delta_ws = nullptr;
-static size_t g_delta_ws_floats = 0;
-
 int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
                      int sn, int sl, int causal, float* delta_ws, int delta_ready, cudaStream_t st) {
   // delta_ready: the caller already filled delta_ws[token * H + head] (llc_colsum_tc_delta)
-  const size_t need = (size_t)N * H * L;
-  if (!delta_ws) {
-    if (g_delta_ws_floats < need) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      LLC_CUDA(cudaStreamIsCapturing(st, &cs));
-      LLC_REQUIRE(cs == cudaStreamCaptureStatusNone,
-                  "llc_attn_bwd: scratch must grow during stream capture; run one eager call of "
-                  "this shape first");
-      LLC_CUDA(cudaStreamSynchronize(st));
-      if (g_delta_ws) LLC_CUDA(cudaFree(g_delta_ws));
-      g_delta_ws = nullptr;
-      g_delta_ws_floats = 0;
-      LLC_CUDA(cudaMalloc(&g_delta_ws, need * sizeof(float)));
-      g_delta_ws_floats = need;
-    }
-    delta_ws = g_delta_ws;
-  }
+  LLC_REQUIRE(delta_ws, "llc_attn_bwd: delta scratch ([N*H*L] floats) is required");
   Bwd4Params p;
   p.lse = lse;
   p.delta = delta_ws;
@@ -611,7 +590,7 @@ int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const
   p.NU = (p.LK + 63) / 64;
   p.sn = sn; p.sl = sl; p.causal = causal;
   p.mat_bytes = p.LK * 128;
-  static const int dbg = getenv("LLC_ATTN_DBG") ? atoi(getenv("LLC_ATTN_DBG")) : 0;
+  static const int dbg = llc_dev_env("LLC_ATTN_DBG") ? atoi(llc_dev_env("LLC_ATTN_DBG")) : 0;
   p.dbg = dbg;
   const int smem = llc_attn_bwd_tc4_smem(L);
   CUtensorMap q64, q16, d64, d16, to;
@@ -620,12 +599,7 @@ int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const
   if (int rc = encode_rows(&d64, d_o, H * HD, ld_do, L, N, sn, sl, 64)) return rc;
   if (int rc = encode_rows(&d16, d_o, H * HD, ld_do, L, N, sn, sl, 16)) return rc;
   if (int rc = encode_rows(&to, dqkv, 3 * H * HD, ld_dqkv, L, N, sn, sl, 128)) return rc;
-  static int configured = 0;
-  if (configured < smem) {
-    LLC_CUDA(cudaFuncSetAttribute(attn_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  smem));
-    configured = smem;
-  }
+  LLC_CONFIGURE_SMEM(attn_bwd4_kernel, smem);
   const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 0, 8.0 * N * H * (double)L * L * HD,
                  16.0 * N * H * (double)L * HD, st);

@@ -456,14 +456,9 @@ int llc_attn_fwd_tc2(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse,
   p.lse = lse;
   p.N = N; p.L = L; p.H = H; p.LK = (L + 15) / 16 * 16; p.NT = (L + 127) / 128;
   p.causal = causal;
-  static const int dbg = getenv("LLC_ATTN_DBG") ? atoi(getenv("LLC_ATTN_DBG")) : 0;
+  static const int dbg = llc_dev_env("LLC_ATTN_DBG") ? atoi(llc_dev_env("LLC_ATTN_DBG")) : 0;
   p.dbg = dbg;
-  static bool configured = false;
-  if (!configured) {
-    LLC_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmem));
-    configured = true;
-  }
+  LLC_CONFIGURE_SMEM(attn_fwd2_kernel, kSmem);
   const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_ATTN_FWD, N * H, L, 0, 4.0 * N * H * (double)L * L * HD,
                  8.0 * N * H * (double)L * HD, st);

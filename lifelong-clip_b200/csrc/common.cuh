@@ -6,8 +6,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/llc.h"
+
+// Development A/B switches (LLC_ATTN_LEGACY, LLC_GEMM_DBG, ...) exist only in -DLLC_DEV builds; the
+// shipped library reads no environment variables.
+#ifdef LLC_DEV
+inline const char* llc_dev_env(const char* name) { return getenv(name); }
+#else
+inline const char* llc_dev_env(const char*) { return nullptr; }
+#endif
 
 // ---------------------------------------------------------------- errors
 void llc_set_error(const char* fmt, ...);
@@ -31,6 +40,20 @@ int llc_check_cuda(cudaError_t e, const char* what);
   do {                                                           \
     cudaError_t _e = cudaGetLastError();                         \
     if (_e != cudaSuccess) return llc_check_cuda(_e, name);      \
+  } while (0)
+
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per DEVICE (the attribute is
+// per device; a process-wide flag would leave the second GPU of a process unconfigured).
+#define LLC_CONFIGURE_SMEM(kernel, bytes)                                                       \
+  do {                                                                                          \
+    static int cfg_done_[64];                                                                   \
+    int dev_ = 0;                                                                               \
+    LLC_CUDA(cudaGetDevice(&dev_));                                                             \
+    if (dev_ < 0 || dev_ >= 64 || cfg_done_[dev_] < (int)(bytes)) {                             \
+      LLC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                    (int)(bytes)));                                             \
+      if (dev_ >= 0 && dev_ < 64) cfg_done_[dev_] = (int)(bytes);                               \
+    }                                                                                           \
   } while (0)
 
 // launch counter (bench.py reports it as gpu_launches)

@@ -9,7 +9,7 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_llc_launches = 0;
-int g_llc_pdl = getenv("LLC_NO_PDL") == nullptr;
+int g_llc_pdl = llc_dev_env("LLC_NO_PDL") == nullptr;
 
 void llc_set_error(const char* fmt, ...) {
   va_list ap;

@@ -229,23 +229,18 @@ template <int MODE>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                  const CUtensorMap& tmO2, int M, int N, int K, const EpiParams& ep,
                  cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    LLC_CUDA(cudaFuncSetAttribute(gemm2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmem));
-    configured = true;
-  }
+  LLC_CONFIGURE_SMEM(gemm2_kernel<MODE>, kSmem);
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int pairs = llc_num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
   LLC_PROF_BEGIN(LLC_K_GEMM, M, N, K, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + (double)M * N * (ep.out_fp32 ? 4 : 2),
                  stream);
-  static const int dbg = getenv("LLC_GEMM_DBG") ? atoi(getenv("LLC_GEMM_DBG")) : 0;
+  static const int dbg = llc_dev_env("LLC_GEMM_DBG") ? atoi(llc_dev_env("LLC_GEMM_DBG")) : 0;
   EpiParams ep2 = ep;
   ep2.dbg = dbg;
   // a bf16 output that fits L2 (dh, d_o: 77 MB) is read again by the next kernel(s): let it stay
-  static const bool nokeep = getenv("LLC_GEMM_NOKEEP") != nullptr;
+  static const bool nokeep = llc_dev_env("LLC_GEMM_NOKEEP") != nullptr;
   ep2.keep_out = (!nokeep && !ep.out_fp32 && (double)M * N * 2.0 <= 100e6) ? 1 : 0;
   LLC_CUDA(llc_launch_pdl(gemm2_kernel<MODE>, dim3(grid), dim3(kThreads), kSmem, stream, tmA, tmB, tmO,
                           tmO2, M, N, K, ep2, dbg));

@@ -275,12 +275,7 @@ template <int BN>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
                 const EpiParams& ep, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    LLC_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kSmem));
-    configured = true;
-  }
+  LLC_CONFIGURE_SMEM(gemm_tn_kernel<BN>, C::kSmem);
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < llc_num_sms() ? tiles : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_GEMM, M, N, K, 2.0 * M * N * K,
@@ -327,7 +322,7 @@ extern "C" int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
 
   // production shapes: 256 x 256 tiles on CTA pairs (gemm2_tcgen05.cu); LLC_GEMM_1CTA=1 forces
   // the single-CTA kernel below (debugging / A-B comparison)
-  static const bool force_1cta = getenv("LLC_GEMM_1CTA") != nullptr;
+  static const bool force_1cta = llc_dev_env("LLC_GEMM_1CTA") != nullptr;
   if (!force_1cta && llc_gemm2_eligible(M, N, K))
     return llc_gemm2_launch(A, lda, B, ldb, M, N, K, ep, reinterpret_cast<cudaStream_t>(stream));
 
@@ -337,7 +332,7 @@ extern "C" int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
   const bool use256 = (N % 256 == 0) && tiles256 >= llc_num_sms();
   // N <= 32: rank-r row products (N = 16), stream A at HBM rate. M <= 512 (the class-token-only
   // last block: M = images): 32-wide tiles spread the few rows over 4x more CTAs
-  static const bool small_m32 = getenv("LLC_GEMM_SMALLM_BN128") == nullptr;
+  static const bool small_m32 = llc_dev_env("LLC_GEMM_SMALLM_BN128") == nullptr;
   const bool use32 = N <= 32 || (small_m32 && M <= 512 && N % 32 == 0 && !use256);
   const int BN = use256 ? 256 : (use32 ? 32 : 128);
 

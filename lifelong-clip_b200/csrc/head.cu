@@ -54,6 +54,9 @@ struct HeadK {
   int64_t* pred;
   const float* d_feat;
   int skip_logit_grad;
+  const int64_t* row_idx;   // row of sample n in x / dx (text tower: the EOT token), else n*cls_stride
+  const float* d_fnorm;     // backward: gradient w.r.t. the NORMALISED features (text side)
+  float* dlogits;           // backward: dL/dlogits [N, C] written out (for llc_head_dtext)
   int rot;   // bit 0: rotate the proj row order per CTA, bit 1: the text row order (LLC_HEAD_ROT)
 };
 
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadK a) {
   // ln_post of each sample's CLS row
   for (int sI = 0; sI < kS; ++sI) {
     const int n = min(n0 + sI, a.N - 1);     // tail samples recompute the last one (not stored)
-    const float* xr = a.x + (size_t)n * a.cls_stride * a.ld_x;
+    const float* xr = a.x + (a.row_idx ? (size_t)a.row_idx[n] : (size_t)n * a.cls_stride) * a.ld_x;
     float* y = sy + sI * a.D;
     float s = 0.f;
     for (int k = tid; k < a.D; k += kThreads) { y[k] = xr[k]; s += y[k]; }
@@ -254,6 +257,9 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
         dot = block_sum(dot, red);
         for (int c = tid; c < a.C; c += kThreads) g[c] = pr[c] * (g[c] - dot);
       }
+      if (a.dlogits && n0 + sI < a.N) {
+        for (int c = tid; c < a.C; c += kThreads) a.dlogits[(size_t)n * a.C + c] = g[c];
+      }
       for (int e = tid; e < a.E; e += kThreads) sf[sI * a.E + e] = a.fnorm[(size_t)n * a.E + e];
     }
     __syncthreads();
@@ -313,6 +319,29 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
         sz[sI * a.E + e] = v;
       }
     }
+  } else if (a.d_fnorm) {
+    // gradient arrives w.r.t. f = z/|z| (the text side of the logit product):
+    // dz = (df - f (f.df)) / |z|  [+ d_feat]
+    for (int sI = 0; sI < kS; ++sI) {
+      const int n = min(n0 + sI, a.N - 1);
+      float fd = 0.f, zz = 0.f;
+      for (int e = tid; e < a.E; e += kThreads) {
+        const float f = a.fnorm[(size_t)n * a.E + e];
+        const float v = a.d_fnorm[(size_t)n * a.E + e] * loss_scale;
+        const float zf = a.feat[(size_t)n * a.E + e];
+        sf[sI * a.E + e] = f;
+        sz[sI * a.E + e] = v;
+        fd += v * f;
+        zz += zf * zf;
+      }
+      fd = block_sum(fd, red);
+      const float inv_norm = 1.0f / sqrtf(block_sum(zz, red));
+      for (int e = tid; e < a.E; e += kThreads) {
+        float v = (sz[sI * a.E + e] - sf[sI * a.E + e] * fd) * inv_norm;
+        if (a.d_feat) v += a.d_feat[(size_t)n * a.E + e] * loss_scale;
+        sz[sI * a.E + e] = v;
+      }
+    }
   } else {
     for (int sI = 0; sI < kS; ++sI) {
       const int n = min(n0 + sI, a.N - 1);
@@ -348,7 +377,8 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
   for (int sI = 0; sI < kS; ++sI) {
     const int n = n0 + sI;
     if (n >= a.N) break;
-    const float* xr = a.x + (size_t)n * a.cls_stride * a.ld_x;
+    const size_t xrow = a.row_idx ? (size_t)a.row_idx[n] : (size_t)n * a.cls_stride;
+    const float* xr = a.x + xrow * a.ld_x;
     float* xh_ = sxh + sI * a.D;
     float* dy_ = sdy + sI * a.D;
     float s = 0.f;
@@ -368,7 +398,7 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
     }
     c1 = block_sum(c1, red) / a.D;
     c2 = block_sum(c2, red) / a.D;
-    float* dr = dx + (size_t)n * a.cls_stride * ld_dx;
+    float* dr = dx + xrow * ld_dx;
     for (int k = tid; k < a.D; k += kThreads) dr[k] = rstd * (dy_[k] - c1 - xh_[k] * c2);
   }
 }
@@ -395,6 +425,21 @@ __global__ void loss_acc_kernel(const float* __restrict__ loss_rows,
   if (threadIdx.x == 0) { out[0] = l; out[1] = c; }
 }
 
+// d_text[c, e] = scale * sum_n dlogits[n, c] * fnorm[n, e]: the gradient of the logit product
+// (model.py:972) w.r.t. the normalised text row of visible class c. One CTA per class, samples in
+// a fixed order: deterministic.
+__global__ void __launch_bounds__(kThreads)
+head_dtext_kernel(const float* __restrict__ dlogits, const float* __restrict__ fnorm, int N, int C,
+                  int E, float scale, float* __restrict__ d_text) {
+  const int c = blockIdx.x;
+  for (int e = threadIdx.x; e < E; e += kThreads) {
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n)
+      acc = fmaf(__ldg(dlogits + (size_t)n * C + c), __ldg(fnorm + (size_t)n * E + e), acc);
+    d_text[(size_t)c * E + e] = acc * scale;
+  }
+}
+
 int to_k(const llc_head_args* a, HeadK* k, const char* who) {
   LLC_REQUIRE(a && a->x && a->ln_g && a->ln_b && a->proj && a->text, "%s: null input", who);
   LLC_REQUIRE(a->N > 0 && a->D > 0 && a->E > 0 && a->C > 0, "%s: empty problem", who);
@@ -407,7 +452,8 @@ int to_k(const llc_head_args* a, HeadK* k, const char* who) {
   k->feat = a->feat; k->fnorm = a->fnorm; k->logits = a->logits; k->probs = a->probs;
   k->loss_rows = a->loss_rows; k->pred = a->pred;
   k->d_feat = a->d_feat; k->skip_logit_grad = a->skip_logit_grad;
-  static const int rot = getenv("LLC_HEAD_ROT") ? atoi(getenv("LLC_HEAD_ROT")) : 1;
+  k->row_idx = a->row_idx; k->d_fnorm = a->d_fnorm; k->dlogits = a->dlogits;
+  static const int rot = llc_dev_env("LLC_HEAD_ROT") ? atoi(llc_dev_env("LLC_HEAD_ROT")) : 1;
   k->rot = rot;
   return 0;
 }
@@ -419,9 +465,7 @@ extern "C" int llc_head_fwd(const llc_head_args* a, void* stream) {
   if (int rc = to_k(a, &k, "llc_head_fwd")) return rc;
   const size_t smem = (size_t)(kS * (a->D + a->E + a->C) + 32) * sizeof(float);
   LLC_REQUIRE(smem <= 200 * 1024, "llc_head_fwd: D+E+C too large for one CTA");
-  if (smem > 48 * 1024)
-    LLC_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+  if (smem > 48 * 1024) LLC_CONFIGURE_SMEM(head_fwd_kernel, smem);
   LLC_PROF_BEGIN(LLC_K_HEAD, a->N, a->C, 0, 2.0 * a->N * ((double)a->D * a->E + (double)a->E * a->C),
                  4.0 * a->N * (a->D + 2 * a->E + 2 * a->C), (cudaStream_t)stream);
   head_fwd_kernel<<<(a->N + kS - 1) / kS, kThreads, smem, (cudaStream_t)stream>>>(k);
@@ -436,14 +480,13 @@ extern "C" int llc_head_bwd(const llc_head_args* a, const float* d_probs, float 
   HeadK k;
   if (int rc = to_k(a, &k, "llc_head_bwd")) return rc;
   LLC_REQUIRE(dx && ld_dx >= a->D, "llc_head_bwd: bad dx");
-  LLC_REQUIRE(d_probs || a->labels || (a->skip_logit_grad && a->d_feat),
-              "llc_head_bwd: need d_probs, labels or d_feat");
-  LLC_REQUIRE(!a->skip_logit_grad || a->d_feat, "llc_head_bwd: skip_logit_grad needs d_feat");
+  LLC_REQUIRE(d_probs || a->labels || (a->skip_logit_grad && (a->d_feat || a->d_fnorm)),
+              "llc_head_bwd: need d_probs, labels or d_feat / d_fnorm");
+  LLC_REQUIRE(!a->skip_logit_grad || a->d_feat || a->d_fnorm,
+              "llc_head_bwd: skip_logit_grad needs d_feat or d_fnorm");
   const size_t smem = (size_t)(kS * (a->C + 2 * a->E + 2 * a->D) + 32) * sizeof(float);
   LLC_REQUIRE(smem <= 200 * 1024, "llc_head_bwd: sizes too large for one CTA");
-  if (smem > 48 * 1024)
-    LLC_CUDA(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+  if (smem > 48 * 1024) LLC_CONFIGURE_SMEM(head_bwd_kernel, smem);
   LLC_PROF_BEGIN(LLC_K_HEAD, a->N, a->C, 1, 2.0 * a->N * ((double)a->D * a->E + (double)a->E * a->C),
                  4.0 * a->N * (2 * a->D + 2 * a->E + a->C), (cudaStream_t)stream);
   head_bwd_kernel<<<(a->N + kS - 1) / kS, kThreads, smem, (cudaStream_t)stream>>>(
@@ -451,6 +494,18 @@ extern "C" int llc_head_bwd(const llc_head_args* a, const float* d_probs, float 
   LLC_PROF_END((cudaStream_t)stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("head_bwd_kernel");
+  return 0;
+}
+
+extern "C" int llc_head_dtext(const float* dlogits, const float* fnorm, int N, int C, int E,
+                              float scale, float* d_text, void* stream) {
+  LLC_REQUIRE(dlogits && fnorm && d_text && N > 0 && C > 0 && E > 0, "llc_head_dtext: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  LLC_PROF_BEGIN(LLC_K_HEAD, N, C, 4, 2.0 * N * C * E, 4.0 * ((double)N * C + (double)N * E + (double)C * E), st);
+  head_dtext_kernel<<<C, kThreads, 0, st>>>(dlogits, fnorm, N, C, E, scale, d_text);
+  LLC_PROF_END(st);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("head_dtext_kernel");
   return 0;
 }
 

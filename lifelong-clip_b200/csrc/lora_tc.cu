@@ -414,12 +414,7 @@ int llc_lora_fused_tc(const void* X, int ld_x, int T, int C, int R, const void* 
   const int nslabs = (T + 127) / 128;
   const int grid = nslabs < llc_num_sms() ? nslabs : llc_num_sms();
   const int smem = 1024 + 2 * kFWTile + kFStages * kFStage + 256;
-  static int configured = 0;
-  if (configured < smem) {
-    LLC_CUDA(cudaFuncSetAttribute(lora_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  smem));
-    configured = smem;
-  }
+  LLC_CONFIGURE_SMEM(lora_fused_tc_kernel, smem);
   LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 3, 4.0 * T * C * 16, 2.0 * T * C, st);
   LLC_CUDA(llc_launch_pdl(lora_fused_tc_kernel, dim3(grid), dim3(kThreads), (size_t)smem, st, tm, tf,
                           reinterpret_cast<const __nv_bfloat16*>(w), ld_w,
@@ -458,12 +453,7 @@ int llc_colsum_tc_delta(const void* X, int ld_x, int T, int C, int R, const void
   int per = (T + splits - 1) / splits;
   per = (per + kKB - 1) / kKB * kKB;          // k-blocks never straddle two slices
   splits = (T + per - 1) / per;
-  static bool configured = false;
-  if (!configured) {
-    LLC_CUDA(cudaFuncSetAttribute(lora_colsum_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmem));
-    configured = true;
-  }
+  LLC_CONFIGURE_SMEM(lora_colsum_tc_kernel, kSmem);
   LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, delta ? 4 : 2, 2.0 * T * C * 16,
                  (delta ? 4.0 : 2.0) * T * C, st);
   LLC_CUDA(llc_launch_pdl(lora_colsum_tc_kernel, dim3(mtiles, splits), dim3(kThreads), kSmem, st, tm,

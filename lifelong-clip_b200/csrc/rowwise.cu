@@ -710,21 +710,11 @@ extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float
     const int grid = min((T + 31) / 32, 4 * llc_num_sms());
     LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 0, 2.0 * T * C * r, 2.0 * T * C, st);
     if (R == 4) {
-      static bool cfg4 = false;
-      if (!cfg4) {
-        LLC_CUDA(cudaFuncSetAttribute(lora_rowdot_kernel<4>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        cfg4 = true;
-      }
+      LLC_CONFIGURE_SMEM(lora_rowdot_kernel<4>, 160 * 1024);
       lora_rowdot_kernel<4><<<grid, kSideThreads, smem, st>>>((__nv_bfloat16*)X, ld_x, T, C, r, Mrd,
                                                              rd_sc, rd_sj, rd_scale);
     } else {
-      static bool cfg8 = false;
-      if (!cfg8) {
-        LLC_CUDA(cudaFuncSetAttribute(lora_rowdot_kernel<8>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        cfg8 = true;
-      }
+      LLC_CONFIGURE_SMEM(lora_rowdot_kernel<8>, 160 * 1024);
       lora_rowdot_kernel<8><<<grid, kSideThreads, smem, st>>>((__nv_bfloat16*)X, ld_x, T, C, r, Mrd,
                                                              rd_sc, rd_sj, rd_scale);
     }
@@ -732,7 +722,7 @@ extern "C" int llc_lora_side(void* X, int ld_x, int T, int C, int r, const float
     LLC_COUNT_LAUNCH();
     LLC_LAUNCH_CHECK("lora_rowdot_kernel");
   }
-  static const bool cc_colsum = getenv("LLC_COLSUM_LEGACY") != nullptr;
+  static const bool cc_colsum = llc_dev_env("LLC_COLSUM_LEGACY") != nullptr;
   if (w != nullptr && !cc_colsum && llc_colsum_tc_eligible(X, ld_x, T, C, w, ld_w))
     return llc_colsum_tc(X, ld_x, T, C, R, w, ld_w, partial, n_partials, st);
   if (w != nullptr) {

@@ -37,11 +37,12 @@ struct Dims {
   int N, L, T, D, H, M, E, G, P, PK /* padded 3*P*P */, r, layers;
 };
 
-Dims make_dims(const llc_vit_cfg* c, int N) {
+// context > 0: a text tower (sequence length = context, no patch front end)
+Dims make_dims(const llc_vit_cfg* c, int N, int context = 0) {
   Dims d;
   d.N = N;
-  d.G = c->image_size / c->patch;
-  d.L = d.G * d.G + 1;
+  d.G = context > 0 ? 0 : c->image_size / c->patch;
+  d.L = context > 0 ? context : d.G * d.G + 1;
   d.T = N * d.L;
   d.D = c->width;
   d.H = c->heads;
@@ -120,7 +121,8 @@ int check_cfg(const llc_vit_cfg* c, const char* who) {
   LLC_REQUIRE(c, "%s: null cfg", who);
   LLC_REQUIRE(c->width % 128 == 0 && c->heads * 64 == c->width,
               "%s: width %d / heads %d unsupported (head dim must be 64)", who, c->width, c->heads);
-  LLC_REQUIRE(c->patch % 2 == 0 && c->image_size % c->patch == 0, "%s: bad patch geometry", who);
+  LLC_REQUIRE(c->patch > 0 && c->patch % 2 == 0 && c->image_size % c->patch == 0,
+              "%s: bad patch geometry", who);
   LLC_REQUIRE(c->mlp_dim % 8 == 0 && c->layers > 0 && c->embed_dim > 0, "%s: bad dims", who);
   LLC_REQUIRE(c->lora_r >= 1 && c->lora_r <= 8, "%s: LoRA rank %d unsupported (1..8)", who,
               c->lora_r);
@@ -183,17 +185,15 @@ extern "C" int llc_cast_bf16(const float* src, void* dst, int T, int D, int ld_d
   return 0;
 }
 
-extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
-                                 const llc_block_bufs* b, int N, int L, int sn, int sl, int causal,
-                                 void* stream) {
-  RUN(check_cfg(cfg, "llc_block_forward"));
-  LLC_REQUIRE(w && b && N > 0 && L > 0, "llc_block_forward: bad args");
-  const int D = cfg->width, M = cfg->mlp_dim, H = cfg->heads, r = cfg->lora_r;
+// attention half of a block, from the normalised (or raw, for llc_mha_forward) input in b->h1
+// (bf16 | u = h A_in^T in the pad columns) to the out-projection, whose epilogue is given by `eo`
+static int attn_half_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
+                             llc_gemm_epi eo, int N, int L, int sn, int sl, int causal,
+                             void* stream) {
+  const int D = cfg->width, H = cfg->heads;
   const int T = N * L, DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;  // row pitches
-  const int KA = D + LLC_LORA_PAD, KQ = 3 * D + LLC_LORA_PAD;              // K extents
+  const int KA = D + LLC_LORA_PAD;                                       // K extent
   llc_gemm_epi e;
-  // x -> ln_1 -> h1 | u = h1 A_in^T
-  RUN(llc_ln_fwd(b->x_in, D, w->ln1_g, w->ln1_b, T, D, b->h1, DA, w->in_A, r, stream));
   // qkv = h1 W_in^T + b_in + s (h1 A^T) B^T   (one accumulator, K = D + 16)
   e = llc_gemm_epi{};
   e.bias = w->bqkv; e.out = b->qkv; e.ld_out = QA;
@@ -203,11 +203,26 @@ extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   e = llc_gemm_epi{};
   e.out = reinterpret_cast<__nv_bfloat16*>(b->o) + D; e.ld_out = DA;
   RUN(llc_gemm_bf16_tn(b->o, DA, w->f_out_A, D, T, LLC_LORA_PAD, D, &e, stream));
-  // x_mid = x + o W_o^T + b_o + s (o A_o^T) B_o^T
+  // out = [resid +] o W_o^T + b_o + s (o A_o^T) B_o^T
+  eo.bias = w->bo;
+  RUN(llc_gemm_bf16_tn(b->o, DA, w->wo_aug, DA, T, D, KA, &eo, stream));
+  return 0;
+}
+
+extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                                 const llc_block_bufs* b, int N, int L, int sn, int sl, int causal,
+                                 void* stream) {
+  RUN(check_cfg(cfg, "llc_block_forward"));
+  LLC_REQUIRE(w && b && N > 0 && L > 0, "llc_block_forward: bad args");
+  const int D = cfg->width, M = cfg->mlp_dim, r = cfg->lora_r;
+  const int T = N * L, DA = D + LLC_LORA_LD;
+  llc_gemm_epi e;
+  // x -> ln_1 -> h1 | u = h1 A_in^T
+  RUN(llc_ln_fwd(b->x_in, D, w->ln1_g, w->ln1_b, T, D, b->h1, DA, w->in_A, r, stream));
+  // x_mid = x + attention(h1)
   e = llc_gemm_epi{};
-  e.bias = w->bo; e.resid = b->x_in; e.ld_resid = D; e.out = b->x_mid; e.ld_out = D;
-  e.out_fp32 = 1;
-  RUN(llc_gemm_bf16_tn(b->o, DA, w->wo_aug, DA, T, D, KA, &e, stream));
+  e.resid = b->x_in; e.ld_resid = D; e.out = b->x_mid; e.ld_out = D; e.out_fp32 = 1;
+  RUN(attn_half_forward(cfg, w, b, e, N, L, sn, sl, causal, stream));
   // mlp
   RUN(llc_ln_fwd(b->x_mid, D, w->ln2_g, w->ln2_b, T, D, b->h2, D, nullptr, 0, stream));
   e = llc_gemm_epi{};
@@ -220,14 +235,32 @@ extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   return 0;
 }
 
-extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
-                                  const llc_block_bufs* b, const llc_block_bwd_bufs* s, int N,
-                                  int L, int sn, int sl, int causal, int need_dx_in,
-                                  void* stream) {
-  RUN(check_cfg(cfg, "llc_block_backward"));
-  LLC_REQUIRE(w && b && s && N > 0 && L > 0, "llc_block_backward: bad args");
-  LLC_REQUIRE(b->z, "llc_block_backward: forward was not run in training mode");
-  const int D = cfg->width, M = cfg->mlp_dim, H = cfg->heads, r = cfg->lora_r;
+// lora.MultiheadAttention.forward for self-attention (reference models/clip/lora.py:454-702 ->
+// multi_head_attention_forward :732-1082): x fp32 [T, D] -> out fp32 [T, D]. b->h1 / qkv / lse / o
+// are written (saved for llc_mha_backward); b->x_in = x, b->x_out = out; the other members are
+// unused.
+extern "C" int llc_mha_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                               const llc_block_bufs* b, int N, int L, int sn, int sl, int causal,
+                               void* stream) {
+  RUN(check_cfg(cfg, "llc_mha_forward"));
+  LLC_REQUIRE(w && b && b->x_in && b->x_out && b->h1 && b->qkv && b->o && b->lse && N > 0 && L > 0,
+              "llc_mha_forward: bad args");
+  const int D = cfg->width, r = cfg->lora_r, T = N * L, DA = D + LLC_LORA_LD;
+  RUN(llc_cast_bf16(b->x_in, b->h1, T, D, DA, stream));
+  // u = x A_in^T (fp32 factor [r, D]: element (j, c) at j*D + c) into the pad columns of h1
+  RUN(llc_lora_side(b->h1, DA, T, D, r, w->in_A, 1, D, 1.0f, nullptr, 0, nullptr, nullptr, stream));
+  llc_gemm_epi e{};
+  e.out = b->x_out; e.ld_out = D; e.out_fp32 = 1;
+  return attn_half_forward(cfg, w, b, e, N, L, sn, sl, causal, stream);
+}
+
+// attention half of the backward: from s->dxb = bf16 gradient of the out-projection's output
+// (pad columns free) to the LoRA gradients and, if need_dh1, s->dh = gradient of the attention
+// input h1 (bf16 [T, D])
+static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                              const llc_block_bufs* b, const llc_block_bwd_bufs* s, int N, int L,
+                              int sn, int sl, int causal, int need_dh1, void* stream) {
+  const int D = cfg->width, H = cfg->heads, r = cfg->lora_r;
   const float sc = cfg->lora_scale;
   const int T = N * L, DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;  // row pitches
   const int KA = D + LLC_LORA_PAD, KQ = 3 * D + LLC_LORA_PAD;              // K extents
@@ -236,19 +269,6 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   __nv_bfloat16* h1 = reinterpret_cast<__nv_bfloat16*>(b->h1);
   __nv_bfloat16* dqkv = reinterpret_cast<__nv_bfloat16*>(s->dqkv);
   llc_gemm_epi e;
-  // dz = (dx W_proj) o QuickGELU'(z)
-  e = llc_gemm_epi{};
-  e.act = 2; e.aux = b->z; e.ld_aux = M; e.out = s->dz; e.ld_out = M;
-  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->wprojT, D, T, M, D, &e, stream));
-  // dh2 = dz W_fc
-  e = llc_gemm_epi{};
-  e.out = s->dh; e.ld_out = D;
-  RUN(llc_gemm_bf16_tn(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
-  // dx_mid = dx + LN2'(dh2); bf16 copy | du_o = s dx_mid B_o
-  // (the row product du_o = s dx_mid B_o runs as a skinny GEMM on the tensor cores: fused into the
-  // LayerNorm kernel it cost 52 us per launch in L1 traffic for the factor, profiles/)
-  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
-                 stream));
   // LoRA weight gradients: four column sums, each into its own partial region, reduced by ONE
   // finish launch at the end of the layer.
   const size_t preg = (size_t)llc_lora_side_max_partials() * 3 * D * 2;   // floats per region
@@ -306,15 +326,57 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
     };
     RUN(llc_lora_colsum_finish_multi(jobs, 4, r, stream));
   }
-  if (need_dx_in) {
-    // dh1 = dqkv W_in + du A_in ; dx_in = dx_mid + LN1'(dh1)
+  if (need_dh1) {
+    // dh1 = dqkv W_in + du A_in
     e = llc_gemm_epi{};
     e.out = s->dh; e.ld_out = D;
     RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->wqkvT_aug, QA, T, D, KQ, &e, stream));
-    RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
-                   stream));
   }
   return 0;
+}
+
+extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                                  const llc_block_bufs* b, const llc_block_bwd_bufs* s, int N,
+                                  int L, int sn, int sl, int causal, int need_dx_in,
+                                  void* stream) {
+  RUN(check_cfg(cfg, "llc_block_backward"));
+  LLC_REQUIRE(w && b && s && N > 0 && L > 0, "llc_block_backward: bad args");
+  LLC_REQUIRE(b->z, "llc_block_backward: forward was not run in training mode");
+  const int D = cfg->width, M = cfg->mlp_dim;
+  const int T = N * L, DA = D + LLC_LORA_LD;
+  llc_gemm_epi e;
+  // dz = (dx W_proj) o QuickGELU'(z)
+  e = llc_gemm_epi{};
+  e.act = 2; e.aux = b->z; e.ld_aux = M; e.out = s->dz; e.ld_out = M;
+  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->wprojT, D, T, M, D, &e, stream));
+  // dh2 = dz W_fc
+  e = llc_gemm_epi{};
+  e.out = s->dh; e.ld_out = D;
+  RUN(llc_gemm_bf16_tn(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
+  // dx_mid = dx + LN2'(dh2); bf16 copy (the row product du_o = s dx_mid B_o runs on the tensor
+  // cores inside attn_half_backward: fused into the LayerNorm kernel it cost 52 us per launch in
+  // L1 traffic for the factor, profiles/)
+  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
+                 stream));
+  RUN(attn_half_backward(cfg, w, b, s, N, L, sn, sl, causal, need_dx_in, stream));
+  if (need_dx_in)   // dx_in = dx_mid + LN1'(dh1)
+    RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
+                   stream));
+  return 0;
+}
+
+// backward of llc_mha_forward: s->dx = fp32 gradient of the output [T, D] (read only);
+// LoRA gradients -> w->g_*; if need_dx_in, s->dh = bf16 gradient of the input x [T, D].
+// s->dz is unused.
+extern "C" int llc_mha_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                                const llc_block_bufs* b, const llc_block_bwd_bufs* s, int N, int L,
+                                int sn, int sl, int causal, int need_dx_in, void* stream) {
+  RUN(check_cfg(cfg, "llc_mha_backward"));
+  LLC_REQUIRE(w && b && s && s->dx && s->dxb && s->dh && s->d_o && s->dqkv && s->partial &&
+              s->delta && N > 0 && L > 0, "llc_mha_backward: bad args");
+  const int D = cfg->width, T = N * L, DA = D + LLC_LORA_LD;
+  RUN(llc_cast_bf16(s->dx, s->dxb, T, D, DA, stream));
+  return attn_half_backward(cfg, w, b, s, N, L, sn, sl, causal, need_dx_in, stream);
 }
 
 extern "C" size_t llc_vit_arena_bytes(const llc_vit_cfg* cfg, int N, int training) {
@@ -507,15 +569,22 @@ extern "C" int llc_vit_refresh_lora(const llc_vit_cfg* cfg, const llc_vit_weight
 }
 
 static int vit_forward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, const float* images,
-                            int N, void* arena, int training, float** x_final, void* stream,
-                            bool cls_only) {
+                            const llc_img_transform* tx, int N, void* arena, int training,
+                            float** x_final, void* stream, bool cls_only) {
   RUN(check_cfg(cfg, "llc_vit_forward"));
-  LLC_REQUIRE(w && w->layers && images && arena && N > 0, "llc_vit_forward: bad args");
+  LLC_REQUIRE(w && w->layers && (images || tx) && arena && N > 0, "llc_vit_forward: bad args");
   const Dims d = make_dims(cfg, N);
   const Arena a = plan(d, training);
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
-  // patch embedding: im2col -> GEMM -> class token, positional embedding, ln_pre
-  RUN(llc_patchify(images, N, 3, cfg->image_size, cfg->patch, base + a.patches, d.PK, stream));
+  // patch embedding: (input transform +) im2col -> GEMM -> class token, positional embedding,
+  // ln_pre
+  if (tx) {
+    LLC_REQUIRE(tx->out_size == cfg->image_size, "llc_vit_forward_tx: transform output %d != %d",
+                tx->out_size, cfg->image_size);
+    RUN(llc_transform_patchify(tx, N, cfg->patch, base + a.patches, d.PK, stream));
+  } else {
+    RUN(llc_patchify(images, N, 3, cfg->image_size, cfg->patch, base + a.patches, d.PK, stream));
+  }
   llc_gemm_epi e{};
   e.out = base + a.patch_out; e.ld_out = d.D; e.out_fp32 = 1;
   RUN(llc_gemm_bf16_tn(base + a.patches, d.PK, w->wpatch, d.PK, N * d.G * d.G, d.D, d.PK, &e,
@@ -538,13 +607,20 @@ static int vit_forward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, co
 extern "C" int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w,
                                const float* images, int N, void* arena, int training,
                                float** x_final, void* stream) {
-  return vit_forward_impl(cfg, w, images, N, arena, training, x_final, stream, false);
+  return vit_forward_impl(cfg, w, images, nullptr, N, arena, training, x_final, stream, false);
 }
 
 extern "C" int llc_vit_forward_cls(const llc_vit_cfg* cfg, const llc_vit_weights* w,
                                    const float* images, int N, void* arena, int training,
                                    float** x_final, void* stream) {
-  return vit_forward_impl(cfg, w, images, N, arena, training, x_final, stream, true);
+  return vit_forward_impl(cfg, w, images, nullptr, N, arena, training, x_final, stream, true);
+}
+
+extern "C" int llc_vit_forward_tx(const llc_vit_cfg* cfg, const llc_vit_weights* w,
+                                  const llc_img_transform* tx, int N, void* arena, int training,
+                                  int cls_only, float** x_final, void* stream) {
+  LLC_REQUIRE(tx, "llc_vit_forward_tx: null transform");
+  return vit_forward_impl(cfg, w, nullptr, tx, N, arena, training, x_final, stream, cls_only != 0);
 }
 
 static int vit_backward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N, void* arena,
@@ -583,4 +659,100 @@ extern "C" int llc_vit_backward(const llc_vit_cfg* cfg, const llc_vit_weights* w
 extern "C" int llc_vit_backward_cls(const llc_vit_cfg* cfg, const llc_vit_weights* w, int N,
                                     void* arena, float* dx_final, void* stream) {
   return vit_backward_impl(cfg, w, N, arena, dx_final, stream, true);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Text tower: CLIP.encode_text, reference models/clip/model.py:941-956, for
+// peft_encoder='both' (what scripts/lora_clip.sh sets): token embedding + positional embedding ->
+// LoRA blocks under the causal mask (:926-932) -> [C*ctx, D] fp32. ln_final, the EOT gather
+// (:953-954) and text_projection run in the head kernels (llc_head_fwd with row_idx).
+namespace {
+template <int NV>
+__global__ void __launch_bounds__(256)
+text_embed_kernel(const int64_t* __restrict__ tokens, const float* __restrict__ emb, int vocab,
+                  const float* __restrict__ pos, int T, int ctx, float* __restrict__ x0) {
+  constexpr int D = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= T) return;
+  int64_t tok = tokens[row];
+  if (tok < 0 || tok >= vocab) tok = 0;   // checked on the host side of the binding
+  const float4* e = reinterpret_cast<const float4*>(emb + (size_t)tok * D);
+  const float4* p = reinterpret_cast<const float4*>(pos + (size_t)(row % ctx) * D);
+  float4* o = reinterpret_cast<float4*>(x0 + (size_t)row * D);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = __ldg(e + lane + 32 * i), b = __ldg(p + lane + 32 * i);
+    o[lane + 32 * i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+}  // namespace
+
+extern "C" size_t llc_text_arena_bytes(const llc_vit_cfg* cfg, int context, int C, int training) {
+  if (check_cfg(cfg, "llc_text_arena_bytes") != 0 || C <= 0 || context <= 0) return 0;
+  return plan(make_dims(cfg, C, context), training).total;
+}
+
+extern "C" int llc_text_forward(const llc_vit_cfg* cfg, const llc_text_weights* w,
+                                const int64_t* tokens, int C, void* arena, int training,
+                                float** x_final, void* stream) {
+  RUN(check_cfg(cfg, "llc_text_forward"));
+  LLC_REQUIRE(w && w->layers && w->tok_emb && w->pos_emb && tokens && arena && C > 0 &&
+              w->context > 0 && w->vocab > 0, "llc_text_forward: bad args");
+  const Dims d = make_dims(cfg, C, w->context);
+  const Arena a = plan(d, training);
+  uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  float* x0 = reinterpret_cast<float*>(base + a.x);
+  cudaStream_t st = (cudaStream_t)stream;
+  LLC_PROF_BEGIN(LLC_K_EMBED, d.T, d.D, 4, 0.0, 8.0 * d.T * d.D, st);
+  switch (d.D / 128) {
+    case 4: text_embed_kernel<4><<<(d.T + 7) / 8, 256, 0, st>>>(tokens, w->tok_emb, w->vocab, w->pos_emb, d.T, d.L, x0); break;
+    case 5: text_embed_kernel<5><<<(d.T + 7) / 8, 256, 0, st>>>(tokens, w->tok_emb, w->vocab, w->pos_emb, d.T, d.L, x0); break;
+    case 6: text_embed_kernel<6><<<(d.T + 7) / 8, 256, 0, st>>>(tokens, w->tok_emb, w->vocab, w->pos_emb, d.T, d.L, x0); break;
+    case 8: text_embed_kernel<8><<<(d.T + 7) / 8, 256, 0, st>>>(tokens, w->tok_emb, w->vocab, w->pos_emb, d.T, d.L, x0); break;
+    case 3: text_embed_kernel<3><<<(d.T + 7) / 8, 256, 0, st>>>(tokens, w->tok_emb, w->vocab, w->pos_emb, d.T, d.L, x0); break;
+    case 1: text_embed_kernel<1><<<(d.T + 7) / 8, 256, 0, st>>>(tokens, w->tok_emb, w->vocab, w->pos_emb, d.T, d.L, x0); break;
+    case 2: text_embed_kernel<2><<<(d.T + 7) / 8, 256, 0, st>>>(tokens, w->tok_emb, w->vocab, w->pos_emb, d.T, d.L, x0); break;
+    default:
+      llc_set_error("llc_text_forward: width %d unsupported", d.D);
+      return LLC_ERR_ARG;
+  }
+  LLC_PROF_END(st);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("text_embed_kernel");
+  llc_block_bufs b;
+  for (int l = 0; l < d.layers; ++l) {
+    fill_bufs(d, a, base, l, training, &b);
+    RUN(llc_block_forward(cfg, &w->layers[l], &b, C, d.L, d.L, 1, 1, stream));
+  }
+  if (x_final) *x_final = b.x_out;
+  return 0;
+}
+
+extern "C" int llc_text_backward(const llc_vit_cfg* cfg, const llc_text_weights* w, int C,
+                                 void* arena, float* dx_final, void* stream) {
+  RUN(check_cfg(cfg, "llc_text_backward"));
+  LLC_REQUIRE(w && w->layers && arena && dx_final && C > 0 && w->context > 0,
+              "llc_text_backward: bad args");
+  const Dims d = make_dims(cfg, C, w->context);
+  const Arena a = plan(d, 1);
+  uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  llc_block_bwd_bufs s;
+  s.dx = dx_final;
+  s.dxb = base + a.dxb;
+  s.dz = base + a.dz;
+  s.dh = base + a.dh;
+  s.d_o = base + a.d_o;
+  s.dqkv = base + a.dqkv;
+  s.partial = reinterpret_cast<float*>(base + a.partial);
+  s.delta = reinterpret_cast<float*>(base + a.delta);
+  RUN(llc_cast_bf16(dx_final, s.dxb, d.T, d.D, d.D + LLC_LORA_LD, stream));
+  llc_block_bufs b;
+  for (int l = d.layers - 1; l >= 0; --l) {
+    fill_bufs(d, a, base, l, 1, &b);
+    // token / positional embeddings are frozen: the first block needs no input gradient
+    RUN(llc_block_backward(cfg, &w->layers[l], &b, &s, C, d.L, d.L, 1, 1, l > 0, stream));
+  }
+  return 0;
 }

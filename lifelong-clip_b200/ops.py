@@ -95,11 +95,13 @@ def attn_fwd(qkv, o, lse, N, L, H, sn, sl, causal=False):
     return o
 
 
-def attn_bwd(qkv, o, d_o, lse, dqkv, N, L, H, sn, sl, causal=False):
+def attn_bwd(qkv, o, d_o, lse, dqkv, N, L, H, sn, sl, causal=False, delta=None):
+    if delta is None:   # rowsum(dO o O) scratch: caller-owned, the library keeps no buffer
+        delta = torch.empty(N * H * L, dtype=torch.float32, device=qkv.device)
     K.check(_lib().llc_attn_bwd(qkv.data_ptr(), qkv.stride(0), o.data_ptr(), o.stride(0),
                                 d_o.data_ptr(), d_o.stride(0), lse.data_ptr(), dqkv.data_ptr(),
-                                dqkv.stride(0), N, L, H, sn, sl, int(causal), _s()),
-            "llc_attn_bwd")
+                                dqkv.stride(0), N, L, H, sn, sl, int(causal), delta.data_ptr(),
+                                _s()), "llc_attn_bwd")
     return dqkv
 
 
@@ -185,16 +187,93 @@ def adamw(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
                              lr, beta1, beta2, eps, wd, step, grad_scale, _s()), "llc_adamw")
 
 
+def head_dtext(dlogits, fnorm, scale, d_text=None):
+    """d_text [C, E] = scale * dlogits^T [C, N] @ fnorm [N, E] (gradient of the logit product w.r.t.
+    the normalised text features; model.py:972 with a trainable text tower)."""
+    N, Cn = dlogits.shape
+    E = fnorm.shape[1]
+    if d_text is None:
+        d_text = torch.empty(Cn, E, device=dlogits.device)
+    K.check(_lib().llc_head_dtext(dlogits.data_ptr(), fnorm.data_ptr(), N, Cn, E, float(scale),
+                                  d_text.data_ptr(), _s()), "llc_head_dtext")
+    return d_text
+
+
+def eval_accum(y, pred, n_tasks, n_classes, cm, counts):
+    """counts [22] int64: per-task totals / corrects of methods/_trainer.py:519-534 (slot 10 and
+    21: bins past the reference's ten); cm [n_classes, n_classes] int64 confusion counts."""
+    _req(y, torch.int64, "y"); _req(pred, torch.int64, "pred")
+    K.check(_lib().llc_eval_accum(y.data_ptr(), pred.data_ptr(), y.numel(), int(n_tasks),
+                                  int(n_classes), K.ptr(cm), counts.data_ptr(), _s()),
+            "llc_eval_accum")
+
+
+def l2norm_rows(x, scale=1.0, y=None, y_bf16=None):
+    _req(x, torch.float32, "x")
+    N, E = x.shape
+    K.check(_lib().llc_l2norm_rows(x.data_ptr(), x.stride(0), N, E, float(scale), K.ptr(y),
+                                   y.stride(0) if y is not None else 0, K.ptr(y_bf16),
+                                   y_bf16.stride(0) if y_bf16 is not None else 0, _s()),
+            "llc_l2norm_rows")
+
+
+def softmax_argmax(logits, C_, add_mask=None, probs=None, pred=None):
+    _req(logits, torch.float32, "logits")
+    K.check(_lib().llc_softmax_argmax(logits.data_ptr(), logits.stride(0), logits.shape[0], C_,
+                                      K.ptr(add_mask), K.ptr(probs),
+                                      probs.stride(0) if probs is not None else 0, K.ptr(pred),
+                                      _s()), "llc_softmax_argmax")
+
+
+def cast_bf16(src, dst):
+    """dst bf16 [T, ld] <- src fp32 [T, D] contiguous."""
+    _req(src, torch.float32, "src"); _req(dst, torch.bfloat16, "dst")
+    T, D = src.shape
+    K.check(_lib().llc_cast_bf16(src.data_ptr(), dst.data_ptr(), T, D, dst.stride(0), _s()),
+            "llc_cast_bf16")
+    return dst
+
+
+def make_transform(src, out_size, mean, std, pad=0, crop=(0, 0), flip=False, dyn=None):
+    """llc_img_transform for a raw batch [N, 3, h, w] (uint8 0..255 or float32 0..1)."""
+    if not src.is_cuda or src.dim() != 4 or src.shape[1] != 3 or not src.is_contiguous():
+        raise RuntimeError("transform: expected a contiguous CUDA batch [N, 3, h, w]")
+    if src.dtype not in (torch.uint8, torch.float32):
+        raise RuntimeError(f"transform: uint8 or float32 input, got {src.dtype}")
+    t = K.ImgTransform()
+    t.src = src.data_ptr(); t.src_u8 = int(src.dtype == torch.uint8)
+    t.h, t.w, t.out_size, t.pad = src.shape[2], src.shape[3], int(out_size), int(pad)
+    t.crop_i, t.crop_j, t.flip = int(crop[0]), int(crop[1]), int(bool(flip))
+    t.dyn_params = K.ptr(dyn)
+    for i in range(3):
+        t.mean[i] = float(mean[i]); t.std[i] = float(std[i])
+    return t
+
+
+def transform_images(t, N, out):
+    K.check(_lib().llc_transform_images(C.byref(t), N, out.data_ptr(), _s()),
+            "llc_transform_images")
+    return out
+
+
+def transform_patchify(t, N, P, out):
+    K.check(_lib().llc_transform_patchify(C.byref(t), N, P, out.data_ptr(), out.stride(0), _s()),
+            "llc_transform_patchify")
+    return out
+
+
 class Head:
     """Argument block of llc_head_fwd / llc_head_bwd; owns the small output tensors."""
 
     def __init__(self, x, cls_stride, ln_g, ln_b, proj, text, logit_scale_exp, N, *, cls_idx=None,
-                 add_mask=None, labels=None, double_softmax=True, inv_batch=None):
+                 add_mask=None, labels=None, double_softmax=True, inv_batch=None, row_idx=None,
+                 want_dlogits=False):
         D, E = proj.shape
         Cn = cls_idx.numel() if cls_idx is not None else text.shape[0]
         dev = x.device
         self.N, self.D, self.E, self.C = N, D, E, Cn
-        self.keep = (x, ln_g, ln_b, proj, text, cls_idx, add_mask, labels)
+        self.keep = (x, ln_g, ln_b, proj, text, cls_idx, add_mask, labels, row_idx)
+        self.dlogits = torch.empty(N, Cn, device=dev) if want_dlogits else None
         self.feat = torch.empty(N, E, device=dev)
         self.fnorm = torch.empty(N, E, device=dev)
         self.logits = torch.empty(N, Cn, device=dev)
@@ -212,6 +291,7 @@ class Head:
         a.feat = self.feat.data_ptr(); a.fnorm = self.fnorm.data_ptr()
         a.logits = self.logits.data_ptr(); a.probs = self.probs.data_ptr()
         a.loss_rows = self.loss_rows.data_ptr(); a.pred = self.pred.data_ptr()
+        a.row_idx = K.ptr(row_idx); a.dlogits = K.ptr(self.dlogits)
         self.args = a
 
     def forward(self):

@@ -23,6 +23,7 @@ import torch.distributed as dist
 from . import dp, ops
 from .adapter_clip import AdapterCLIP
 from .engine import FlatAdamW
+from .transform import GpuTransform
 
 
 class LoRAClipTrainer:
@@ -41,13 +42,17 @@ class LoRAClipTrainer:
         self.visible_classes = visible_classes
         self.memory, self.memory_provider = memory, memory_provider
         self.memory_batchsize, self.memory_size = memory_batchsize, memory_size
+        # train_transform / test_transform: any callable on the device batch (the reference's
+        # torchvision Compose), or a GpuTransform - then the raw batch is transformed inside the
+        # tower's first kernel (llc_vit_forward_tx)
         self.train_transform = train_transform or (lambda x: x)
         self.test_transform = test_transform or (lambda x: x)
         self.use_amp = use_amp          # bf16 tensor-core operands are always on; no GradScaler
         self.double_softmax = double_softmax
         self.exposed_classes, self.exposed_classes_names = [], []
         self.batch_exposed_classes, self.batch_exposed_classes_names = [], []
-        self._total_classes = 0
+        self._total_classes = 0         # set by the driver loop (methods/_trainer.py:322)
+        self._known_classes = 0
         ddp = dist.is_available() and dist.is_initialized()
         self.rank = rank if rank is not None else (dist.get_rank() if ddp else 0)
         self.world = world_size if world_size is not None else (dist.get_world_size() if ddp else 1)
@@ -67,6 +72,11 @@ class LoRAClipTrainer:
         self._lut = torch.full((self.n_classes,), -1, dtype=torch.int64, device=self.device)
         self._lut_src = None
         self._scal = torch.zeros(2, device=self.device)
+        self._comm_stream = None
+
+    @property
+    def text_trainable(self) -> bool:
+        return self.custom_clip.peft_encoder == 'both'
 
     # ---- class bookkeeping (methods/_trainer.py:404-416, methods/adapter_clip.py:256-283) ------
     def add_new_class(self, class_name):
@@ -105,15 +115,24 @@ class LoRAClipTrainer:
                 v.requires_grad = False
         self.reset_opt()
 
+    def _towers(self):
+        m = self.custom_clip.model
+        return [m.visual] + ([m.text_side()] if self.text_trainable else [])
+
     def reset_opt(self):
         """utils/train_utils.py:27-28: AdamW(lr, weight_decay=1e-5) over the trainable tensors."""
-        self.optimizer = FlatAdamW(self.custom_clip.model.visual.engine(), lr=self.lr,
-                                   weight_decay=1e-5)
+        self.optimizer = FlatAdamW(self._towers(), lr=self.lr, weight_decay=1e-5)
 
     def online_after_task(self, task_id):
-        """methods/adapter_clip.py:129-130: evaluation sees every class exposed so far."""
-        self._total_classes = len(self.exposed_classes)
-        self.custom_clip.set_token(self.exposed_classes_names)
+        """methods/adapter_clip.py:129-130: set_token(self.all_classnames[:self._total_classes]),
+        so that an evaluation prediction IS the raw class id (online_evaluate compares it with the
+        dataset label). `_total_classes` is maintained by the driver loop
+        (methods/_trainer.py:322,355); a caller that never sets it gets every class id up to the
+        largest one exposed so far."""
+        total = self._total_classes
+        if not total:
+            total = (max(self.exposed_classes) + 1) if self.exposed_classes else 0
+        self.custom_clip.set_token(self.all_classnames[:total])
 
     # ---- hot loop ------------------------------------------------------------------------------
     def online_step(self, images, labels, idx=None):
@@ -132,10 +151,10 @@ class LoRAClipTrainer:
             _iter += 1
         return _loss / _iter, _acc / _iter
 
-    def online_train(self, data):
-        """methods/adapter_clip.py:49-107. Returns (loss: float, acc: float) of the GLOBAL batch."""
-        if self.optimizer is None:
-            self.reset_opt()
+    def prepare_batch(self, data):
+        """Host-side half of online_train (methods/adapter_clip.py:53-76): pick the visible class
+        list, concatenate the replay batch, let unseen replay classes join the list. Returns
+        (x, y_global [host int64], train_class_list, train_class_name_list)."""
         if self.visible_classes == 'batch':
             train_class_list = self.batch_exposed_classes
             train_class_name_list = self.batch_exposed_classes_names
@@ -153,39 +172,98 @@ class LoRAClipTrainer:
             # stream images may already sit on the device (DevicePrefetcher); labels stay on host
             x = torch.cat([x, memory_images.to(x.device, non_blocking=True)], dim=0)
             y = torch.cat([y.cpu(), memory_labels.cpu()], dim=0)
+        return x, y, train_class_list, train_class_name_list
+
+    def online_train(self, data):
+        """methods/adapter_clip.py:49-107. Returns (loss: float, acc: float) of the GLOBAL batch."""
+        if self.optimizer is None:
+            self.reset_opt()
+        x, y, train_class_list, train_class_name_list = self.prepare_batch(data)
         B = y.shape[0]
         # data-parallel shard of the combined stream+replay batch (SURVEY.md §8e)
         if self.world > 1:
             if self.sharded_input:
-                B = B * self.world
+                B = int(dp.global_count(B, self.world, self.device))
             else:
                 x, y = dp.shard_batch(x, y, self.rank, self.world)
         x = x.to(self.device, non_blocking=True)
         y = y.to(self.device, non_blocking=True)
         y_local = ops.label_remap(y, self._class_lut(train_class_list))
-        x = self.train_transform(x)
+        if not isinstance(self.train_transform, GpuTransform):
+            x = self.train_transform(x)
         self.custom_clip.set_token(train_class_name_list)
         loss_sum, n_correct = self.fused_step(x, y_local, B)
         return loss_sum, n_correct / B
 
-    def _step_body(self, x, y_local, global_batch, force_refresh=False):
-        """forward + loss + backward; leaves LoRA grads in eng.grad_flat and (loss_sum, n_correct)
-        of this shard in self._scal. All llc_* launches on the current stream."""
+    def model_forward(self, x, y):
+        """(logit, loss) as the classic methods' model_forward (methods/er_baseline.py:132-147):
+        `logit` are the class probabilities the reference's criterion is applied to, `loss` the
+        mean loss; both stay on the device, no parameter is updated."""
+        m = self.custom_clip
+        with torch.no_grad():
+            eng = m.model.visual.engine()
+            eng.forward(self.test_transform(x.to(self.device)), training=False)
+            head = self._image_head(eng, labels=y.to(self.device), inv_batch=1.0 / y.shape[0])
+        return head.probs, head.loss_rows.sum()
+
+    # ---- the fused step ------------------------------------------------------------------------
+    def _image_head(self, eng, labels=None, inv_batch=None, text=None, want_dlogits=False):
+        m = self.custom_clip
+        if text is not None:
+            return eng.head(text, m.model.logit_scale_exp(), add_mask=m._add_mask, labels=labels,
+                            double_softmax=self.double_softmax, inv_batch=inv_batch,
+                            want_dlogits=want_dlogits)
+        return eng.head(m._text_all, m.model.logit_scale_exp(), cls_idx=m._cls_idx,
+                        add_mask=m._add_mask, labels=labels, double_softmax=self.double_softmax,
+                        inv_batch=inv_batch)
+
+    def _step_body(self, x, y_local, global_batch, force_refresh=False, tx=None):
+        """forward + loss + backward; leaves the LoRA grads in the engines' grad_flat and
+        (loss_sum, n_correct) of this shard in self._scal. All llc_* launches on the current
+        stream. tx: llc_img_transform of the raw batch x (GpuTransform path)."""
         m = self.custom_clip
         eng = m.model.visual.engine()
-        eng.forward(x, training=True, force_refresh=force_refresh)
-        head = eng.head(m._text_all, m.model.logit_scale_exp(),
-                        cls_idx=m._cls_idx, add_mask=m._add_mask, labels=y_local,
-                        double_softmax=self.double_softmax, inv_batch=1.0 / global_batch)
+        thead = None
+        if self.text_trainable:
+            teng = m.model.text_engine()
+            from .adapter_clip import eot_rows
+            if getattr(self, "_eot_src", None) is not m._tokens:
+                self._eot, self._eot_src = eot_rows(m._tokens), m._tokens
+            thead = teng.forward(m._tokens, self._eot, training=True, force_refresh=force_refresh)
+        if tx is not None:
+            eng.forward(training=True, force_refresh=force_refresh, transform=tx, n=x.shape[0])
+        else:
+            eng.forward(x, training=True, force_refresh=force_refresh)
+        head = self._image_head(eng, labels=y_local, inv_batch=1.0 / global_batch,
+                                text=None if thead is None else thead.fnorm,
+                                want_dlogits=thead is not None)
         eng.backward_from_head(head)
+        if thead is not None:
+            d_t = ops.head_dtext(head.dlogits, head.fnorm, m.model.logit_scale_exp())
+            head.keep = head.keep + (d_t,)
+            teng.backward(d_t)
         ops.loss_acc(head.loss_rows, head.pred, y_local, self._scal)
         return head
 
-    def _graph_step(self, x, y_local, global_batch):
+    def _graph_signature(self, x, y_local, global_batch):
         m = self.custom_clip
-        key = (tuple(x.shape), x.dtype, global_batch, m._cls_idx.data_ptr(), m._cls_idx.numel(),
-               None if m._add_mask is None else m._add_mask.data_ptr(), m._text_all.data_ptr(),
-               m.model.logit_scale_exp(), self.double_softmax)
+        sig = (tuple(x.shape), x.dtype, tuple(y_local.shape), global_batch,
+               m.model.logit_scale_exp(), self.double_softmax,
+               None if m._add_mask is None else m._add_mask.data_ptr(),
+               m.model.visual.engine().graph_signature(),
+               isinstance(self.train_transform, GpuTransform))
+        if self.text_trainable:
+            return sig + (m._tokens.data_ptr(), tuple(m._tokens.shape),
+                          m.model.text_engine().graph_signature())
+        return sig + (m._cls_idx.data_ptr(), m._cls_idx.numel(), m._text_all.data_ptr())
+
+    def _make_tx(self, raw, dynamic):
+        if not isinstance(self.train_transform, GpuTransform):
+            return None
+        return self.train_transform.struct(self.train_transform._check(raw), dynamic=dynamic)
+
+    def _graph_step(self, x, y_local, global_batch):
+        key = self._graph_signature(x, y_local, global_batch)
         if key != self._graph_key:
             # a capture costs tens of ms: worth it only when the (batch, class list) signature is
             # stable (visible_classes='all', one change per task). If it keeps changing
@@ -196,25 +274,35 @@ class LoRAClipTrainer:
                     self.use_cuda_graph = False
                     self._graph = None
                     self._graph_key = None
-                    return self._step_body(x, y_local, global_batch)
+                    return self._step_body(x, y_local, global_batch, tx=self._make_tx(x, False))
             else:
                 self._graph_churn = 0
             self._graph_hits = 0
             self._graph = None
+            if isinstance(self.train_transform, GpuTransform):
+                x = self.train_transform._check(x)
             self._gx = torch.empty_like(x)
             self._gy = torch.empty_like(y_local)
             self._gx.copy_(x); self._gy.copy_(y_local)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):      # warm-up: arena, smem attributes, allocator pool
-                self._step_body(self._gx, self._gy, global_batch, force_refresh=True)
+                self._step_body(self._gx, self._gy, global_batch, force_refresh=True,
+                                tx=self._make_tx(self._gx, True))
             torch.cuda.current_stream(self.device).wait_stream(side)
+            # the warm-up may have (re)allocated the arenas: the key is taken after it
+            key = self._graph_signature(x, y_local, global_batch)
             g = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
+            tx = self._make_tx(self._gx, True)     # struct with the stable dyn pointer
             with torch.cuda.graph(g):
-                self._ghead = self._step_body(self._gx, self._gy, global_batch, force_refresh=True)
+                self._ghead = self._step_body(self._gx, self._gy, global_batch,
+                                              force_refresh=True, tx=tx)
             self.graph_kernels = ops.launch_count() - n0   # libllc kernel nodes per replay
             self._graph, self._graph_key = g, key
+        if isinstance(self.train_transform, GpuTransform):
+            x = self.train_transform._check(x)
+            self._make_tx(self._gx, True)          # fresh crop / flip draw -> device buffer
         self._gx.copy_(x, non_blocking=True)
         self._gy.copy_(y_local, non_blocking=True)
         self._graph.replay()
@@ -223,12 +311,16 @@ class LoRAClipTrainer:
 
     def fused_step(self, x, y_local, global_batch, sync=True):
         """forward + loss + backward + gradient all-reduce + AdamW, all on the device."""
-        eng = self.custom_clip.model.visual.engine()
-        if self.use_cuda_graph:
+        if self.optimizer is None:
+            self.reset_opt()
+        if x.shape[0] == 0:
+            head = self._empty_shard_step()
+        elif self.use_cuda_graph:
             head = self._graph_step(x, y_local, global_batch)
         else:
-            head = self._step_body(x, y_local, global_batch)
-        dp.allreduce_step(eng.grad_flat, self._scal, self.world)
+            head = self._step_body(x, y_local, global_batch, tx=self._make_tx(x, False))
+        engines = self.optimizer.engines()
+        dp.allreduce_step([e.grad_flat for e in engines], self._scal, self.world)
         self.optimizer.step()
         self.last_head = head
         if not sync:
@@ -236,40 +328,81 @@ class LoRAClipTrainer:
         loss_sum, n_correct = self._scal.tolist()  # the step's only host sync
         return loss_sum, n_correct
 
+    def _empty_shard_step(self):
+        """A rank whose shard of a ragged last batch is empty contributes zeros and still joins
+        the collectives (the other ranks would block in all_reduce otherwise)."""
+        for e in self.optimizer.engines():
+            e.grad_flat.zero_()
+        self._scal.zero_()
+        return None
+
     # ---- evaluation (methods/adapter_clip.py:132-176, methods/_trainer.py:519-534) --------------
     @torch.no_grad()
     def online_evaluate(self, test_loader, samples_cnt=None):
-        from sklearn.metrics import confusion_matrix
-        correct_l = torch.zeros(self.n_tasks)
-        num_data_l = torch.zeros(self.n_tasks)
-        label, pred_list = [], []
+        """Same dictionary as the reference. Per-task counters and the confusion matrix are
+        accumulated on the device (llc_eval_accum) and read back ONCE at the end; the reference
+        does two .tolist() per batch and runs sklearn on the host."""
         self.custom_clip.eval()
         m = self.custom_clip
         eng = m.model.visual.engine()
-        for x, y in test_loader:
-            x = self.test_transform(x.to(self.device))
-            y = y.to(self.device)
-            eng.forward(x, training=False)
-            head = eng.head(m._text_all, m.model.logit_scale_exp(),
-                            cls_idx=m._cls_idx, add_mask=m._add_mask)
-            pred = head.pred
-            xlabel_cnt, correct_xlabel_cnt = self._interpret_pred(y, pred)
-            correct_l += correct_xlabel_cnt
-            num_data_l += xlabel_cnt
-            label += y.tolist()
-            pred_list += pred.tolist()
+        Cn = self.n_classes
+        cm = torch.zeros(Cn, Cn, dtype=torch.int64, device=self.device)
+        counts = torch.zeros(22, dtype=torch.int64, device=self.device)
+        text = None
+        if self.text_trainable:   # text features of the evaluated class list, once per call
+            from .adapter_clip import eot_rows
+            text = m.model.text_engine().forward(m._tokens, eot_rows(m._tokens),
+                                                 training=False).fnorm
+        for batch in test_loader:
+            x, y = batch[0], batch[1]
+            x = x.to(self.device, non_blocking=True)
+            y = y.to(self.device, non_blocking=True)
+            if isinstance(self.test_transform, GpuTransform):
+                tt = self.test_transform
+                eng.forward(training=False, transform=tt.struct(tt._check(x)), n=x.shape[0])
+            else:
+                eng.forward(self.test_transform(x), training=False)
+            if text is not None:
+                head = eng.eval_head(text, m.model.logit_scale_exp(), add_mask=m._add_mask,
+                                     want_probs=False)
+            else:
+                head = eng.eval_head(m._text_all, m.model.logit_scale_exp(), cls_idx=m._cls_idx,
+                                     add_mask=m._add_mask, want_probs=False)
+            ops.eval_accum(y, head.pred, self.n_tasks, Cn, cm, counts)
+        counts = counts.cpu()
+        if int(counts[10]) or int(counts[21]):
+            # methods/_trainer.py:521-527 indexes ten-element tensors with y // n_tasks
+            raise IndexError(f"label // n_tasks ({self.n_tasks}) reached bin >= 10: the "
+                             "reference's _interpret_pred holds ten bins")
+        num_data_l = counts[:10].float()
+        correct_l = counts[11:21].float()
+        if self.n_tasks != 10:
+            # the reference adds the ten-bin result to zeros(n_tasks) (methods/adapter_clip.py:134,
+            # 152-153), which only broadcasts for n_tasks == 10; keep the first n_tasks bins
+            # when they hold everything, else report all ten
+            k = self.n_tasks if float(num_data_l[self.n_tasks:].sum()) == 0 else 10
+            num_data_l, correct_l = num_data_l[:k], correct_l[:k]
         avg_acc = torch.sum(correct_l) / torch.sum(num_data_l)
         task_acc = (correct_l / (num_data_l + 1e-5)).numpy().tolist()
-        cm = confusion_matrix(label, pred_list)
+        # sklearn.metrics.confusion_matrix(label, pred_list) with labels=None: rows / columns are
+        # the sorted union of the values present in either list
+        cmh = cm.cpu()
+        present = ((cmh.sum(0) + cmh.sum(1)) > 0).nonzero().flatten()
+        cmh = cmh[present][:, present]
         return {"avg_loss": 0.0 / torch.sum(num_data_l), "avg_acc": avg_acc, "cls_acc": task_acc,
-                "task_acc": task_acc, "confusion_matrix": cm.tolist()}
+                "task_acc": task_acc, "confusion_matrix": cmh.tolist()}
 
     def _interpret_pred(self, y, pred):
-        """methods/_trainer.py:519-534 (per-task counts via y // n_tasks), on the device."""
-        cls = (y // self.n_tasks).clamp(0, self.n_tasks - 1)
-        num = torch.bincount(cls, minlength=self.n_tasks).float().cpu()[:self.n_tasks]
-        ok = torch.bincount(cls[y == pred], minlength=self.n_tasks).float().cpu()[:self.n_tasks]
-        return num, ok
+        """methods/_trainer.py:519-534: (ret_num_data, ret_corrects), ten float bins indexed by
+        y // n_tasks, computed on the device with one llc_eval_accum launch."""
+        counts = torch.zeros(22, dtype=torch.int64, device=y.device)
+        ops.eval_accum(y.contiguous(), pred.contiguous(), self.n_tasks, self.n_classes, None,
+                       counts)
+        c = counts.cpu()
+        if int(c[10]) or int(c[21]):
+            raise IndexError("index out of bounds for the ten bins of _interpret_pred "
+                             "(methods/_trainer.py:521-527)")
+        return c[:10].float(), c[11:21].float()
 
 
 class DevicePrefetcher:

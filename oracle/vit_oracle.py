@@ -280,3 +280,168 @@ def online_step_oracle(images: np.ndarray, labels_local: np.ndarray, w_np: dict,
     res = {k: v.detach().cpu().numpy() for k, v in out.items()}
     res["grads"] = {k: v.grad.detach().cpu().numpy() for k, v in w.items() if v.requires_grad}
     return res
+
+
+# ------------------------------------------------------------------------------ text tower (N1)
+@dataclass(frozen=True)
+class TextCfg:
+    """CLIP text transformer (model.py:833-846): context 77, vocab 49408, width 512, 8 heads,
+    12 layers for ViT-B/16."""
+    context: int = 77
+    vocab: int = 49408
+    width: int = 512
+    heads: int = 8
+    layers: int = 12
+    embed_dim: int = 512
+    lora_r: int = 4
+    lora_alpha: float = 1.0
+
+    @property
+    def mlp_dim(self) -> int:
+        return 4 * self.width
+
+    @property
+    def lora_scale(self) -> float:
+        return self.lora_alpha / self.lora_r
+
+
+TEXT_B16 = TextCfg()
+TEXT_TINY = TextCfg(context=16, vocab=300, width=128, heads=2, layers=2, embed_dim=64)
+
+
+def text_param_shapes(cfg: TextCfg) -> dict[str, tuple[int, ...]]:
+    """Text-side parameter names/shapes as in the reference's CLIP state_dict (model.py:833-846)
+    with LoRA blocks (peft_encoder='both')."""
+    D, r = cfg.width, cfg.lora_r
+    s: dict[str, tuple[int, ...]] = {
+        "token_embedding.weight": (cfg.vocab, D),
+        "positional_embedding": (cfg.context, D),
+        "ln_final.weight": (D,), "ln_final.bias": (D,),
+        "text_projection": (D, cfg.embed_dim),
+    }
+    for i in range(cfg.layers):
+        p = f"transformer.resblocks.{i}."
+        s[p + "attn.in_proj_weight"] = (3 * D, D)
+        s[p + "attn.in_proj_bias"] = (3 * D,)
+        s[p + "attn.in_proj_weight_lora_A"] = (r, D)
+        s[p + "attn.in_proj_weight_lora_B"] = (3 * D, r)
+        s[p + "attn.out_proj.weight"] = (D, D)
+        s[p + "attn.out_proj.bias"] = (D,)
+        s[p + "attn.out_proj.lora_A"] = (r, D)
+        s[p + "attn.out_proj.lora_B"] = (D, r)
+        s[p + "ln_1.weight"] = (D,); s[p + "ln_1.bias"] = (D,)
+        s[p + "ln_2.weight"] = (D,); s[p + "ln_2.bias"] = (D,)
+        s[p + "mlp.c_fc.weight"] = (cfg.mlp_dim, D); s[p + "mlp.c_fc.bias"] = (cfg.mlp_dim,)
+        s[p + "mlp.c_proj.weight"] = (D, cfg.mlp_dim); s[p + "mlp.c_proj.bias"] = (D,)
+    return s
+
+
+def synth_text_weights(cfg: TextCfg, seed: int = 0) -> dict[str, np.ndarray]:
+    """Deterministic random-init text-tower weights, scales of model.py:852-885."""
+    rng = np.random.default_rng(seed)
+    D = cfg.width
+    out: dict[str, np.ndarray] = {}
+    for name, shape in text_param_shapes(cfg).items():
+        if name.endswith(("ln_final.weight", "ln_1.weight", "ln_2.weight")):
+            v = 1.0 + 0.1 * rng.standard_normal(shape)
+        elif name.endswith(("ln_final.bias", "ln_1.bias", "ln_2.bias")):
+            v = 0.1 * rng.standard_normal(shape)
+        elif name.endswith("bias"):
+            v = 0.02 * rng.standard_normal(shape)
+        elif name == "token_embedding.weight":
+            v = 0.02 * rng.standard_normal(shape)
+        elif name == "positional_embedding":
+            v = 0.01 * rng.standard_normal(shape)
+        elif name == "text_projection":
+            v = D ** -0.5 * rng.standard_normal(shape)
+        elif name.endswith("in_proj_weight"):
+            v = D ** -0.5 * rng.standard_normal(shape)
+        elif name.endswith(("out_proj.weight", "c_proj.weight")):
+            v = D ** -0.5 * (2 * cfg.layers) ** -0.5 * rng.standard_normal(shape)
+        elif name.endswith("c_fc.weight"):
+            v = (2 * D) ** -0.5 * rng.standard_normal(shape)
+        elif name.endswith(("lora_A", "lora_B")):
+            bound = math.sqrt(6.0 / (shape[0] + shape[1]))
+            v = rng.uniform(-bound, bound, shape)
+        else:
+            raise KeyError(name)
+        out[name] = v.astype(np.float32)
+    return out
+
+
+def synth_tokens(num_classes: int, cfg: TextCfg, seed: int = 0) -> np.ndarray:
+    """[C, context] int64 prompts: SOT, 3..8 random ids, EOT (= vocab-1, the row arg-max that
+    model.py:953-954 gathers), zero padding."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((num_classes, cfg.context), dtype=np.int64)
+    for c in range(num_classes):
+        k = int(rng.integers(3, min(9, cfg.context - 2)))
+        out[c, 0] = cfg.vocab - 2
+        out[c, 1:1 + k] = rng.integers(1, cfg.vocab - 2, size=k)
+        out[c, 1 + k] = cfg.vocab - 1
+    return out
+
+
+def text_forward(tokens, w, cfg: TextCfg):
+    """CLIP.encode_text model.py:941-956: token + positional embedding -> LoRA blocks under the
+    causal mask (:926-932) -> ln_final -> EOT row -> @ text_projection. tokens: int64 [C, ctx]."""
+    x = w["token_embedding.weight"][tokens] + w["positional_embedding"]
+    bcfg = VitCfg(width=cfg.width, heads=cfg.heads, layers=cfg.layers, lora_r=cfg.lora_r,
+                  lora_alpha=cfg.lora_alpha)
+    for i in range(cfg.layers):
+        x = block_forward(x, w, f"transformer.resblocks.{i}.", bcfg, causal=True)
+    x = layer_norm(x, w["ln_final.weight"], w["ln_final.bias"])
+    eot = tokens.argmax(dim=-1)
+    return x[torch.arange(x.shape[0]), eot] @ w["text_projection"]
+
+
+def clip_step_oracle(images: np.ndarray, labels_local: np.ndarray, tokens: np.ndarray, wv_np: dict,
+                     wt_np: dict, cfg: VitCfg, tcfg: TextCfg, logit_scale_exp: float = 1.0 / 0.07,
+                     dtype=torch.float64, double_softmax: bool = True):
+    """One forward+backward with BOTH towers trainable (peft_encoder='both', the value
+    scripts/lora_clip.sh sets): model.py:958-975 + models/adapter_clip.py:99 +
+    methods/adapter_clip.py:89. Returns probs, loss, pred, text features and the LoRA gradients of
+    both towers keyed by parameter name."""
+    wv, wt = to_torch(wv_np, dtype), to_torch(wt_np, dtype)
+    x = torch.from_numpy(images).to(dtype)
+    tok = torch.from_numpy(tokens)
+    y = torch.from_numpy(labels_local)
+    feat = vit_forward(x, wv, cfg)
+    tfeat = text_forward(tok, wt, tcfg)
+    tn = tfeat / tfeat.norm(dim=-1, keepdim=True)
+    probs, logits, f = head_forward(feat, tn, logit_scale_exp)
+    loss = reference_loss(probs, y, logits, double_softmax)
+    loss.backward()
+    out = {"feat": feat, "tfeat": tfeat, "tnorm": tn, "probs": probs, "logits": logits,
+           "loss": loss, "pred": predict(probs)}
+    res = {k: v.detach().cpu().numpy() for k, v in out.items()}
+    res["grads"] = {k: v.grad.detach().cpu().numpy() for k, v in wv.items() if v.requires_grad}
+    res["grads"].update({k: v.grad.detach().cpu().numpy() for k, v in wt.items()
+                         if v.requires_grad})
+    return res
+
+
+# --------------------------------------------------------------------------- evaluation tail (N4)
+def interpret_pred(y: np.ndarray, pred: np.ndarray, n_tasks: int):
+    """methods/_trainer.py:519-534: ten float bins indexed by y // n_tasks: number of samples and
+    number of correct predictions per bin (IndexError past ten bins, as the reference)."""
+    num = np.zeros(10, np.float32)
+    ok = np.zeros(10, np.float32)
+    cls = y // n_tasks
+    for c in np.unique(cls):
+        num[c] = float((cls == c).sum())          # IndexError when c >= 10
+    good = y[y == pred] // n_tasks
+    for c in np.unique(good):
+        ok[c] = float((good == c).sum())
+    return num, ok
+
+
+def confusion(y: np.ndarray, pred: np.ndarray) -> np.ndarray:
+    """sklearn.metrics.confusion_matrix(y, pred) with labels=None (methods/adapter_clip.py:166):
+    rows/columns = sorted union of the values present."""
+    labels = np.unique(np.concatenate([y, pred]))
+    idx = {int(v): i for i, v in enumerate(labels)}
+    cm = np.zeros((len(labels), len(labels)), np.int64)
+    for a, b in zip(y, pred):
+        cm[idx[int(a)], idx[int(b)]] += 1
+    return cm

@@ -11,6 +11,12 @@ methods/adapter_clip.py:115-119; run the sound lines of VisualTransformer.forwar
 (model.py:756-767, Transformer.forward :685-686, :782-785), the head (model.py:966-973,
 models/adapter_clip.py:99) and the reference loss (methods/adapter_clip.py:89) in fp32; backward.
 Only OUTPUTS are stored (weights/inputs are re-synthesised from seeds by the tests).
+
+Production-shape cases (vitb16_b16 = BASELINE config C1, _b32 = C2 per GPU, _b256 = the bench
+shape) store probs / loss / pred / the 48 LoRA gradients only. Batches above 64 images are run
+through the reference in micro-batches of 64 with the per-sample CE summed and divided by the
+full batch (the samples are independent, so this IS CrossEntropyLoss(mean) over the whole batch up
+to fp32 summation order; a 256-image autograd graph of the reference needs > 50 GB of host memory).
 """
 from __future__ import annotations
 
@@ -41,7 +47,7 @@ def synth_inputs(cfg: vo.VitCfg, n: int, num_classes: int, seed: int):
     return images, labels
 
 
-def run_reference(cfg: vo.VitCfg, n: int, num_classes: int, seed: int):
+def build_reference(cfg: vo.VitCfg, seed: int):
     ref_model = load_reference()
     torch.manual_seed(0)
     # text tower kept minimal (unused: text features are cached inputs on this path)
@@ -59,9 +65,12 @@ def run_reference(cfg: vo.VitCfg, n: int, num_classes: int, seed: int):
     for k, p in clip.named_parameters():  # methods/adapter_clip.py:117-119
         if "adaptmlp" not in k and "lora" not in k:
             p.requires_grad = False
+    return clip
+
+
+def reference_forward(clip, images: np.ndarray, text: np.ndarray):
+    """images -> (feat, logits, probs) through the reference's own modules."""
     vis = clip.visual
-    images, labels = synth_inputs(cfg, n, num_classes, seed + 100)
-    text = vo.synth_text_features(num_classes, cfg.embed_dim, seed + 200)
     x = torch.from_numpy(images)
     # model.py:756-767
     x = vis.conv1(x)
@@ -81,13 +90,32 @@ def run_reference(cfg: vo.VitCfg, n: int, num_classes: int, seed: int):
     logit_scale = clip.logit_scale.exp()
     logits = logit_scale * f @ t.t()
     probs = logits.softmax(dim=-1)
-    loss = torch.nn.CrossEntropyLoss()(probs, torch.from_numpy(labels))  # adapter_clip.py:89
-    loss.backward()
-    out = {
-        "feat": feat.detach().numpy(), "logits": logits.detach().numpy(),
-        "probs": probs.detach().numpy(), "loss": loss.detach().numpy(),
-        "pred": probs.argmax(-1).numpy(), "logit_scale_exp": logit_scale.detach().numpy(),
-    }
+    return feat, logits, probs, logit_scale
+
+
+def run_reference(cfg: vo.VitCfg, n: int, num_classes: int, seed: int, slim: bool = False,
+                  chunk: int = 64):
+    clip = build_reference(cfg, seed)
+    images, labels = synth_inputs(cfg, n, num_classes, seed + 100)
+    text = vo.synth_text_features(num_classes, cfg.embed_dim, seed + 200)
+    feats, logit_l, prob_l, loss = [], [], [], 0.0
+    for i in range(0, n, chunk):
+        feat, logits, probs, logit_scale = reference_forward(clip, images[i:i + chunk], text)
+        y = torch.from_numpy(labels[i:i + chunk])
+        if n <= chunk:
+            part = torch.nn.CrossEntropyLoss()(probs, y)           # adapter_clip.py:89
+        else:
+            part = torch.nn.CrossEntropyLoss(reduction="sum")(probs, y) / n
+        part.backward()                                              # grads accumulate
+        loss += float(part.detach())
+        feats.append(feat.detach().numpy()); logit_l.append(logits.detach().numpy())
+        prob_l.append(probs.detach().numpy())
+    probs = np.concatenate(prob_l)
+    out = {"probs": probs, "loss": np.float32(loss), "pred": probs.argmax(-1),
+           "logit_scale_exp": logit_scale.detach().numpy()}
+    if not slim:
+        out["feat"] = np.concatenate(feats)
+        out["logits"] = np.concatenate(logit_l)
     ng = 0
     for k, p in clip.named_parameters():
         if p.grad is not None:
@@ -103,15 +131,123 @@ CASES = {
     "tiny": (vo.VIT_TINY, 3, 10, 11),
     "vitb16": (vo.VIT_B16, 8, 100, 7),
 }
+# production shapes (outputs only): C1 batch, C2 per-GPU batch, the bench batch
+BIG_CASES = {
+    "vitb16_b16": (vo.VIT_B16, 16, 100, 7),
+    "vitb16_b32": (vo.VIT_B16, 32, 100, 7),
+    "vitb16_b256": (vo.VIT_B16, 256, 100, 7),
+}
+
+
+def run_reference_both(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes: int, seed: int):
+    """peft_encoder='both' (scripts/lora_clip.sh:10): the reference's CLIP with LoRA blocks in BOTH
+    towers; text features from its own encode_text (model.py:941-956), head model.py:966-973."""
+    ref_model = load_reference()
+    torch.manual_seed(0)
+    clip = ref_model.CLIP(cfg.embed_dim, cfg.image_size, cfg.layers, cfg.width, cfg.patch,
+                          tcfg.context, tcfg.vocab, tcfg.width, tcfg.heads, tcfg.layers,
+                          {"method": "lora", "peft_encoder": "both",
+                           "lora_alpha": cfg.lora_alpha, "lora_r": cfg.lora_r}).float()
+    wv, wt = vo.synth_weights(cfg, seed), vo.synth_text_weights(tcfg, seed + 1)
+    sd = clip.state_dict()
+    for k, v in {**wv, **wt}.items():
+        assert k in sd and tuple(sd[k].shape) == v.shape, (k, v.shape)
+        sd[k] = torch.from_numpy(v)
+    clip.load_state_dict(sd)
+    for k, p in clip.named_parameters():  # methods/adapter_clip.py:117-119
+        if "adaptmlp" not in k and "lora" not in k:
+            p.requires_grad = False
+    images, labels = synth_inputs(cfg, n, num_classes, seed + 100)
+    tokens = vo.synth_tokens(num_classes, tcfg, seed + 300)
+    vis = clip.visual
+    x = vis.conv1(torch.from_numpy(images))
+    x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+    x = torch.cat([vis.class_embedding.to(x.dtype) + torch.zeros(
+        x.shape[0], 1, x.shape[-1], dtype=x.dtype), x], dim=1)
+    x = x + vis.positional_embedding.to(x.dtype)
+    x = vis.ln_pre(x).permute(1, 0, 2)
+    x = vis.transformer(x).permute(1, 0, 2)
+    feat = vis.ln_post(x[:, 0, :]) @ vis.proj
+    tfeat = clip.encode_text(torch.from_numpy(tokens))          # model.py:941-956
+    f = feat / feat.norm(dim=-1, keepdim=True)                  # model.py:966-973
+    t = tfeat / tfeat.norm(dim=-1, keepdim=True)
+    logit_scale = clip.logit_scale.exp()
+    logits = logit_scale * f @ t.t()
+    probs = logits.softmax(dim=-1)                              # models/adapter_clip.py:99
+    loss = torch.nn.CrossEntropyLoss()(probs, torch.from_numpy(labels))
+    loss.backward()
+    out = {"feat": feat.detach().numpy(), "tfeat": tfeat.detach().numpy(),
+           "logits": logits.detach().numpy(), "probs": probs.detach().numpy(),
+           "loss": loss.detach().numpy(), "pred": probs.argmax(-1).numpy(),
+           "logit_scale_exp": logit_scale.detach().numpy()}
+    ng = 0
+    for k, p in clip.named_parameters():
+        if p.grad is not None:
+            assert "lora" in k
+            out["grad:" + k] = p.grad.numpy()
+            ng += 1
+    assert ng == 4 * (cfg.layers + tcfg.layers), ng
+    return out
+
+
+BOTH_CASES = {
+    # name: (vision cfg, text cfg, batch, classes, seed)
+    "both_tiny": (vo.VIT_TINY, vo.TEXT_TINY, 4, 6, 21),
+    "both_vitb16": (vo.VIT_B16, vo.TEXT_B16, 8, 20, 23),
+}
+
+
+def run_interpret_pred():
+    """Execute the reference's OWN _interpret_pred (methods/_trainer.py:519-534; the module itself
+    cannot be imported here - it pulls randaugment / timm - so the function's source is compiled
+    out of the file) and sklearn's confusion_matrix as methods/adapter_clip.py:166 calls it, on
+    seeded labels/predictions. Stores inputs and outputs."""
+    import ast
+    import types
+    from sklearn.metrics import confusion_matrix
+    path = os.path.join(REF, "methods", "_trainer.py")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)
+              and n.name == "_interpret_pred")
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ns = {"torch": torch}
+    exec(compile(mod, path, "exec"), ns)
+    out = {}
+    rng = np.random.default_rng(5)
+    for i, (n, ncls, n_tasks) in enumerate([(257, 100, 10), (64, 37, 10), (1000, 100, 10),
+                                            (33, 50, 5)]):
+        y = rng.integers(0, ncls, size=n).astype(np.int64)
+        pred = np.where(rng.random(n) < 0.6, y, rng.integers(0, ncls, size=n)).astype(np.int64)
+        self_ = types.SimpleNamespace(n_tasks=n_tasks)
+        num, ok = ns["_interpret_pred"](self_, torch.from_numpy(y), torch.from_numpy(pred))
+        out[f"y{i}"], out[f"pred{i}"] = y, pred
+        out[f"meta{i}"] = np.asarray([ncls, n_tasks], np.int64)
+        out[f"num{i}"], out[f"ok{i}"] = num.numpy(), ok.numpy()
+        out[f"cm{i}"] = confusion_matrix(y.tolist(), pred.tolist())
+    return out
 
 
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
-    for name, (cfg, n, c, seed) in CASES.items():
-        out = run_reference(cfg, n, c, seed)
+    only = sys.argv[1:]
+    for name, (cfg, n, c, seed) in {**CASES, **BIG_CASES}.items():
+        if only and name not in only:
+            continue
+        out = run_reference(cfg, n, c, seed, slim=name in BIG_CASES)
         path = os.path.join(HERE, f"ref_{name}.npz")
         np.savez_compressed(path, **out)
         print(name, "loss", float(out["loss"]), "->", path, os.path.getsize(path), "bytes")
+    for name, (cfg, tcfg, n, c, seed) in BOTH_CASES.items():
+        if only and name not in only:
+            continue
+        out = run_reference_both(cfg, tcfg, n, c, seed)
+        path = os.path.join(HERE, f"ref_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(name, "loss", float(out["loss"]), "->", path, os.path.getsize(path), "bytes")
+    if not only or "interpret_pred" in only:
+        path = os.path.join(HERE, "ref_interpret_pred.npz")
+        np.savez_compressed(path, **run_interpret_pred())
+        print("interpret_pred ->", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

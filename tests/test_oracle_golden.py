@@ -59,3 +59,43 @@ def test_double_softmax_loss_is_ce_on_probs():
     want = (-p[torch.arange(5), y] + torch.logsumexp(p, -1)).mean()
     got = vo.reference_loss(p, y)
     assert abs(float(want) - float(got)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["both_tiny", "both_vitb16"])
+def test_text_tower_oracle_matches_reference_golden(name, golden_dir):
+    """peft_encoder='both': the oracle's text tower (model.py:941-956 restated) and the two-tower
+    step against the reference's own CLIP with LoRA blocks in both transformers."""
+    from tests.golden.make_golden import BOTH_CASES
+    cfg, tcfg, n, c, seed = BOTH_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    torch.set_num_threads(os.cpu_count() or 1)
+    wv, wt = vo.synth_weights(cfg, seed), vo.synth_text_weights(tcfg, seed + 1)
+    images, labels = synth_inputs(cfg, n, c, seed + 100)
+    tokens = vo.synth_tokens(c, tcfg, seed + 300)
+    dtype = torch.float64 if name == "both_tiny" else torch.float32
+    out = vo.clip_step_oracle(images, labels, tokens, wv, wt, cfg, tcfg,
+                              logit_scale_exp=float(gold["logit_scale_exp"]), dtype=dtype)
+    assert _rel(out["tfeat"], gold["tfeat"]) < 2e-5
+    assert _rel(out["probs"], gold["probs"]) < 2e-5
+    assert abs(float(out["loss"]) - float(gold["loss"])) < 1e-5
+    np.testing.assert_array_equal(out["pred"], gold["pred"])
+    grads = {k[5:]: gold[k] for k in gold.files if k.startswith("grad:")}
+    assert set(grads) == set(out["grads"]) and len(grads) == 4 * (cfg.layers + tcfg.layers)
+    worst = max(_rel(out["grads"][k], v) for k, v in grads.items())
+    assert worst < 1e-3, worst
+
+
+def test_interpret_pred_and_confusion_match_reference(golden_dir):
+    """oracle.interpret_pred / confusion against the outputs of the reference's own
+    _interpret_pred (methods/_trainer.py:519-534) and sklearn's confusion_matrix: bit-exact."""
+    gold = np.load(os.path.join(golden_dir, "ref_interpret_pred.npz"))
+    i = 0
+    while f"y{i}" in gold.files:
+        y, pred = gold[f"y{i}"], gold[f"pred{i}"]
+        n_tasks = int(gold[f"meta{i}"][1])
+        num, ok = vo.interpret_pred(y, pred, n_tasks)
+        np.testing.assert_array_equal(num, gold[f"num{i}"])
+        np.testing.assert_array_equal(ok, gold[f"ok{i}"])
+        np.testing.assert_array_equal(vo.confusion(y, pred), gold[f"cm{i}"])
+        i += 1
+    assert i == 4
