@@ -6,14 +6,21 @@
 
 A "step" is one pass of the hot path over one combined stream+replay batch: image tower forward,
 head + loss, backward to the LoRA factors (frozen-backbone weight gradients skipped), all-reduce
-of the flat LoRA gradient (N > 1) and AdamW. Workload = BASELINE.json configs[1] on one GPU:
-ViT-B/16, batch 256 per GPU (weak scaling: every rank holds its own 256), 100 visible classes,
-synthetic images, random-init weights.
+of the flat LoRA gradient (N > 1) and AdamW. Workload = BASELINE.json configs[1]: ViT-B/16,
+stream+replay batch 256, 100 visible classes, synthetic images, random-init weights. N = 1 runs the
+256 images on one GPU; N > 1 shards the SAME global batch (256 / N per GPU: strong scaling, the
+configuration BASELINE.json states); --scaling weak keeps 256 per GPU instead.
+
+    python bench.py --mode eval                              # BASELINE config 5: inference-only,
+                                                             # 4096 images x 1000 cached classes
+    python bench.py --peft both                              # LoRA text tower recomputed per step
 
   value   images/s with the inputs already resident in HBM (CUDA events, max over ranks)
   e2e     images/s through the public API LoRAClipTrainer.online_step(images, labels, idx) fed
-          from pinned HOST memory: the H2D copy of every step's images and labels and the D2H read
-          of (loss, acc) are inside the timed region
+          from pinned HOST memory with the RAW CIFAR-shaped uint8 batch the reference's DataLoader
+          yields (the reference, too, resizes on the GPU: methods/_trainer.py:236-242); the H2D
+          copy of the step's images and labels, the fused resize/crop/flip/normalise and the D2H
+          read of (loss, acc) are inside the timed region
   roofline       the tcgen05 GEMM kernel: algorithmic FLOPs / CUDA-event time per launch
   cpu_baseline   the oracle port of the reference path on this box's host cores (bounded sample)
 """
@@ -132,29 +139,45 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 class CpuReference:
-    """The reference's CPU path as restated by oracle/vit_oracle.py (the reference itself is
-    Python and absent on the GPU box; kind = "port"): fp32 torch CPU ops on all host threads,
-    forward + reference loss + backward + AdamW over the LoRA tensors."""
+    """The reference's CPU path: its OWN modules when a checkout is reachable ($LLC_REFERENCE,
+    /root/reference, baseline/_ref; kind = "reference"), else the restatement in
+    oracle/vit_oracle.py (the reference is Python and absent on the GPU box; kind = "port").
+    fp32 torch CPU ops on all host threads: forward + reference loss + backward + AdamW over the
+    LoRA tensors."""
 
     def __init__(self, model: str, classes: int, batch: int, seed: int = 0):
         import numpy as np
         import torch
+        from oracle import ref_runner
         from oracle import vit_oracle as vo
         self.torch, self.vo = torch, vo
         S, p, D, layers, H, E = MODELS[model]
         self.cfg = vo.VitCfg(image_size=S, patch=p, width=D, layers=layers, heads=H, embed_dim=E)
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
-        self.w = vo.to_torch(vo.synth_weights(self.cfg, seed), torch.float32)
-        self.text = torch.from_numpy(vo.synth_text_features(classes, E, seed + 1))
+        w_np = vo.synth_weights(self.cfg, seed)
+        text_np = vo.synth_text_features(classes, E, seed + 1)
         rng = np.random.default_rng(seed + 2)
         self.x = torch.from_numpy(rng.standard_normal((batch, 3, S, S)).astype(np.float32))
         self.y = torch.from_numpy(rng.integers(0, classes, size=(batch,)).astype(np.int64))
-        self.opt = torch.optim.AdamW([t for t in self.w.values() if t.requires_grad], lr=1e-3,
-                                     weight_decay=1e-5)
         self.batch = batch
+        ref_root = ref_runner.find_reference()
+        self.kind = "reference" if ref_root else "port"
+        if ref_root:
+            self.ref = ref_runner.ReferenceStep(ref_root, self.cfg, w_np, text_np)
+        else:
+            self.w = vo.to_torch(w_np, torch.float32)
+            self.text = torch.from_numpy(text_np)
+            self.opt = torch.optim.AdamW([t for t in self.w.values() if t.requires_grad],
+                                         lr=1e-3, weight_decay=1e-5)
+
+    def describe(self) -> str:
+        return ("the reference's own models/clip modules" if self.kind == "reference" else
+                "fp32 oracle port of the reference's PyTorch path")
 
     def step(self) -> float:
+        if self.kind == "reference":
+            return self.ref.step(self.x, self.y)
         vo = self.vo
         self.opt.zero_grad(set_to_none=True)
         feat = vo.vit_forward(self.x, self.w, self.cfg)
@@ -182,34 +205,190 @@ def run_reference(args):
     ref = CpuReference(args.model, args.classes, b)
     sec = ref.time_steps(args.steps, args.warmup)
     v = b / sec
-    sample = (f"{b}-image batch per step (of the {args.batch}-image workload), fp32 oracle port of "
-              f"the reference's PyTorch path, fwd+loss+bwd+AdamW, {ref.cores} threads")
+    sample = (f"{b}-image batch per step (of the {global_batch(args, args.gpus)}-image workload), "
+              f"{ref.describe()}, fp32, fwd+loss+bwd+AdamW, {ref.cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.cores, "kind": "port",
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
                          "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
 
 
+def per_gpu_batch(args, world: int) -> int:
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"--batch {args.batch} is not divisible by {world} GPUs")
+        return args.batch // world
+    return args.batch
+
+
+def global_batch(args, world: int) -> int:
+    return args.batch if args.scaling == "strong" else args.batch * world
+
+
 def workload_config(args, world: int) -> dict:
-    """The workload both arms report (BASELINE.json configs[1] on `world` GPUs, weak scaling)."""
+    """The workload both arms report: BASELINE.json configs[1] (train) / configs[4] (eval)."""
     S, p = MODELS[args.model][0], MODELS[args.model][1]
-    return {"workload": workload_name(args), "batch_per_gpu": args.batch,
-            "global_batch": args.batch * world, "classes": args.classes,
+    return {"workload": workload_name(args), "global_batch": global_batch(args, world),
+            "batch_per_gpu": per_gpu_batch(args, world), "classes": args.classes,
             "tokens": (S // p) ** 2 + 1, "parallelism": f"dp{world}", "weights": "random-init",
-            "l2": "inputs larger than L2 (154 MB images per step; activations 1 GB/layer)",
+            "peft_encoder": args.peft, "mode": args.mode,
+            "l2": "inputs larger than L2 (154 MB of images per 256; activations 1 GB/layer)",
             "loss": "CE on probabilities (reference double softmax)"}
 
 
 def workload_name(args) -> str:
-    return (f"CLIP {args.model} LoRA online step, stream+replay batch {args.batch} per GPU "
-            f"(BASELINE.json configs[1] on one GPU; weak scaling), bf16 operands")
+    if args.mode == "eval":
+        return (f"CLIP {args.model} inference-only eval: masked cosine logits over {args.classes} "
+                f"cached class text embeddings, batch {args.batch} (BASELINE.json configs[4])")
+    return (f"CLIP {args.model} LoRA online step, stream+replay batch {args.batch} "
+            f"(BASELINE.json configs[1]; data-parallel shards of the same global batch), "
+            f"bf16 operands")
+
+
+# ------------------------------------------------------------------------------------------------
+def run_eval(args, model, names, dev, world, rank, local_rank):
+    """BASELINE.json configs[4]: inference-only evaluation, ViT-B/16, masked cosine logits over
+    1000 cached class text embeddings, batch 4096 (sharded over the GPUs: no collective, every
+    rank evaluates its own images). A step = tower forward (no saved activations) + the
+    tensor-core head (ln_post -> proj GEMM -> L2 norm -> logit GEMM -> softmax/arg-max) + the
+    on-device confusion/per-task counters."""
+    import torch
+    import torch.distributed as dist
+    from lifelong_clip_b200 import ops
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+    from lifelong_clip_b200.transform import GpuTransform
+
+    S, p, D, layers, H, E = MODELS[args.model]
+    B, C = per_gpu_batch(args, world), args.classes
+    gB = global_batch(args, world)
+    trainer = LoRAClipTrainer(model, names, n_classes=C, n_tasks=100, visible_classes="all")
+    model.set_token(names)
+    eng = model.model.visual.engine()
+    seen = torch.arange(0, C, 2, device=dev)          # seen-class mask: every other class
+    mask = torch.full((C,), float("-inf"), device=dev)
+    mask[seen] = 0.0
+    model.set_additive_mask(mask)
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    dev_x = [torch.randn(B, 3, S, S, generator=gen, device=dev) for _ in range(2)]
+    dev_y = [torch.randint(0, C, (B,), generator=gen, device=dev) for _ in range(2)]
+    cm = torch.zeros(C, C, dtype=torch.int64, device=dev)
+    counts = torch.zeros(22, dtype=torch.int64, device=dev)
+    scale = model.model.logit_scale_exp()
+
+    def step(i):
+        eng.forward(dev_x[i % 2], training=False)
+        if args.peft == "both":
+            raise SystemExit("--mode eval measures the cached-text configuration (--peft image)")
+        head = eng.eval_head(model._text_all, scale, cls_idx=model._cls_idx,
+                             add_mask=model._add_mask, want_probs=True)
+        ops.eval_accum(dev_y[i % 2], head.pred, trainer.n_tasks, C, cm, counts)
+        return head
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        launches = ops.launch_count() - l0
+        ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        clocks = sampler.stop() if sampler else None
+        # e2e: online_evaluate over a loader of RAW uint8 32x32 host batches (test_transform =
+        # Resize + Normalize fused into the tower's first kernel); the dict comes back on the host
+        mean, std = (0.5071, 0.4867, 0.4408), (0.2675, 0.2565, 0.2761)
+        trainer.test_transform = GpuTransform.test(S, mean, std)
+        hg = torch.Generator().manual_seed(50 + rank)
+        host = [(torch.randint(0, 256, (B, 3, 32, 32), generator=hg, dtype=torch.uint8).pin_memory(),
+                 torch.randint(0, C, (B,), generator=hg).pin_memory()) for _ in range(2)]
+        trainer.online_evaluate([host[i % 2] for i in range(2)], 0)      # warm-up (arena, caches)
+        barrier()
+        t0 = time.perf_counter()
+        res = trainer.online_evaluate([host[i % 2] for i in range(args.steps)], 0)
+        torch.cuda.synchronize()
+        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        # per-kernel pass
+        ops.prof_enable(True)
+        for i in range(args.prof_steps):
+            step(i)
+        torch.cuda.synchronize()
+        recs = ops.prof_read()
+        ops.prof_enable(False)
+    by_kind = {}
+    for kind, m_, n_, k_, ms, fl, by in recs:
+        d = by_kind.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["launches"] += 1; d["ms"] += ms; d["flops"] += fl; d["bytes"] += by
+    peaks = load_peaks()
+    gemm = by_kind.get("gemm", {"launches": 0, "ms": 1e-9, "flops": 0.0})
+    total_ms = sum(d["ms"] for d in by_kind.values()) or 1.0
+    achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+    peak = peaks["bf16_sustained"] or peaks["bf16"]
+    fwd_flops = train_flops_per_image(args.model)   # forward share computed below
+    S_, p_, D_, layers_, H_, E_ = MODELS[args.model]
+    L_ = (S_ // p_) ** 2 + 1
+    lin = 2 * L_ * (3 * D_ * D_ + D_ * D_ + 2 * D_ * 4 * D_)
+    attn = 2 * 2 * H_ * L_ * L_ * 64
+    lora = 2 * L_ * (D_ * 4 + 4 * 3 * D_ + D_ * 4 + 4 * D_)
+    fwd_flops = float(2 * (L_ - 1) * D_ * 3 * p_ * p_ + layers_ * (lin + attn + lora) +
+                      2 * D_ * E_ + 2 * E_ * C)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    value = gB / (ms_dev * 1e-3)
+    out = {
+        "metric": "eval img/s, CLIP ViT-B/16 masked cosine logits over cached class text embeddings",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, world), "clocks": clocks,
+        "e2e": {"value": gB / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": (host[0][0].numel() + host[0][1].numel() * 8) * world,
+                "d2h_bytes_per_step": (C * C * 8 + 22 * 8) * world / args.steps,
+                "api": "LoRAClipTrainer.online_evaluate(loader of raw uint8 host batches) -> dict",
+                "avg_acc": float(res["avg_acc"])},
+        "gpu_launches": launches * world,
+        "step_tensor_frac": {"achieved_tflops_per_gpu": value / world * fwd_flops / 1e12,
+                             "of_burst_peak": value / world * fwd_flops / 1e12 / peaks["bf16"],
+                             "flop_per_image": fwd_flops},
+        "roofline": {"bound": "tensor", "kernel": "gemm2_kernel / gemm_tn_kernel (tcgen05): tower "
+                     "GEMMs + the feature and logit GEMMs of the evaluation head",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "peak_source": peaks["source"],
+                     "share_of_step": gemm["ms"] / total_ms},
+        "kernel_breakdown": {k: {"ms_per_step": d["ms"] / args.prof_steps,
+                                 "launches_per_step": d["launches"] / args.prof_steps}
+                             for k, d in sorted(by_kind.items())},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -239,33 +418,47 @@ def run_ours(args):
     from lifelong_clip_b200.adapter_clip import AdapterCLIP
     from lifelong_clip_b200.trainer import LoRAClipTrainer
 
+    from lifelong_clip_b200.adapter_clip import SyntheticTokenizer
+    from lifelong_clip_b200.transform import GpuTransform
+
     S, p, D, layers, H, E = MODELS[args.model]
-    B, C = args.batch, args.classes
+    B, C = per_gpu_batch(args, world), args.classes
+    gB = global_batch(args, world)
     torch.manual_seed(0)                       # identical replicas on every rank
-    model = AdapterCLIP(vision_config=(S, p, D, layers, E)).to(dev)
+    model = AdapterCLIP(model_name=args.model, peft_encoder=args.peft,
+                        vision_config=(S, p, D, layers, E)).to(dev)
     names = [f"class {i}" for i in range(C)]
     g = torch.Generator().manual_seed(1)
-    model.set_text_features(names, torch.randn(C, E, generator=g))
+    if args.peft == "both":
+        model.set_tokenizer(SyntheticTokenizer())
+    else:
+        model.set_text_features(names, torch.randn(C, E, generator=g))
+    if args.mode == "eval":
+        return run_eval(args, model, names, dev, world, rank, local_rank)
     trainer = LoRAClipTrainer(model, names, n_classes=C, n_tasks=5, lr=1e-3, online_iter=1,
                               visible_classes="all", sharded_input=True,
                               use_cuda_graph=not args.no_graph)
     trainer.online_before_task(0)
 
-    # synthetic stream: a pool of distinct pinned host batches (each 154 MB fp32 at B=256, i.e.
-    # larger than the 126 MB L2, so no step finds its input cached)
+    # synthetic stream: a pool of distinct batches per rank. `value` reads pre-transformed fp32
+    # 224x224 images resident in HBM; `e2e` starts from the RAW CIFAR-shaped uint8 batch in
+    # pinned host memory (what the reference's DataLoader yields before its GPU transform).
     n_pool = 3
+    RAW = 32
     gen = torch.Generator().manual_seed(100 + rank)
-    host_x = [torch.randn(B, 3, S, S, generator=gen).pin_memory() for _ in range(n_pool)]
+    host_raw = [torch.randint(0, 256, (B, 3, RAW, RAW), generator=gen, dtype=torch.uint8)
+                .pin_memory() for _ in range(n_pool)]
     host_y = [torch.randint(0, C, (B,), generator=gen).pin_memory() for _ in range(n_pool)]
     idx = torch.arange(B)
+    mean, std = (0.5071, 0.4867, 0.4408), (0.2675, 0.2565, 0.2761)   # datasets/__init__.py:38-39
 
     # every class exposed once up front so the visible-class list (C columns) is fixed
     trainer.add_new_class(torch.arange(C))
     model.set_token(trainer.exposed_classes_names)
     lut = trainer._class_lut(trainer.exposed_classes)
-    dev_x = [x.to(dev) for x in host_x[:2]]
+    dev_x = [torch.randn(B, 3, S, S, generator=torch.Generator(device=dev).manual_seed(7 + i + 10 * rank),
+                         device=dev) for i in range(2)]
     dev_y = [ops.label_remap(y.to(dev), lut) for y in host_y[:2]]
-    gB = B * world
 
     def barrier():
         if world > 1:
@@ -278,6 +471,31 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---------------------------------------------------------------- DP equivalence (N > 1)
+    # one-off: the all-reduced gradient of the sharded global batch against the gradient rank 0
+    # computes alone on the concatenated batch
+    dp_check = None
+    if world > 1:
+        gg = torch.Generator().manual_seed(999)
+        gx = torch.randn(gB, 3, S, S, generator=gg)
+        gy = torch.randint(0, C, (gB,), generator=gg)
+        engines = trainer.optimizer.engines()
+        trainer._step_body(gx[rank::world].to(dev), ops.label_remap(gy[rank::world].to(dev), lut),
+                           gB)
+        red = torch.cat([e.grad_flat for e in engines]).clone()
+        dist.all_reduce(red)
+        if rank == 0:
+            trainer._step_body(gx.to(dev), ops.label_remap(gy.to(dev), lut), gB)
+            full = torch.cat([e.grad_flat for e in engines])
+            dp_check = {"rel_l2": float((red - full).norm() / full.norm()),
+                        "max_abs": float((red - full).abs().max()),
+                        "grad_norm": float(full.norm()),
+                        "what": f"all-reduce of {world} shard gradients vs one GPU on the "
+                                f"concatenated {gB}-image batch (fp32 summation order only)"}
+            for e in engines:           # back to the per-GPU shard size
+                e.arena, e.arena_key, e.dx = None, None, None
+        barrier()
 
     # ---------------------------------------------------------------- device-resident: `value`
     for i in range(args.warmup):
@@ -302,15 +520,21 @@ def run_ours(args):
 
     # ---------------------------------------------------------------- end to end: `e2e`
     # the user-facing loop: DevicePrefetcher over a loader of pinned HOST batches (the H2D copy of
-    # batch i+1 overlaps step i on a side stream) -> online_step -> (loss, acc) floats on the host
+    # batch i+1 overlaps step i on a side stream) -> online_step -> (loss, acc) floats on the
+    # host. The batches are RAW uint8 32x32 (CIFAR-shaped); the reference's train_transform
+    # (Resize 224 / RandomCrop / flip / Normalize, methods/_trainer.py:236-242) runs fused in
+    # front of the patch embedding.
     from lifelong_clip_b200.trainer import DevicePrefetcher
+    trainer.train_transform = GpuTransform.train(S, mean, std)
 
     def host_loader(n):
         for i in range(n):
-            yield host_x[i % n_pool], host_y[i % n_pool], idx
+            yield host_raw[i % n_pool], host_y[i % n_pool], idx
 
     # one continuous loop in steady state (as a long run is): W untimed steps, then exactly K
-    # timed ones; every timed step's H2D copy is issued and completes inside the timed region
+    # timed ones. The prefetcher stages one batch ahead, so the copies of the first timed batch
+    # (and of batch W+1) are issued before e0; the other K-1 (K-2) are inside the timed region,
+    # as are all K transforms, steps and (loss, acc) reads.
     last = None
     for i, (images, labels, ids) in enumerate(
             DevicePrefetcher(host_loader(args.warmup + args.steps), dev)):
@@ -322,8 +546,9 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = gB / (ms_e2e * 1e-3)
-    h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
+    h2d = host_raw[0].numel() + host_y[0].numel() * 8
     d2h = 8
+    trainer.train_transform = (lambda x: x)
 
     # ---------------------------------------------------------------- per-kernel pass (roofline)
     trainer.use_cuda_graph = False          # per-launch events need eager launches
@@ -356,6 +581,8 @@ def run_ours(args):
     # launches of one block inside this same bench command; profiles/r01_ncu_gemm2_in_step.csv)
     traffic = None
     try:
+        if B != 256:
+            raise LookupError("the ncu capture was taken at 256 images per GPU")
         import csv
         with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm2_in_step.csv")) as f:
             rows = list(csv.DictReader(f))
@@ -400,10 +627,9 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref = CpuReference(args.model, C, args.cpu_batch)
         sec = ref.time_steps(2, 1)
-        cpu = {"value": args.cpu_batch / sec, "unit": UNIT, "cores": ref.cores, "kind": "port",
+        cpu = {"value": args.cpu_batch / sec, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
                "sample": f"{args.cpu_batch}-image batch x 2 timed steps (1 warm-up) of the same "
-                         "model/classes: fp32 oracle port of the reference's PyTorch path, "
-                         "fwd+loss+bwd+AdamW"}
+                         f"model/classes: {ref.describe()}, fp32, fwd+loss+bwd+AdamW"}
 
     if world > 1:
         dist.destroy_process_group()
@@ -415,11 +641,17 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {**workload_config(args, world),
-                   "cuda_graph": not args.no_graph,
-                   "last_block": ("class-token rows only (llc_vit_forward_cls: identical outputs)"
-                                  if os.environ.get("LLC_FULL_LAST_BLOCK") is None else "full")},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, world),
+        "impl_details": {"cuda_graph": not args.no_graph,
+                         "last_block": ("class-token rows only (llc_vit_forward_cls: identical "
+                                        "outputs)" if os.environ.get("LLC_FULL_LAST_BLOCK") is None
+                                        else "full"),
+                         "value_input": "pre-transformed fp32 224x224 images resident in HBM",
+                         "e2e_input": "raw uint8 32x32 batches in pinned host memory; resize / "
+                                      "crop / flip / normalise fused into the step "
+                                      "(llc_vit_forward_tx)"},
+        "dp_check": dp_check,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
@@ -453,14 +685,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="ViT-B/16", choices=sorted(MODELS))
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--classes", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=None,
+                    help="images per step: the GLOBAL batch under --scaling strong (default 256 "
+                         "train / 4096 eval), per GPU under --scaling weak")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--mode", default="train", choices=["train", "eval"])
+    ap.add_argument("--peft", default="image", choices=["image", "both"],
+                    help="'both': LoRA text tower recomputed every step (scripts/lora_clip.sh)")
+    ap.add_argument("--classes", type=int, default=None)
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--prof-steps", type=int, default=2)
     ap.add_argument("--dump-prof", default=None, help="write per-launch records (json) here")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 4096 if args.mode == "eval" else 256
+    if args.classes is None:
+        args.classes = 1000 if args.mode == "eval" else 100
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)

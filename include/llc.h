@@ -79,7 +79,18 @@ typedef struct llc_gemm_epi {
   int out_fp32;       /* 0: bf16, 1: fp32 */
   void* out2;         /* bf16 [M, ld_out2], only act==1 */
   int ld_out2;
+  void* ws;           /* optional stream-K workspace: llc_gemm_ws_bytes() bytes of device memory,
+                         16 B aligned, whose first 8 KB (flags) were zero before the first use;
+                         the kernel leaves them zero. NULL: whole-tile schedule only */
+  size_t ws_bytes;
 } llc_gemm_epi;
+/* Workspace size of the stream-K schedule: when the 256 x 256 tile count leaves a poorly filled
+ * last wave on the 74 CTA pairs (T = 197 x images rarely divides), the (tile, k-block) units are
+ * cut into equal contiguous ranges and split tiles are summed through this workspace. */
+size_t llc_gemm_ws_bytes(void);
+/* process-wide switch of the stream-K schedule (default on; A/B measurements); returns the
+ * previous setting */
+int llc_gemm_set_stream_k(int on);
 int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
                      const llc_gemm_epi* epi, void* stream);
 
@@ -286,7 +297,9 @@ typedef struct llc_vit_weights {
   const llc_vit_layer* layers;
 } llc_vit_weights;
 
-/* activation arena: sizes from llc_vit_arena_bytes; saved-for-backward tensors live here */
+/* activation arena: sizes from llc_vit_arena_bytes; saved-for-backward tensors live here. Its
+ * first 8 KB (the flag words of the GEMMs' stream-K workspace) must be ZERO before the first
+ * call that uses the arena; every call leaves them zero. */
 size_t llc_vit_arena_bytes(const llc_vit_cfg* cfg, int N, int training);
 /* images fp32 NCHW [N,3,S,S] -> x_final fp32 [N*L, D] (pointer returned inside the arena) */
 int llc_vit_forward(const llc_vit_cfg* cfg, const llc_vit_weights* w, const float* images, int N,

@@ -23,6 +23,7 @@ class GemmEpi(C.Structure):
         ("bias", c_void), ("resid", c_void), ("ld_resid", c_int), ("act", c_int),
         ("aux", c_void), ("ld_aux", c_int), ("out", c_void), ("ld_out", c_int),
         ("out_fp32", c_int), ("out2", c_void), ("ld_out2", c_int),
+        ("ws", c_void), ("ws_bytes", C.c_size_t),
     ]
 
 
@@ -103,6 +104,8 @@ SIGNATURES = {
     "llc_last_error": (C.c_char_p, []),
     "llc_check_device": (c_int, [c_int]),
     "llc_launch_count": (C.c_ulonglong, []),
+    "llc_gemm_ws_bytes": (C.c_size_t, []),
+    "llc_gemm_set_stream_k": (c_int, [c_int]),
     "llc_gemm_bf16_tn": (c_int, [c_void, c_int, c_void, c_int, c_int, c_int, c_int,
                                  C.POINTER(GemmEpi), c_void]),
     "llc_ln_fwd": (c_int, [c_void, c_int, c_void, c_void, c_int, c_int, c_void, c_int, c_void,
@@ -192,6 +195,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the export is missing
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("LLC_STREAM_K") == "0":     # A/B measurements of the GEMM schedule
+        lib.llc_gemm_set_stream_k(0)
     _lib = lib
     return lib
 

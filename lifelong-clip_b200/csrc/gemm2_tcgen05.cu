@@ -12,6 +12,15 @@
 //   warp 1      MMA issuer (leader CTA, one lane); commits multicast to both CTAs' barriers
 //   warps 2..9  epilogue (gemm_epilogue.cuh): two warps per TMEM lane quarter, 128 columns each
 // TMEM holds two 256-column accumulators, so a tile's epilogue overlaps the next tile's mainloop.
+//
+// Stream-K schedule (SK = true): with T = 197 x images tokens the tile count rarely divides the 74
+// CTA pairs (32 images, N = 768: 75 tiles -> a second wave holding ONE tile, 51 % efficiency). The
+// (tile, k-block) units are then cut into 74 equal contiguous ranges. A range that starts inside
+// a tile (k0 > 0) leaves its fp32 partial in a caller-provided workspace and raises a flag; the
+// pair whose range holds the tile's k-block 0 owns the tile: it adds the partials of the pairs
+// after it into its TMEM accumulator and runs the normal epilogue. A contributor's partial is the
+// FIRST thing it computes and an owner's tile the LAST, so nobody waits in practice, and the
+// result is deterministic (fixed ranges, fixed summation order).
 #include <stdlib.h>
 
 #include "gemm_epilogue.cuh"
@@ -32,12 +41,82 @@ constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
 constexpr int kBarBytes = 256;
 constexpr int kSmem = 1024 + kStages * kStageBytes + kEpiBytes + kBarBytes;
 constexpr int kTmemCols = 512;
+constexpr int kSkFlagBytes = 8192;                    // flags[pair][rank][epilogue warp] (ints)
+constexpr int kSkSlotFloats = 32 * (BN / 2);          // one epilogue warp's 32 rows x 128 columns
 
-template <int MODE>
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_all() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Work list of one CTA pair. !SK: whole tiles pair, pair + P, ...; SK: the pair's contiguous
+// range of (tile, k-block) units, cut at tile boundaries into segments [kb0, kb1).
+template <bool SK>
+struct WorkIter {
+  int num_pairs, num_tiles, num_kb, tile_next;
+  long long u, u1;
+  __device__ WorkIter(int pair, int num_pairs_, int num_tiles_, int num_kb_)
+      : num_pairs(num_pairs_), num_tiles(num_tiles_), num_kb(num_kb_), tile_next(pair) {
+    const long long total = (long long)num_tiles_ * num_kb_;
+    u = SK ? total * pair / num_pairs_ : 0;
+    u1 = SK ? total * (pair + 1) / num_pairs_ : 0;
+  }
+  __device__ bool next(int& tile, int& kb0, int& kb1) {
+    if (SK) {
+      if (u >= u1) return false;
+      tile = (int)(u / num_kb);
+      kb0 = (int)(u - (long long)tile * num_kb);
+      const long long len = min((long long)(num_kb - kb0), u1 - u);
+      kb1 = kb0 + (int)len;
+      u += len;
+      return true;
+    }
+    if (tile_next >= num_tiles) return false;
+    tile = tile_next;
+    tile_next += num_pairs;
+    kb0 = 0;
+    kb1 = num_kb;
+    return true;
+  }
+  // next segment / next segment this pair OWNS (kb0 == 0), without advancing; tile -1 if none
+  __device__ void peek(int& tile, int& kb0) const {
+    WorkIter c = *this;
+    int kb1;
+    if (!c.next(tile, kb0, kb1)) tile = -1;
+  }
+  __device__ int peek_owned() const {
+    WorkIter c = *this;
+    int t, a, b;
+    while (c.next(t, a, b))
+      if (a == 0) return t;
+    return -1;
+  }
+};
+
+template <int MODE, bool SK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2,
-             int M, int N, int K, EpiParams ep, int dbg) {
+             int M, int N, int K, EpiParams ep, int dbg, uint8_t* sk_ws) {
   // dbg (LLC_GEMM_DBG, development only): 1 = epilogue does no work, 2 = producer issues no TMA,
   // 4 = no MMA is issued, 8 = no L2 prefetch, 32 = producer does not wait for free slots,
   // 64 = MMA issuer does not wait for data, 128 = no per-stage commit (wrong results: timing only)
@@ -95,12 +174,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // the whole warp runs the loop; one elected lane issues (operands stay uniform)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    WorkIter<SK> wi(pair, num_pairs, num_tiles, num_kb);
+    int tile, kb0, kb1;
+    while (wi.next(tile, kb0, kb1)) {
       const int m0 = (tile / tiles_n) * BM + (int)rank * 128;
       const int n0 = (tile % tiles_n) * BN + (int)rank * 128;
-      const int next_tile = tile + num_pairs;
+      int next_tile, next_kb0;
+      wi.peek(next_tile, next_kb0);
       const int m0_next = (next_tile / tiles_n) * BM + (int)rank * 128;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         if (!(dbg & 32)) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb_local = smem_u32(&full_bar[stage]);
         const uint32_t fb_leader = mapa_shared(fb_local, 0);
@@ -110,9 +192,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // smem ring so the ring's own loads see L2 latency. B (weights) stays L2-resident.
           if (!(dbg & 8)) {
             const int pk = kb + kPrefetchKb;
-            if (pk < num_kb) tma_prefetch_2d(&tmA, pk * BK, m0);
-            else if (next_tile < num_tiles && pk - num_kb < num_kb)
-              tma_prefetch_2d(&tmA, (pk - num_kb) * BK, m0_next);
+            if (pk < kb1) tma_prefetch_2d(&tmA, pk * BK, m0);
+            else if (next_tile >= 0 && next_kb0 + pk - kb1 < num_kb)
+              tma_prefetch_2d(&tmA, (next_kb0 + pk - kb1) * BK, m0_next);
           }
           if (dbg & 2) {
             if (rank == 0) mbar_arrive(fb_local);
@@ -140,13 +222,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      WorkIter<SK> wi(pair, num_pairs, num_tiles, num_kb);
+      int tile, kb0, kb1;
+      for (; wi.next(tile, kb0, kb1); ++it) {
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
         mbar_wait(smem_u32(&tempty_bar[buf]), bphase ^ 1);  // both epilogues drained this buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!(dbg & 64)) mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_ab + stage * kStageBytes);
@@ -156,10 +240,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (elect_one()) {
             if (!(dbg & 4))
               for (int k = 0; k < ksteps; ++k)
-                umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                umma_bf16_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kb - kb0) | k) != 0);
             if (!(dbg & 128))
               umma_commit_mc(smem_u32(&empty_bar[stage]), 0x3);  // frees the slot in both CTAs
-            if (kb == num_kb - 1)
+            if (kb == kb1 - 1)
               umma_commit_mc(smem_u32(&tfull_bar[buf]), 0x3);  // accumulator complete (both CTAs)
           }
           __syncwarp();
@@ -178,35 +262,94 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     EpiF32State f32st;
     f32st.ph[0] = f32st.ph[1] = 0;
     const bool f32_resid = MODE == EPI_F32 && ep.resid != nullptr;
-    if (f32_resid && pair < num_tiles && lane == 0)   // residual tiles of the first output tile
-      epi_f32_prime(&tmO2, tile_s, my_bar, (pair / tiles_n) * BM + (int)rank * 128 + q * 32,
-                    (pair % tiles_n) * BN + hh * (BN / 2));
+    WorkIter<SK> wi(pair, num_pairs, num_tiles, num_kb);
+    {
+      const int ft = wi.peek_owned();   // residual tiles of the first output tile
+      if (f32_resid && ft >= 0 && lane == 0)
+        epi_f32_prime(&tmO2, tile_s, my_bar, (ft / tiles_n) * BM + (int)rank * 128 + q * 32,
+                      (ft % tiles_n) * BN + hh * (BN / 2));
+    }
+    int* sk_flags = reinterpret_cast<int*>(sk_ws);
+    float* sk_part = reinterpret_cast<float*>(sk_ws + kSkFlagBytes);
+    const long long sk_total = (long long)num_tiles * num_kb;
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    int tile, kb0, kb1;
+    for (; wi.next(tile, kb0, kb1); ++it) {
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       const int row0 = (tile / tiles_n) * BM + (int)rank * 128 + q * 32;
       const int col0 = (tile % tiles_n) * BN + hh * (BN / 2);
-      {  // while this tile's mainloop runs: pull the NEXT tile's aux / residual rows into L2
-        const int nt = tile + num_pairs;
-        if (nt < num_tiles)
-          epi_l2_prefetch<MODE, BN / 2 / 32>(ep, (nt / tiles_n) * BM + (int)rank * 128 + q * 32,
-                                             (nt % tiles_n) * BN + hh * (BN / 2), M, lane);
-      }
+      const int nt = wi.peek_owned();
+      if (nt >= 0)   // while this tile's mainloop runs: pull the NEXT tile's aux / residual rows into L2
+        epi_l2_prefetch<MODE, BN / 2 / 32>(ep, (nt / tiles_n) * BM + (int)rank * 128 + q * 32,
+                                           (nt % tiles_n) * BN + hh * (BN / 2), M, lane);
       mbar_wait_relaxed(smem_u32(&tfull_bar[buf]), bphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * BN + hh * (BN / 2) + ((uint32_t)(q * 32) << 16);
-      if (!(dbg & 1)) {
-        if (MODE == EPI_F32) {
-          epi_warp_tile_f32_tma<BN / 2 / 32>(ep, &tmO, &tmO2, t_addr, tile_s, my_bar, f32st, row0,
-                                             col0, N, lane);
-          const int nt = tile + num_pairs;
-          if (f32_resid && nt < num_tiles && lane == 0)
-            epi_f32_prime(&tmO2, tile_s, my_bar, (nt / tiles_n) * BM + (int)rank * 128 + q * 32,
-                          (nt % tiles_n) * BN + hh * (BN / 2));
-        } else
-          epi_warp_tile_tma<MODE, BN / 2 / 32>(ep, &tmO, &tmO2, t_addr, tile_s, row0, col0, M, N,
-                                               lane);
+      if (SK && kb0 > 0) {
+        // contributor: this pair's range starts inside the tile. Leave the fp32 partial (element
+        // (row = lane, column c) at c * 32 + lane: 128 B per store instruction) and raise the flag
+        const size_t slot = ((size_t)(pair * 2 + (int)rank) * kEpiWarps + ew);
+        float* dst = sk_part + slot * kSkSlotFloats;
+#pragma unroll 1
+        for (int c = 0; c < BN / 2 / 32; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32(t_addr + c * 32, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(dst + (c * 32 + j) * 32 + lane, __uint_as_float(acc[j]));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(sk_flags + slot, 1);
+      } else {
+        if (SK && kb1 < num_kb) {
+          // owner of a split tile: add the partials of the pairs whose ranges start inside it
+          const long long tile_end = (long long)(tile + 1) * num_kb;
+          int q1 = pair + 1;
+          while (q1 < num_pairs && sk_total * q1 / num_pairs < tile_end) ++q1;   // contributors: (pair, q1)
+          for (int cq = pair + 1; cq < q1; ++cq) {
+            const int* f = sk_flags + ((size_t)(cq * 2 + (int)rank) * kEpiWarps + ew);
+            if (lane == 0) {
+              unsigned spins = 0;
+              while (ld_acquire_gpu(f) == 0) {
+                __nanosleep(64);
+                if (++spins > (1u << 25)) __trap();   // seconds: a lost partial, not a slow one
+              }
+            }
+            __syncwarp();
+          }
+#pragma unroll 1
+          for (int c = 0; c < BN / 2 / 32; ++c) {
+            uint32_t acc[32];
+            tmem_ld_32x32(t_addr + c * 32, acc);
+            tmem_ld_wait();
+            for (int cq = pair + 1; cq < q1; ++cq) {
+              const float* src = sk_part +
+                  ((size_t)(cq * 2 + (int)rank) * kEpiWarps + ew) * kSkSlotFloats;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __ldcg(src + (c * 32 + j) * 32 + lane));
+            }
+            tmem_st_32x32(t_addr + c * 32, acc);
+          }
+          tmem_st_wait_all();
+          __syncwarp();
+          if (lane == 0)
+            for (int cq = pair + 1; cq < q1; ++cq)
+              sk_flags[(size_t)(cq * 2 + (int)rank) * kEpiWarps + ew] = 0;   // clean for the next launch
+        }
+        if (!(dbg & 1)) {
+          if (MODE == EPI_F32) {
+            epi_warp_tile_f32_tma<BN / 2 / 32>(ep, &tmO, &tmO2, t_addr, tile_s, my_bar, f32st, row0,
+                                               col0, N, lane);
+            if (f32_resid && nt >= 0 && lane == 0)
+              epi_f32_prime(&tmO2, tile_s, my_bar, (nt / tiles_n) * BM + (int)rank * 128 + q * 32,
+                            (nt % tiles_n) * BN + hh * (BN / 2));
+          } else
+            epi_warp_tile_tma<MODE, BN / 2 / 32>(ep, &tmO, &tmO2, t_addr, tile_s, row0, col0, M, N,
+                                                 lane);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -225,14 +368,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+int g_stream_k = 1;   // llc_gemm_set_stream_k
+
+// stream-K pays when the plain schedule leaves a poorly filled last wave and every pair still gets
+// a few k-blocks
+bool gemm2_wants_sk(int M, int N, int K) {
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int pairs = llc_num_sms() / 2;
+  const int num_kb = (K + BK - 1) / BK;
+  const int waves = (tiles + pairs - 1) / pairs;
+  const double eff = (double)tiles / ((double)waves * pairs);
+  return eff < 0.92 && (long long)tiles * num_kb >= 4LL * pairs;
+}
+
 template <int MODE>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                  const CUtensorMap& tmO2, int M, int N, int K, const EpiParams& ep,
                  cudaStream_t stream) {
-  LLC_CONFIGURE_SMEM(gemm2_kernel<MODE>, kSmem);
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int pairs = llc_num_sms() / 2;
-  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  const bool sk = g_stream_k && ep.ws != nullptr && ep.ws_bytes >= llc_gemm_ws_bytes() &&
+                  gemm2_wants_sk(M, N, K);
+  const int grid = 2 * ((sk || tiles >= pairs) ? pairs : tiles);
   LLC_PROF_BEGIN(LLC_K_GEMM, M, N, K, 2.0 * M * N * K,
                  2.0 * ((double)M * K + (double)N * K) + (double)M * N * (ep.out_fp32 ? 4 : 2),
                  stream);
@@ -242,8 +399,16 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   // a bf16 output that fits L2 (dh, d_o: 77 MB) is read again by the next kernel(s): let it stay
   static const bool nokeep = llc_dev_env("LLC_GEMM_NOKEEP") != nullptr;
   ep2.keep_out = (!nokeep && !ep.out_fp32 && (double)M * N * 2.0 <= 100e6) ? 1 : 0;
-  LLC_CUDA(llc_launch_pdl(gemm2_kernel<MODE>, dim3(grid), dim3(kThreads), kSmem, stream, tmA, tmB, tmO,
-                          tmO2, M, N, K, ep2, dbg));
+  if (sk) {
+    LLC_CONFIGURE_SMEM((gemm2_kernel<MODE, true>), kSmem);
+    LLC_CUDA(llc_launch_pdl(gemm2_kernel<MODE, true>, dim3(grid), dim3(kThreads), kSmem, stream,
+                            tmA, tmB, tmO, tmO2, M, N, K, ep2, dbg,
+                            reinterpret_cast<uint8_t*>(ep.ws)));
+  } else {
+    LLC_CONFIGURE_SMEM((gemm2_kernel<MODE, false>), kSmem);
+    LLC_CUDA(llc_launch_pdl(gemm2_kernel<MODE, false>, dim3(grid), dim3(kThreads), kSmem, stream,
+                            tmA, tmB, tmO, tmO2, M, N, K, ep2, dbg, (uint8_t*)nullptr));
+  }
   LLC_PROF_END(stream);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("gemm2_kernel");
@@ -252,11 +417,24 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
 
 }  // namespace
 
-// Chosen by llc_gemm_bf16_tn for shapes that fill the machine with 256 x 256 pair tiles.
-bool llc_gemm2_eligible(int M, int N, int K) {
+extern "C" int llc_gemm_set_stream_k(int on) {
+  const int old = g_stream_k;
+  g_stream_k = on != 0;
+  return old;
+}
+
+extern "C" size_t llc_gemm_ws_bytes(void) {
+  return (size_t)kSkFlagBytes +
+         (size_t)(llc_num_sms() / 2) * 2 * kEpiWarps * kSkSlotFloats * sizeof(float);
+}
+
+// Chosen by llc_gemm_bf16_tn for shapes that fill the machine with 256 x 256 pair tiles, or -
+// with a stream-K workspace - whose (tile, k-block) units do.
+bool llc_gemm2_eligible(int M, int N, int K, bool have_ws) {
   if (N % BN != 0 || K < BK) return false;
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
-  return tiles >= llc_num_sms() / 2;
+  if (tiles >= llc_num_sms() / 2) return true;
+  return g_stream_k && have_ws && tiles >= 16 && gemm2_wants_sk(M, N, K);
 }
 
 int llc_gemm2_launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K,

@@ -33,6 +33,8 @@ struct EpiParams {
   int ld_out2;
   int dbg;  // development only (LLC_GEMM_DBG): 256 = no global stores, 512 = no TMEM loads
   int keep_out;  // the bf16 output is small enough to stay in L2 for its consumer: no evict-first
+  void* ws;      // stream-K workspace (llc_gemm_ws_bytes, flags zero) or nullptr
+  size_t ws_bytes;
 };
 
 constexpr int kEpiWarpBytes = 8192;  // TMA-store tiles (see epi_warp_tile_tma) / one 4 KB fp32 tile

@@ -14,7 +14,7 @@
 
 #include "gemm_epilogue.cuh"
 
-bool llc_gemm2_eligible(int M, int N, int K);
+bool llc_gemm2_eligible(int M, int N, int K, bool have_ws);
 int llc_gemm2_launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
                      const EpiParams& ep, cudaStream_t stream);
 
@@ -319,11 +319,14 @@ extern "C" int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
   ep.out2 = reinterpret_cast<__nv_bfloat16*>(e->out2); ep.ld_out2 = e->ld_out2;
   ep.dbg = 0;
   ep.keep_out = 0;
+  ep.ws = e->ws; ep.ws_bytes = e->ws_bytes;
+  LLC_REQUIRE(e->ws == nullptr || ((uintptr_t)e->ws & 15) == 0, "llc_gemm_bf16_tn: ws misaligned");
 
   // production shapes: 256 x 256 tiles on CTA pairs (gemm2_tcgen05.cu); LLC_GEMM_1CTA=1 forces
   // the single-CTA kernel below (debugging / A-B comparison)
   static const bool force_1cta = llc_dev_env("LLC_GEMM_1CTA") != nullptr;
-  if (!force_1cta && llc_gemm2_eligible(M, N, K))
+  if (!force_1cta &&
+      llc_gemm2_eligible(M, N, K, e->ws != nullptr && e->ws_bytes >= llc_gemm_ws_bytes()))
     return llc_gemm2_launch(A, lda, B, ldb, M, N, K, ep, reinterpret_cast<cudaStream_t>(stream));
 
   // BN=256 keeps smem traffic per MMA lowest; fall back to 128-wide tiles when the problem would

@@ -33,6 +33,21 @@ int llc_refresh_lora_all(const llc_vit_layer* layers, int n_layers, int D, int r
 namespace {
 inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
 
+// stream-K workspace of the GEMMs launched by the tower calls: lives at the head of the arena
+// (caller-zeroed once, see llc_vit_arena_bytes); block-level calls have none and keep the
+// whole-tile schedule
+thread_local void* t_gemm_ws = nullptr;
+struct WsScope {
+  explicit WsScope(void* ws) { t_gemm_ws = ws; }
+  ~WsScope() { t_gemm_ws = nullptr; }
+};
+inline int GEMM(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                llc_gemm_epi* e, void* stream) {
+  e->ws = t_gemm_ws;
+  e->ws_bytes = t_gemm_ws ? llc_gemm_ws_bytes() : 0;
+  return llc_gemm_bf16_tn(A, lda, B, ldb, M, N, K, e, stream);
+}
+
 struct Dims {
   int N, L, T, D, H, M, E, G, P, PK /* padded 3*P*P */, r, layers;
 };
@@ -58,6 +73,7 @@ Dims make_dims(const llc_vit_cfg* c, int N, int context = 0) {
 // Arena layout. Training keeps one activation set per layer (saved for backward); inference
 // reuses a single set.
 struct Arena {
+  size_t gemm_ws;   // first: its flag words must be zero before the first launch
   size_t patches, patch_out, x /*[layers+1]*/, x_stride;
   size_t h1, qkv, lse, o, x_mid, z, layer_stride;  // per-layer block (training) or shared
   size_t h2, g;
@@ -72,6 +88,7 @@ Arena plan(const Dims& d, int training) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   const size_t T = d.T;
+  a.gemm_ws = take(llc_gemm_ws_bytes());
   a.patches = take((size_t)d.N * d.G * d.G * d.PK * 2);
   a.patch_out = take((size_t)d.N * d.G * d.G * d.D * 4);
   a.x_stride = align_up(T * d.D * 4);
@@ -197,15 +214,15 @@ static int attn_half_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w, con
   // qkv = h1 W_in^T + b_in + s (h1 A^T) B^T   (one accumulator, K = D + 16)
   e = llc_gemm_epi{};
   e.bias = w->bqkv; e.out = b->qkv; e.ld_out = QA;
-  RUN(llc_gemm_bf16_tn(b->h1, DA, w->wqkv_aug, DA, T, 3 * D, KA, &e, stream));
+  RUN(GEMM(b->h1, DA, w->wqkv_aug, DA, T, 3 * D, KA, &e, stream));
   RUN(llc_attn_fwd(b->qkv, QA, b->o, DA, b->lse, N, L, H, sn, sl, causal, stream));
   // u_o = o A_o^T into o's pad columns
   e = llc_gemm_epi{};
   e.out = reinterpret_cast<__nv_bfloat16*>(b->o) + D; e.ld_out = DA;
-  RUN(llc_gemm_bf16_tn(b->o, DA, w->f_out_A, D, T, LLC_LORA_PAD, D, &e, stream));
+  RUN(GEMM(b->o, DA, w->f_out_A, D, T, LLC_LORA_PAD, D, &e, stream));
   // out = [resid +] o W_o^T + b_o + s (o A_o^T) B_o^T
   eo.bias = w->bo;
-  RUN(llc_gemm_bf16_tn(b->o, DA, w->wo_aug, DA, T, D, KA, &eo, stream));
+  RUN(GEMM(b->o, DA, w->wo_aug, DA, T, D, KA, &eo, stream));
   return 0;
 }
 
@@ -227,11 +244,11 @@ extern "C" int llc_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   RUN(llc_ln_fwd(b->x_mid, D, w->ln2_g, w->ln2_b, T, D, b->h2, D, nullptr, 0, stream));
   e = llc_gemm_epi{};
   e.bias = w->bfc; e.act = 1; e.out = b->z; e.ld_out = M; e.out2 = b->g; e.ld_out2 = M;
-  RUN(llc_gemm_bf16_tn(b->h2, D, w->wfc, D, T, M, D, &e, stream));
+  RUN(GEMM(b->h2, D, w->wfc, D, T, M, D, &e, stream));
   e = llc_gemm_epi{};
   e.bias = w->bproj; e.resid = b->x_mid; e.ld_resid = D; e.out = b->x_out; e.ld_out = D;
   e.out_fp32 = 1;
-  RUN(llc_gemm_bf16_tn(b->g, M, w->wproj, M, T, D, M, &e, stream));
+  RUN(GEMM(b->g, M, w->wproj, M, T, D, M, &e, stream));
   return 0;
 }
 
@@ -283,13 +300,13 @@ static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   } else {
     e = llc_gemm_epi{};
     e.out = dxb + D; e.ld_out = DA;
-    RUN(llc_gemm_bf16_tn(s->dxb, DA, w->f_out_B, D, T, LLC_LORA_PAD, D, &e, stream));
+    RUN(GEMM(s->dxb, DA, w->f_out_B, D, T, LLC_LORA_PAD, D, &e, stream));
     RUN(llc_lora_side(s->dxb, DA, T, D, r, nullptr, 0, 0, 0.f, o + D, DA, pr[0], &np4[0], stream));
   }
   // d_o = dx_mid W_o + du_o A_o
   e = llc_gemm_epi{};
   e.out = s->d_o; e.ld_out = D;
-  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->woT_aug, DA, T, D, KA, &e, stream));
+  RUN(GEMM(s->dxb, DA, w->woT_aug, DA, T, D, KA, &e, stream));
   // dA_o = du_o^T o. The same pass over O also forms delta = rowsum(dO o O) for the attention
   // backward (from the O tiles it streams anyway and the L2-hot dO), when the shapes allow
   int delta_ready = 0;
@@ -311,7 +328,7 @@ static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   } else {
     e = llc_gemm_epi{};
     e.out = dqkv + 3 * D; e.ld_out = QA;
-    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
+    RUN(GEMM(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
     RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, pr[2], &np4[2],
                       stream));
   }
@@ -330,7 +347,7 @@ static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
     // dh1 = dqkv W_in + du A_in
     e = llc_gemm_epi{};
     e.out = s->dh; e.ld_out = D;
-    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->wqkvT_aug, QA, T, D, KQ, &e, stream));
+    RUN(GEMM(s->dqkv, QA, w->wqkvT_aug, QA, T, D, KQ, &e, stream));
   }
   return 0;
 }
@@ -348,11 +365,11 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   // dz = (dx W_proj) o QuickGELU'(z)
   e = llc_gemm_epi{};
   e.act = 2; e.aux = b->z; e.ld_aux = M; e.out = s->dz; e.ld_out = M;
-  RUN(llc_gemm_bf16_tn(s->dxb, DA, w->wprojT, D, T, M, D, &e, stream));
+  RUN(GEMM(s->dxb, DA, w->wprojT, D, T, M, D, &e, stream));
   // dh2 = dz W_fc
   e = llc_gemm_epi{};
   e.out = s->dh; e.ld_out = D;
-  RUN(llc_gemm_bf16_tn(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
+  RUN(GEMM(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
   // dx_mid = dx + LN2'(dh2); bf16 copy (the row product du_o = s dx_mid B_o runs on the tensor
   // cores inside attn_half_backward: fused into the LayerNorm kernel it cost 52 us per launch in
   // L1 traffic for the factor, profiles/)
@@ -449,29 +466,29 @@ int block_forward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_
   const __nv_bfloat16* wqkv = reinterpret_cast<const __nv_bfloat16*>(w->wqkv_aug);
   e = llc_gemm_epi{};
   e.bias = w->bqkv + D; e.out = qkv + D; e.ld_out = QA;
-  RUN(llc_gemm_bf16_tn(b->h1, DA, wqkv + (size_t)D * DA, DA, T, 2 * D, KA, &e, stream));
+  RUN(GEMM(b->h1, DA, wqkv + (size_t)D * DA, DA, T, 2 * D, KA, &e, stream));
   e = llc_gemm_epi{};
   e.bias = w->bqkv; e.out = qkv; e.ld_out = L * QA;
-  RUN(llc_gemm_bf16_tn(b->h1, L * DA, wqkv, DA, N, D, KA, &e, stream));
+  RUN(GEMM(b->h1, L * DA, wqkv, DA, N, D, KA, &e, stream));
   // one query per (sample, head)
   RUN(llc_attn_cls_fwd(b->qkv, QA, c.o, DA, c.p, N, L, H, L, 1, st));
   e = llc_gemm_epi{};
   e.out = c.o + D; e.ld_out = DA;
-  RUN(llc_gemm_bf16_tn(c.o, DA, w->f_out_A, D, N, LLC_LORA_PAD, D, &e, stream));
+  RUN(GEMM(c.o, DA, w->f_out_A, D, N, LLC_LORA_PAD, D, &e, stream));
   // x_mid[cls] = x[cls] + o W_o^T + b_o + s (o A_o^T) B_o^T : N rows, residual rows L*D apart
   e = llc_gemm_epi{};
   e.bias = w->bo; e.resid = b->x_in; e.ld_resid = L * D; e.out = c.x_mid; e.ld_out = D;
   e.out_fp32 = 1;
-  RUN(llc_gemm_bf16_tn(c.o, DA, w->wo_aug, DA, N, D, KA, &e, stream));
+  RUN(GEMM(c.o, DA, w->wo_aug, DA, N, D, KA, &e, stream));
   RUN(llc_ln_fwd(c.x_mid, D, w->ln2_g, w->ln2_b, N, D, c.h2, D, nullptr, 0, stream));
   e = llc_gemm_epi{};
   e.bias = w->bfc; e.act = 1; e.out = c.z; e.ld_out = M; e.out2 = c.g; e.ld_out2 = M;
-  RUN(llc_gemm_bf16_tn(c.h2, D, w->wfc, D, N, M, D, &e, stream));
+  RUN(GEMM(c.h2, D, w->wfc, D, N, M, D, &e, stream));
   // x_out[cls rows of the full buffer] = x_mid + g W_proj^T + b
   e = llc_gemm_epi{};
   e.bias = w->bproj; e.resid = c.x_mid; e.ld_resid = D; e.out = b->x_out; e.ld_out = L * D;
   e.out_fp32 = 1;
-  RUN(llc_gemm_bf16_tn(c.g, M, w->wproj, M, N, D, M, &e, stream));
+  RUN(GEMM(c.g, M, w->wproj, M, N, D, M, &e, stream));
   return 0;
 }
 
@@ -494,10 +511,10 @@ int block_backward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc
   // MLP backward on N rows
   e = llc_gemm_epi{};
   e.act = 2; e.aux = c.z; e.ld_aux = M; e.out = c.dz; e.ld_out = M;
-  RUN(llc_gemm_bf16_tn(c.dxb, DA, w->wprojT, D, N, M, D, &e, stream));
+  RUN(GEMM(c.dxb, DA, w->wprojT, D, N, M, D, &e, stream));
   e = llc_gemm_epi{};
   e.out = c.dh; e.ld_out = D;
-  RUN(llc_gemm_bf16_tn(c.dz, M, w->wfcT, M, N, D, M, &e, stream));
+  RUN(GEMM(c.dz, M, w->wfcT, M, N, D, M, &e, stream));
   RUN(llc_ln_bwd(c.x_mid, D, w->ln2_g, c.dh, D, c.dx, c.dx, N, D, c.dxb, DA, nullptr, 0, 0.f,
                  stream));
   // out-proj LoRA: du_o = s dx_mid B_o, dB_o = s dx_mid^T u_o, dA_o = du_o^T o   (N rows)
@@ -506,13 +523,13 @@ int block_backward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc
   int np4[4] = {0, 0, 0, 0};
   e = llc_gemm_epi{};
   e.out = c.dxb + D; e.ld_out = DA;
-  RUN(llc_gemm_bf16_tn(c.dxb, DA, w->f_out_B, D, N, LLC_LORA_PAD, D, &e, stream));
+  RUN(GEMM(c.dxb, DA, w->f_out_B, D, N, LLC_LORA_PAD, D, &e, stream));
   RUN(llc_lora_side(c.dxb, DA, N, D, r, nullptr, 0, 0, 0.f, c.o + D, DA, pr[0], &np4[0], stream));
   RUN(llc_lora_side(c.o, DA, N, D, r, nullptr, 0, 0, 0.f, c.dxb + D, DA, pr[1], &np4[1], stream));
   // d_o = dx_mid W_o + du_o A_o ; attention backward of the CLS query -> dqkv of every token
   e = llc_gemm_epi{};
   e.out = c.d_o; e.ld_out = D;
-  RUN(llc_gemm_bf16_tn(c.dxb, DA, w->woT_aug, DA, N, D, KA, &e, stream));
+  RUN(GEMM(c.dxb, DA, w->woT_aug, DA, N, D, KA, &e, stream));
   RUN(llc_attn_cls_bwd(b->qkv, QA, c.p, c.d_o, D, s->dqkv, QA, N, L, H, L, 1, st));
   // in-projection: full size again
   if (llc_lora_fused_eligible(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D,
@@ -522,7 +539,7 @@ int block_backward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc
   } else {
     e = llc_gemm_epi{};
     e.out = dqkv + 3 * D; e.ld_out = QA;
-    RUN(llc_gemm_bf16_tn(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
+    RUN(GEMM(s->dqkv, QA, w->f_in_B, 3 * D, T, LLC_LORA_PAD, 3 * D, &e, stream));
     RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, pr[2], &np4[2],
                       stream));
   }
@@ -544,10 +561,10 @@ int block_backward_cls(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc
     const __nv_bfloat16* wT = reinterpret_cast<const __nv_bfloat16*>(w->wqkvT_aug);
     e = llc_gemm_epi{};
     e.out = s->dh; e.ld_out = D;
-    RUN(llc_gemm_bf16_tn(dqkv + D, QA, wT + D, QA, T, D, KQ - D, &e, stream));
+    RUN(GEMM(dqkv + D, QA, wT + D, QA, T, D, KQ - D, &e, stream));
     e = llc_gemm_epi{};
     e.out = s->dh; e.ld_out = L * D;
-    RUN(llc_gemm_bf16_tn(s->dqkv, L * QA, w->wqkvT_aug, QA, N, D, KQ, &e, stream));
+    RUN(GEMM(s->dqkv, L * QA, w->wqkvT_aug, QA, N, D, KQ, &e, stream));
     RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, nullptr, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
                    stream));
     add_cls_rows_kernel<<<N, 256, 0, st>>>(s->dx, (size_t)L * D, N, D, c.dx, dxb_full,
@@ -576,6 +593,7 @@ static int vit_forward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, co
   const Dims d = make_dims(cfg, N);
   const Arena a = plan(d, training);
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  WsScope ws_scope(base + a.gemm_ws);
   // patch embedding: (input transform +) im2col -> GEMM -> class token, positional embedding,
   // ln_pre
   if (tx) {
@@ -587,7 +605,7 @@ static int vit_forward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, co
   }
   llc_gemm_epi e{};
   e.out = base + a.patch_out; e.ld_out = d.D; e.out_fp32 = 1;
-  RUN(llc_gemm_bf16_tn(base + a.patches, d.PK, w->wpatch, d.PK, N * d.G * d.G, d.D, d.PK, &e,
+  RUN(GEMM(base + a.patches, d.PK, w->wpatch, d.PK, N * d.G * d.G, d.D, d.PK, &e,
                        stream));
   float* x0 = reinterpret_cast<float*>(base + a.x);
   RUN(llc_embed_ln_pre(reinterpret_cast<float*>(base + a.patch_out), d.D, w->class_emb, w->pos_emb,
@@ -630,6 +648,7 @@ static int vit_backward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, i
   const Dims d = make_dims(cfg, N);
   const Arena a = plan(d, 1);
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  WsScope ws_scope(base + a.gemm_ws);
   llc_block_bwd_bufs s;
   s.dx = dx_final;
   s.dxb = base + a.dxb;
@@ -703,6 +722,7 @@ extern "C" int llc_text_forward(const llc_vit_cfg* cfg, const llc_text_weights* 
   const Dims d = make_dims(cfg, C, w->context);
   const Arena a = plan(d, training);
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  WsScope ws_scope(base + a.gemm_ws);
   float* x0 = reinterpret_cast<float*>(base + a.x);
   cudaStream_t st = (cudaStream_t)stream;
   LLC_PROF_BEGIN(LLC_K_EMBED, d.T, d.D, 4, 0.0, 8.0 * d.T * d.D, st);
@@ -738,6 +758,7 @@ extern "C" int llc_text_backward(const llc_vit_cfg* cfg, const llc_text_weights*
   const Dims d = make_dims(cfg, C, w->context);
   const Arena a = plan(d, 1);
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
+  WsScope ws_scope(base + a.gemm_ws);
   llc_block_bwd_bufs s;
   s.dx = dx_final;
   s.dxb = base + a.dxb;

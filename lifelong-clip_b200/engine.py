@@ -79,7 +79,7 @@ class _TowerEngine:
                     K.check(-1, "arena_bytes")
                 self.arena = None
                 self.dx = None
-                self.arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                self.arena = self._new_arena(nbytes)
                 self.dx = torch.empty(N * self.L, self.D, device=self.device)
                 self.arena_key = N
             return self.arena, 1
@@ -90,9 +90,14 @@ class _TowerEngine:
             if nbytes == 0:
                 K.check(-1, "arena_bytes")
             self.eval_arena = None
-            self.eval_arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.eval_arena = self._new_arena(nbytes)
             self.eval_key = N
         return self.eval_arena, 0
+
+    def _new_arena(self, nbytes):
+        a = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        a[:8192].zero_()     # flag words of the stream-K GEMM workspace (include/llc.h)
+        return a
 
     def graph_signature(self):
         """What a captured CUDA graph of this engine's step depends on besides its inputs."""

@@ -257,12 +257,15 @@ class LoRAClipTrainer:
                           m.model.text_engine().graph_signature())
         return sig + (m._cls_idx.data_ptr(), m._cls_idx.numel(), m._text_all.data_ptr())
 
-    def _make_tx(self, raw, dynamic):
+    def _make_tx(self, raw, dynamic, draw=None):
         if not isinstance(self.train_transform, GpuTransform):
             return None
-        return self.train_transform.struct(self.train_transform._check(raw), dynamic=dynamic)
+        return self.train_transform.struct(self.train_transform._check(raw), dynamic=dynamic,
+                                           draw=draw)
 
     def _graph_step(self, x, y_local, global_batch):
+        gpu_tf = isinstance(self.train_transform, GpuTransform)
+        draw = self.train_transform.draw() if gpu_tf else None   # ONE draw per step
         key = self._graph_signature(x, y_local, global_batch)
         if key != self._graph_key:
             # a capture costs tens of ms: worth it only when the (batch, class list) signature is
@@ -274,12 +277,13 @@ class LoRAClipTrainer:
                     self.use_cuda_graph = False
                     self._graph = None
                     self._graph_key = None
-                    return self._step_body(x, y_local, global_batch, tx=self._make_tx(x, False))
+                    return self._step_body(x, y_local, global_batch,
+                                           tx=self._make_tx(x, False, draw))
             else:
                 self._graph_churn = 0
             self._graph_hits = 0
             self._graph = None
-            if isinstance(self.train_transform, GpuTransform):
+            if gpu_tf:
                 x = self.train_transform._check(x)
             self._gx = torch.empty_like(x)
             self._gy = torch.empty_like(y_local)
@@ -288,21 +292,21 @@ class LoRAClipTrainer:
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):      # warm-up: arena, smem attributes, allocator pool
                 self._step_body(self._gx, self._gy, global_batch, force_refresh=True,
-                                tx=self._make_tx(self._gx, True))
+                                tx=self._make_tx(self._gx, True, draw))
             torch.cuda.current_stream(self.device).wait_stream(side)
             # the warm-up may have (re)allocated the arenas: the key is taken after it
             key = self._graph_signature(x, y_local, global_batch)
             g = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
-            tx = self._make_tx(self._gx, True)     # struct with the stable dyn pointer
+            tx = self._make_tx(self._gx, True, draw)     # struct with the stable dyn pointer
             with torch.cuda.graph(g):
                 self._ghead = self._step_body(self._gx, self._gy, global_batch,
                                               force_refresh=True, tx=tx)
             self.graph_kernels = ops.launch_count() - n0   # libllc kernel nodes per replay
             self._graph, self._graph_key = g, key
-        if isinstance(self.train_transform, GpuTransform):
+        if gpu_tf:
             x = self.train_transform._check(x)
-            self._make_tx(self._gx, True)          # fresh crop / flip draw -> device buffer
+            self.train_transform.push(draw, x.device)   # this step's crop / flip -> device buffer
         self._gx.copy_(x, non_blocking=True)
         self._gy.copy_(y_local, non_blocking=True)
         self._graph.replay()

@@ -29,7 +29,6 @@ class GpuTransform:
         self.padding, self.flip_p = int(padding), float(flip_p)
         self.device = device
         self._dyn = None       # device int32 [3]: crop_i, crop_j, flip (CUDA-graph replays)
-        self._host = None
         self.last_draw = (0, 0, False)
 
     @classmethod
@@ -61,19 +60,23 @@ class GpuTransform:
             x = x.float()
         return x.contiguous()
 
-    def struct(self, x, dynamic: bool = False):
-        """Draw this batch's parameters and describe the transform of raw batch `x` for the C
-        call. dynamic=True routes the draw through a device buffer (stable pointer) so a captured
-        graph sees fresh values on every replay."""
-        i, j, flip = self.draw()
-        dyn = None
-        if dynamic:
-            if self._dyn is None or self._dyn.device != x.device:
-                self._dyn = torch.zeros(3, dtype=torch.int32, device=x.device)
-                self._host = torch.zeros(3, dtype=torch.int32).pin_memory()
-            self._host[0], self._host[1], self._host[2] = i, j, int(flip)
-            self._dyn.copy_(self._host, non_blocking=True)
-            dyn = self._dyn
+    def push(self, draw, device):
+        """Write a draw into the device parameter buffer (stable pointer: a captured CUDA graph
+        reads it on every replay). The source is a fresh pageable tensor, so the copy is staged
+        before this call returns and the next draw cannot overwrite it."""
+        if self._dyn is None or self._dyn.device != torch.device(device):
+            self._dyn = torch.zeros(3, dtype=torch.int32, device=device)
+        i, j, flip = draw
+        self._dyn.copy_(torch.tensor([i, j, int(flip)], dtype=torch.int32))
+        return self._dyn
+
+    def struct(self, x, dynamic: bool = False, draw=None):
+        """Describe the transform of raw batch `x` for the C call; draws this batch's parameters
+        unless `draw` is given. dynamic=True routes them through the device buffer."""
+        if draw is None:
+            draw = self.draw()
+        i, j, flip = draw
+        dyn = self.push(draw, x.device) if dynamic else None
         return ops.make_transform(x, self.S, self.mean, self.std, pad=self.padding, crop=(i, j),
                                   flip=flip, dyn=dyn)
 

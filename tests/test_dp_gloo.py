@@ -63,3 +63,32 @@ def test_two_rank_allreduce_equals_single_process(tmp_path):
     # gathered labels = rank-major concatenation of the rank::2 shards = a permutation of the batch
     assert sorted(r0["seen"].tolist()) == sorted(labels.tolist())
     assert r0["seen"].tolist() == labels[0::2].tolist() + labels[1::2].tolist()
+
+
+def _ragged_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lifelong_clip_b200 import dp
+    # last batch of a stream: rank 0 holds 3 labels, rank 1 none (ragged shards)
+    mine = torch.tensor([5, 1, 5]) if rank == 0 else torch.empty(0, dtype=torch.int64)
+    seen = dp.gather_labels(mine, world)
+    total = dp.global_count(mine.numel(), world)
+    # an empty shard contributes zeros and still joins the collectives
+    g1 = torch.full((8,), float(rank + 1)) if mine.numel() else torch.zeros(8)
+    g2 = torch.full((4,), 2.0) if mine.numel() else torch.zeros(4)
+    scal = torch.tensor([0.5, 2.0]) if mine.numel() else torch.zeros(2)
+    dp.allreduce_step([g1, g2], scal, world)
+    torch.save({"seen": seen, "total": total, "g1": g1, "g2": g2, "scal": scal},
+               os.path.join(out_dir, f"q{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_ragged_shards_and_multi_tower_allreduce(tmp_path):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_ragged_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        q = torch.load(os.path.join(tmp_path, f"q{r}.pt"))
+        assert q["seen"].tolist() == [5, 1, 5] and q["total"] == 3
+        assert torch.equal(q["g1"], torch.ones(8)) and torch.equal(q["g2"], torch.full((4,), 2.0))
+        assert q["scal"].tolist() == [0.5, 2.0]
