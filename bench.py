@@ -578,13 +578,13 @@ def run_ours(args):
     gemm = by_kind.get("gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
     total_ms = sum(d["ms"] for d in by_kind.values()) or 1.0
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (forward
-    # launches of one block inside this same bench command; profiles/r01_ncu_gemm2_in_step.csv)
+    # launches of one block inside this same bench command; profiles/r02_ncu_gemm2_in_step.csv)
     traffic = None
     try:
         if B != 256:
             raise LookupError("the ncu capture was taken at 256 images per GPU")
         import csv
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm2_in_step.csv")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_gemm2_in_step.csv")) as f:
             rows = list(csv.DictReader(f))
         tot = [(float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"])) * 1e6
                for r in rows]
@@ -603,7 +603,7 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_burst": peaks["bf16"], "frac_of_burst_peak": achieved / peaks["bf16"],
                 "traffic_note": "mean dram read+write bytes per launch, ncu --set full, 8 forward "
-                                "launches inside this bench (profiles/r01_ncu_gemm2_in_step.csv)",
+                                "launches inside this bench (profiles/r02_ncu_gemm2_in_step.csv)",
                 "peak_source": peaks["source"] + (", sustained (kernel timed inside a long step)"
                                                   if peaks["bf16_sustained"] else ", burst"),
                 "flop_per_launch": gemm["flops"] / gemm["launches"],

@@ -208,6 +208,8 @@ typedef struct llc_head_args {
   const float* d_fnorm;  /* backward only: [N, E] gradient w.r.t. the NORMALISED features (used
                             with skip_logit_grad; chained through f = z/|z| in the kernel) */
   float* dlogits;        /* backward only: [N, C] dL/dlogits written out, or NULL */
+  int d_is_logits;       /* backward only: llc_head_bwd's d_probs is the gradient w.r.t. the LOGITS
+                            (models/maple.py:250-253 returns logits; methods/maple.py:96) */
 } llc_head_args;
 int llc_head_fwd(const llc_head_args* a, void* stream);
 /* d_probs (may be NULL: then the analytic gradient of the fused loss is used, scaled by

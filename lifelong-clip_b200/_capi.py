@@ -37,7 +37,7 @@ class HeadArgs(C.Structure):
         ("double_softmax", c_int), ("inv_batch", c_float),
         ("feat", c_void), ("fnorm", c_void), ("logits", c_void), ("probs", c_void),
         ("loss_rows", c_void), ("pred", c_void),
-        ("row_idx", c_void), ("d_fnorm", c_void), ("dlogits", c_void),
+        ("row_idx", c_void), ("d_fnorm", c_void), ("dlogits", c_void), ("d_is_logits", c_int),
     ]
 
 

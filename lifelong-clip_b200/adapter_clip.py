@@ -333,7 +333,7 @@ class AdapterCLIP(nn.Module):
         self._tokenizer = fn
         self._tok_cache = {}
 
-    def labels_tokenize(self, labels, context_length: int = 77):
+    def labels_tokenize(self, labels, context_length: int = None):
         """models/adapter_clip.py:39-74: prompt template + tokenizer -> int64 [C, ctx] on the
         model's device."""
         if self._tokenizer is None:
@@ -342,6 +342,8 @@ class AdapterCLIP(nn.Module):
                                "set_text_features()")
         if isinstance(labels, str):
             labels = [labels]
+        if context_length is None:
+            context_length = self.model.context_length or 77
         missing = [c for c in labels if c not in self._tok_cache]
         if missing:
             toks = self._tokenizer([self.prompt_template.format(c) for c in missing])

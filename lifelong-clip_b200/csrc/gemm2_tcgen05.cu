@@ -287,17 +287,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * BN + hh * (BN / 2) + ((uint32_t)(q * 32) << 16);
       if (SK && kb0 > 0) {
-        // contributor: this pair's range starts inside the tile. Leave the fp32 partial (element
-        // (row = lane, column c) at c * 32 + lane: 128 B per store instruction) and raise the flag
+        // contributor: this pair's range starts inside the tile. Leave the fp32 partial and raise
+        // the flag
         const size_t slot = ((size_t)(pair * 2 + (int)rank) * kEpiWarps + ew);
-        float* dst = sk_part + slot * kSkSlotFloats;
+        // slot layout: float4 (chunk c, quad j, lane) at (c * 8 + j) * 32 + lane - every store /
+        // load instruction of the warp moves 512 contiguous bytes
+        float4* dst = reinterpret_cast<float4*>(sk_part + slot * kSkSlotFloats);
 #pragma unroll 1
         for (int c = 0; c < BN / 2 / 32; ++c) {
           uint32_t acc[32];
           tmem_ld_32x32(t_addr + c * 32, acc);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) __stcg(dst + (c * 32 + j) * 32 + lane, __uint_as_float(acc[j]));
+          for (int j = 0; j < 8; ++j)
+            __stcg(dst + (c * 8 + j) * 32 + lane,
+                   make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                               __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])));
         }
         __threadfence();
         __syncwarp();
@@ -325,11 +330,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tmem_ld_32x32(t_addr + c * 32, acc);
             tmem_ld_wait();
             for (int cq = pair + 1; cq < q1; ++cq) {
-              const float* src = sk_part +
-                  ((size_t)(cq * 2 + (int)rank) * kEpiWarps + ew) * kSkSlotFloats;
+              const float4* src = reinterpret_cast<const float4*>(
+                  sk_part + ((size_t)(cq * 2 + (int)rank) * kEpiWarps + ew) * kSkSlotFloats);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __ldcg(src + (c * 32 + j) * 32 + lane));
+              for (int j = 0; j < 8; ++j) {
+                const float4 v = __ldcg(src + (c * 8 + j) * 32 + lane);
+                acc[4 * j] = __float_as_uint(__uint_as_float(acc[4 * j]) + v.x);
+                acc[4 * j + 1] = __float_as_uint(__uint_as_float(acc[4 * j + 1]) + v.y);
+                acc[4 * j + 2] = __float_as_uint(__uint_as_float(acc[4 * j + 2]) + v.z);
+                acc[4 * j + 3] = __float_as_uint(__uint_as_float(acc[4 * j + 3]) + v.w);
+              }
             }
             tmem_st_32x32(t_addr + c * 32, acc);
           }
@@ -378,7 +388,10 @@ bool gemm2_wants_sk(int M, int N, int K) {
   const int num_kb = (K + BK - 1) / BK;
   const int waves = (tiles + pairs - 1) / pairs;
   const double eff = (double)tiles / ((double)waves * pairs);
-  return eff < 0.92 && (long long)tiles * num_kb >= 4LL * pairs;
+  // a split tile costs a 256 KB partial through L2 plus an unoverlapped fix-up epilogue (~6 us):
+  // measured at 32 images per GPU (T = 6304) it pays for K >= 2320 (36+ k-blocks; 45 -> 39 us at
+  // K = 3072) and loses for the K = 768 / 784 GEMMs, whose whole tile takes 2 us
+  return eff < 0.92 && num_kb >= 32 && (long long)tiles * num_kb >= 4LL * pairs;
 }
 
 template <int MODE>

@@ -14,7 +14,19 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+// 1024 threads per sample: the two fat loops (y @ proj and dlogits @ T) are chains of L2-latency
+// bound loads; with 256 threads a sample took ~190 us whatever the batch (a third of a 32-image
+// step's critical path). Every loop below is split so that all 32 warps hold loads in flight.
+constexpr int kThreads = 1024;
+constexpr int kMaxSplit = 8;
+
+// number of slices the reduction dimension of an [n_out]-wide loop is cut into so that
+// n_out * split covers the CTA (power of two, <= kMaxSplit)
+__device__ __forceinline__ int split_for(int n_out) {
+  int s = 1;
+  while (s < kMaxSplit && n_out * s * 2 <= kThreads) s *= 2;
+  return s;
+}
 constexpr float kLnEps = 1e-5f;
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -57,13 +69,12 @@ struct HeadK {
   const int64_t* row_idx;   // row of sample n in x / dx (text tower: the EOT token), else n*cls_stride
   const float* d_fnorm;     // backward: gradient w.r.t. the NORMALISED features (text side)
   float* dlogits;           // backward: dL/dlogits [N, C] written out (for llc_head_dtext)
+  int d_is_logits;          // backward: the incoming gradient is w.r.t. the LOGITS, not the probs
   int rot;   // bit 0: rotate the proj row order per CTA, bit 1: the text row order (LLC_HEAD_ROT)
 };
 
-// Both head kernels are written for kS samples per CTA (the two fat loops read every proj / text
-// element once for the kS samples). Measured at N = 256: kS = 1 is fastest (97 / 122 us fwd / bwd
-// against 189 / 126 us at kS = 4): with 64 CTAs the work no longer covers the machine and the
-// loops are latency-, not L2-bandwidth-bound.
+// One sample per CTA (kS = 1; more samples per CTA measured slower at N = 256: the loops are
+// latency-, not L2-bandwidth-bound, and fewer CTAs cover less of the machine).
 constexpr int kS = 1;
 
 // smem: y[kS][D] | f[kS][E] | p[kS][C] | red[32]
@@ -91,53 +102,56 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(HeadK a) {
   }
   __syncthreads();
 
-  // z = y @ proj for the kS samples at once
-  float nrm[kS];
-#pragma unroll
-  for (int sI = 0; sI < kS; ++sI) nrm[sI] = 0.f;
-  for (int e = tid; e < a.E; e += kThreads) {
-    float acc[kS][2];
-#pragma unroll
-    for (int sI = 0; sI < kS; ++sI) acc[sI][0] = acc[sI][1] = 0.f;
-    // Every CTA walks the proj rows from its own starting row: in lock step all CTAs would ask
-    // the same L2 lines at the same time (one slice serving 256 requesters per line).
-    const int k0 = (a.rot & 1) ? ((int)((blockIdx.x * 6u) % (unsigned)a.D) & ~1) : 0;
-    int i = 0;
-#pragma unroll 4
-    for (; i + 2 <= a.D; i += 2) {
-      int k = i + k0;
-      if (k >= a.D) k -= a.D;            // D even or the tail loop below takes the odd row
-      const int k1 = (k + 1 < a.D) ? k + 1 : 0;
-      const float p0 = __ldg(a.proj + (size_t)k * a.E + e);
-      const float p1 = __ldg(a.proj + (size_t)k1 * a.E + e);
-#pragma unroll
-      for (int sI = 0; sI < kS; ++sI) {
-        acc[sI][0] = fmaf(sy[sI * a.D + k], p0, acc[sI][0]);
-        acc[sI][1] = fmaf(sy[sI * a.D + k1], p1, acc[sI][1]);
+  // z = y @ proj: thread (e, slice) accumulates its slice of the D rows for output e; the
+  // slices are summed through shared memory in a fixed order
+  {
+    float* part = red + 32;                         // [split][E]
+    const int split = split_for(a.E);
+    const int per = kThreads / split;               // threads per slice
+    const int sl = tid / per, e0 = tid - sl * per;
+    const int kb = (int)((long long)a.D * sl / split), ke = (int)((long long)a.D * (sl + 1) / split);
+    // every CTA walks the proj rows from its own starting row: in lock step all CTAs would ask
+    // the same L2 lines at the same time (one slice serving every requester per line)
+    const int rot = (a.rot & 1) ? (int)((blockIdx.x * 6u) % (unsigned)(ke - kb)) : 0;
+    for (int e = e0; e < a.E; e += per) {
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      int i = 0;
+      const int len = ke - kb;
+#pragma unroll 2
+      for (; i + 4 <= len; i += 4) {
+        int k0 = i + rot; if (k0 >= len) k0 -= len;
+        int k1 = k0 + 1; if (k1 >= len) k1 -= len;
+        int k2 = k1 + 1; if (k2 >= len) k2 -= len;
+        int k3 = k2 + 1; if (k3 >= len) k3 -= len;
+        const float p0 = __ldg(a.proj + (size_t)(kb + k0) * a.E + e);
+        const float p1 = __ldg(a.proj + (size_t)(kb + k1) * a.E + e);
+        const float p2 = __ldg(a.proj + (size_t)(kb + k2) * a.E + e);
+        const float p3 = __ldg(a.proj + (size_t)(kb + k3) * a.E + e);
+        acc0 = fmaf(sy[kb + k0], p0, acc0);
+        acc1 = fmaf(sy[kb + k1], p1, acc1);
+        acc2 = fmaf(sy[kb + k2], p2, acc2);
+        acc3 = fmaf(sy[kb + k3], p3, acc3);
       }
+      for (; i < len; ++i) {
+        int k0 = i + rot; if (k0 >= len) k0 -= len;
+        acc0 = fmaf(sy[kb + k0], __ldg(a.proj + (size_t)(kb + k0) * a.E + e), acc0);
+      }
+      part[sl * a.E + e] = (acc0 + acc1) + (acc2 + acc3);
     }
-    for (; i < a.D; ++i) {
-      int k = i + k0;
-      if (k >= a.D) k -= a.D;
-      const float p0 = __ldg(a.proj + (size_t)k * a.E + e);
-#pragma unroll
-      for (int sI = 0; sI < kS; ++sI) acc[sI][0] = fmaf(sy[sI * a.D + k], p0, acc[sI][0]);
-    }
-#pragma unroll
-    for (int sI = 0; sI < kS; ++sI) {
-      const float v = acc[sI][0] + acc[sI][1];
-      sf[sI * a.E + e] = v;
-      if (n0 + sI < a.N) a.feat[(size_t)(n0 + sI) * a.E + e] = v;
-      nrm[sI] += v * v;
-    }
-  }
-#pragma unroll
-  for (int sI = 0; sI < kS; ++sI) {
-    const float inv_norm = 1.0f / sqrtf(block_sum(nrm[sI], red));
+    __syncthreads();
+    float nrm = 0.f;
     for (int e = tid; e < a.E; e += kThreads) {
-      const float v = sf[sI * a.E + e] * inv_norm;
-      sf[sI * a.E + e] = v;
-      if (n0 + sI < a.N) a.fnorm[(size_t)(n0 + sI) * a.E + e] = v;
+      float v = 0.f;
+      for (int j = 0; j < split; ++j) v += part[j * a.E + e];
+      sf[e] = v;
+      a.feat[(size_t)n0 * a.E + e] = v;
+      nrm += v * v;
+    }
+    const float inv_norm = 1.0f / sqrtf(block_sum(nrm, red));
+    for (int e = tid; e < a.E; e += kThreads) {
+      const float v = sf[e] * inv_norm;
+      sf[e] = v;
+      a.fnorm[(size_t)n0 * a.E + e] = v;
     }
   }
   __syncthreads();
@@ -236,7 +250,10 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
       const int n = min(n0 + sI, a.N - 1);
       const float* pr = a.probs + (size_t)n * a.C;
       float* g = sg + sI * a.C;
-      if (d_probs == nullptr && !a.double_softmax) {
+      if (d_probs != nullptr && a.d_is_logits) {
+        for (int c = tid; c < a.C; c += kThreads) g[c] = d_probs[(size_t)n * a.C + c] * loss_scale;
+        __syncthreads();
+      } else if (d_probs == nullptr && !a.double_softmax) {
         const int64_t yv = a.labels[n];
         for (int c = tid; c < a.C; c += kThreads)
           g[c] = (pr[c] - (c == yv ? 1.f : 0.f)) * a.inv_batch * loss_scale;
@@ -264,47 +281,41 @@ head_bwd_kernel(HeadK a, const float* __restrict__ d_probs, float loss_scale,
     }
     __syncthreads();
 
-    // df = scale * dlogits @ T for the kS samples per text element read
+    // df = scale * dlogits @ T: thread (e, slice) sums its slice of the classes
     float fd[kS], zz[kS];
-#pragma unroll
-    for (int sI = 0; sI < kS; ++sI) fd[sI] = zz[sI] = 0.f;
-    for (int e = tid; e < a.E; e += kThreads) {
-      float acc[kS][2];
-#pragma unroll
-      for (int sI = 0; sI < kS; ++sI) acc[sI][0] = acc[sI][1] = 0.f;
-      const int cs0 = (a.rot & 2) ? (int)((blockIdx.x * 3u) % (unsigned)a.C) : 0;
-      int i = 0;
+    fd[0] = zz[0] = 0.f;
+    {
+      float* part = red + 32;                         // [split][E]
+      const int split = split_for(a.E);
+      const int per = kThreads / split;
+      const int sl = tid / per, e0 = tid - sl * per;
+      const int cb = (int)((long long)a.C * sl / split), ce = (int)((long long)a.C * (sl + 1) / split);
+      for (int e = e0; e < a.E; e += per) {
+        float acc0 = 0.f, acc1 = 0.f;
+        int c = cb;
 #pragma unroll 4
-      for (; i + 2 <= a.C; i += 2) {
-        int c = i + cs0;
-        if (c >= a.C) c -= a.C;
-        const int c1 = (c + 1 < a.C) ? c + 1 : 0;
-        const int64_t r0 = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
-        const int64_t r1 = a.cls_idx ? a.cls_idx[c1] : (int64_t)c1;
-        const float t0 = __ldg(a.text + (size_t)r0 * a.E + e);
-        const float t1 = __ldg(a.text + (size_t)r1 * a.E + e);
-#pragma unroll
-        for (int sI = 0; sI < kS; ++sI) {
-          acc[sI][0] = fmaf(sg[sI * a.C + c], t0, acc[sI][0]);
-          acc[sI][1] = fmaf(sg[sI * a.C + c1], t1, acc[sI][1]);
+        for (; c + 2 <= ce; c += 2) {
+          const int64_t r0 = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
+          const int64_t r1 = a.cls_idx ? a.cls_idx[c + 1] : (int64_t)(c + 1);
+          acc0 = fmaf(sg[c], __ldg(a.text + (size_t)r0 * a.E + e), acc0);
+          acc1 = fmaf(sg[c + 1], __ldg(a.text + (size_t)r1 * a.E + e), acc1);
         }
+        if (c < ce) {
+          const int64_t r0 = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
+          acc0 = fmaf(sg[c], __ldg(a.text + (size_t)r0 * a.E + e), acc0);
+        }
+        part[sl * a.E + e] = acc0 + acc1;
       }
-      for (; i < a.C; ++i) {
-        int c = i + cs0;
-        if (c >= a.C) c -= a.C;
-        const int64_t r0 = a.cls_idx ? a.cls_idx[c] : (int64_t)c;
-        const float t0 = __ldg(a.text + (size_t)r0 * a.E + e);
-#pragma unroll
-        for (int sI = 0; sI < kS; ++sI) acc[sI][0] = fmaf(sg[sI * a.C + c], t0, acc[sI][0]);
-      }
-#pragma unroll
-      for (int sI = 0; sI < kS; ++sI) {
-        const int n = min(n0 + sI, a.N - 1);
-        const float v = (acc[sI][0] + acc[sI][1]) * a.logit_scale;
-        sz[sI * a.E + e] = v;
-        fd[sI] += v * sf[sI * a.E + e];
+      __syncthreads();
+      const int n = n0;
+      for (int e = tid; e < a.E; e += kThreads) {
+        float v = 0.f;
+        for (int j = 0; j < split; ++j) v += part[j * a.E + e];
+        v *= a.logit_scale;
+        sz[e] = v;
+        fd[0] += v * sf[e];
         const float zf = a.feat[(size_t)n * a.E + e];
-        zz[sI] += zf * zf;
+        zz[0] += zf * zf;
       }
     }
     // dz = (df - f (f.df)) / |z|
@@ -453,6 +464,7 @@ int to_k(const llc_head_args* a, HeadK* k, const char* who) {
   k->loss_rows = a->loss_rows; k->pred = a->pred;
   k->d_feat = a->d_feat; k->skip_logit_grad = a->skip_logit_grad;
   k->row_idx = a->row_idx; k->d_fnorm = a->d_fnorm; k->dlogits = a->dlogits;
+  k->d_is_logits = a->d_is_logits;
   static const int rot = llc_dev_env("LLC_HEAD_ROT") ? atoi(llc_dev_env("LLC_HEAD_ROT")) : 1;
   k->rot = rot;
   return 0;
@@ -463,7 +475,7 @@ int to_k(const llc_head_args* a, HeadK* k, const char* who) {
 extern "C" int llc_head_fwd(const llc_head_args* a, void* stream) {
   HeadK k;
   if (int rc = to_k(a, &k, "llc_head_fwd")) return rc;
-  const size_t smem = (size_t)(kS * (a->D + a->E + a->C) + 32) * sizeof(float);
+  const size_t smem = (size_t)(kS * (a->D + a->E + a->C) + 32 + kMaxSplit * a->E) * sizeof(float);
   LLC_REQUIRE(smem <= 200 * 1024, "llc_head_fwd: D+E+C too large for one CTA");
   if (smem > 48 * 1024) LLC_CONFIGURE_SMEM(head_fwd_kernel, smem);
   LLC_PROF_BEGIN(LLC_K_HEAD, a->N, a->C, 0, 2.0 * a->N * ((double)a->D * a->E + (double)a->E * a->C),
@@ -484,7 +496,8 @@ extern "C" int llc_head_bwd(const llc_head_args* a, const float* d_probs, float 
               "llc_head_bwd: need d_probs, labels or d_feat / d_fnorm");
   LLC_REQUIRE(!a->skip_logit_grad || a->d_feat || a->d_fnorm,
               "llc_head_bwd: skip_logit_grad needs d_feat or d_fnorm");
-  const size_t smem = (size_t)(kS * (a->C + 2 * a->E + 2 * a->D) + 32) * sizeof(float);
+  const size_t smem =
+      (size_t)(kS * (a->C + 2 * a->E + 2 * a->D) + 32 + kMaxSplit * a->E) * sizeof(float);
   LLC_REQUIRE(smem <= 200 * 1024, "llc_head_bwd: sizes too large for one CTA");
   if (smem > 48 * 1024) LLC_CONFIGURE_SMEM(head_bwd_kernel, smem);
   LLC_PROF_BEGIN(LLC_K_HEAD, a->N, a->C, 1, 2.0 * a->N * ((double)a->D * a->E + (double)a->E * a->C),

@@ -445,3 +445,98 @@ def confusion(y: np.ndarray, pred: np.ndarray) -> np.ndarray:
     for a, b in zip(y, pred):
         cm[idx[int(a)], idx[int(b)]] += 1
     return cm
+
+
+# ------------------------------------------------------------------------ MaPLe deep prompts (N3)
+def strip_lora(w: dict) -> dict:
+    """Weights of the vanilla (frozen) towers MaPLe runs on: the LoRA tensors dropped."""
+    return {k: v for k, v in w.items() if "lora" not in k}
+
+
+def synth_maple_weights(tcfg: TextCfg, vis_width: int, n_ctx: int = 3, depth: int = 3,
+                        seed: int = 0) -> dict[str, np.ndarray]:
+    """prompt_learner.* of models/maple.py:74-136: ctx [n_ctx, ctx_dim], proj Linear(ctx_dim ->
+    vis_width), depth-1 compound text prompts and their projection layers (all trainable)."""
+    rng = np.random.default_rng(seed)
+    D = tcfg.width
+    out = {"prompt_learner.ctx": 0.02 * rng.standard_normal((n_ctx, D)),
+           "prompt_learner.proj.weight": D ** -0.5 * rng.standard_normal((vis_width, D)),
+           "prompt_learner.proj.bias": 0.02 * rng.standard_normal((vis_width,))}
+    for i in range(depth - 1):
+        out[f"prompt_learner.compound_prompts_text.{i}"] = 0.02 * rng.standard_normal((n_ctx, D))
+        out[f"prompt_learner.compound_prompt_projections.{i}.weight"] = \
+            D ** -0.5 * rng.standard_normal((vis_width, D))
+        out[f"prompt_learner.compound_prompt_projections.{i}.bias"] = \
+            0.02 * rng.standard_normal((vis_width,))
+    return {k: v.astype(np.float32) for k, v in out.items()}
+
+
+def _h(x):
+    """The reference rounds every prompt it splices in to fp16 (`.half()`,
+    models/maple_clip/model.py:306,380,395,562) before concatenating with the activations."""
+    return x.half().to(x.dtype)
+
+
+def maple_forward(images, tokens, wv, wt, wp, cfg: VitCfg, tcfg: TextCfg, n_ctx: int = 3,
+                  depth: int = 3, logit_scale_exp: float = 1.0 / 0.07):
+    """MaPLe.forward models/maple.py:226-253 on vanilla towers:
+    prompt learner (:138-175) -> text encoder (:45-71 over ResidualAttentionBlock_MaPLe,
+    maple_clip/model.py:353-401: rows 1..n_ctx replaced at layers 1..depth-1) -> image encoder
+    (VisionTransformer_MaPLe.forward :548-589: n_ctx shared tokens appended before ln_pre, the last
+    n_ctx rows replaced at layers 1..depth-1) -> cosine logits. Returns logits [N, C]."""
+    N, C = images.shape[0], tokens.shape[0]
+    ctx = wp["prompt_learner.ctx"]
+    # ---- text side
+    emb = wt["token_embedding.weight"][tokens]                      # [C, ctx_len, D] frozen
+    prompts = torch.cat([emb[:, :1], ctx.unsqueeze(0).expand(C, -1, -1), emb[:, 1 + n_ctx:]], 1)
+    x = prompts + wt["positional_embedding"]
+    bt = VitCfg(width=tcfg.width, heads=tcfg.heads, layers=tcfg.layers)
+    zero_t = {k: torch.zeros(s, dtype=x.dtype) for k, s in text_param_shapes(tcfg).items()
+              if "lora" in k}
+    wtt = {**wt, **zero_t}
+    for i in range(tcfg.layers):
+        if 1 <= i <= depth - 1:
+            c = _h(wp[f"prompt_learner.compound_prompts_text.{i - 1}"])
+            x = torch.cat([x[:, :1], c.unsqueeze(0).expand(C, -1, -1), x[:, 1 + n_ctx:]], 1)
+        x = block_forward(x, wtt, f"transformer.resblocks.{i}.", bt, causal=True)
+    x = layer_norm(x, wt["ln_final.weight"], wt["ln_final.bias"])
+    tfeat = x[torch.arange(C), tokens.argmax(-1)] @ wt["text_projection"]
+    # ---- image side
+    P, G, D = cfg.patch, cfg.grid, cfg.width
+    pt = images.reshape(N, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(N, G * G, 3 * P * P)
+    y = pt @ wv["visual.conv1.weight"].reshape(D, -1).T
+    y = torch.cat([wv["visual.class_embedding"].expand(N, 1, D), y], 1) + \
+        wv["visual.positional_embedding"]
+    shared = ctx @ wp["prompt_learner.proj.weight"].T + wp["prompt_learner.proj.bias"]
+    y = torch.cat([y, _h(shared).unsqueeze(0).expand(N, -1, -1)], 1)
+    y = layer_norm(y, wv["visual.ln_pre.weight"], wv["visual.ln_pre.bias"])
+    zero_v = {k: torch.zeros(s, dtype=y.dtype) for k, s in param_shapes(cfg).items() if "lora" in k}
+    wvv = {**wv, **zero_v}
+    for i in range(cfg.layers):
+        if 1 <= i <= depth - 1:
+            c = wp[f"prompt_learner.compound_prompts_text.{i - 1}"] @ \
+                wp[f"prompt_learner.compound_prompt_projections.{i - 1}.weight"].T + \
+                wp[f"prompt_learner.compound_prompt_projections.{i - 1}.bias"]
+            y = torch.cat([y[:, :y.shape[1] - n_ctx], _h(c).unsqueeze(0).expand(N, -1, -1)], 1)
+        y = block_forward(y, wvv, f"visual.transformer.resblocks.{i}.", cfg)
+    feat = layer_norm(y[:, 0], wv["visual.ln_post.weight"], wv["visual.ln_post.bias"]) @ \
+        wv["visual.proj"]
+    f = feat / feat.norm(dim=-1, keepdim=True)
+    t = tfeat / tfeat.norm(dim=-1, keepdim=True)
+    return logit_scale_exp * f @ t.T
+
+
+def maple_step_oracle(images, labels, tokens, wv_np, wt_np, wp_np, cfg, tcfg, n_ctx=3, depth=3,
+                      logit_scale_exp=1.0 / 0.07, dtype=torch.float64):
+    """logits, CE(logits, y) (methods/maple.py:94-96) and the gradients of prompt_learner.*."""
+    wv = to_torch(strip_lora(wv_np), dtype, lora_grad=False)
+    wt = to_torch(strip_lora(wt_np), dtype, lora_grad=False)
+    wp = {k: torch.from_numpy(v).to(dtype).requires_grad_(True) for k, v in wp_np.items()}
+    logits = maple_forward(torch.from_numpy(images).to(dtype), torch.from_numpy(tokens), wv, wt,
+                           wp, cfg, tcfg, n_ctx, depth, logit_scale_exp)
+    loss = F.cross_entropy(logits, torch.from_numpy(labels))
+    loss.backward()
+    return {"logits": logits.detach().numpy(), "loss": loss.detach().numpy(),
+            "pred": logits.argmax(-1).numpy(),
+            "grads": {k: (v.grad if v.grad is not None else torch.zeros_like(v)).detach().numpy()
+                      for k, v in wp.items()}}

@@ -197,6 +197,121 @@ BOTH_CASES = {
 }
 
 
+MAPLE_CASES = {
+    # name: (vision cfg, text cfg, batch, classes, seed)   (n_ctx = 3, prompt depth = 3)
+    # (the reference hard-codes the 512 / 768 widths of ViT-B/16, models/maple.py:118,127,134)
+    "maple_small": (vo.VitCfg(image_size=64, patch=16, width=768, layers=4, heads=12,
+                              embed_dim=512),
+                    vo.TextCfg(context=16, vocab=300, width=512, heads=8, layers=4, embed_dim=512),
+                    5, 6, 31),
+    "maple_vitb16": (vo.VIT_B16, vo.TEXT_B16, 4, 10, 33),
+}
+
+
+def run_reference_maple(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes: int, seed: int):
+    """BASELINE config 4: the reference's MaPLe (models/maple.py:74-253) on its own
+    models/maple_clip/model.py CLIP (VisionTransformer_MaPLe, ResidualAttentionBlock_MaPLe).
+    maple_clip's package __init__ pulls the BPE tokenizer (ftfy, not installed), so model.py is
+    loaded as a file and models/maple.py is imported with a stub `clip` module whose tokenize()
+    returns fixed ids (only used to initialise ctx, which is overwritten with synthetic values)."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location(
+        "maple_clip_model", os.path.join(REF, "models", "maple_clip", "model.py"))
+    mm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mm)
+    stub_pkg = types.ModuleType("models")
+    stub_pkg.__path__ = [os.path.join(REF, "models")]
+    stub_mc = types.ModuleType("models.maple_clip")
+    stub_mc.__path__ = []
+    stub_clip = types.ModuleType("models.maple_clip.clip")
+    stub_clip.tokenize = lambda text: torch.tensor([[tcfg.vocab - 2, 5, 6, 7, 8, 9,
+                                                     tcfg.vocab - 1] + [0] * (tcfg.context - 7)])
+    stub_tok = types.ModuleType("models.maple_clip.simple_tokenizer")
+    stub_tok.SimpleTokenizer = lambda: None
+    stub_mc.clip = stub_clip
+    saved = {k: sys.modules.get(k) for k in ("models", "models.maple_clip",
+                                             "models.maple_clip.clip",
+                                             "models.maple_clip.simple_tokenizer")}
+    sys.modules.update({"models": stub_pkg, "models.maple_clip": stub_mc,
+                        "models.maple_clip.clip": stub_clip,
+                        "models.maple_clip.simple_tokenizer": stub_tok})
+    try:
+        spec2 = importlib.util.spec_from_file_location("ref_maple",
+                                                       os.path.join(REF, "models", "maple.py"))
+        maple = importlib.util.module_from_spec(spec2)
+        spec2.loader.exec_module(maple)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    torch.manual_seed(0)
+    clip_model = mm.CLIP(cfg.embed_dim, cfg.image_size, cfg.layers, cfg.width, cfg.patch,
+                         tcfg.context, tcfg.vocab, tcfg.width, tcfg.heads, tcfg.layers,
+                         {"trainer": "MaPLe", "vision_depth": 0, "language_depth": 0,
+                          "vision_ctx": 0, "language_ctx": 0, "maple_length": 3}).float()
+    wv = vo.strip_lora(vo.synth_weights(cfg, seed))
+    wt = vo.strip_lora(vo.synth_text_weights(tcfg, seed + 1))
+    wp = vo.synth_maple_weights(tcfg, cfg.width, seed=seed + 2)
+    sd = clip_model.state_dict()
+    for k, v in {**wv, **wt}.items():
+        assert k in sd and tuple(sd[k].shape) == v.shape, (k, v.shape)
+        sd[k] = torch.from_numpy(v)
+    clip_model.load_state_dict(sd)
+    # MaPLe.__init__ downloads a checkpoint (models/maple.py:181): assemble the module by hand
+    m = maple.MaPLe.__new__(maple.MaPLe)
+    torch.nn.Module.__init__(m)
+    maple.MultiModalPromptLearner.__init__.__globals__["clip"] = stub_clip
+    m.prompt_learner = maple.MultiModalPromptLearner(clip_model, n_ctx=3)
+    psd = m.prompt_learner.state_dict()
+    for k, v in wp.items():
+        kk = k[len("prompt_learner."):]
+        assert kk in psd and tuple(psd[kk].shape) == v.shape, (kk, v.shape, psd[kk].shape)
+        psd[kk] = torch.from_numpy(v)
+    m.prompt_learner.load_state_dict(psd)
+    m.image_encoder, m.text_encoder = clip_model.visual, maple.TextEncoder(clip_model)
+    m.logit_scale, m.dtype, m.n_ctx = clip_model.logit_scale, clip_model.dtype, 3
+    for k, p in m.named_parameters():       # methods/maple.py: only the prompt learner trains
+        p.requires_grad = "prompt_learner" in k
+    images, labels = synth_inputs(cfg, n, num_classes, seed + 100)
+    tokens = torch.from_numpy(vo.synth_tokens(num_classes, tcfg, seed + 300))
+    with torch.no_grad():                   # MaPLe.get_tokenized_prompts (:205-224)
+        emb = clip_model.token_embedding(tokens).type(m.dtype)
+    prefix, suffix = emb[:, :1, :], emb[:, 1 + 3:, :]
+    logits = m(torch.from_numpy(images), tokens, prefix, suffix)      # MaPLe.forward :226-253
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.from_numpy(labels))   # methods/maple.py:96
+    loss.backward()
+    out = {"logits": logits.detach().numpy(), "loss": loss.detach().numpy(),
+           "pred": logits.argmax(-1).numpy(),
+           "logit_scale_exp": clip_model.logit_scale.exp().detach().numpy()}
+    ng = 0
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            g = p.grad.numpy()
+            ng += 1
+            if g.size > 100_000:
+                # the three [768, 512] projection-weight gradients: kept as scaled fp16 (6e-4
+                # relative rounding, far below the 1e-2 parity tolerance) to keep fixtures small
+                sc = float(np.abs(g).max()) or 1.0
+                out["grad16:" + k] = (g / sc).astype(np.float16)
+                out["gscale:" + k] = np.float32(sc)
+            else:
+                out["grad:" + k] = g
+    assert ng == 9
+    return out
+
+
+def load_maple_grads(gold) -> dict:
+    """name -> fp32 gradient from a ref_maple_*.npz (undoes the fp16 packing above)."""
+    out = {k[5:]: gold[k] for k in gold.files if k.startswith("grad:")}
+    for k in gold.files:
+        if k.startswith("grad16:"):
+            out[k[7:]] = gold[k].astype(np.float32) * float(gold["gscale:" + k[7:]])
+    return out
+
+
 def run_interpret_pred():
     """Execute the reference's OWN _interpret_pred (methods/_trainer.py:519-534; the module itself
     cannot be imported here - it pulls randaugment / timm - so the function's source is compiled
@@ -241,6 +356,13 @@ def main():
         if only and name not in only:
             continue
         out = run_reference_both(cfg, tcfg, n, c, seed)
+        path = os.path.join(HERE, f"ref_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(name, "loss", float(out["loss"]), "->", path, os.path.getsize(path), "bytes")
+    for name, (cfg, tcfg, n, c, seed) in MAPLE_CASES.items():
+        if only and name not in only:
+            continue
+        out = run_reference_maple(cfg, tcfg, n, c, seed)
         path = os.path.join(HERE, f"ref_{name}.npz")
         np.savez_compressed(path, **out)
         print(name, "loss", float(out["loss"]), "->", path, os.path.getsize(path), "bytes")

@@ -65,11 +65,26 @@ def test_batch_additivity_and_independence(setup):
     h = N // 2
     pa, la, _, ga = step(eng, images[:h], labels[:h], text, inv_batch=1.0 / N)
     pb, lb, _, gb = step(eng, images[h:], labels[h:], text, inv_batch=1.0 / N)
-    # an image's probabilities do not depend on what else is in the batch
-    assert torch.equal(p[:h], pa) and torch.equal(p[h:], pb)
+    # an image's probabilities do not depend on what else is in the batch: the per-sample
+    # arithmetic has no cross-sample term. Bit-exact under the whole-tile GEMM schedule; the
+    # stream-K schedule cuts a tile's K range at shape-dependent points, so the fp32 summation
+    # order (and, rarely, a bf16 rounding) changes with the batch size
+    assert rel(p[:h], pa) < 2e-3 and rel(p[h:], pb) < 2e-3
+    from lifelong_clip_b200 import _capi
+    old = _capi.load().llc_gemm_set_stream_k(0)
+    try:
+        p0, _, _, g0 = step(eng, images, labels, text)
+        pa0, _, _, ga0 = step(eng, images[:h], labels[:h], text, inv_batch=1.0 / N)
+        pb0, _, _, gb0 = step(eng, images[h:], labels[h:], text, inv_batch=1.0 / N)
+        assert torch.equal(p0[:h], pa0) and torch.equal(p0[h:], pb0)
+        # whole-tile schedule: only the fp32 order of the token sums differs
+        assert rel(ga0 + gb0, g0) < 2e-4
+    finally:
+        _capi.load().llc_gemm_set_stream_k(old)
     assert abs(float(l) - float(la) - float(lb)) < 1e-5 * abs(float(l))
-    # the gradient is a sum over images: only the fp32 order of the token sums differs
-    assert rel(ga + gb, g) < 2e-4
+    # the gradient is a sum over images (stream-K on: a few bf16 roundings flip with the batch
+    # size, as in test_permutation - far below the bf16 noise floor of the parity policy)
+    assert rel(ga + gb, g) < 5e-3
 
 
 def test_permutation(setup):

@@ -99,3 +99,29 @@ def test_interpret_pred_and_confusion_match_reference(golden_dir):
         np.testing.assert_array_equal(vo.confusion(y, pred), gold[f"cm{i}"])
         i += 1
     assert i == 4
+
+
+@pytest.mark.parametrize("name", ["maple_small", "maple_vitb16"])
+def test_maple_oracle_matches_reference_golden(name, golden_dir):
+    """BASELINE config 4: the oracle's MaPLe restatement (deep multi-modal prompts over frozen
+    towers) against the reference's own models/maple.py + models/maple_clip/model.py."""
+    from tests.golden.make_golden import MAPLE_CASES, load_maple_grads
+    cfg, tcfg, n, c, seed = MAPLE_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    torch.set_num_threads(os.cpu_count() or 1)
+    wv, wt = vo.synth_weights(cfg, seed), vo.synth_text_weights(tcfg, seed + 1)
+    wp = vo.synth_maple_weights(tcfg, cfg.width, seed=seed + 2)
+    images, labels = synth_inputs(cfg, n, c, seed + 100)
+    tokens = vo.synth_tokens(c, tcfg, seed + 300)
+    out = vo.maple_step_oracle(images, labels, tokens, wv, wt, wp, cfg, tcfg,
+                               logit_scale_exp=float(gold["logit_scale_exp"]),
+                               dtype=torch.float32)
+    assert _rel(out["logits"], gold["logits"]) < 2e-5
+    assert abs(float(out["loss"]) - float(gold["loss"])) < 1e-5
+    np.testing.assert_array_equal(out["pred"], gold["pred"])
+    want = load_maple_grads(gold)
+    assert {"prompt_learner." + k if not k.startswith("prompt_learner.") else k
+            for k in want} == set(out["grads"])
+    for k, v in want.items():
+        kk = k if k.startswith("prompt_learner.") else "prompt_learner." + k
+        assert _rel(out["grads"][kk], v) < 2e-3, (k, _rel(out["grads"][kk], v))

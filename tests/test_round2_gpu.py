@@ -141,7 +141,8 @@ def test_lora_linear_forward_backward():
     xd = x.detach().double().requires_grad_(True)
     A, B = (lin.lora_A.detach().double().requires_grad_(True),
             lin.lora_B.detach().double().requires_grad_(True))
-    yd = xd @ lin.weight.double().T + lin.bias.double() + (xd @ A.T @ B.T) * lin.scaling
+    yd = xd @ lin.weight.detach().double().T + lin.bias.detach().double() + \
+        (xd @ A.T @ B.T) * lin.scaling
     yd.backward(dy.double())
     assert rel(y, yd) < 5e-3
     assert rel(x.grad, xd.grad) < TOL
@@ -184,7 +185,7 @@ def test_multihead_attention_forward_is_the_reference_call(causal):
     yd = vo.lora_linear(o, wd[pre + "attn.out_proj.weight"], wd[pre + "attn.out_proj.bias"],
                         wd[pre + "attn.out_proj.lora_A"], wd[pre + "attn.out_proj.lora_B"], s)
     yd.backward(dy.double().transpose(0, 1))
-    assert rel(out.detach().cpu().transpose(0, 1), yd.detach()) < 5e-3
+    assert rel(out.detach().cpu().transpose(0, 1), yd.detach()) < TOL
     assert rel(xc.grad.cpu().transpose(0, 1), xd.grad) < TOL
     for k, p in blk.attn.named_parameters():
         if "lora" in k:
@@ -230,7 +231,7 @@ def test_vanilla_residual_attention_block():
     D = cfg.width
     o = vo.attention_core(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], cfg.heads)
     want = o @ wd[pre + "attn.out_proj.weight"].T + wd[pre + "attn.out_proj.bias"]
-    assert rel(a.cpu().transpose(0, 1), want) < 5e-3
+    assert rel(a.cpu().transpose(0, 1), want) < TOL
 
 
 # ------------------------------------------------------------------------------------------------
@@ -391,7 +392,21 @@ def build_both(cfg, tcfg, wv, wt):
     return m
 
 
-def check_both(probs, loss, pred, grads, gold, n_layers):
+# With BOTH towers in bf16 the logit gradient only sees the DIFFERENCES between the class text
+# features (softmax gradients sum to zero), and random-init prompts give features with pairwise
+# cosine ~0.77: relative errors are amplified ~2x compared with the cached-text case. Calibration
+# (tools/parity_both_calib.py -> profiles/r02_parity_both_vs_autocast.txt): PyTorch's OWN bf16
+# autocast of the same two-tower step measures, against the reference's fp32 output,
+#   both_vitb16: flat 1.4e-2 / 1.5e-2 (image / text tower), median tensor 1.5e-2 / 1.8e-2, worst
+#                tensor 3.4e-2 / 4.3e-2 (the same out_proj.lora_A tensors that are worst here);
+#   both_tiny:   flat 2.7e-2 / 3.0e-2, worst 4.0e-2.
+# This path measures 1.2e-2 flat / 3.5e-2 worst on both_vitb16. The bounds below are autocast's
+# level, not a looser one.
+TOL_BOTH = {"both_vitb16": (2e-2, 5e-2), "both_tiny": (3.5e-2, 6e-2)}
+
+
+def check_both(probs, loss, pred, grads, gold, n_layers, name):
+    tol_flat, tol_worst = TOL_BOTH[name]
     assert rel(probs, gold["probs"]) < TOL
     assert abs(float(loss) - float(gold["loss"])) < TOL * abs(float(gold["loss"]))
     p = np.asarray(gold["probs"], np.float64)
@@ -404,11 +419,11 @@ def check_both(probs, loss, pred, grads, gold, n_layers):
         keys = sorted(k for k in want if k.startswith(tower))
         fg = np.concatenate([np.asarray(grads[k], np.float64).ravel() for k in keys])
         fw = np.concatenate([np.asarray(want[k], np.float64).ravel() for k in keys])
-        assert rel(fg, fw) < TOL, (tower, rel(fg, fw))
-        assert cos(fg, fw) > COS
+        assert rel(fg, fw) < tol_flat, (tower, rel(fg, fw))
+        assert cos(fg, fw) > 1.0 - tol_flat ** 2
         rels = [rel(grads[k], want[k]) for k in keys]
-        assert float(np.median(rels)) < TOL
-        assert max(rels) < TOL_WORST_TENSOR, (max(rels), keys[int(np.argmax(rels))])
+        assert float(np.median(rels)) < tol_flat
+        assert max(rels) < tol_worst, (max(rels), keys[int(np.argmax(rels))])
 
 
 @pytest.mark.parametrize("name", ["both_tiny", "both_vitb16"])
@@ -441,7 +456,7 @@ def test_text_tower_lora_matches_reference_golden(name, path, golden_dir):
         torch.cuda.synchronize()
         assert tuple(ft.shape) == (c, cfg.embed_dim)
         check_both(probs.detach().cpu().numpy(), loss.item(), probs.argmax(-1).cpu().numpy(),
-                   grads_by_name(m), gold, cfg.layers + tcfg.layers)
+                   grads_by_name(m), gold, cfg.layers + tcfg.layers, name)
         return
     from lifelong_clip_b200.trainer import LoRAClipTrainer
     tr = LoRAClipTrainer(m, names, n_classes=c, lr=0.0, visible_classes="all",
@@ -457,7 +472,7 @@ def test_text_tower_lora_matches_reference_golden(name, path, golden_dir):
                                                      teng.lora_grad_views)})
     head = tr.last_head
     check_both(head.probs.cpu().numpy(), loss_sum, head.pred.cpu().numpy(), grads, gold,
-               cfg.layers + tcfg.layers)
+               cfg.layers + tcfg.layers, name)
 
 
 def test_text_tower_trains_and_evaluates():
@@ -563,3 +578,89 @@ def test_trainer_with_gpu_transform_and_graph():
     b, _ = run(False)
     assert tr_a._graph is not None and tr_a._graph_hits >= 4
     np.testing.assert_allclose(a, b, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["maple_small", "maple_vitb16"])
+def test_maple_matches_reference_golden(name, golden_dir):
+    """BASELINE config 4: MaPLe deep multi-modal prompts (models/maple.py:74-253 over
+    models/maple_clip/model.py) on frozen towers: logits, CE-on-logits loss and the gradients of
+    the nine prompt_learner tensors against the reference's own classes. Attention runs over
+    197 + 3 image tokens and 16 / 77 text tokens; the activation gradient flows through every
+    frozen block down to the prompt rows."""
+    from lifelong_clip_b200.maple import MaPLe
+    from tests.golden.make_golden import MAPLE_CASES, load_maple_grads
+    cfg, tcfg, n, c, seed = MAPLE_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    wv = vo.strip_lora(vo.synth_weights(cfg, seed))
+    wt = vo.strip_lora(vo.synth_text_weights(tcfg, seed + 1))
+    wp = vo.synth_maple_weights(tcfg, cfg.width, seed=seed + 2)
+    images, labels = synth_inputs(cfg, n, c, seed + 100)
+    tokens = torch.from_numpy(vo.synth_tokens(c, tcfg, seed + 300))
+    m = MaPLe(vision_config=(cfg.image_size, cfg.patch, cfg.width, cfg.layers, cfg.embed_dim),
+              text_config=(tcfg.context, tcfg.vocab, tcfg.width, tcfg.heads, tcfg.layers))
+    missing, unexpected = m.base_clip_model.load_state_dict(
+        {k: torch.from_numpy(v) for k, v in {**wv, **wt}.items()}, strict=False)
+    assert not unexpected and set(missing) <= {"logit_scale"}, (missing, unexpected)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in wp.items()}, strict=False)
+    m.cuda()
+    with torch.no_grad():
+        m.logit_scale.fill_(float(np.log(gold["logit_scale_exp"])))
+    for k, p in m.named_parameters():          # methods/maple.py: only the prompt learner trains
+        p.requires_grad = "prompt_learner" in k
+    assert sum(p.requires_grad for p in m.parameters()) == 9
+    tok = tokens.cuda()
+    with torch.no_grad():
+        emb = m.base_clip_model.token_embedding(tok)
+    prefix, suffix = emb[:, :1, :], emb[:, 1 + 3:, :]
+    logits = m(torch.from_numpy(images).cuda(), tok, prefix, suffix)
+    loss = torch.nn.CrossEntropyLoss()(logits, torch.from_numpy(labels).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel(logits.detach().cpu(), gold["logits"]) < TOL
+    assert abs(loss.item() - float(gold["loss"])) < TOL * abs(float(gold["loss"]))
+    lg = np.sort(gold["logits"].astype(np.float64), axis=-1)
+    safe = (lg[:, -1] - lg[:, -2]) > 0.05
+    np.testing.assert_array_equal(logits.argmax(-1).cpu().numpy()[safe], gold["pred"][safe])
+    want = load_maple_grads(gold)
+    got = {k: p.grad.detach().cpu().numpy() for k, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(want)
+    # prompt gradients pass through EVERY frozen block in bf16 (12 layers back to the prompt
+    # rows): same two-sided error amplification as the two-tower LoRA case above
+    rels = {k: rel(got[k], want[k]) for k in want}
+    assert float(np.median(list(rels.values()))) < 2e-2, rels
+    assert max(rels.values()) < 5e-2, rels
+    # frozen towers: no gradient was formed for any backbone tensor
+    assert all(p.grad is None for k, p in m.named_parameters() if "prompt_learner" not in k)
+
+
+def test_maple_prompt_training_step():
+    """A few AdamW steps on the prompt learner only (methods/maple.py:85-105 flow): update_class_names
+    -> tokenized prompts, forward(image) -> logits, CE, backward, step; the loss goes down and the
+    frozen towers stay bit-identical."""
+    from lifelong_clip_b200.adapter_clip import SyntheticTokenizer
+    from lifelong_clip_b200.maple import MaPLe
+    cfg = vo.VitCfg(image_size=64, patch=16, width=256, layers=3, heads=4, embed_dim=128)
+    m = MaPLe(vision_config=(cfg.image_size, cfg.patch, cfg.width, cfg.layers, cfg.embed_dim),
+              text_config=(16, 300, 128, 2, 3)).cuda()
+    m.set_tokenizer(SyntheticTokenizer(16, 300))
+    for k, p in m.named_parameters():
+        p.requires_grad = "prompt_learner" in k
+    frozen = {k: p.detach().clone() for k, p in m.named_parameters() if "prompt_learner" not in k}
+    names = [f"class{i}" for i in range(5)]
+    assert m.update_class_names(names).shape == (5, 16)
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=2e-2)
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.standard_normal((6, 3, 64, 64)).astype(np.float32)).cuda()
+    y = torch.tensor([0, 1, 2, 3, 4, 0]).cuda()
+    losses = []
+    for _ in range(10):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(m(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0] - 1e-3, losses
+    for k, p in m.named_parameters():
+        if "prompt_learner" not in k:
+            assert torch.equal(p.detach(), frozen[k]), k
