@@ -41,6 +41,10 @@ int llc_version(void);
 const char* llc_last_error(void);
 /* 0 when device `dev` is sm_100 (B200); LLC_ERR_ARCH otherwise. */
 int llc_check_device(int dev);
+/* process-wide switch (default off; returns the previous setting): the persistent kernels
+ * (GEMM, attention) release their programmatic dependents when every CTA has started its last
+ * work item, so the next kernel's prologue overlaps this kernel's tail */
+int llc_set_pdl_trigger(int on);
 /* number of kernels this process has launched through the library (bench.py: gpu_launches) */
 unsigned long long llc_launch_count(void);
 

@@ -188,6 +188,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
     for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x, ++it) {
       const int n = pr / p.H, h = pr % p.H;
       const uint32_t par = (it & 1) ^ 1;
+      if ((p.dbg & 4096) && pr + (int)gridDim.x >= pairs && elect_one()) pdl_trigger();
       auto load_kv = [&](int j) {
         const int Kj = min(128, LK - 128 * j);
         mbar_wait(smem_u32(&kv_empty[j]), par);
@@ -591,7 +592,7 @@ int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const
   p.sn = sn; p.sl = sl; p.causal = causal;
   p.mat_bytes = p.LK * 128;
   static const int dbg = llc_dev_env("LLC_ATTN_DBG") ? atoi(llc_dev_env("LLC_ATTN_DBG")) : 0;
-  p.dbg = dbg;
+  p.dbg = dbg | (g_llc_pdl_trigger ? 4096 : 0);
   const int smem = llc_attn_bwd_tc4_smem(L);
   CUtensorMap q64, q16, d64, d16, to;
   if (int rc = encode_rows(&q64, qkv, 3 * H * HD, ld_qkv, L, N, sn, sl, 64)) return rc;

@@ -158,6 +158,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int n = pr / p.H, h = pr % p.H;
+      if ((p.dbg & 4096) && it == n_it - 1 && elect_one()) pdl_trigger();   // last pair
       mbar_wait(smem_u32(&kv_empty[st]), ph ^ 1);
       if (elect_one()) {
         const uint32_t fb = smem_u32(&kv_full[st]);
@@ -457,7 +458,7 @@ int llc_attn_fwd_tc2(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse,
   p.N = N; p.L = L; p.H = H; p.LK = (L + 15) / 16 * 16; p.NT = (L + 127) / 128;
   p.causal = causal;
   static const int dbg = llc_dev_env("LLC_ATTN_DBG") ? atoi(llc_dev_env("LLC_ATTN_DBG")) : 0;
-  p.dbg = dbg;
+  p.dbg = dbg | (g_llc_pdl_trigger ? 4096 : 0);
   LLC_CONFIGURE_SMEM(attn_fwd2_kernel, kSmem);
   const int grid = N * H < llc_num_sms() ? N * H : llc_num_sms();
   LLC_PROF_BEGIN(LLC_K_ATTN_FWD, N * H, L, 0, 4.0 * N * H * (double)L * L * HD,

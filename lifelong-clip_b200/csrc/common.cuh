@@ -79,6 +79,7 @@ void llc_prof_end(cudaStream_t st);
 // pdl_wait() until the predecessor has completed and its writes are visible. Saves the launch
 // latency + tail + prologue (~8 us) between the ~260 kernels of a step. LLC_NO_PDL=1 disables it.
 extern int g_llc_pdl;
+extern int g_llc_pdl_trigger;   // llc_set_pdl_trigger: persistent kernels trigger dependents early
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 cudaError_t llc_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
@@ -97,6 +98,15 @@ cudaError_t llc_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
 }
 __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// Early trigger: a persistent kernel calls this when a CTA starts its LAST work item. Once every
+// CTA of the grid has (or has exited), the next kernel of the stream may be scheduled: its CTAs
+// take SMs as ours retire, run their prologue (barriers, TMEM, descriptor prefetch) and park in
+// pdl_wait() until this grid has completed and flushed. Hides the launch + prologue latency in our
+// tail. (Triggering at kernel START was measured slower in round 1: dependents parked for the
+// whole kernel compete with multi-wave kernels' own CTAs.)
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 #endif
 

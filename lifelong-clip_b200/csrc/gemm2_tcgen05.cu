@@ -182,6 +182,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int next_tile, next_kb0;
       wi.peek(next_tile, next_kb0);
       const int m0_next = (next_tile / tiles_n) * BM + (int)rank * 128;
+      if ((dbg & 4096) && next_tile < 0 && elect_one()) pdl_trigger();   // last work item
       for (int kb = kb0; kb < kb1; ++kb) {
         if (!(dbg & 32)) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t fb_local = smem_u32(&full_bar[stage]);
@@ -388,10 +389,15 @@ bool gemm2_wants_sk(int M, int N, int K) {
   const int num_kb = (K + BK - 1) / BK;
   const int waves = (tiles + pairs - 1) / pairs;
   const double eff = (double)tiles / ((double)waves * pairs);
-  // a split tile costs a 256 KB partial through L2 plus an unoverlapped fix-up epilogue (~6 us):
-  // measured at 32 images per GPU (T = 6304) it pays for K >= 2320 (36+ k-blocks; 45 -> 39 us at
-  // K = 3072) and loses for the K = 768 / 784 GEMMs, whose whole tile takes 2 us
-  return eff < 0.92 && num_kb >= 32 && (long long)tiles * num_kb >= 4LL * pairs;
+  // Measured per shape (tools/sk_bench.py -> profiles/r02_streamk_ab.txt): the schedule pays when
+  // the whole problem is about ONE wave (39 / 75 tiles at 16 / 32 images: 1.2-1.5x at K = 3072,
+  // 1.1-1.3x at K = 2320) and K is long enough to amortise the partial's trip through L2 and the
+  // un-overlapped fix-up epilogue (~6 us; the K = 768 / 784 GEMMs, whose whole tile takes 2 us,
+  // got slower). From two waves on it ties (64 images) or loses (128 images: 0.86x): contiguous
+  // unit ranges make the pairs walk far-apart tiles, so the three n-tiles that share an A row
+  // block are no longer in flight together and A is re-read from HBM.
+  return eff < 0.92 && num_kb >= 32 && tiles <= pairs + pairs / 4 &&
+         (long long)tiles * num_kb >= 4LL * pairs;
 }
 
 template <int MODE>
@@ -409,18 +415,19 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   static const int dbg = llc_dev_env("LLC_GEMM_DBG") ? atoi(llc_dev_env("LLC_GEMM_DBG")) : 0;
   EpiParams ep2 = ep;
   ep2.dbg = dbg;
+  const int kdbg = dbg | (g_llc_pdl_trigger ? 4096 : 0);
   // a bf16 output that fits L2 (dh, d_o: 77 MB) is read again by the next kernel(s): let it stay
   static const bool nokeep = llc_dev_env("LLC_GEMM_NOKEEP") != nullptr;
   ep2.keep_out = (!nokeep && !ep.out_fp32 && (double)M * N * 2.0 <= 100e6) ? 1 : 0;
   if (sk) {
     LLC_CONFIGURE_SMEM((gemm2_kernel<MODE, true>), kSmem);
     LLC_CUDA(llc_launch_pdl(gemm2_kernel<MODE, true>, dim3(grid), dim3(kThreads), kSmem, stream,
-                            tmA, tmB, tmO, tmO2, M, N, K, ep2, dbg,
+                            tmA, tmB, tmO, tmO2, M, N, K, ep2, kdbg,
                             reinterpret_cast<uint8_t*>(ep.ws)));
   } else {
     LLC_CONFIGURE_SMEM((gemm2_kernel<MODE, false>), kSmem);
     LLC_CUDA(llc_launch_pdl(gemm2_kernel<MODE, false>, dim3(grid), dim3(kThreads), kSmem, stream,
-                            tmA, tmB, tmO, tmO2, M, N, K, ep2, dbg, (uint8_t*)nullptr));
+                            tmA, tmB, tmO, tmO2, M, N, K, ep2, kdbg, (uint8_t*)nullptr));
   }
   LLC_PROF_END(stream);
   LLC_COUNT_LAUNCH();

@@ -162,6 +162,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM;
       const int n0 = (tile % tiles_n) * BN;
+      if ((ep.dbg & 4096) && tile + (int)gridDim.x >= num_tiles && elect_one()) pdl_trigger();
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         if (elect_one()) {
@@ -317,7 +318,7 @@ extern "C" int llc_gemm_bf16_tn(const void* A, int lda, const void* B, int ldb, 
   ep.aux = reinterpret_cast<const __nv_bfloat16*>(e->aux); ep.ld_aux = e->ld_aux;
   ep.out = e->out; ep.ld_out = e->ld_out; ep.out_fp32 = e->out_fp32;
   ep.out2 = reinterpret_cast<__nv_bfloat16*>(e->out2); ep.ld_out2 = e->ld_out2;
-  ep.dbg = 0;
+  ep.dbg = g_llc_pdl_trigger ? 4096 : 0;
   ep.keep_out = 0;
   ep.ws = e->ws; ep.ws_bytes = e->ws_bytes;
   LLC_REQUIRE(e->ws == nullptr || ((uintptr_t)e->ws & 15) == 0, "llc_gemm_bf16_tn: ws misaligned");

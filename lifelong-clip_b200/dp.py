@@ -64,4 +64,5 @@ def allreduce_step(grad_flats, scalars: torch.Tensor, world: int) -> None:
         grad_flats = [grad_flats]
     for g in grad_flats:
         dist.all_reduce(g)
-    dist.all_reduce(scalars)
+    if scalars is not None:
+        dist.all_reduce(scalars)

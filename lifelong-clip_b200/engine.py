@@ -30,7 +30,11 @@ class _TowerEngine:
         self.lora_params = [p for b in blocks for p in b.lora_params()]
         n = sum(p.numel() for p in self.lora_params)
         self.lora_flat = torch.empty(n, device=dev, dtype=torch.float32)
-        self.grad_flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        # gradient buffer with two trailing floats (loss_sum, n_correct of the step): the
+        # data-parallel exchange is then ONE all-reduce per tower instead of two
+        self.grad_store = torch.zeros(n + 2, device=dev, dtype=torch.float32)
+        self.grad_flat = self.grad_store[:n]
+        self.scal = self.grad_store[n:]
         self.lora_grad_views, off = [], 0
         for p in self.lora_params:
             view = self.lora_flat[off:off + p.numel()].view(p.shape)

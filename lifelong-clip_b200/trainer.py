@@ -71,8 +71,13 @@ class LoRAClipTrainer:
         self.optimizer = None
         self._lut = torch.full((self.n_classes,), -1, dtype=torch.int64, device=self.device)
         self._lut_src = None
-        self._scal = torch.zeros(2, device=self.device)
         self._comm_stream = None
+
+    @property
+    def _scal(self):
+        """(loss_sum, n_correct) of the step: the two floats behind the image tower's flat LoRA
+        gradient, so that they travel in the same all-reduce."""
+        return self.custom_clip.model.visual.engine().scal
 
     @property
     def text_trainable(self) -> bool:
@@ -324,7 +329,9 @@ class LoRAClipTrainer:
         else:
             head = self._step_body(x, y_local, global_batch, tx=self._make_tx(x, False))
         engines = self.optimizer.engines()
-        dp.allreduce_step([e.grad_flat for e in engines], self._scal, self.world)
+        # image tower: gradient + (loss_sum, n_correct) in one buffer; text tower: its gradient
+        dp.allreduce_step([engines[0].grad_store] + [e.grad_flat for e in engines[1:]], None,
+                          self.world)
         self.optimizer.step()
         self.last_head = head
         if not sync:
@@ -336,8 +343,7 @@ class LoRAClipTrainer:
         """A rank whose shard of a ragged last batch is empty contributes zeros and still joins
         the collectives (the other ranks would block in all_reduce otherwise)."""
         for e in self.optimizer.engines():
-            e.grad_flat.zero_()
-        self._scal.zero_()
+            e.grad_store.zero_()
         return None
 
     # ---- evaluation (methods/adapter_clip.py:132-176, methods/_trainer.py:519-534) --------------
