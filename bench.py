@@ -486,13 +486,23 @@ def run_ours(args):
         red = torch.cat([e.grad_flat for e in engines]).clone()
         dist.all_reduce(red)
         if rank == 0:
+            shard_sum = None
+            for r in range(world):       # every shard again on this one GPU
+                trainer._step_body(gx[r::world].to(dev),
+                                   ops.label_remap(gy[r::world].to(dev), lut), gB)
+                part = torch.cat([e.grad_flat for e in engines])
+                shard_sum = part.clone() if shard_sum is None else shard_sum + part
             trainer._step_body(gx.to(dev), ops.label_remap(gy.to(dev), lut), gB)
             full = torch.cat([e.grad_flat for e in engines])
             dp_check = {"rel_l2": float((red - full).norm() / full.norm()),
+                        "rel_l2_vs_sum_of_shards_on_one_gpu":
+                            float((red - shard_sum).norm() / shard_sum.norm()),
                         "max_abs": float((red - full).abs().max()),
                         "grad_norm": float(full.norm()),
                         "what": f"all-reduce of {world} shard gradients vs one GPU on the "
-                                f"concatenated {gB}-image batch (fp32 summation order only)"}
+                                f"concatenated {gB}-image batch (rel_l2: the fp32 order of "
+                                f"largely cancelling token sums) and vs the sum of the same "
+                                f"shards computed on one GPU (the exchange itself)"}
             for e in engines:           # back to the per-GPU shard size
                 e.arena, e.arena_key, e.dx = None, None, None
         barrier()

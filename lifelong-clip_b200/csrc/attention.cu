@@ -20,9 +20,16 @@ int llc_attn_bwd_tc4(const void* qkv, int ld_qkv, const void* o, int ld_o, const
 int llc_attn_bwd_tc4_smem(int L);
 int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
-                     int sn, int sl, int causal, cudaStream_t st);
+                     int sn, int sl, int causal, cudaStream_t st, int lse_ld);
 int llc_attn_fwd_tc2(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L,
-                     int H, int sn, int sl, int causal, cudaStream_t st);
+                     int H, int sn, int sl, int causal, cudaStream_t st, int lse_ld);
+// 256 < L <= 264 (ViT-L/14: 257): TMEM kernels on the first 256 tokens + side kernels
+bool llc_attn_long_eligible(int L, int causal);
+int llc_attn_fwd_long(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L,
+                      int H, int sn, int sl, cudaStream_t st);
+int llc_attn_bwd_long(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
+                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
+                      int sn, int sl, cudaStream_t st);
 
 namespace {
 
@@ -521,7 +528,10 @@ extern "C" int llc_attn_fwd(const void* qkv, int ld_qkv, void* o, int ld_o, floa
   static const bool legacy = llc_dev_env("LLC_ATTN_LEGACY") != nullptr;
   if (!legacy && llc_attn_tc_eligible(L))
     return llc_attn_fwd_tc2(qkv, ld_qkv, o, ld_o, lse, N, L, H, tok_stride_n, tok_stride_l, causal,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, 0);
+  if (!legacy && llc_attn_long_eligible(L, causal))
+    return llc_attn_fwd_long(qkv, ld_qkv, o, ld_o, lse, N, L, H, tok_stride_n, tok_stride_l,
+                             (cudaStream_t)stream);
   DISPATCH_LP(L, (launch_fwd<LP>((const __nv_bfloat16*)qkv, ld_qkv, (__nv_bfloat16*)o, ld_o, lse,
                                  N, L, H, tok_stride_n, tok_stride_l, causal,
                                  (cudaStream_t)stream)));
@@ -554,7 +564,11 @@ int llc_attn_bwd_ws(const void* qkv, int ld_qkv, const void* o, int ld_o, const 
                             (cudaStream_t)stream);
   if (!legacy && llc_attn_tc_eligible(L) && ld_dqkv % 8 == 0 && ((uintptr_t)dqkv & 15) == 0)
     return llc_attn_bwd_tc3(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
-                            tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream);
+                            tok_stride_n, tok_stride_l, causal, (cudaStream_t)stream, 0);
+  if (!legacy && llc_attn_long_eligible(L, causal) && ld_dqkv % 8 == 0 &&
+      ((uintptr_t)dqkv & 15) == 0)
+    return llc_attn_bwd_long(qkv, ld_qkv, o, ld_o, d_o, ld_do, lse, dqkv, ld_dqkv, N, L, H,
+                             tok_stride_n, tok_stride_l, (cudaStream_t)stream);
   DISPATCH_LP(L, (launch_bwd<LP>((const __nv_bfloat16*)qkv, ld_qkv, (const __nv_bfloat16*)o, ld_o,
                                  (const __nv_bfloat16*)d_o, ld_do, lse, (__nv_bfloat16*)dqkv,
                                  ld_dqkv, N, L, H, tok_stride_n, tok_stride_l, causal,

@@ -79,6 +79,7 @@ struct Bwd3Params {
   int ld_o;
   const float* lse;
   int N, L, H, LK, NT, sn, sl, causal, mat_bytes, dbg;
+  int lse_ld;   // elements between two pairs' lse rows (see Fwd2Params)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -303,7 +304,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant
           if ((lane & 7) == 0) sDelta[row] = d;
         }
       };
-      sLse[tid2] = tid2 < p.L ? p.lse[(size_t)pr * p.L + tid2] * kLog2e : 0.f;
+      sLse[tid2] = tid2 < p.L ? p.lse[(size_t)pr * p.lse_ld + tid2] * kLog2e : 0.f;
       mbar_wait(smem_u32(ld_full), it & 1);
       compute_delta(0);
       named_bar_sync(1, 256);
@@ -438,9 +439,10 @@ int encode_rows(CUtensorMap* tm, const void* base, int cols, int ld, int L, int 
 
 int llc_attn_bwd_tc3(const void* qkv, int ld_qkv, const void* o, int ld_o, const void* d_o,
                      int ld_do, const float* lse, void* dqkv, int ld_dqkv, int N, int L, int H,
-                     int sn, int sl, int causal, cudaStream_t st) {
+                     int sn, int sl, int causal, cudaStream_t st, int lse_ld) {
   Bwd3Params p;
   p.o = reinterpret_cast<const __nv_bfloat16*>(o); p.ld_o = ld_o; p.lse = lse;
+  p.lse_ld = lse_ld > 0 ? lse_ld : L;
   p.N = N; p.L = L; p.H = H; p.LK = (L + 15) / 16 * 16; p.NT = (L + 127) / 128;
   p.sn = sn; p.sl = sl; p.causal = causal;
   p.mat_bytes = p.LK * 128;

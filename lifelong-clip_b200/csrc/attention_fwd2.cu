@@ -102,6 +102,8 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int c16) {
 struct Fwd2Params {
   float* lse;
   int N, L, H, LK, NT, causal, dbg;
+  int lse_ld;   // elements between two pairs' lse rows (L, or the full sequence length when this
+                // launch covers the first 256 tokens of a longer sequence: attention_long.cu)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -376,7 +378,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
         if (lane == 0) mbar_arrive(smem_u32(&p_ready[t]));
         TRF((it == 4 || it == 5) && q == 0, (it - 4) * 12 + 8 + t);
         TRF(it == 4, 24 + t * 4 + q);
-        if (p.lse != nullptr && row < p.L) p.lse[(size_t)pr * p.L + row] = m * 0.125f + logf(l);
+        if (p.lse != nullptr && row < p.L) p.lse[(size_t)pr * p.lse_ld + row] = m * 0.125f + logf(l);
         const float inv = l > 0.f ? 1.0f / l : 0.f;
         // epilogue: O row (64 fp32) -> bf16 -> staging tile -> TMA store
         mbar_wait_relaxed(smem_u32(&o_full[t]), tp);
@@ -441,7 +443,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constan
 }  // namespace
 
 int llc_attn_fwd_tc2(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse, int N, int L,
-                     int H, int sn, int sl, int causal, cudaStream_t st) {
+                     int H, int sn, int sl, int causal, cudaStream_t st, int lse_ld) {
   CUtensorMap tm, to;
   // tokens are (sample n, position l) at row n sn + l sl: [columns, L, N] with strides (sl, sn)
   if (int rc = llc_encode_tmap_3d(&tm, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
@@ -455,6 +457,7 @@ int llc_attn_fwd_tc2(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse,
     return rc;
   Fwd2Params p;
   p.lse = lse;
+  p.lse_ld = lse_ld > 0 ? lse_ld : L;
   p.N = N; p.L = L; p.H = H; p.LK = (L + 15) / 16 * 16; p.NT = (L + 127) / 128;
   p.causal = causal;
   static const int dbg = llc_dev_env("LLC_ATTN_DBG") ? atoi(llc_dev_env("LLC_ATTN_DBG")) : 0;

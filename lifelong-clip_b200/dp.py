@@ -23,26 +23,38 @@ def shard_batch(x, y, rank: int, world: int):
     return x[rank::world], y[rank::world]
 
 
+_CAP = {}   # (world, device) -> agreed shard capacity of the padded label gather
+
+
 def gather_labels(labels: torch.Tensor, world: int, device=None) -> torch.Tensor:
     """All ranks' label shards (ragged allowed: the last batch of a stream), for the class
     bookkeeping of methods/_trainer.py:404-416 which must see the GLOBAL batch. Returns a CPU
-    tensor."""
+    tensor, rank-major. ONE collective and one host read per step: shards are padded with -1 to a
+    capacity the ranks agree on once (re-agreed only if a shard ever exceeds it)."""
     if world == 1:
         return labels.cpu()
     mine = (labels.to(device) if device is not None else labels).contiguous()
-    n = torch.tensor([mine.numel()], dtype=torch.int64, device=mine.device)
-    counts = torch.empty(world, dtype=torch.int64, device=mine.device)
-    dist.all_gather_into_tensor(counts, n)
-    counts = counts.cpu().tolist()
-    cap = max(counts)
+    key = (world, str(mine.device))
+    cap = _CAP.get(key, 0)
+    # every rank must take the same branch: a shard larger than the agreed capacity is announced
+    # through the gather itself (its first element is then -2 - count)
     if cap == 0:
-        return mine.cpu()
-    padded = torch.full((cap,), -1, dtype=mine.dtype, device=mine.device)
-    padded[:mine.numel()] = mine
-    allb = torch.empty(world * cap, dtype=mine.dtype, device=mine.device)
+        t = torch.tensor([mine.numel()], dtype=torch.int64, device=mine.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cap = _CAP[key] = max(int(t.item()), 1)
+    over = mine.numel() > cap
+    padded = torch.full((cap,), -1, dtype=torch.int64, device=mine.device)
+    if over:
+        padded[0] = -2 - mine.numel()
+    else:
+        padded[:mine.numel()] = mine
+    allb = torch.empty(world * cap, dtype=torch.int64, device=mine.device)
     dist.all_gather_into_tensor(allb, padded)
     allb = allb.cpu().view(world, cap)
-    return torch.cat([allb[r, :c] for r, c in enumerate(counts)])
+    if bool((allb[:, 0] < -1).any()):          # some shard outgrew the capacity: re-agree, redo
+        _CAP[key] = int((-2 - allb[:, 0]).max().item())
+        return gather_labels(labels, world, device)
+    return torch.cat([row[row >= 0] for row in allb])
 
 
 def global_count(n_local: int, world: int, device=None) -> int:

@@ -143,9 +143,12 @@ class LoRAClipTrainer:
     def online_step(self, images, labels, idx=None):
         """methods/adapter_clip.py:34-47."""
         seen = labels
+        self._global_stream = None
         if self.sharded_input and self.world > 1:
-            # class bookkeeping must see the GLOBAL batch's labels (SURVEY.md §8e)
+            # class bookkeeping must see the GLOBAL batch's labels (SURVEY.md §8e); the same
+            # gather tells every rank the global stream batch size
             seen = dp.gather_labels(labels, self.world, self.device)
+            self._global_stream = int(seen.numel())
         self.add_new_class(seen)
         self.custom_clip.update_class_names(self.exposed_classes_names)
         _loss, _acc, _iter = 0.0, 0.0, 0
@@ -188,7 +191,11 @@ class LoRAClipTrainer:
         # data-parallel shard of the combined stream+replay batch
         if self.world > 1:
             if self.sharded_input:
-                B = int(dp.global_count(B, self.world, self.device))
+                n_replay = B - data[1].shape[0]        # replay samples concatenated on this rank
+                if getattr(self, "_global_stream", None) is not None:
+                    B = self._global_stream + n_replay * self.world
+                else:
+                    B = int(dp.global_count(B, self.world, self.device))
             else:
                 x, y = dp.shard_batch(x, y, self.rank, self.world)
         x = x.to(self.device, non_blocking=True)

@@ -1,6 +1,6 @@
-"""N-GPU CUDA gradients == 1-GPU gradients of the concatenated batch: two
-NCCL ranks, rank::2 shards of one global batch through the fused trainer step, ONE all-reduce of
-the flat LoRA gradient; rank 0 then computes the same global batch alone. Runs only where two
+"""N-GPU CUDA gradients vs 1-GPU gradients: two NCCL ranks, rank::2 shards
+of one global batch through the fused trainer step, ONE all-reduce of the flat LoRA gradient;
+rank 0 then recomputes every shard and the concatenated batch alone. Runs only where two
 CUDA devices are visible (gpurun --gpus 2); bench.py repeats the check at every N > 1
 ("dp_check" in its JSON line)."""
 import os
@@ -50,9 +50,16 @@ def _worker(rank, world, port, out_dir):
     same = all(torch.equal(o, red) for o in other)
     if rank == 0:
         tr.world = 1
+        # every shard again on this one GPU: the all-reduce of two buffers is a + b exactly
+        parts = []
+        for r in range(world):
+            xr, yr = dp.shard_batch(x, y, r, world)
+            tr._step_body(xr.contiguous(), yr.contiguous(), N)
+            parts.append(eng.grad_flat.clone())
         tr._step_body(x, y, N)
         full = eng.grad_flat.clone()
         torch.save({"rel": float((red - full).norm() / full.norm()), "same": same,
+                    "shard_sum_exact": bool(torch.equal(parts[0] + parts[1], red)),
                     "loss": (float(scal[0]), float(tr._scal[0])),
                     "correct": (float(scal[1]), float(tr._scal[1]))},
                    os.path.join(out_dir, "r0.pt"))
@@ -67,8 +74,14 @@ def test_two_gpu_allreduced_gradient_equals_single_gpu(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r = torch.load(os.path.join(tmp_path, "r0.pt"))
     assert r["same"]
-    # identical per-sample arithmetic; only the fp32 order of the token/sample sums differs
-    # (12 tokens x 24 images of largely cancelling terms): measured ~1e-5
-    assert r["rel"] < 2e-4, r["rel"]
+    # the exchange itself is exact: the reduced buffer IS the sum of the per-shard gradients one
+    # GPU computes for the same shards, bit for bit
+    assert r["shard_sum_exact"]
+    # against the concatenated batch on one GPU only the fp32 ORDER of the token sums differs
+    # (per-sample arithmetic is identical, tests/test_fullsize_properties_gpu.py); the LoRA
+    # gradients are sums of largely cancelling terms, so that order shows at ~1e-3 of the result
+    # (measured 9.6e-4 here, 2e-3 at 2 x 128 ViT-B/16 images in bench.py's dp_check) - the same
+    # level a batch permutation moves it, far below the bf16 noise floor of the parity policy
+    assert r["rel"] < 5e-3, r["rel"]
     assert abs(r["loss"][0] - r["loss"][1]) < 1e-5 * abs(r["loss"][1])
     assert r["correct"][0] == r["correct"][1]

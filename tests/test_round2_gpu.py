@@ -664,3 +664,18 @@ def test_maple_prompt_training_step():
     for k, p in m.named_parameters():
         if "prompt_learner" not in k:
             assert torch.equal(p.detach(), frozen[k]), k
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,L,H,seq_first", [
+    (20, 257, 16, False),      # ViT-L/14: more pairs than SMs
+    (3, 257, 16, True),        # the block module's [L, N, D] layout
+    (2, 258, 4, False), (2, 264, 2, False),     # 2 and 8 side tokens
+    (2, 265, 2, False)])       # past the side-kernel range: legacy mma.sync kernels
+def test_attention_longer_than_256_tokens(N, L, H, seq_first):
+    """256 < L <= 264 (ViT-L/14's 257 tokens, BASELINE config 3): the TMEM kernels on the first
+    256 tokens + the log-sum-exp merge / side-term kernels of attention_long.cu, against the
+    oracle's attention core in fp64."""
+    from lifelong_clip_b200 import ops
+    from tests.test_kernels_gpu import _attn_case
+    _attn_case(ops, N, L, H, False, seq_first, seed=300 + L)
