@@ -45,6 +45,10 @@ int llc_check_device(int dev);
  * (GEMM, attention) release their programmatic dependents when every CTA has started its last
  * work item, so the next kernel's prologue overlaps this kernel's tail */
 int llc_set_pdl_trigger(int on);
+/* process-wide traversal order of the row kernels (returns the previous mask): bit 0 - llc_ln_fwd,
+ * bit 1 - llc_ln_bwd walk their rows from the END, so that they start on the rows their producer
+ * (a GEMM walking m-tiles upwards) wrote last and that are still in L2 */
+int llc_set_traversal(int mask);
 /* number of kernels this process has launched through the library (bench.py: gpu_launches) */
 unsigned long long llc_launch_count(void);
 

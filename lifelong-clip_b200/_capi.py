@@ -105,6 +105,7 @@ SIGNATURES = {
     "llc_check_device": (c_int, [c_int]),
     "llc_launch_count": (C.c_ulonglong, []),
     "llc_set_pdl_trigger": (c_int, [c_int]),
+    "llc_set_traversal": (c_int, [c_int]),
     "llc_gemm_ws_bytes": (C.c_size_t, []),
     "llc_gemm_set_stream_k": (c_int, [c_int]),
     "llc_gemm_bf16_tn": (c_int, [c_void, c_int, c_void, c_int, c_int, c_int, c_int,
@@ -198,6 +199,8 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if os.environ.get("LLC_STREAM_K") == "0":     # A/B measurements of the GEMM schedule
         lib.llc_gemm_set_stream_k(0)
+    if os.environ.get("LLC_TRAVERSAL") is not None:
+        lib.llc_set_traversal(int(os.environ["LLC_TRAVERSAL"]))
     if os.environ.get("LLC_PDL_TRIGGER") is not None:
         lib.llc_set_pdl_trigger(int(os.environ["LLC_PDL_TRIGGER"]))
     _lib = lib

@@ -415,9 +415,16 @@ class AdapterCLIP(nn.Module):
         self._add_mask = None if mask is None else mask.detach().float().to(dev).contiguous()
 
     def update_class_names(self, new_class_names):
-        """models/adapter_clip.py:81-92 (bookkeeping only; returns None like the reference)."""
+        """models/adapter_clip.py:81-92 (bookkeeping only; returns None like the reference).
+        Membership through a set: the reference's `c not in list` is O(classes^2) per step."""
+        known = getattr(self, "_known_names", None)
+        if known is None or len(known) != len(self.current_class_names):
+            known = self._known_names = set(self.current_class_names)
+        if len(new_class_names) == len(known) and all(c in known for c in new_class_names):
+            return None
         for c in new_class_names:
-            if c not in self.current_class_names:
+            if c not in known:
+                known.add(c)
                 self.current_class_names.append(c)
         return None
 

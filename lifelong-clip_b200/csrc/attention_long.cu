@@ -55,6 +55,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 }
 
 // smem: ks[r][64] | vs[r][64] | sc[L] | part[kWarps][64] | red[kWarps]
+template <int R>   // R >= r: compile-time bound of the side-token count (1, 2, 4, 8)
 __global__ void __launch_bounds__(kThreads)
 attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, __nv_bfloat16* __restrict__ o,
                      int ld_o, float* __restrict__ lse, int L, int H, int sn, int sl) {
@@ -78,37 +79,61 @@ attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, __nv_bfl
     vs[i] = __bfloat162float(qrow(L0 + j)[2 * D + d]);
   }
   __syncthreads();
-  // ---- queries < 256: merge the side keys into the block kernel's (o_A, lse_A)
-  for (int q = warp; q < L0; q += kWarps) {
-    const float2 qv = ld2(qrow(q) + 2 * lane);
-    const float2 oa = ld2(orow(q) + 2 * lane);
-    const float la = lse_p[q];
-    float s[kMaxSide];
-    float m = la;
-    for (int j = 0; j < r; ++j) {
-      s[j] = 0.125f * warp_sum2(qv.x * ks[j * HD + 2 * lane] + qv.y * ks[j * HD + 2 * lane + 1]);
-      m = fmaxf(m, s[j]);
+  // ---- queries < 256: merge the side keys into the block kernel's (o_A, lse_A). kU rows per
+  // warp iteration: their loads are all in flight before the first shuffle chain starts
+  constexpr int kU = 4;
+  for (int q0 = warp * kU; q0 < L0; q0 += kWarps * kU) {
+    float2 qv[kU], oa[kU];
+    float la[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      qv[u] = ld2(qrow(q0 + u) + 2 * lane);
+      oa[u] = ld2(orow(q0 + u) + 2 * lane);
+      la[u] = lse_p[q0 + u];
     }
-    const float wa = __expf(la - m);
-    float den = wa, a0 = wa * oa.x, a1 = wa * oa.y;
-    for (int j = 0; j < r; ++j) {
-      const float w = __expf(s[j] - m);
-      den += w;
-      a0 = fmaf(w, vs[j * HD + 2 * lane], a0);
-      a1 = fmaf(w, vs[j * HD + 2 * lane + 1], a1);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      float s[R];
+      float m = la[u];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        s[j] = -INFINITY;
+        if (j < r) {
+          s[j] = 0.125f * warp_sum2(qv[u].x * ks[j * HD + 2 * lane] +
+                                    qv[u].y * ks[j * HD + 2 * lane + 1]);
+          m = fmaxf(m, s[j]);
+        }
+      }
+      const float wa = __expf(la[u] - m);
+      float den = wa, a0 = wa * oa[u].x, a1 = wa * oa[u].y;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (j < r) {
+          const float w = __expf(s[j] - m);
+          den += w;
+          a0 = fmaf(w, vs[j * HD + 2 * lane], a0);
+          a1 = fmaf(w, vs[j * HD + 2 * lane + 1], a1);
+        }
+      }
+      const float inv = 1.0f / den;
+      *reinterpret_cast<uint32_t*>(orow(q0 + u) + 2 * lane) = pack_bf16(a0 * inv, a1 * inv);
+      if (lane == 0) lse_p[q0 + u] = m + __logf(den);
     }
-    const float inv = 1.0f / den;
-    *reinterpret_cast<uint32_t*>(orow(q) + 2 * lane) = pack_bf16(a0 * inv, a1 * inv);
-    if (lane == 0) lse_p[q] = m + __logf(den);
   }
   // ---- side queries: full rows over all L keys
   for (int i = 0; i < r; ++i) {
     const float2 qv = ld2(qrow(L0 + i) + 2 * lane);
     __syncthreads();
-    for (int k = warp; k < L; k += kWarps) {
-      const float2 kv = ld2(qrow(k) + D + 2 * lane);
-      const float v = 0.125f * warp_sum2(qv.x * kv.x + qv.y * kv.y);
-      if (lane == 0) sc[k] = v;
+    for (int k0 = warp * kU; k0 < L; k0 += kWarps * kU) {
+      float2 kv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        kv[u] = k0 + u < L ? ld2(qrow(k0 + u) + D + 2 * lane) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const float v = 0.125f * warp_sum2(qv.x * kv[u].x + qv.y * kv[u].y);
+        if (lane == 0 && k0 + u < L) sc[k0 + u] = v;
+      }
     }
     __syncthreads();
     float m = -INFINITY;
@@ -122,6 +147,7 @@ attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, __nv_bfl
     }
     z = block_reduce(z, red, false);
     float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
     for (int k = warp; k < L; k += kWarps) {
       const float2 vv = ld2(qrow(k) + 2 * D + 2 * lane);
       a0 = fmaf(sc[k], vv.x, a0);
@@ -142,6 +168,7 @@ attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, __nv_bfl
 
 // smem: ks | vs | qs[r][64] | gos[r][64] (dO of side queries) | dks[r][64] | dvs[r][64]
 //       | dqs[r][64] | part[kWarps][3][64] | lse_s[r] | delta_s[r]
+template <int R>
 __global__ void __launch_bounds__(kThreads)
 attn_long_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv,
                      const __nv_bfloat16* __restrict__ o, int ld_o,
@@ -183,36 +210,48 @@ attn_long_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv,
   }
   __syncthreads();
   // ---- (query < 256) x (side key): dQ_q += dS k_s / 8 (row q: this warp only), dK_s, dV_s sums
-  float ak[kMaxSide][2], av[kMaxSide][2];
+  float ak[R][2], av[R][2];
 #pragma unroll
-  for (int j = 0; j < kMaxSide; ++j) ak[j][0] = ak[j][1] = av[j][0] = av[j][1] = 0.f;
-  for (int q = warp; q < L0; q += kWarps) {
-    const float2 qv = ld2(qrow(q) + 2 * lane);
-    const float2 gv = ld2(d_o + (tok0 + (size_t)q * sl) * ld_do + h * HD + 2 * lane);
-    const float2 ov = ld2(o + (tok0 + (size_t)q * sl) * ld_o + h * HD + 2 * lane);
-    const float dl = warp_sum2(gv.x * ov.x + gv.y * ov.y);
-    const float lq = lse_p[q];
-    float2 dq = ld2(grow(q) + 2 * lane);
+  for (int j = 0; j < R; ++j) ak[j][0] = ak[j][1] = av[j][0] = av[j][1] = 0.f;
+  constexpr int kU = 4;
+  for (int q0 = warp * kU; q0 < L0; q0 += kWarps * kU) {
+    float2 qv[kU], gv[kU], ov[kU], dq[kU];
+    float lq[kU];
 #pragma unroll
-    for (int j = 0; j < kMaxSide; ++j) {
-      if (j < r) {
-        const float k0 = ks[j * HD + 2 * lane], k1 = ks[j * HD + 2 * lane + 1];
-        const float v0 = vs[j * HD + 2 * lane], v1 = vs[j * HD + 2 * lane + 1];
-        const float s = 0.125f * warp_sum2(qv.x * k0 + qv.y * k1);
-        const float dp = warp_sum2(gv.x * v0 + gv.y * v1);
-        const float p = __expf(s - lq);
-        const float ds = p * (dp - dl) * 0.125f;
-        dq.x = fmaf(ds, k0, dq.x);
-        dq.y = fmaf(ds, k1, dq.y);
-        ak[j][0] = fmaf(ds, qv.x, ak[j][0]);
-        ak[j][1] = fmaf(ds, qv.y, ak[j][1]);
-        av[j][0] = fmaf(p, gv.x, av[j][0]);
-        av[j][1] = fmaf(p, gv.y, av[j][1]);
-      }
+    for (int u = 0; u < kU; ++u) {
+      const int q = q0 + u;
+      qv[u] = ld2(qrow(q) + 2 * lane);
+      gv[u] = ld2(d_o + (tok0 + (size_t)q * sl) * ld_do + h * HD + 2 * lane);
+      ov[u] = ld2(o + (tok0 + (size_t)q * sl) * ld_o + h * HD + 2 * lane);
+      dq[u] = ld2(grow(q) + 2 * lane);
+      lq[u] = lse_p[q];
     }
-    *reinterpret_cast<uint32_t*>(grow(q) + 2 * lane) = pack_bf16(dq.x, dq.y);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const float dl = warp_sum2(gv[u].x * ov[u].x + gv[u].y * ov[u].y);
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (j < r) {
+          const float k0 = ks[j * HD + 2 * lane], k1 = ks[j * HD + 2 * lane + 1];
+          const float v0 = vs[j * HD + 2 * lane], v1 = vs[j * HD + 2 * lane + 1];
+          const float s = 0.125f * warp_sum2(qv[u].x * k0 + qv[u].y * k1);
+          const float dp = warp_sum2(gv[u].x * v0 + gv[u].y * v1);
+          const float p = __expf(s - lq[u]);
+          const float ds = p * (dp - dl) * 0.125f;
+          dq[u].x = fmaf(ds, k0, dq[u].x);
+          dq[u].y = fmaf(ds, k1, dq[u].y);
+          ak[j][0] = fmaf(ds, qv[u].x, ak[j][0]);
+          ak[j][1] = fmaf(ds, qv[u].y, ak[j][1]);
+          av[j][0] = fmaf(p, gv[u].x, av[j][0]);
+          av[j][1] = fmaf(p, gv[u].y, av[j][1]);
+        }
+      }
+      *reinterpret_cast<uint32_t*>(grow(q0 + u) + 2 * lane) = pack_bf16(dq[u].x, dq[u].y);
+    }
   }
-  for (int j = 0; j < r; ++j) {   // cross-warp sums of the side keys' dK, dV (fixed order)
+#pragma unroll
+  for (int j = 0; j < R; ++j) {   // cross-warp sums of the side keys' dK, dV (fixed order)
+    if (j >= r) break;            // uniform
     part[(warp * 3 + 0) * HD + 2 * lane] = ak[j][0];
     part[(warp * 3 + 0) * HD + 2 * lane + 1] = ak[j][1];
     part[(warp * 3 + 1) * HD + 2 * lane] = av[j][0];
@@ -234,25 +273,37 @@ attn_long_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv,
     const float g0 = gos[i * HD + 2 * lane], g1 = gos[i * HD + 2 * lane + 1];
     const float li = lse_s[i], dl = delta_s[i];
     float a0 = 0.f, a1 = 0.f;
-    for (int k = warp; k < L; k += kWarps) {
-      const float2 kv = ld2(qrow(k) + D + 2 * lane);
-      const float2 vv = ld2(qrow(k) + 2 * D + 2 * lane);
-      const float s = 0.125f * warp_sum2(q0 * kv.x + q1 * kv.y);
-      const float dp = warp_sum2(g0 * vv.x + g1 * vv.y);
-      const float p = __expf(s - li);
-      const float ds = p * (dp - dl) * 0.125f;
-      a0 = fmaf(ds, kv.x, a0);
-      a1 = fmaf(ds, kv.y, a1);
-      if (k < L0) {
-        float2 dk = ld2(grow(k) + D + 2 * lane), dv = ld2(grow(k) + 2 * D + 2 * lane);
-        dk.x = fmaf(ds, q0, dk.x); dk.y = fmaf(ds, q1, dk.y);
-        dv.x = fmaf(p, g0, dv.x); dv.y = fmaf(p, g1, dv.y);
-        *reinterpret_cast<uint32_t*>(grow(k) + D + 2 * lane) = pack_bf16(dk.x, dk.y);
-        *reinterpret_cast<uint32_t*>(grow(k) + 2 * D + 2 * lane) = pack_bf16(dv.x, dv.y);
-      } else {          // a side key: exactly one warp sees (i, k), accumulate in shared memory
-        const int j = k - L0;
-        dks[j * HD + 2 * lane] += ds * q0; dks[j * HD + 2 * lane + 1] += ds * q1;
-        dvs[j * HD + 2 * lane] += p * g0; dvs[j * HD + 2 * lane + 1] += p * g1;
+    for (int k0 = warp * kU; k0 < L; k0 += kWarps * kU) {
+      float2 kv[kU], vv[kU], dk[kU], dv[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int k = k0 + u;
+        const bool in = k < L;
+        kv[u] = in ? ld2(qrow(k) + D + 2 * lane) : make_float2(0.f, 0.f);
+        vv[u] = in ? ld2(qrow(k) + 2 * D + 2 * lane) : make_float2(0.f, 0.f);
+        dk[u] = k < L0 ? ld2(grow(k) + D + 2 * lane) : make_float2(0.f, 0.f);
+        dv[u] = k < L0 ? ld2(grow(k) + 2 * D + 2 * lane) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int k = k0 + u;
+        const float s = 0.125f * warp_sum2(q0 * kv[u].x + q1 * kv[u].y);
+        const float dp = warp_sum2(g0 * vv[u].x + g1 * vv[u].y);
+        if (k >= L) continue;                     // warp-uniform
+        const float p = __expf(s - li);
+        const float ds = p * (dp - dl) * 0.125f;
+        a0 = fmaf(ds, kv[u].x, a0);
+        a1 = fmaf(ds, kv[u].y, a1);
+        if (k < L0) {
+          dk[u].x = fmaf(ds, q0, dk[u].x); dk[u].y = fmaf(ds, q1, dk[u].y);
+          dv[u].x = fmaf(p, g0, dv[u].x); dv[u].y = fmaf(p, g1, dv[u].y);
+          *reinterpret_cast<uint32_t*>(grow(k) + D + 2 * lane) = pack_bf16(dk[u].x, dk[u].y);
+          *reinterpret_cast<uint32_t*>(grow(k) + 2 * D + 2 * lane) = pack_bf16(dv[u].x, dv[u].y);
+        } else {        // a side key: exactly one warp sees (i, k), accumulate in shared memory
+          const int j = k - L0;
+          dks[j * HD + 2 * lane] += ds * q0; dks[j * HD + 2 * lane + 1] += ds * q1;
+          dvs[j * HD + 2 * lane] += p * g0; dvs[j * HD + 2 * lane + 1] += p * g1;
+        }
       }
     }
     part[(warp * 3 + 2) * HD + 2 * lane] = a0;
@@ -289,9 +340,13 @@ int llc_attn_fwd_long(const void* qkv, int ld_qkv, void* o, int ld_o, float* lse
   const size_t smem = (size_t)(2 * r * HD + L + kWarps * HD + kWarps) * sizeof(float);
   LLC_PROF_BEGIN(LLC_K_ATTN_FWD, N * H, L, 2, 4.0 * N * H * (double)(2 * r) * L * HD,
                  2.0 * N * H * (double)L * HD * (3 + 2 * r), st);
-  LLC_CUDA(llc_launch_pdl(attn_long_fwd_kernel, dim3(N * H), dim3(kThreads), smem, st,
-                          reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv,
-                          reinterpret_cast<__nv_bfloat16*>(o), ld_o, lse, L, H, sn, sl));
+#define LLC_LONG_FWD(RR)                                                                      \
+  LLC_CUDA(llc_launch_pdl(attn_long_fwd_kernel<RR>, dim3(N * H), dim3(kThreads), smem, st,     \
+                          reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv,                 \
+                          reinterpret_cast<__nv_bfloat16*>(o), ld_o, lse, L, H, sn, sl))
+  if (r == 1) LLC_LONG_FWD(1); else if (r == 2) LLC_LONG_FWD(2);
+  else if (r <= 4) LLC_LONG_FWD(4); else LLC_LONG_FWD(8);
+#undef LLC_LONG_FWD
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("attn_long_fwd_kernel");
@@ -308,11 +363,15 @@ int llc_attn_bwd_long(const void* qkv, int ld_qkv, const void* o, int ld_o, cons
   const size_t smem = (size_t)(7 * r * HD + kWarps * 3 * HD + 2 * kMaxSide) * sizeof(float);
   LLC_PROF_BEGIN(LLC_K_ATTN_BWD, N * H, L, 2, 8.0 * N * H * (double)(2 * r) * L * HD,
                  2.0 * N * H * (double)L * HD * (6 + 4 * r), st);
-  LLC_CUDA(llc_launch_pdl(attn_long_bwd_kernel, dim3(N * H), dim3(kThreads), smem, st,
-                          reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv,
-                          reinterpret_cast<const __nv_bfloat16*>(o), ld_o,
-                          reinterpret_cast<const __nv_bfloat16*>(d_o), ld_do, lse,
-                          reinterpret_cast<__nv_bfloat16*>(dqkv), ld_dqkv, L, H, sn, sl));
+#define LLC_LONG_BWD(RR)                                                                      \
+  LLC_CUDA(llc_launch_pdl(attn_long_bwd_kernel<RR>, dim3(N * H), dim3(kThreads), smem, st,     \
+                          reinterpret_cast<const __nv_bfloat16*>(qkv), ld_qkv,                 \
+                          reinterpret_cast<const __nv_bfloat16*>(o), ld_o,                     \
+                          reinterpret_cast<const __nv_bfloat16*>(d_o), ld_do, lse,             \
+                          reinterpret_cast<__nv_bfloat16*>(dqkv), ld_dqkv, L, H, sn, sl))
+  if (r == 1) LLC_LONG_BWD(1); else if (r == 2) LLC_LONG_BWD(2);
+  else if (r <= 4) LLC_LONG_BWD(4); else LLC_LONG_BWD(8);
+#undef LLC_LONG_BWD
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("attn_long_bwd_kernel");

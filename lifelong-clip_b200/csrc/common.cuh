@@ -79,7 +79,8 @@ void llc_prof_end(cudaStream_t st);
 // pdl_wait() until the predecessor has completed and its writes are visible. Saves the launch
 // latency + tail + prologue (~8 us) between the ~260 kernels of a step. LLC_NO_PDL=1 disables it.
 extern int g_llc_pdl;
-extern int g_llc_pdl_trigger;   // llc_set_pdl_trigger: persistent kernels trigger dependents early
+extern int g_llc_pdl_trigger;
+extern int g_llc_traversal;     // llc_set_traversal: bit 0 ln_fwd, bit 1 ln_bwd walk rows from the end   // llc_set_pdl_trigger: persistent kernels trigger dependents early
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 cudaError_t llc_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,

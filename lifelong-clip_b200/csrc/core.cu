@@ -11,6 +11,12 @@ static thread_local char g_err[512] = "";
 unsigned long long g_llc_launches = 0;
 int g_llc_pdl = llc_dev_env("LLC_NO_PDL") == nullptr;
 int g_llc_pdl_trigger = 0;
+int g_llc_traversal = 0;
+extern "C" int llc_set_traversal(int mask) {
+  const int old = g_llc_traversal;
+  g_llc_traversal = mask;
+  return old;
+}
 extern "C" int llc_set_pdl_trigger(int on) {
   const int old = g_llc_pdl_trigger;
   g_llc_pdl_trigger = on != 0;

@@ -19,12 +19,16 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
               const float* __restrict__ beta, int T, __nv_bfloat16* __restrict__ y, int ld_y,
-              const float* __restrict__ lora_A, int r) {
+              const float* __restrict__ lora_A, int r, int rev) {
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
+  int row = blockIdx.x * 8 + warp;
   pdl_wait();
   if (row >= T) return;
+  // rev: walk the rows from the END. The producer (a GEMM walking its m-tiles upwards) wrote the
+  // last rows last: they are the ones still in L2 (x is larger than L2), and this kernel's own
+  // output then has its FIRST rows freshest for the GEMM that consumes it upwards.
+  if (rev) row = T - 1 - row;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld_x);
   float4 v[NV];
   float s = 0.f;
@@ -91,12 +95,13 @@ __global__ void __launch_bounds__(256, NV <= 6 ? 3 : 2)
 ln_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ dy, int ld_dy, const float* dx_in, float* dx_out,
               int T, __nv_bfloat16* __restrict__ dxb, int ld_dxb,
-              const float* __restrict__ lora_B, int r, float scale) {
+              const float* __restrict__ lora_B, int r, float scale, int rev) {
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
+  int row = blockIdx.x * 8 + warp;
   pdl_wait();
   if (row >= T) return;
+  if (rev) row = T - 1 - row;   // see ln_fwd_kernel
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * ld_x);
   const uint2* dyr = reinterpret_cast<const uint2*>(dy + (size_t)row * ld_dy);
   const float4* dir = dx_in ? reinterpret_cast<const float4*>(dx_in + (size_t)row * D) : nullptr;
@@ -661,7 +666,8 @@ extern "C" int llc_ln_fwd(const float* x, int ld_x, const float* gamma, const fl
   cudaStream_t st = (cudaStream_t)stream;
   LLC_PROF_BEGIN(LLC_K_LN_FWD, T, D, 0, 0.0, 6.0 * T * D, st);
   DISPATCH_NV(D, (llc_launch_pdl(ln_fwd_kernel<NV>, dim3((T + 7) / 8), dim3(256), 0, st, x, ld_x,
-                                 gamma, beta, T, (__nv_bfloat16*)y, ld_y, lora_A, r)));
+                                 gamma, beta, T, (__nv_bfloat16*)y, ld_y, lora_A, r,
+                                 g_llc_traversal & 1)));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("ln_fwd_kernel");
@@ -684,7 +690,8 @@ extern "C" int llc_ln_bwd(const float* x, int ld_x, const float* gamma, const vo
                  (double)T * D * (4 + 2 + (dx_in ? 4 : 0) + 4 + (dxb ? 2 : 0)), st);
   DISPATCH_NV(D, (llc_launch_pdl(ln_bwd_kernel<NV>, dim3((T + 7) / 8), dim3(256), 0, st, x, ld_x,
                                  gamma, (const __nv_bfloat16*)dy, ld_dy, dx_in, dx_out, T,
-                                 (__nv_bfloat16*)dxb, ld_dxb, lora_B, r, scale)));
+                                 (__nv_bfloat16*)dxb, ld_dxb, lora_B, r, scale,
+                                 (g_llc_traversal >> 1) & 1)));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("ln_bwd_kernel");
