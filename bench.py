@@ -87,15 +87,55 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md). NVML in a
+    sampling thread (every 5 ms, so that even the ~90 ms region of a 32-image-per-GPU run gets a
+    dozen samples); falls back to `nvidia-smi -lms 50` when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/llc_clocks_{os.getpid()}.csv"
+        self.thread, self.stop_flag, self.samples = None, False, []
+
+    def _nvml_loop(self, nv, handle):
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(handle) / 1000.0
+                except Exception:
+                    pw = 0.0
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((float(sm), pw, [n for n, bit in names if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(
@@ -105,6 +145,19 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            sm = [s[0] for s in self.samples]
+            pw = [s[1] for s in self.samples]
+            reasons = sorted({r for s in self.samples for r in s[2]})
+            lo = (min(pw) + max(pw)) / 2
+            load = [a for a, p in zip(sm, pw) if p >= lo] or sm
+            return {"sm_mhz": statistics.median(load), "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(pw), "samples": len(sm), "reasons": reasons,
+                    "how": "NVML, 5 ms period, during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -134,7 +187,8 @@ class ClockSampler:
         lo = (min(pw) + max(pw)) / 2
         load = [s for s, p in zip(sm, pw) if p >= lo] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx),
-                "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons),
+                "how": "nvidia-smi -lms 50 during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -117,12 +117,28 @@ def run_reference(cfg: vo.VitCfg, n: int, num_classes: int, seed: int, slim: boo
         out["feat"] = np.concatenate(feats)
         out["logits"] = np.concatenate(logit_l)
     ng = 0
+    total = sum(p.grad.numel() for p in clip.parameters() if p.grad is not None)
     for k, p in clip.named_parameters():
         if p.grad is not None:
             assert "lora" in k
-            out["grad:" + k] = p.grad.numpy()
+            g = p.grad.numpy()
+            if total > 400_000:     # ViT-L/14: per-tensor scaled fp16 (6e-4 relative rounding)
+                sc = float(np.abs(g).max()) or 1.0
+                out["grad16:" + k] = (g / sc).astype(np.float16)
+                out["gscale:" + k] = np.float32(sc)
+            else:
+                out["grad:" + k] = g
             ng += 1
     assert ng == 4 * cfg.layers, ng
+    return out
+
+
+def load_grads(gold) -> dict:
+    """name -> fp32 gradient from a golden file (undoes the per-tensor fp16 packing)."""
+    out = {k[5:]: gold[k] for k in gold.files if k.startswith("grad:")}
+    for k in gold.files:
+        if k.startswith("grad16:"):
+            out[k[7:]] = gold[k].astype(np.float32) * float(gold["gscale:" + k[7:]])
     return out
 
 
@@ -136,6 +152,8 @@ BIG_CASES = {
     "vitb16_b16": (vo.VIT_B16, 16, 100, 7),
     "vitb16_b32": (vo.VIT_B16, 32, 100, 7),
     "vitb16_b256": (vo.VIT_B16, 256, 100, 7),
+    # BASELINE config 3 geometry: all 24 layers of ViT-L/14 (257 tokens), 200 classes
+    "vitl14": (vo.VIT_L14, 3, 200, 9),
 }
 
 

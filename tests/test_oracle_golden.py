@@ -125,3 +125,25 @@ def test_maple_oracle_matches_reference_golden(name, golden_dir):
     for k, v in want.items():
         kk = k if k.startswith("prompt_learner.") else "prompt_learner." + k
         assert _rel(out["grads"][kk], v) < 2e-3, (k, _rel(out["grads"][kk], v))
+
+
+def test_vitl14_oracle_matches_reference_golden(golden_dir):
+    """BASELINE config 3 geometry: all 24 layers of ViT-L/14 (257 tokens, width 1024, 16 heads,
+    embed 768) through the reference's own classes vs the oracle in fp32."""
+    from tests.golden.make_golden import BIG_CASES, load_grads
+    cfg, n, c, seed = BIG_CASES["vitl14"]
+    gold = np.load(os.path.join(golden_dir, "ref_vitl14.npz"))
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = vo.synth_weights(cfg, seed)
+    images, labels = synth_inputs(cfg, n, c, seed + 100)
+    text = vo.synth_text_features(c, cfg.embed_dim, seed + 200)
+    out = vo.online_step_oracle(images, labels, w, text, cfg,
+                                logit_scale_exp=float(gold["logit_scale_exp"]),
+                                dtype=torch.float32)
+    assert _rel(out["probs"], gold["probs"]) < 2e-5
+    assert abs(float(out["loss"]) - float(gold["loss"])) < 1e-5
+    np.testing.assert_array_equal(out["pred"], gold["pred"])
+    want = load_grads(gold)
+    assert set(want) == set(out["grads"]) and len(want) == 96
+    worst = max(_rel(out["grads"][k], v) for k, v in want.items())
+    assert worst < 2e-3, worst      # fp16-packed fixture: 6e-4 rounding

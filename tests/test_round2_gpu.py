@@ -679,3 +679,29 @@ def test_attention_longer_than_256_tokens(N, L, H, seq_first):
     from lifelong_clip_b200 import ops
     from tests.test_kernels_gpu import _attn_case
     _attn_case(ops, N, L, H, False, seq_first, seed=300 + L)
+
+
+def test_vitl14_full_depth_matches_reference_golden(golden_dir):
+    """BASELINE config 3: all 24 layers of ViT-L/14 on the production path (257-token attention on
+    the TMEM kernels + side kernels, class-token-only last block, analytic loss gradient) against
+    the reference's own modules."""
+    from tests.golden.make_golden import load_grads
+    cfg, n, c, seed = BIG_CASES["vitl14"]
+    gold = np.load(os.path.join(golden_dir, "ref_vitl14.npz"))
+    want = {"probs": gold["probs"], "loss": gold["loss"], "pred": gold["pred"],
+            "grads": load_grads(gold)}
+    w = vo.synth_weights(cfg, seed)
+    images, labels = synth_inputs(cfg, n, c, seed + 100)
+    text = vo.synth_text_features(c, cfg.embed_dim, seed + 200)
+    m = build_model(cfg, w)
+    eng = m.model.visual.engine()
+    eng.forward(torch.from_numpy(images).cuda(), training=True)
+    head = eng.head(torch.from_numpy(text).cuda(), float(gold["logit_scale_exp"]),
+                    labels=torch.from_numpy(labels).cuda())
+    eng.backward_from_head(head)
+    torch.cuda.synchronize()
+    names = [k for k in w if "lora" in k]
+    grads = {k: g.cpu().numpy() for k, g in zip(names, eng.lora_grad_views)}
+    # 3 images through 24 layers: little averaging (cf. test_single_image_batches)
+    check_step(head.probs.cpu().numpy(), float(head.loss_rows.sum()), head.pred.cpu().numpy(),
+               grads, want, cfg, tol=2e-2)
