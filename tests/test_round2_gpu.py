@@ -705,3 +705,31 @@ def test_vitl14_full_depth_matches_reference_golden(golden_dir):
     # 3 images through 24 layers: little averaging (cf. test_single_image_batches)
     check_step(head.probs.cpu().numpy(), float(head.loss_rows.sum()), head.pred.cpu().numpy(),
                grads, want, cfg, tol=2e-2)
+
+
+def test_online_evaluate_with_gpu_test_transform():
+    """online_evaluate fed RAW uint8 batches with GpuTransform.test as test_transform (Resize +
+    Normalize fused into the tower's first kernel) equals evaluating the pre-transformed images."""
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+    from lifelong_clip_b200.transform import GpuTransform
+    cfg = vo.VitCfg(image_size=64, patch=16, width=128, layers=2, heads=2, embed_dim=64)
+    c = 10
+    mean, std = (0.5, 0.45, 0.4), (0.25, 0.2, 0.3)
+    m = build_model(cfg, vo.synth_weights(cfg, 3))
+    names = [f"class{i}" for i in range(c)]
+    m.set_text_features(names, torch.from_numpy(vo.synth_text_features(c, cfg.embed_dim, 4)))
+    g = torch.Generator().manual_seed(0)
+    raw = torch.randint(0, 256, (37, 3, 16, 16), generator=g, dtype=torch.uint8)
+    y = torch.randint(0, c, (37,), generator=g)
+    tf = GpuTransform.test(64, mean, std)
+    tr = LoRAClipTrainer(m, names, n_classes=c, n_tasks=10, visible_classes="all",
+                         test_transform=tf)
+    tr._total_classes = c
+    tr.online_after_task(0)
+    fused = tr.online_evaluate([(raw[:20], y[:20]), (raw[20:], y[20:])], 0)
+    tr.test_transform = lambda x: x
+    pre = tf(raw.cuda())
+    plain = tr.online_evaluate([(pre[:20], y[:20]), (pre[20:], y[20:])], 0)
+    assert float(fused["avg_acc"]) == float(plain["avg_acc"])
+    assert fused["confusion_matrix"] == plain["confusion_matrix"]
+    assert fused["task_acc"] == plain["task_acc"]
