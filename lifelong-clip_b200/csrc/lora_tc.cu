@@ -213,7 +213,7 @@ constexpr uint32_t kFUCol = 288;           // U accumulators behind the column s
 __global__ void __launch_bounds__(kThreads, 1)
 lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmF,
                      const __nv_bfloat16* __restrict__ w, int ld_w, __nv_bfloat16* __restrict__ U,
-                     int ld_u, int T, int C, int R, float* __restrict__ partial) {
+                     int ld_u, int T, int C, int R, float* __restrict__ partial, int rev) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~(uintptr_t)1023);
@@ -263,8 +263,10 @@ lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint32_t fb = smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_u32(sX + stage * kFStage);
           mbar_expect_tx(fb, kFStage);
-          tma_load_2d(sa, &tmX, fb, ct * 128, slab * 128);
-          tma_load_2d(sa + 128 * 128, &tmX, fb, ct * 128 + 64, slab * 128);
+          // rev: walk the slabs downwards (llc_set_traversal bit 2)
+          const int srow = (rev ? nslabs - 1 - slab : slab) * 128;
+          tma_load_2d(sa, &tmX, fb, ct * 128, srow);
+          tma_load_2d(sa + 128 * 128, &tmX, fb, ct * 128 + 64, srow);
           // the factor rows of these columns ride along (72 KB in all: L2-resident)
           tma_load_2d(sa + kFXTile, &tmF, fb, ct * 128, 0);
           tma_load_2d(sa + kFXTile + 16 * 128, &tmF, fb, ct * 128 + 64, 0);
@@ -314,7 +316,7 @@ lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
     // this thread's w row of a slab: two 16 B pieces, TMA's 128 B swizzle (MN-major operand)
     auto load_w = [&](int slab, int buf) {
-      const int t = slab * 128 + row;
+      const int t = (rev ? nslabs - 1 - slab : slab) * 128 + row;
       const __nv_bfloat16* src = w + (size_t)(t < T ? t : 0) * ld_w;
       const uint32_t nbytes = t < T ? 16u : 0u;
       const uint32_t dst = smem_u32(sW + buf * kFWTile + row * 128);
@@ -348,7 +350,7 @@ lora_fused_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&u_free[wb]));
-      const int t = slab * 128 + row;
+      const int t = (rev ? nslabs - 1 - slab : slab) * 128 + row;
       if (t < T) {
         uint4* dst = reinterpret_cast<uint4*>(U + (size_t)t * ld_u);
         dst[0] = make_uint4(pack_bf16(__uint_as_float(v[0]), __uint_as_float(v[1])),
@@ -418,7 +420,8 @@ int llc_lora_fused_tc(const void* X, int ld_x, int T, int C, int R, const void* 
   LLC_PROF_BEGIN(LLC_K_LORA_SIDE, T, C, 3, 4.0 * T * C * 16, 2.0 * T * C, st);
   LLC_CUDA(llc_launch_pdl(lora_fused_tc_kernel, dim3(grid), dim3(kThreads), (size_t)smem, st, tm, tf,
                           reinterpret_cast<const __nv_bfloat16*>(w), ld_w,
-                          reinterpret_cast<__nv_bfloat16*>(U), ld_u, T, C, R, partial));
+                          reinterpret_cast<__nv_bfloat16*>(U), ld_u, T, C, R, partial,
+                          (g_llc_traversal >> 2) & 1));
   LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("lora_fused_tc_kernel");
