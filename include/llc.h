@@ -377,6 +377,64 @@ int llc_mha_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_b
                      const llc_block_bwd_bufs* s, int N, int L, int tok_stride_n, int tok_stride_l,
                      int causal, int need_dx_in, void* stream);
 
+/* ---- bottleneck adapter of the adapter-clip method (models/clip/adapter.py:11-73) --------------
+ * adapter(y) = y + scale * (dropout(relu(y W_d^T + b_d)) W_u^T + b_u), W_d [64, D], W_u [D, 64]
+ * (down_proj is hard-coded 64 wide, adapter.py:39; scale = 0.1, dropout = 0.1, init "lora",
+ * model.py:432-439). The live fp32 parameters are the module's; llc_adapter_refresh prepares the
+ * bf16 operands from them (after every optimizer step). */
+#define LLC_ADAPTER_DIM 64
+typedef struct llc_adapter {
+  float scale;             /* adapter_scalar */
+  float dropout;           /* p, applied when the call says training */
+  unsigned long long seed; /* dropout stream of this call (ignored with an explicit mask) */
+  const float *down_w, *down_b, *up_w, *up_b;   /* [64, D] [64] [D, 64] [D] */
+  float *g_down_w, *g_down_b, *g_up_w, *g_up_b; /* gradient slots (backward only) */
+  void *wd, *wu, *wdT, *wuT;                    /* bf16 [64,D] [D,64] [D,64] [64,D] (wu, wuT scaled) */
+  float* bu_s;                                  /* [D] scale * b_u */
+} llc_adapter;
+int llc_adapter_refresh(const llc_adapter* ad, int D, void* stream);
+/* floats of the `partial` scratch of llc_adapter_backward */
+size_t llc_adapter_partial_floats(int D);
+/* out fp32 [T, D] = [resid +] [y +] scale * up(drop(relu(down(y)))): y bf16 [T, ld_y]; resid fp32
+ * [T, D] or NULL; a bf16 [T, 64] receives the bottleneck after ReLU and dropout (saved for the
+ * backward). mask: optional uint8 [T, 64] keep flags replacing the generated dropout stream
+ * (seed, use). Adapter.forward(x) with add_residual: resid = x, y = bf16(x), add_y = 0; the
+ * block's x + adaptmlp(branch): resid = x, y = branch, add_y = 1. */
+int llc_adapter_forward(const llc_adapter* ad, const void* y, int ld_y, const float* resid,
+                        int add_y, void* a, const unsigned char* mask, unsigned use, int training,
+                        float* out, int T, int D, void* stream);
+/* dx fp32 [T, D] = gradient of `out`, dxb its bf16 copy [T, ld_dxb]. Writes (accumulate = 0) or
+ * adds (1: the block applies the same module twice) the four parameter gradients; d_y fp32 [T, D]
+ * (may be NULL) = [dx +] dz W_d, the gradient of y. da: scratch bf16 [T, 64]. */
+int llc_adapter_backward(const llc_adapter* ad, const void* y, int ld_y, const void* a,
+                         const float* dx, const void* dxb, int ld_dxb, float* d_y, int pass_dx,
+                         void* da, float* partial, int accumulate, int training, int T, int D,
+                         void* stream);
+/* ResidualAttentionBlock_Adapter.forward (model.py:440-442):
+ *   x_mid = x + adaptmlp(attention(ln_1(x)));  x_out = x_mid + adaptmlp(mlp(ln_2(x_mid)))
+ * on the frozen block `w` (zero LoRA factors) with ONE adapter shared by both branches. */
+typedef struct llc_adapter_bufs {
+  void* ya;  /* [T, D] bf16 attention branch (saved)   */
+  void* a1;  /* [T, 64] bf16 (saved)                   */
+  void* m;   /* [T, D] bf16 MLP branch (saved)         */
+  void* a2;  /* [T, 64] bf16 (saved)                   */
+  const unsigned char *mask1, *mask2; /* optional explicit dropout masks [T, 64] */
+  void* da;        /* backward scratch [T, 64] bf16                        */
+  float* d_branch; /* backward scratch [T, D] fp32                         */
+  float* partial;  /* backward scratch, llc_adapter_partial_floats(D)      */
+} llc_adapter_bufs;
+int llc_adapter_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_adapter* ad,
+                              const llc_block_bufs* b, const llc_adapter_bufs* ab, int N, int L,
+                              int tok_stride_n, int tok_stride_l, int causal, int training,
+                              void* stream);
+/* s->dx = gradient of x_out (fp32, becomes the gradient of x_in when need_dx_in), s->dxb its bf16
+ * copy on entry; adapter gradients -> ad->g_* (written, both branches summed) */
+int llc_adapter_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_adapter* ad,
+                               const llc_block_bufs* b, const llc_adapter_bufs* ab,
+                               const llc_block_bwd_bufs* s, int N, int L, int tok_stride_n,
+                               int tok_stride_l, int causal, int need_dx_in, int training,
+                               void* stream);
+
 /* ---- text tower with LoRA (CLIP.encode_text model.py:941-956, causal mask :926-932;
  *      peft_encoder='both' of scripts/lora_clip.sh) ------------------------------------------- */
 typedef struct llc_text_weights {

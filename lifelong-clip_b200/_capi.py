@@ -83,6 +83,20 @@ class BlockBwdBufs(C.Structure):
         "dx", "dxb", "dz", "dh", "d_o", "dqkv", "partial", "delta")]
 
 
+class Adapter(C.Structure):
+    _fields_ = [("scale", c_float), ("dropout", c_float), ("seed", C.c_ulonglong)] + \
+        [(n, c_void) for n in ("down_w", "down_b", "up_w", "up_b", "g_down_w", "g_down_b",
+                               "g_up_w", "g_up_b", "wd", "wu", "wdT", "wuT", "bu_s")]
+
+
+class AdapterBufs(C.Structure):
+    _fields_ = [(n, c_void) for n in ("ya", "a1", "m", "a2", "mask1", "mask2", "da", "d_branch",
+                                      "partial")]
+
+
+ADAPTER_DIM = 64
+
+
 class FinishJob(C.Structure):
     _fields_ = [("partial", c_void), ("n_partials", c_int), ("C", c_int), ("scale", c_float),
                 ("out", c_void), ("o_sc", c_int), ("o_sj", c_int)]
@@ -153,6 +167,21 @@ SIGNATURES = {
     "llc_mha_backward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitLayer), C.POINTER(BlockBufs),
                                  C.POINTER(BlockBwdBufs), c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_void]),
+    "llc_adapter_refresh": (c_int, [C.POINTER(Adapter), c_int, c_void]),
+    "llc_adapter_partial_floats": (C.c_size_t, [c_int]),
+    "llc_adapter_forward": (c_int, [C.POINTER(Adapter), c_void, c_int, c_void, c_int, c_void,
+                                    c_void, C.c_uint, c_int, c_void, c_int, c_int, c_void]),
+    "llc_adapter_backward": (c_int, [C.POINTER(Adapter), c_void, c_int, c_void, c_void, c_void,
+                                     c_int, c_void, c_int, c_void, c_void, c_int, c_int, c_int,
+                                     c_int, c_void]),
+    "llc_adapter_block_forward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitLayer),
+                                          C.POINTER(Adapter), C.POINTER(BlockBufs),
+                                          C.POINTER(AdapterBufs), c_int, c_int, c_int, c_int,
+                                          c_int, c_int, c_void]),
+    "llc_adapter_block_backward": (c_int, [C.POINTER(VitCfg), C.POINTER(VitLayer),
+                                           C.POINTER(Adapter), C.POINTER(BlockBufs),
+                                           C.POINTER(AdapterBufs), C.POINTER(BlockBwdBufs), c_int,
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_void]),
     "llc_text_arena_bytes": (C.c_size_t, [C.POINTER(VitCfg), c_int, c_int, c_int]),
     "llc_text_forward": (c_int, [C.POINTER(VitCfg), C.POINTER(TextWeights), c_void, c_int, c_void,
                                  c_int, C.POINTER(c_void), c_void]),

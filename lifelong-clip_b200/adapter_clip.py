@@ -170,8 +170,32 @@ class CLIP(nn.Module):
 
     def encode_text(self, text):
         """model.py:941-956: text int64 [C, ctx] -> [C, E] (before normalisation)."""
+        if self.text_block_by_block:
+            return self._encode_text_blocks(text, normalise=False)
         lora = self.text_lora_params()
         return _TextFn.apply(self, text, *lora)
+
+    @property
+    def text_block_by_block(self) -> bool:
+        from .adapter_modules import ResidualAttentionBlock_Adapter
+        return self.has_text and isinstance(self.transformer.resblocks[0],
+                                            ResidualAttentionBlock_Adapter)
+
+    def _encode_text_blocks(self, text, normalise):
+        """model.py:941-956 with adapter blocks: embedding gather (frozen) -> blocks under
+        autograd -> ln_final(x[eot]) @ text_projection through the head kernels."""
+        from .clip_modules import _RowFeatFn
+        dev = self.positional_embedding.device
+        text = text.to(dev)
+        with torch.no_grad():
+            x = self.token_embedding(text).float() + self.positional_embedding.float()
+        x = x.permute(1, 0, 2).contiguous()                         # NLD -> LND
+        x = self.transformer(x)
+        Cn = text.shape[0]
+        rows = (text.argmax(dim=-1) * Cn + torch.arange(Cn, device=dev)).contiguous()
+        f32 = lambda t: t.detach().float().contiguous()
+        return _RowFeatFn.apply(x, rows, f32(self.ln_final.weight), f32(self.ln_final.bias),
+                                f32(self.text_projection), normalise)
 
     def forward(self, image, text):
         """model.py:958-975."""
@@ -295,12 +319,15 @@ class AdapterCLIP(nn.Module):
     def __init__(self, model_name="ViT-B/16", peft_method='lora', peft_encoder='image',
                  device=None, vision_config=None, text_config=None):
         super().__init__()
-        if peft_method != 'lora':
-            raise NotImplementedError("lifelong_clip_b200 implements the lora-clip method only")
+        if peft_method not in ('lora', 'adapter'):
+            raise NotImplementedError("lifelong_clip_b200 implements the lora-clip and "
+                                      "adapter-clip methods (scripts/lora_clip.sh, "
+                                      "scripts/adapter_clip.sh)")
         if peft_encoder not in ('image', 'both'):
             raise NotImplementedError("peft_encoder must be 'image' (cached text features) or "
-                                      "'both' (LoRA text tower recomputed every step)")
+                                      "'both' (text tower recomputed every step)")
         self.device = device
+        self.peft_method = peft_method
         self.peft_encoder = peft_encoder
         design_details = {'method': peft_method, 'peft_encoder': peft_encoder, 'ffn_num': 64,
                           'lora_alpha': 1, 'lora_r': 4}  # models/adapter_clip.py:24-30
@@ -441,6 +468,9 @@ class AdapterCLIP(nn.Module):
             raise RuntimeError("no visible classes: call set_token() (and set_text_features() or "
                                "set_tokenizer()) first")
         vis = self.model.visual
+        if self.peft_method == 'adapter':
+            probs, fnorm, _, _, tf = self._forward_blocks(image, text_tokens)
+            return probs, fnorm, tf
         lv = vis.lora_params()
         if self.peft_encoder == 'both':
             lt = self.model.text_lora_params()
@@ -450,3 +480,35 @@ class AdapterCLIP(nn.Module):
             probs, fnorm, _, tf = _ProbsFn.apply(self.model, image, self._text_all, text_tokens,
                                                  self._add_mask, None, len(lv), *lv)
         return probs, fnorm, tf
+
+    def adapters(self):
+        from .adapter_modules import Adapter
+        return [m for m in self.modules() if isinstance(m, Adapter)]
+
+    def invalidate_adapters(self):
+        """After an in-place update of the adapter parameters (optimizer step): the bf16 operands
+        are re-derived on the next call."""
+        for a in self.adapters():
+            a._ops_key = None
+
+    def text_features_blocks(self, text_tokens):
+        """Normalised text features of the visible classes on the adapter path."""
+        if self.peft_encoder == 'both':
+            return self.model._encode_text_blocks(text_tokens, normalise=True)
+        return self._text_all.index_select(0, text_tokens)
+
+    def _forward_blocks(self, image, text_tokens, labels=None, inv_batch=None,
+                        double_softmax=True, t_hat=None):
+        """adapter-clip: both towers block by block under autograd (the adapters are the only
+        trainable tensors), then the head kernels. Returns (probs, normalised image features,
+        pred, loss_sum, normalised text features); loss_sum is 0 without labels."""
+        from .clip_modules import _HeadProbsFn
+        m, vis = self.model, self.model.visual
+        if t_hat is None:
+            t_hat = self.text_features_blocks(text_tokens)
+        x = vis.forward_tokens(image.type(self.dtype))
+        f32 = lambda t: t.detach().float().contiguous()
+        probs, fnorm, pred, loss = _HeadProbsFn.apply(
+            x, t_hat, f32(vis.ln_post.weight), f32(vis.ln_post.bias), f32(vis.proj),
+            m.logit_scale_exp(), self._add_mask, labels, inv_batch, double_softmax)
+        return probs, fnorm, pred, loss, t_hat.detach()

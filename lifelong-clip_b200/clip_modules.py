@@ -550,9 +550,9 @@ class ResidualAttentionBlock_LoRA(ResidualAttentionBlock):
 
 
 class Transformer(nn.Module):
-    """model.py:639-686: LoRA blocks when method='lora' and peft_encoder covers this modality,
-    vanilla (frozen) blocks otherwise. The adapter / MoE / prefix flavours belong to other methods
-    of the reference (out of scope)."""
+    """model.py:639-686: LoRA blocks when method='lora' (adapter blocks when method='adapter')
+    and peft_encoder covers this modality, vanilla (frozen) blocks otherwise. The MoE / prefix
+    flavours belong to other methods of the reference (out of scope)."""
 
     def __init__(self, width: int, layers: int, heads: int, attn_mask: torch.Tensor = None,
                  design_details: dict = {}, modal='text'):
@@ -560,11 +560,16 @@ class Transformer(nn.Module):
         self.width, self.layers = width, layers
         res_type = design_details.get('method', 'vanilla')
         peft_flag = design_details.get('peft_encoder', 'none') in ['both', modal]
-        if res_type in ('moe', 'adapter', 'prefix_prompt') and peft_flag:
+        if res_type in ('moe', 'prefix_prompt') and peft_flag:
             raise NotImplementedError(
-                f"method={res_type!r}: only the LoRA and vanilla blocks are built by "
-                "lifelong_clip_b200 (scripts/lora_clip.sh)")
-        if res_type == 'lora' and peft_flag:
+                f"method={res_type!r}: only the LoRA, adapter and vanilla blocks are built by "
+                "lifelong_clip_b200 (scripts/lora_clip.sh, scripts/adapter_clip.sh)")
+        if res_type == 'adapter' and peft_flag:
+            from .adapter_modules import ResidualAttentionBlock_Adapter
+            self.resblocks = nn.Sequential(*[
+                ResidualAttentionBlock_Adapter(width, heads, attn_mask, design_details)
+                for _ in range(layers)])
+        elif res_type == 'lora' and peft_flag:
             self.resblocks = nn.Sequential(*[
                 ResidualAttentionBlock_LoRA(width, heads, attn_mask, design_details)
                 for _ in range(layers)])
@@ -646,7 +651,28 @@ class VisualTransformer(nn.Module):
         if prompt_module is not None:
             raise NotImplementedError("prompt_module belongs to the proto-CLIP method "
                                       "(out of scope; SURVEY.md §2)")
+        if self.block_by_block:
+            f32 = lambda t: t.detach().float().contiguous()
+            t = self.forward_tokens(x)
+            rows = torch.arange(t.shape[1], device=t.device, dtype=torch.int64)
+            return _RowFeatFn.apply(t, rows, f32(self.ln_post.weight), f32(self.ln_post.bias),
+                                    f32(self.proj), False)
         return _TowerFn.apply(self, x, *self.lora_params())
+
+    @property
+    def block_by_block(self) -> bool:
+        """Adapter blocks carry their own trainable tensors and run one llc_adapter_block_* call
+        per block under autograd; LoRA / vanilla towers run as ONE llc_vit_forward call."""
+        from .adapter_modules import ResidualAttentionBlock_Adapter
+        return isinstance(self.transformer.resblocks[0], ResidualAttentionBlock_Adapter)
+
+    def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
+        """model.py:757-781 block by block: images -> the transformer's output [L, N, D]."""
+        if x.device.type != "cuda":
+            raise RuntimeError("lifelong_clip_b200 modules compute on CUDA (sm_100a) only; move "
+                               "the module and its input to the GPU (no CPU fallback)")
+        t = embed_images(self, x).permute(1, 0, 2).contiguous()     # NLD -> LND
+        return self.transformer(t)
 
     def get_patch_feature(self, x: torch.Tensor):
         """model.py:731-753: ln_post(CLS) without the projection, returned twice."""
@@ -656,3 +682,121 @@ class VisualTransformer(nn.Module):
             y = F.layer_norm(eng.cls_rows(), (self.width,), self.ln_post.weight.float(),
                              self.ln_post.bias.float(), self.ln_post.eps)
         return y, y
+
+
+class _RowFeatFn(torch.autograd.Function):
+    """x [L, N, D] -> features of one row per sample, LN(x[row_n]) @ proj, L2-normalised unless
+    normalise=False: the tail of both encoders (model.py:782-785 / :951-956 + :966-969) through
+    llc_head_fwd / llc_head_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, rows, ln_g, ln_b, proj, normalise=True):
+        L, N, D = x.shape
+        x2 = x.detach().float().contiguous().view(L * N, D)
+        dummy = torch.zeros(1, proj.shape[1], device=x.device)
+        dummy[0, 0] = 1.0
+        head = ops.Head(x2, 1, ln_g, ln_b, proj, dummy, 1.0, N, row_idx=rows).forward()
+        ctx.head, ctx.shape, ctx.normalise = head, (L, N, D), normalise
+        return (head.fnorm if normalise else head.feat).clone()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        head, (L, N, D) = ctx.head, ctx.shape
+        d = d_out.detach().float().contiguous()
+        head.keep = head.keep + (d,)
+        head.args.d_fnorm = d.data_ptr() if ctx.normalise else None
+        head.args.d_feat = None if ctx.normalise else d.data_ptr()
+        head.args.skip_logit_grad = 1
+        dx = torch.zeros(L * N, D, device=d.device)
+        head.backward(dx)
+        return dx.view(L, N, D), None, None, None, None, None
+
+
+class _CosineLogitFn(torch.autograd.Function):
+    """x_img [L, N, D], t_hat [C, E] -> logits [N, C] = s * normalise(LN(x[0, n]) @ proj) @ t_hat^T
+    (models/maple.py:244-251), gradients to x_img (class-token rows) and t_hat."""
+
+    @staticmethod
+    def forward(ctx, x, text, ln_g, ln_b, proj, scale):
+        L, N, D = x.shape
+        x2 = x.detach().float().contiguous().view(L * N, D)
+        rows = torch.arange(N, device=x.device, dtype=torch.int64)     # token (0, n) = row n
+        t = text.detach().float().contiguous()
+        head = ops.Head(x2, 1, ln_g, ln_b, proj, t, float(scale), N, row_idx=rows,
+                        want_dlogits=True).forward()
+        ctx.head, ctx.shape, ctx.scale = head, (L, N, D), float(scale)
+        return head.logits.clone()
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        head, (L, N, D) = ctx.head, ctx.shape
+        d = d_logits.detach().float().contiguous()
+        head.args.d_is_logits = 1
+        head.args.skip_logit_grad = 0
+        dx = torch.zeros(L * N, D, device=d.device)
+        head.backward(dx, d)
+        d_text = ops.head_dtext(head.dlogits, head.fnorm, ctx.scale)
+        return dx.view(L, N, D), d_text, None, None, None, None
+
+class _HeadProbsFn(torch.autograd.Function):
+    """x [L, N, D] (class-token rows = rows 0..N-1 of the flattened [L*N] axis), normalised text
+    features [C, E] -> (probs, normalised image features, pred, loss_sum): the cosine-logit head
+    of models/adapter_clip.py:94-100 on a tower that ran block by block. With labels the loss
+    (CE on the probabilities, methods/adapter_clip.py:89) and its gradient are formed by the head
+    kernels; without, backward takes the caller's d_probs."""
+
+    @staticmethod
+    def forward(ctx, x, text, ln_g, ln_b, proj, scale, add_mask, labels, inv_batch,
+                double_softmax):
+        L, N, D = x.shape
+        x2 = x.detach().float().contiguous().view(L * N, D)
+        rows = torch.arange(N, device=x.device, dtype=torch.int64)
+        t = text.detach().float().contiguous()
+        head = ops.Head(x2, 1, ln_g, ln_b, proj, t, float(scale), N, row_idx=rows,
+                        add_mask=add_mask, labels=labels, inv_batch=inv_batch,
+                        double_softmax=double_softmax, want_dlogits=True).forward()
+        ctx.head, ctx.shape, ctx.scale, ctx.fused = head, (L, N, D), float(scale), labels is not None
+        ctx.mark_non_differentiable(head.pred)
+        loss = head.loss_rows.sum() if labels is not None else head.loss_rows.new_zeros(())
+        return head.probs, head.fnorm, head.pred, loss
+
+    @staticmethod
+    def backward(ctx, d_probs, d_fnorm, _, d_loss):
+        head, (L, N, D) = ctx.head, ctx.shape
+        dev = head.probs.device
+        dx = torch.zeros(L * N, D, device=dev)
+        head.args.skip_logit_grad = 0
+        if ctx.fused:
+            head.backward(dx, None, float(d_loss) if d_loss is not None else 1.0)
+        else:
+            dp = d_probs.detach().float().contiguous() if d_probs is not None else \
+                torch.zeros_like(head.probs)
+            head.backward(dx, dp)
+        d_text = None
+        if ctx.needs_input_grad[1]:
+            d_text = ops.head_dtext(head.dlogits, head.fnorm, ctx.scale)
+        return (dx.view(L, N, D), d_text) + (None,) * 8
+
+
+def embed_images(v: "VisualTransformer", image: torch.Tensor) -> torch.Tensor:
+    """model.py:757-767: stride-P conv + class token + positional embedding + ln_pre -> fp32
+    [N, L, D] (llc_patchify + tcgen05 GEMM + llc_embed_ln_pre; frozen, no gradient)."""
+    N, P = image.shape[0], v.patch_size
+    G, D = v.input_resolution // P, v.width
+    dev = image.device
+    kp = (3 * P * P + 15) // 16 * 16
+    key = (v.conv1.weight.data_ptr(), v.conv1.weight._version)
+    if getattr(v, "_wpatch_key", None) != key:
+        v._wpatch = ops.pack_weight(
+            v.conv1.weight.detach().float().reshape(D, 3 * P * P).contiguous(),
+            torch.zeros(D, kp, dtype=torch.bfloat16, device=dev))
+        v._wpatch_key = key
+    patches = torch.empty(N * G * G, kp, dtype=torch.bfloat16, device=dev)
+    ops.patchify(image.float().contiguous(), P, patches)
+    po = torch.empty(N * G * G, D, device=dev)
+    ops.gemm_tn(patches, v._wpatch, N * G * G, D, kp, po)
+    x0 = torch.empty(N * (G * G + 1), D, device=dev)
+    f32 = lambda t: t.detach().float().contiguous()
+    ops.embed_ln_pre(po, f32(v.class_embedding), f32(v.positional_embedding),
+                     f32(v.ln_pre.weight), f32(v.ln_pre.bias), N, G * G + 1, D, x0)
+    return x0.view(N, G * G + 1, D)

@@ -396,6 +396,73 @@ extern "C" int llc_mha_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   return attn_half_backward(cfg, w, b, s, N, L, sn, sl, causal, need_dx_in, stream);
 }
 
+// ResidualAttentionBlock_Adapter (reference models/clip/model.py:418-442): the frozen block with
+// the bottleneck adapter (adapter.cu) applied to both branches. The branches leave their GEMMs in
+// bf16 (they are the adapter's A operand), the adapter's up-projection carries the fp32 residual.
+extern "C" int llc_adapter_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                                         const llc_adapter* ad, const llc_block_bufs* b,
+                                         const llc_adapter_bufs* ab, int N, int L, int sn, int sl,
+                                         int causal, int training, void* stream) {
+  RUN(check_cfg(cfg, "llc_adapter_block_forward"));
+  LLC_REQUIRE(w && ad && b && ab && ab->ya && ab->a1 && ab->m && ab->a2 && N > 0 && L > 0,
+              "llc_adapter_block_forward: bad args");
+  const int D = cfg->width, M = cfg->mlp_dim, r = cfg->lora_r;
+  const int T = N * L, DA = D + LLC_LORA_LD;
+  llc_gemm_epi e;
+  RUN(llc_ln_fwd(b->x_in, D, w->ln1_g, w->ln1_b, T, D, b->h1, DA, w->in_A, r, stream));
+  e = llc_gemm_epi{};
+  e.out = ab->ya; e.ld_out = D;
+  RUN(attn_half_forward(cfg, w, b, e, N, L, sn, sl, causal, stream));
+  RUN(llc_adapter_forward(ad, ab->ya, D, b->x_in, 1, ab->a1, ab->mask1, 0, training, b->x_mid, T,
+                          D, stream));
+  RUN(llc_ln_fwd(b->x_mid, D, w->ln2_g, w->ln2_b, T, D, b->h2, D, nullptr, 0, stream));
+  e = llc_gemm_epi{};
+  e.bias = w->bfc; e.act = 1; e.out = b->z; e.ld_out = M; e.out2 = b->g; e.ld_out2 = M;
+  RUN(GEMM(b->h2, D, w->wfc, D, T, M, D, &e, stream));
+  e = llc_gemm_epi{};
+  e.bias = w->bproj; e.out = ab->m; e.ld_out = D;
+  RUN(GEMM(b->g, M, w->wproj, M, T, D, M, &e, stream));
+  RUN(llc_adapter_forward(ad, ab->m, D, b->x_mid, 1, ab->a2, ab->mask2, 1, training, b->x_out, T,
+                          D, stream));
+  return 0;
+}
+
+extern "C" int llc_adapter_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
+                                          const llc_adapter* ad, const llc_block_bufs* b,
+                                          const llc_adapter_bufs* ab, const llc_block_bwd_bufs* s,
+                                          int N, int L, int sn, int sl, int causal, int need_dx_in,
+                                          int training, void* stream) {
+  RUN(check_cfg(cfg, "llc_adapter_block_backward"));
+  LLC_REQUIRE(w && ad && b && ab && s && ab->da && ab->d_branch && ab->partial && N > 0 && L > 0,
+              "llc_adapter_block_backward: bad args");
+  LLC_REQUIRE(b->z, "llc_adapter_block_backward: forward was not run in training mode");
+  const int D = cfg->width, M = cfg->mlp_dim;
+  const int T = N * L, DA = D + LLC_LORA_LD;
+  llc_gemm_epi e;
+  // x_out = x_mid + m + s up(a2): adapter gradients, d_m = dx + dz2 W_d
+  RUN(llc_adapter_backward(ad, ab->m, D, ab->a2, s->dx, s->dxb, DA, ab->d_branch, 1, ab->da,
+                           ab->partial, 0, training, T, D, stream));
+  RUN(llc_cast_bf16(ab->d_branch, s->dxb, T, D, DA, stream));
+  // dz = (d_m W_proj) o QuickGELU'(z); dh2 = dz W_fc; dx_mid = dx + LN2'(dh2)
+  e = llc_gemm_epi{};
+  e.act = 2; e.aux = b->z; e.ld_aux = M; e.out = s->dz; e.ld_out = M;
+  RUN(GEMM(s->dxb, DA, w->wprojT, D, T, M, D, &e, stream));
+  e = llc_gemm_epi{};
+  e.out = s->dh; e.ld_out = D;
+  RUN(GEMM(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
+  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
+                 stream));
+  // x_mid = x + ya + s up(a1)
+  RUN(llc_adapter_backward(ad, ab->ya, D, ab->a1, s->dx, s->dxb, DA, ab->d_branch, 1, ab->da,
+                           ab->partial, 1, training, T, D, stream));
+  RUN(llc_cast_bf16(ab->d_branch, s->dxb, T, D, DA, stream));
+  RUN(attn_half_backward(cfg, w, b, s, N, L, sn, sl, causal, need_dx_in, stream));
+  if (need_dx_in)
+    RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
+                   stream));
+  return 0;
+}
+
 extern "C" size_t llc_vit_arena_bytes(const llc_vit_cfg* cfg, int N, int training) {
   if (check_cfg(cfg, "llc_vit_arena_bytes") != 0 || N <= 0) return 0;
   return plan(make_dims(cfg, N), training).total;

@@ -440,3 +440,53 @@ class FlatAdamW:
 
     def zero_grad(self):
         pass  # every backward overwrites grad_flat completely
+
+
+class ParamAdamW:
+    """torch.optim.AdamW semantics (utils/train_utils.py:27-28) for trainable tensors that live in
+    modules (the adapters of --method adapter-clip): the parameters are re-homed as views of ONE
+    flat fp32 buffer, so a step is one gradient gather + one llc_adamw launch, and data-parallel
+    training all-reduces one buffer. `on_step` is called after every update (in-place kernel
+    writes do not bump tensor versions: modules caching derived operands refresh there)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5,
+                 on_step=None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise RuntimeError("ParamAdamW: no trainable parameters")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, device=dev)
+        self.grad_flat = torch.zeros(n, device=dev)
+        self.views, off = [], 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise RuntimeError("ParamAdamW: parameters must be fp32")
+            v = self.flat[off:off + p.numel()].view_as(p)
+            v.copy_(p.data)
+            p.data = v
+            self.views.append(self.grad_flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.t, self.on_step = 0, on_step
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        """p.grad of every parameter -> grad_flat (zeros where autograd produced none)."""
+        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
+        if len(have) != len(self.params):
+            self.grad_flat.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        return self.grad_flat
+
+    def step(self, grad_scale: float = 1.0):
+        self.t += 1
+        ops.adamw(self.flat, self.grad_flat, self.m, self.v, self.lr, self.betas[0],
+                  self.betas[1], self.eps, self.wd, self.t, grad_scale)
+        if self.on_step is not None:
+            self.on_step()

@@ -28,6 +28,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .adapter_clip import CLIP, TEXT_CONFIGS, VISION_CONFIGS
+from .clip_modules import _CosineLogitFn, _RowFeatFn, embed_images
 
 
 def _h(x):
@@ -62,61 +63,6 @@ class MultiModalPromptLearner(nn.Module):
         visual_deep = [layer(self.compound_prompts_text[i])
                        for i, layer in enumerate(self.compound_prompt_projections)]
         return prompts, self.proj(self.ctx), list(self.compound_prompts_text), visual_deep
-
-
-class _RowFeatFn(torch.autograd.Function):
-    """x [L, N, D] -> L2-normalised features of one row per sample:
-    normalise(LN(x[row_n]) @ proj), the tail of both encoders (model.py:782-785 / :951-956 +
-    :966-969) through llc_head_fwd / llc_head_bwd."""
-
-    @staticmethod
-    def forward(ctx, x, rows, ln_g, ln_b, proj):
-        L, N, D = x.shape
-        x2 = x.detach().float().contiguous().view(L * N, D)
-        dummy = torch.zeros(1, proj.shape[1], device=x.device)
-        dummy[0, 0] = 1.0
-        head = ops.Head(x2, 1, ln_g, ln_b, proj, dummy, 1.0, N, row_idx=rows).forward()
-        ctx.head, ctx.shape = head, (L, N, D)
-        return head.fnorm.clone()
-
-    @staticmethod
-    def backward(ctx, d_fnorm):
-        head, (L, N, D) = ctx.head, ctx.shape
-        d = d_fnorm.detach().float().contiguous()
-        head.keep = head.keep + (d,)
-        head.args.d_fnorm = d.data_ptr()
-        head.args.d_feat = None
-        head.args.skip_logit_grad = 1
-        dx = torch.zeros(L * N, D, device=d.device)
-        head.backward(dx)
-        return dx.view(L, N, D), None, None, None, None
-
-
-class _CosineLogitFn(torch.autograd.Function):
-    """x_img [L, N, D], t_hat [C, E] -> logits [N, C] = s * normalise(LN(x[0, n]) @ proj) @ t_hat^T
-    (models/maple.py:244-251), gradients to x_img (class-token rows) and t_hat."""
-
-    @staticmethod
-    def forward(ctx, x, text, ln_g, ln_b, proj, scale):
-        L, N, D = x.shape
-        x2 = x.detach().float().contiguous().view(L * N, D)
-        rows = torch.arange(N, device=x.device, dtype=torch.int64)     # token (0, n) = row n
-        t = text.detach().float().contiguous()
-        head = ops.Head(x2, 1, ln_g, ln_b, proj, t, float(scale), N, row_idx=rows,
-                        want_dlogits=True).forward()
-        ctx.head, ctx.shape, ctx.scale = head, (L, N, D), float(scale)
-        return head.logits.clone()
-
-    @staticmethod
-    def backward(ctx, d_logits):
-        head, (L, N, D) = ctx.head, ctx.shape
-        d = d_logits.detach().float().contiguous()
-        head.args.d_is_logits = 1
-        head.args.skip_logit_grad = 0
-        dx = torch.zeros(L * N, D, device=d.device)
-        head.backward(dx, d)
-        d_text = ops.head_dtext(head.dlogits, head.fnorm, ctx.scale)
-        return dx.view(L, N, D), d_text, None, None, None, None
 
 
 class MaPLe(nn.Module):
@@ -191,29 +137,12 @@ class MaPLe(nn.Module):
         rows = (eot * Cn + torch.arange(Cn, device=x.device)).contiguous()   # token (l, c) = row l*C + c
         return _RowFeatFn.apply(x, rows, m.ln_final.weight.detach().float().contiguous(),
                                 m.ln_final.bias.detach().float().contiguous(),
-                                m.text_projection.detach().float().contiguous())
+                                m.text_projection.detach().float().contiguous(), True)
 
     def _embed_images(self, image):
         """model.py:548-559 for the image tokens: stride-P conv + class token + positional
         embedding + ln_pre (per token, so it commutes with appending the prompt tokens)."""
-        v = self.image_encoder
-        N, P = image.shape[0], v.patch_size
-        G, D = v.input_resolution // P, v.width
-        dev = image.device
-        kp = (3 * P * P + 15) // 16 * 16
-        if getattr(self, "_wpatch", None) is None or self._wpatch.device != dev:
-            self._wpatch = ops.pack_weight(
-                v.conv1.weight.detach().float().reshape(D, 3 * P * P).contiguous(),
-                torch.zeros(D, kp, dtype=torch.bfloat16, device=dev))
-        patches = torch.empty(N * G * G, kp, dtype=torch.bfloat16, device=dev)
-        ops.patchify(image.float().contiguous(), P, patches)
-        po = torch.empty(N * G * G, D, device=dev)
-        ops.gemm_tn(patches, self._wpatch, N * G * G, D, kp, po)
-        x0 = torch.empty(N * (G * G + 1), D, device=dev)
-        f32 = lambda t: t.detach().float().contiguous()
-        ops.embed_ln_pre(po, f32(v.class_embedding), f32(v.positional_embedding),
-                         f32(v.ln_pre.weight), f32(v.ln_pre.bias), N, G * G + 1, D, x0)
-        return x0.view(N, G * G + 1, D)
+        return embed_images(self.image_encoder, image)
 
     def forward(self, image, tokenized_prompts=None, prefix=None, suffix=None):
         if image.device.type != "cuda":

@@ -77,7 +77,15 @@ class LoRAClipTrainer:
     def _scal(self):
         """(loss_sum, n_correct) of the step: the two floats behind the image tower's flat LoRA
         gradient, so that they travel in the same all-reduce."""
+        if self.block_mode:
+            return self._block_scal
         return self.custom_clip.model.visual.engine().scal
+
+    @property
+    def block_mode(self) -> bool:
+        """--method adapter-clip: the towers run block by block under autograd (adapters are
+        module-owned tensors); lora-clip runs the fused tower calls."""
+        return getattr(self.custom_clip, "peft_method", "lora") == "adapter"
 
     @property
     def text_trainable(self) -> bool:
@@ -136,6 +144,14 @@ class LoRAClipTrainer:
 
     def reset_opt(self):
         """utils/train_utils.py:27-28: AdamW(lr, weight_decay=1e-5) over the trainable tensors."""
+        if self.block_mode:
+            from .engine import ParamAdamW
+            m = self.custom_clip
+            self.optimizer = ParamAdamW([p for _, p in m.named_parameters()], lr=self.lr,
+                                        weight_decay=1e-5, on_step=m.invalidate_adapters)
+            m.invalidate_adapters()         # the parameters moved into the flat buffer
+            self._block_scal = torch.zeros(2, device=self.device)
+            return
         self.optimizer = FlatAdamW(self._towers(), lr=self.lr, weight_decay=1e-5)
 
     def online_after_task(self, task_id):
@@ -214,8 +230,39 @@ class LoRAClipTrainer:
         if not isinstance(self.train_transform, GpuTransform):
             x = self.train_transform(x)
         self.custom_clip.set_token(train_class_name_list)
-        loss_sum, n_correct = self.fused_step(x, y_local, B)
+        if self.block_mode:
+            if isinstance(self.train_transform, GpuTransform):
+                x = self.train_transform(x)
+            loss_sum, n_correct = self.block_step(x, y_local, B)
+        else:
+            loss_sum, n_correct = self.fused_step(x, y_local, B)
         return loss_sum, n_correct / B
+
+    def block_step(self, x, y_local, global_batch, sync=True):
+        """adapter-clip step (methods/adapter_clip.py:84-101 with the adapter blocks of
+        model.py:418-442): block-by-block forward under autograd, loss + its gradient in the head
+        kernels, ONE all-reduce of the flat adapter gradient (+ loss, #correct), fused AdamW."""
+        m, opt = self.custom_clip, self.optimizer
+        m.train()
+        opt.zero_grad()
+        scal = self._block_scal
+        if x.shape[0] == 0:
+            opt.grad_flat.zero_()
+            scal.zero_()
+        else:
+            _, _, pred, loss, _ = m._forward_blocks(
+                x, m.text_tokens, labels=y_local, inv_batch=1.0 / global_batch,
+                double_softmax=self.double_softmax)
+            loss.backward()
+            opt.gather_grads()
+            scal[0] = loss.detach()
+            scal[1] = (pred == y_local).sum()
+        dp.allreduce_step([opt.grad_flat], scal, self.world)
+        opt.step()
+        if not sync:
+            return scal
+        loss_sum, n_correct = scal.tolist()
+        return loss_sum, n_correct
 
     def model_forward(self, x, y):
         """(logit, loss) as the classic methods' model_forward (methods/er_baseline.py:132-147):
@@ -371,6 +418,8 @@ class LoRAClipTrainer:
         does two .tolist() per batch and runs sklearn on the host."""
         self.custom_clip.eval()
         m = self.custom_clip
+        if self.block_mode:
+            return self._block_evaluate(test_loader)
         eng = m.model.visual.engine()
         Cn = self.n_classes
         cm = torch.zeros(Cn, Cn, dtype=torch.int64, device=self.device)
@@ -396,6 +445,22 @@ class LoRAClipTrainer:
                 head = eng.eval_head(m._text_all, m.model.logit_scale_exp(), cls_idx=m._cls_idx,
                                      add_mask=m._add_mask, want_probs=False)
             ops.eval_accum(y, head.pred, self.n_tasks, Cn, cm, counts)
+        return self._eval_dict(cm, counts)
+
+    def _block_evaluate(self, test_loader):
+        m, Cn = self.custom_clip, self.n_classes
+        cm = torch.zeros(Cn, Cn, dtype=torch.int64, device=self.device)
+        counts = torch.zeros(22, dtype=torch.int64, device=self.device)
+        t_hat = m.text_features_blocks(m.text_tokens)      # once per call
+        for batch in test_loader:
+            x = batch[0].to(self.device, non_blocking=True)
+            y = batch[1].to(self.device, non_blocking=True)
+            _, _, pred, _, _ = m._forward_blocks(self.test_transform(x), m.text_tokens,
+                                                 t_hat=t_hat)
+            ops.eval_accum(y, pred, self.n_tasks, Cn, cm, counts)
+        return self._eval_dict(cm, counts)
+
+    def _eval_dict(self, cm, counts):
         counts = counts.cpu()
         if int(counts[10]) or int(counts[21]):
             # methods/_trainer.py:521-527 indexes ten-element tensors with y // n_tasks

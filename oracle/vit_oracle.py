@@ -540,3 +540,116 @@ def maple_step_oracle(images, labels, tokens, wv_np, wt_np, wp_np, cfg, tcfg, n_
             "pred": logits.argmax(-1).numpy(),
             "grads": {k: (v.grad if v.grad is not None else torch.zeros_like(v)).detach().numpy()
                       for k, v in wp.items()}}
+
+
+# ------------------------------------------------------------------- adapter-clip blocks (N4)
+ADAPTER_DIM = 64        # models/clip/adapter.py:39 (down_proj hard-coded to 64 outputs)
+ADAPTER_SCALE = 0.1     # models/clip/model.py:437 adapter_scalar
+ADAPTER_DROPOUT = 0.1   # models/clip/model.py:434
+
+
+def synth_adapter_weights(width: int, layers: int, prefix: str = "visual.transformer.resblocks.",
+                          seed: int = 0) -> dict[str, np.ndarray]:
+    """adaptmlp.* of every block (models/clip/adapter.py:39-52). The reference's init zeroes
+    up_proj (the adapter starts as the identity); every tensor is randomised here so that all four
+    gradients are exercised."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for i in range(layers):
+        p = f"{prefix}{i}.adaptmlp."
+        out[p + "down_proj.weight"] = rng.uniform(-1, 1, (ADAPTER_DIM, width)) * width ** -0.5
+        out[p + "down_proj.bias"] = 0.05 * rng.standard_normal(ADAPTER_DIM)
+        out[p + "up_proj.weight"] = rng.uniform(-1, 1, (width, ADAPTER_DIM)) * ADAPTER_DIM ** -0.5
+        out[p + "up_proj.bias"] = 0.05 * rng.standard_normal(width)
+    return {k: v.astype(np.float32) for k, v in out.items()}
+
+
+def adapter_forward(y, w, prefix: str, mask=None, p: float = 0.0):
+    """Adapter.forward models/clip/adapter.py:53-73 with adapter_layernorm_option='none' and
+    add_residual=True: y + scale * up(dropout(relu(down(y)))). mask: keep flags (same shape as
+    the bottleneck) standing in for torch's dropout draw; the kept values are scaled by
+    1 / (1 - p) as nn.functional.dropout does."""
+    down = torch.relu(y @ w[prefix + "down_proj.weight"].T + w[prefix + "down_proj.bias"])
+    if mask is not None:
+        down = down * mask.to(down.dtype) / (1.0 - p)
+    up = down @ w[prefix + "up_proj.weight"].T + w[prefix + "up_proj.bias"]
+    return up * ADAPTER_SCALE + y
+
+
+def adapter_block_forward(x, w, prefix: str, cfg: VitCfg, causal: bool = False, masks=None,
+                          p: float = 0.0):
+    """ResidualAttentionBlock_Adapter.forward models/clip/model.py:440-442 (vanilla attention and
+    MLP, one shared adaptmlp on both branches). masks: (mask1, mask2) or None."""
+    D = cfg.width
+    m1, m2 = masks if masks is not None else (None, None)
+    h = layer_norm(x, w[prefix + "ln_1.weight"], w[prefix + "ln_1.bias"])
+    qkv = h @ w[prefix + "attn.in_proj_weight"].T + w[prefix + "attn.in_proj_bias"]
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    o = attention_core(q, k, v, cfg.heads, causal)
+    ya = o @ w[prefix + "attn.out_proj.weight"].T + w[prefix + "attn.out_proj.bias"]
+    x = x + adapter_forward(ya, w, prefix + "adaptmlp.", m1, p)
+    h2 = layer_norm(x, w[prefix + "ln_2.weight"], w[prefix + "ln_2.bias"])
+    z = h2 @ w[prefix + "mlp.c_fc.weight"].T + w[prefix + "mlp.c_fc.bias"]
+    m = quick_gelu(z) @ w[prefix + "mlp.c_proj.weight"].T + w[prefix + "mlp.c_proj.bias"]
+    return x + adapter_forward(m, w, prefix + "adaptmlp.", m2, p)
+
+
+def adapter_step_oracle(images, labels_local, w_np, wa_np, text, cfg: VitCfg,
+                        logit_scale_exp: float = 1.0 / 0.07, dtype=torch.float64, masks=None,
+                        p: float = 0.0, tokens=None, wt_np=None, wta_np=None, tcfg=None,
+                        tmasks=None):
+    """One forward + reference loss + backward of the adapter-clip method (scripts/
+    adapter_clip.sh): adapter blocks in the image tower and, when tokens / wt_np / wta_np are
+    given (peft_encoder='both', the reference's default, models/adapter_clip.py:19), in the text
+    tower; else `text` are cached normalised features. masks / tmasks: per layer (mask1, mask2)
+    keep flags [N, L, 64] (training-mode dropout), None = eval-mode. Returns probs, loss, pred and
+    the gradients of every adaptmlp tensor."""
+    wv = to_torch(strip_lora(w_np), dtype, lora_grad=False)
+    wa = {k: torch.from_numpy(v).to(dtype).requires_grad_(True) for k, v in wa_np.items()}
+    w = {**wv, **wa}
+    x = patch_embed(torch.from_numpy(images).to(dtype), w, cfg)
+    for i in range(cfg.layers):
+        x = adapter_block_forward(x, w, f"visual.transformer.resblocks.{i}.", cfg,
+                                  masks=None if masks is None else masks[i], p=p)
+    feat = layer_norm(x[:, 0, :], w["visual.ln_post.weight"], w["visual.ln_post.bias"]) @ \
+        w["visual.proj"]
+    wta = {}
+    if tokens is not None:
+        wt = to_torch(strip_lora(wt_np), dtype, lora_grad=False)
+        wta = {k: torch.from_numpy(v).to(dtype).requires_grad_(True) for k, v in wta_np.items()}
+        wtt = {**wt, **wta}
+        tok = torch.from_numpy(tokens)
+        t = wtt["token_embedding.weight"][tok] + wtt["positional_embedding"]
+        bcfg = VitCfg(width=tcfg.width, heads=tcfg.heads, layers=tcfg.layers)
+        for i in range(tcfg.layers):
+            t = adapter_block_forward(t, wtt, f"transformer.resblocks.{i}.", bcfg, causal=True,
+                                      masks=None if tmasks is None else tmasks[i], p=p)
+        t = layer_norm(t, wtt["ln_final.weight"], wtt["ln_final.bias"])
+        tfeat = t[torch.arange(t.shape[0]), tok.argmax(dim=-1)] @ wtt["text_projection"]
+        tn = tfeat / tfeat.norm(dim=-1, keepdim=True)
+    else:
+        tn = torch.from_numpy(text).to(dtype)
+    y = torch.from_numpy(labels_local)
+    probs, logits, f = head_forward(feat, tn, logit_scale_exp)
+    loss = reference_loss(probs, y, logits, True)
+    loss.backward()
+    out = {"feat": feat, "fnorm": f, "probs": probs, "logits": logits, "loss": loss,
+           "pred": predict(probs), "tnorm": tn}
+    res = {k: v.detach().cpu().numpy() for k, v in out.items()}
+    res["grads"] = {k: v.grad.detach().cpu().numpy() for k, v in {**wa, **wta}.items()}
+    return res
+
+
+def adapter_masks(seed: int, layers: int, L: int, N: int, p: float = ADAPTER_DROPOUT):
+    """Deterministic dropout keep masks standing in for torch's draws: per layer (mask1, mask2),
+    uint8 [L, N, 64] in the reference's sequence-first layout (the order nn.functional.dropout is
+    called in: attention branch, then MLP branch, layer by layer)."""
+    rng = np.random.default_rng(seed)
+    return [tuple((rng.random((L, N, ADAPTER_DIM)) >= p).astype(np.uint8) for _ in range(2))
+            for _ in range(layers)]
+
+
+def masks_sample_major(masks):
+    """[L, N, 64] -> torch [N, L, 64] (this module's activations are sample-major)."""
+    return [tuple(torch.from_numpy(np.ascontiguousarray(m.transpose(1, 0, 2))) for m in pair)
+            for pair in masks]

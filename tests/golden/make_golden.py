@@ -360,6 +360,108 @@ def run_interpret_pred():
     return out
 
 
+ADAPTER_CASES = {
+    # name: (vision cfg, text cfg, batch, classes, seed): adapter-clip, peft_encoder='both',
+    # training mode with injected dropout masks + the eval-mode forward of the same inputs
+    "adapter_tiny": (vo.VIT_TINY, vo.TEXT_TINY, 4, 6, 41),
+    "adapter_vitb16": (vo.VIT_B16, vo.TEXT_B16, 4, 10, 43),
+}
+
+
+def run_reference_adapter(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes: int, seed: int):
+    """--method adapter-clip (scripts/adapter_clip.sh): the reference's CLIP with
+    ResidualAttentionBlock_Adapter in both towers (model.py:418-442, adapter.py:11-73). Dropout
+    draws are replaced by oracle.adapter_masks (nn.functional.dropout is patched for the run: the
+    reference's own draws come from torch's generator and cannot be reproduced by another
+    implementation); everything else is the reference's code."""
+    ref_model = load_reference()
+    torch.manual_seed(0)
+    clip = ref_model.CLIP(cfg.embed_dim, cfg.image_size, cfg.layers, cfg.width, cfg.patch,
+                          tcfg.context, tcfg.vocab, tcfg.width, tcfg.heads, tcfg.layers,
+                          {"method": "adapter", "peft_encoder": "both", "ffn_num": 64}).float()
+    wv = vo.strip_lora(vo.synth_weights(cfg, seed))
+    wt = vo.strip_lora(vo.synth_text_weights(tcfg, seed + 1))
+    wa = vo.synth_adapter_weights(cfg.width, cfg.layers, "visual.transformer.resblocks.", seed + 2)
+    wta = vo.synth_adapter_weights(tcfg.width, tcfg.layers, "transformer.resblocks.", seed + 3)
+    sd = clip.state_dict()
+    for k, v in {**wv, **wt, **wa, **wta}.items():
+        assert k in sd and tuple(sd[k].shape) == v.shape, (k, v.shape)
+        sd[k] = torch.from_numpy(v)
+    clip.load_state_dict(sd)
+    for k, p in clip.named_parameters():  # methods/adapter_clip.py:117-119
+        if "adaptmlp" not in k and "lora" not in k:
+            p.requires_grad = False
+    images, labels = synth_inputs(cfg, n, num_classes, seed + 100)
+    tokens = vo.synth_tokens(num_classes, tcfg, seed + 300)
+    p_drop = vo.ADAPTER_DROPOUT
+    queue = []
+
+    def fake_dropout(x, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return x
+        assert abs(p - p_drop) < 1e-12
+        m = queue.pop(0)
+        assert m.shape == x.shape, (m.shape, x.shape)
+        return x * m.to(x.dtype) / (1.0 - p)
+
+    def forward():
+        vis = clip.visual
+        x = vis.conv1(torch.from_numpy(images))
+        x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+        x = torch.cat([vis.class_embedding.to(x.dtype) + torch.zeros(
+            x.shape[0], 1, x.shape[-1], dtype=x.dtype), x], dim=1)
+        x = x + vis.positional_embedding.to(x.dtype)
+        x = vis.ln_pre(x).permute(1, 0, 2)
+        x = vis.transformer(x).permute(1, 0, 2)
+        feat = vis.ln_post(x[:, 0, :]) @ vis.proj
+        tfeat = clip.encode_text(torch.from_numpy(tokens))          # model.py:941-956
+        f = feat / feat.norm(dim=-1, keepdim=True)                  # model.py:966-973
+        t = tfeat / tfeat.norm(dim=-1, keepdim=True)
+        logits = clip.logit_scale.exp() * f @ t.t()
+        return feat, tfeat, logits, logits.softmax(dim=-1)          # models/adapter_clip.py:99
+
+    real = torch.nn.functional.dropout
+    torch.nn.functional.dropout = fake_dropout
+    try:
+        clip.train()
+        for pair in vo.adapter_masks(seed + 400, cfg.layers, cfg.tokens, n):
+            queue += [torch.from_numpy(m) for m in pair]
+        for pair in vo.adapter_masks(seed + 500, tcfg.layers, tcfg.context, num_classes):
+            queue += [torch.from_numpy(m) for m in pair]
+        feat, tfeat, logits, probs = forward()
+        assert not queue
+        loss = torch.nn.CrossEntropyLoss()(probs, torch.from_numpy(labels))
+        loss.backward()
+        clip.eval()
+        with torch.no_grad():
+            _, _, _, probs_eval = forward()
+    finally:
+        torch.nn.functional.dropout = real
+    out = {"feat": feat.detach().numpy(), "tfeat": tfeat.detach().numpy(),
+           "logits": logits.detach().numpy(), "probs": probs.detach().numpy(),
+           "probs_eval": probs_eval.numpy(),
+           "loss": loss.detach().numpy(), "pred": probs.argmax(-1).numpy(),
+           "logit_scale_exp": clip.logit_scale.exp().detach().numpy()}
+    ng = 0
+    for k, p in clip.named_parameters():
+        if p.grad is not None:
+            assert "adaptmlp" in k
+            g = p.grad.numpy()
+            ng += 1
+            layer = int(k.split("resblocks.")[1].split(".")[0])
+            if g.size > 4096 and cfg.layers > 4 and layer not in (0, cfg.layers // 2,
+                                                                  cfg.layers - 1):
+                continue            # full-size case: weight gradients of three layers per tower
+            if g.size > 4096:       # scaled fp16 keeps the file small (as load_grads undoes)
+                sc = float(np.abs(g).max()) / 32768.0 or 1.0
+                out["grad16:" + k] = (g / sc).astype(np.float16)
+                out["gscale:" + k] = np.float32(sc)
+            else:
+                out["grad:" + k] = g
+    assert ng == 4 * (cfg.layers + tcfg.layers), ng
+    return out
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     only = sys.argv[1:]
@@ -381,6 +483,13 @@ def main():
         if only and name not in only:
             continue
         out = run_reference_maple(cfg, tcfg, n, c, seed)
+        path = os.path.join(HERE, f"ref_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(name, "loss", float(out["loss"]), "->", path, os.path.getsize(path), "bytes")
+    for name, (cfg, tcfg, n, c, seed) in ADAPTER_CASES.items():
+        if only and name not in only:
+            continue
+        out = run_reference_adapter(cfg, tcfg, n, c, seed)
         path = os.path.join(HERE, f"ref_{name}.npz")
         np.savez_compressed(path, **out)
         print(name, "loss", float(out["loss"]), "->", path, os.path.getsize(path), "bytes")

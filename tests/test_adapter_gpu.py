@@ -1,0 +1,301 @@
+"""--method adapter-clip: the bottleneck adapter (models/clip/adapter.py:11-73),
+ResidualAttentionBlock_Adapter (models/clip/model.py:418-442) and the adapter-clip step through
+AdapterCLIP / the trainer, on the GPU through the C-ABI, against the fp64 oracle and the golden
+vectors produced by the reference's own classes (dropout draws injected as explicit masks on both
+sides; tests/golden/make_golden.py:run_reference_adapter)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as vo
+from tests.test_e2e_gpu import TOL, cos, rel
+from tests.test_oracle_golden import adapter_case_inputs
+
+pytestmark = pytest.mark.gpu
+
+P = vo.ADAPTER_DROPOUT
+
+
+def _adapter_weights(D, seed):
+    w = vo.synth_adapter_weights(D, 1, "blk.", seed)
+    return {k.replace("blk.0.adaptmlp.", ""): v for k, v in w.items()}
+
+
+def _load_adapter(mod, w):
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    return mod.cuda()
+
+
+@pytest.mark.parametrize("D,T", [(128, 300), (768, 1576), (512, 4100)])
+@pytest.mark.parametrize("training", [True, False])
+def test_adapter_module_matches_oracle(D, T, training):
+    """Adapter.forward(x) (add_residual=True) and its four parameter gradients + dx: the two
+    tcgen05 projections, the ReLU/dropout pass and the token-reduction weight-gradient kernel."""
+    from lifelong_clip_b200.adapter_modules import Adapter
+    rng = np.random.default_rng(D + T)
+    w = _adapter_weights(D, 5)
+    x = rng.standard_normal((T, D)).astype(np.float32)
+    dy = rng.standard_normal((T, D)).astype(np.float32)
+    mask = (rng.random((T, vo.ADAPTER_DIM)) >= P).astype(np.uint8)
+    mod = _load_adapter(Adapter(d_model=D, dropout=P, bottleneck=64, init_option="lora",
+                                adapter_scalar=0.1, adapter_layernorm_option="none"), w)
+    mod.train(training)
+    if training:
+        mod.push_masks(torch.from_numpy(mask))
+    xg = torch.from_numpy(x).cuda().requires_grad_(True)
+    out = mod(xg)
+    out.backward(torch.from_numpy(dy).cuda())
+    torch.cuda.synchronize()
+
+    wt = {("a." + k): torch.from_numpy(v).double().requires_grad_(True) for k, v in w.items()}
+    xo = torch.from_numpy(x).double().requires_grad_(True)
+    want = vo.adapter_forward(xo, wt, "a.", torch.from_numpy(mask) if training else None,
+                              P if training else 0.0)
+    want.backward(torch.from_numpy(dy).double())
+    # the residual is carried in fp32: the output is exact up to the bf16 bottleneck branch
+    assert rel(out, want) < 2e-3
+    assert rel(out - xg.detach(), (want - xo).detach()) < TOL
+    assert rel(xg.grad, xo.grad) < 2e-3
+    assert rel(xg.grad.cpu() - torch.from_numpy(dy), xo.grad - torch.from_numpy(dy).double()) < TOL
+    for name, p in mod.named_parameters():
+        g, gw = p.grad, wt["a." + name].grad
+        assert rel(g, gw) < TOL and cos(g, gw) > 0.9999, (name, rel(g, gw))
+
+
+def test_adapter_add_residual_false_and_explicit_residual():
+    """The two other call forms of Adapter.forward (adapter.py:53,55,69-72)."""
+    from lifelong_clip_b200.adapter_modules import Adapter
+    D, T = 256, 777
+    rng = np.random.default_rng(3)
+    w = _adapter_weights(D, 9)
+    mod = _load_adapter(Adapter(d_model=D, dropout=0.0, bottleneck=64, adapter_scalar=0.1,
+                                adapter_layernorm_option="none"), w).eval()
+    x = torch.from_numpy(rng.standard_normal((T, D)).astype(np.float32)).cuda()
+    r = torch.from_numpy(rng.standard_normal((T, D)).astype(np.float32)).cuda()
+    wt = {("a." + k): torch.from_numpy(v).double() for k, v in w.items()}
+    base = vo.adapter_forward(x.double().cpu(), wt, "a.") - x.double().cpu()     # scale * up
+    assert rel(mod(x, add_residual=False), base) < TOL
+    assert rel(mod(x, residual=r) - r, base) < TOL
+    xg, rg = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    mod(xg, residual=rg).sum().backward()
+    assert torch.equal(rg.grad, torch.ones_like(r))
+    xo = x.double().cpu().requires_grad_(True)
+    (vo.adapter_forward(xo, wt, "a.") - xo).sum().backward()
+    assert rel(xg.grad, xo.grad) < TOL
+
+
+def test_adapter_dropout_stream():
+    """Generated dropout (no injected mask): keep rate 1 - p, kept values scaled by 1 / (1 - p),
+    a new draw on every call, none in eval mode."""
+    from lifelong_clip_b200.adapter_modules import Adapter
+    D, T = 128, 4096
+    w = _adapter_weights(D, 1)
+    w["down_proj.bias"] = np.full(64, 5.0, np.float32)          # every pre-activation positive
+    w["up_proj.weight"] = np.eye(D, 64, dtype=np.float32)       # out[:, :64] = scale * bottleneck
+    w["up_proj.bias"] = np.zeros(D, np.float32)
+    mod = _load_adapter(Adapter(d_model=D, dropout=P, bottleneck=64, adapter_scalar=0.1,
+                                adapter_layernorm_option="none"), w)
+    x = torch.zeros(T, D, device="cuda")
+    mod.eval()
+    full = mod(x, add_residual=False)[:, :64]
+    assert float((full - 0.5).abs().max()) < 5e-3               # 0.1 * relu(5)
+    mod.train()
+    a = mod(x, add_residual=False)[:, :64]
+    b = mod(x, add_residual=False)[:, :64]
+    keep = (a != 0).float().mean().item()
+    assert abs(keep - (1 - P)) < 0.01, keep
+    kept = a[a != 0]
+    assert float((kept - 0.5 / (1 - P)).abs().max()) < 5e-3
+    assert float(((a != 0) != (b != 0)).float().mean()) > 0.1   # independent draws
+    rows = (a != 0).float().mean(1)
+    assert float(rows.std()) < 0.06                             # no structure along tokens
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_adapter_block_matches_oracle(causal):
+    """ResidualAttentionBlock_Adapter on [L, N, D] (training mode, injected masks): output, dx
+    and the gradients of the shared adapter (both applications summed) vs the fp64 oracle."""
+    from lifelong_clip_b200.adapter_modules import ResidualAttentionBlock_Adapter
+    cfg = vo.VitCfg(image_size=64, patch=16, width=256, layers=1, heads=4, embed_dim=64)
+    L, N, D = (24, 50, 256) if causal else (17, 70, 256)
+    rng = np.random.default_rng(11 + causal)
+    w = vo.strip_lora(vo.synth_weights(cfg, 3))
+    wa = vo.synth_adapter_weights(D, 1, "visual.transformer.resblocks.", 4)
+    pre = "visual.transformer.resblocks.0."
+    mask = torch.full((L, L), float("-inf")).triu(1) if causal else None
+    blk = ResidualAttentionBlock_Adapter(D, cfg.heads, mask, {"ffn_num": 64})
+    sd = {k[len(pre):]: torch.from_numpy(v) for k, v in {**w, **wa}.items() if k.startswith(pre)}
+    blk.load_state_dict(sd)
+    blk.cuda().train()
+    for k, p in blk.named_parameters():
+        p.requires_grad = "adaptmlp" in k
+    masks = vo.adapter_masks(77, 1, L, N)
+    blk.adaptmlp.push_masks(*[torch.from_numpy(m).reshape(L * N, -1) for m in masks[0]])
+    x = rng.standard_normal((L, N, D)).astype(np.float32)
+    dy = rng.standard_normal((L, N, D)).astype(np.float32)
+    xg = torch.from_numpy(x).cuda().requires_grad_(True)
+    out = blk(xg)
+    out.backward(torch.from_numpy(dy).cuda())
+    torch.cuda.synchronize()
+
+    wt = {k: torch.from_numpy(v).double() for k, v in w.items()}
+    wat = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in wa.items()}
+    xo = torch.from_numpy(x).double().permute(1, 0, 2).contiguous().requires_grad_(True)
+    want = vo.adapter_block_forward(xo, {**wt, **wat}, pre, cfg, causal=causal,
+                                    masks=vo.masks_sample_major(masks)[0], p=P)
+    want.backward(torch.from_numpy(dy).double().permute(1, 0, 2))
+    assert rel(out.permute(1, 0, 2), want) < TOL
+    assert rel(xg.grad.permute(1, 0, 2), xo.grad) < TOL
+    for k, p in blk.named_parameters():
+        if "adaptmlp" in k:
+            gw = wat[pre + k].grad
+            assert rel(p.grad, gw) < TOL and cos(p.grad, gw) > 0.9999, (k, rel(p.grad, gw))
+        else:
+            assert p.grad is None
+    # eval mode: no dropout, no mask consumed
+    blk.eval()
+    with torch.no_grad():
+        out_e = blk(torch.from_numpy(x).cuda())
+    want_e = vo.adapter_block_forward(xo.detach(), {**wt, **wat}, pre, cfg, causal=causal)
+    assert rel(out_e.permute(1, 0, 2), want_e.detach()) < TOL
+
+
+def build_adapter_clip(cfg, tcfg, wv, wt, wa, wta):
+    from lifelong_clip_b200.adapter_clip import AdapterCLIP
+    m = AdapterCLIP(peft_method="adapter", peft_encoder="both",
+                    vision_config=(cfg.image_size, cfg.patch, cfg.width, cfg.layers,
+                                   cfg.embed_dim),
+                    text_config=(tcfg.context, tcfg.vocab, tcfg.width, tcfg.heads, tcfg.layers))
+    sd = {k: torch.from_numpy(v) for k, v in {**vo.strip_lora(wv), **vo.strip_lora(wt), **wa,
+                                              **wta}.items()}
+    missing, unexpected = m.model.load_state_dict(sd, strict=False)
+    assert not unexpected and set(missing) <= {"logit_scale"}, (missing, unexpected)
+    m.cuda()
+    for k, p in m.named_parameters():           # methods/adapter_clip.py:117-119
+        if "adaptmlp" not in k and "lora" not in k:
+            p.requires_grad = False
+    return m
+
+
+def _push_case_masks(m, masks, tmasks):
+    # the image tower runs after the text tower in AdapterCLIP._forward_blocks; every block pops
+    # its own two masks, so the order between towers does not matter
+    for blk, pair in zip(m.model.visual.transformer.resblocks, masks):
+        blk.adaptmlp.push_masks(*[torch.from_numpy(x).reshape(-1, vo.ADAPTER_DIM) for x in pair])
+    for blk, pair in zip(m.model.transformer.resblocks, tmasks):
+        blk.adaptmlp.push_masks(*[torch.from_numpy(x).reshape(-1, vo.ADAPTER_DIM) for x in pair])
+
+
+# bf16 operands in BOTH towers: the calibration of tests/test_round2_gpu.py (TOL_BOTH) applies
+TOL_ADAPTER = {"adapter_tiny": (3.5e-2, 6e-2), "adapter_vitb16": (2e-2, 5e-2)}
+
+
+@pytest.mark.parametrize("name", ["adapter_tiny", "adapter_vitb16"])
+def test_adapter_clip_matches_reference_golden(name, golden_dir):
+    """AdapterCLIP(peft_method='adapter', peft_encoder='both') - what scripts/adapter_clip.sh
+    runs - against the reference's own CLIP with ResidualAttentionBlock_Adapter in both towers:
+    probabilities, loss, predictions and the adapter gradients of the training-mode step, and the
+    eval-mode probabilities."""
+    from tests.golden.make_golden import load_grads
+    cfg, tcfg, wv, wt, wa, wta, images, labels, tokens, masks, tmasks = adapter_case_inputs(name)
+    gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    m = build_adapter_clip(cfg, tcfg, wv, wt, wa, wta)
+    with torch.no_grad():
+        m.model.logit_scale.fill_(float(np.log(gold["logit_scale_exp"])))
+    c = tokens.shape[0]
+    names = [f"c{i}" for i in range(c)]
+    table = {m.prompt_template.format(nm): torch.from_numpy(tokens[i]) for i, nm in enumerate(names)}
+    m.set_tokenizer(lambda texts: torch.stack([table[t] for t in texts]))
+    m.set_token(names)
+    x, y = torch.from_numpy(images).cuda(), torch.from_numpy(labels).cuda()
+    m.train()
+    _push_case_masks(m, masks, tmasks)
+    probs, fi, ft = m(x)
+    loss = torch.nn.CrossEntropyLoss()(probs, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    tol_flat, tol_worst = TOL_ADAPTER[name]
+    assert tuple(ft.shape) == (c, cfg.embed_dim)
+    assert rel(probs, gold["probs"]) < TOL
+    assert abs(loss.item() - float(gold["loss"])) < TOL * abs(float(gold["loss"]))
+    p64 = np.sort(np.asarray(gold["probs"], np.float64), axis=-1)
+    safe = (p64[:, -1] - p64[:, -2]) > 0.05 * p64[:, -1]
+    np.testing.assert_array_equal(probs.argmax(-1).cpu().numpy()[safe],
+                                  np.asarray(gold["pred"])[safe])
+    want = load_grads(gold)
+    got = {k[len("model."):]: p.grad.cpu().numpy() for k, p in m.named_parameters()
+           if p.grad is not None}
+    assert len(got) == 4 * (cfg.layers + tcfg.layers) and all("adaptmlp" in k for k in got)
+    assert set(want) <= set(got)
+    for tower in ("visual.", "transformer."):
+        keys = sorted(k for k in want if k.startswith(tower))
+        fg = np.concatenate([got[k].ravel() for k in keys]).astype(np.float64)
+        fw = np.concatenate([want[k].ravel() for k in keys]).astype(np.float64)
+        assert rel(fg, fw) < tol_flat, (tower, rel(fg, fw))
+        assert cos(fg, fw) > 1.0 - tol_flat ** 2
+        rels = [rel(got[k], want[k]) for k in keys]
+        assert max(rels) < tol_worst, (max(rels), keys[int(np.argmax(rels))])
+    # the fused-loss path of the trainer gives the same gradients as CrossEntropyLoss(probs, y)
+    m.zero_grad()
+    _push_case_masks(m, masks, tmasks)
+    _, _, pred, loss2, _ = m._forward_blocks(x, m.text_tokens, labels=y, inv_batch=1.0 / len(y))
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) < 1e-4 * abs(loss.item())
+    got2 = {k[len("model."):]: p.grad.cpu().numpy() for k, p in m.named_parameters()
+            if p.grad is not None}
+    f1 = np.concatenate([got[k].ravel() for k in sorted(got)])
+    f2 = np.concatenate([got2[k].ravel() for k in sorted(got)])
+    assert rel(f2, f1) < 2e-3
+    m.eval()
+    with torch.no_grad():
+        pe, _, _ = m(x)
+    assert rel(pe, gold["probs_eval"]) < TOL
+
+
+def test_adapter_trainer_steps_and_evaluates():
+    """LoRAClipTrainer on the adapter-clip model: the freeze filter leaves exactly the adaptmlp
+    tensors trainable, steps update them through ONE flat AdamW launch (state matches
+    torch.optim.AdamW on the same gradients), the loss falls, evaluation returns the reference's
+    dictionary with raw class ids."""
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+    cfg, tcfg = vo.VIT_TINY, vo.TEXT_TINY
+    wv, wt = vo.synth_weights(cfg, 1), vo.synth_text_weights(tcfg, 2)
+    wa = vo.synth_adapter_weights(cfg.width, cfg.layers, "visual.transformer.resblocks.", 3)
+    wta = vo.synth_adapter_weights(tcfg.width, tcfg.layers, "transformer.resblocks.", 4)
+    m = build_adapter_clip(cfg, tcfg, wv, wt, wa, wta)
+    C_, n = 6, 12
+    names = [f"c{i}" for i in range(C_)]
+    tokens = vo.synth_tokens(C_, tcfg, 5)
+    table = {m.prompt_template.format(nm): torch.from_numpy(tokens[i]) for i, nm in enumerate(names)}
+    m.set_tokenizer(lambda texts: torch.stack([table[t] for t in texts]))
+    tr = LoRAClipTrainer(m, names, n_classes=C_, n_tasks=2, lr=3e-3, online_iter=1,
+                         visible_classes="all")
+    tr.online_before_task(0)
+    trainable = [k for k, p in m.named_parameters() if p.requires_grad]
+    assert trainable and all("adaptmlp" in k for k in trainable)
+    assert len(trainable) == 4 * (cfg.layers + tcfg.layers)
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.standard_normal((n, 3, cfg.image_size, cfg.image_size))
+                         .astype(np.float32))
+    y = torch.from_numpy(rng.integers(0, C_, n))
+    ref_params = [p.detach().clone().requires_grad_(True) for p in tr.optimizer.params]
+    ref_opt = torch.optim.AdamW(ref_params, lr=3e-3, weight_decay=1e-5)
+    losses = []
+    for it in range(6):
+        loss, acc = tr.online_step(x, y, torch.arange(n))
+        losses.append(loss)
+        if it == 0:      # same gradients through torch's AdamW -> same parameters
+            for rp, v in zip(ref_params, tr.optimizer.views):
+                rp.grad = v.detach().clone()
+            ref_opt.step()
+            for rp, p in zip(ref_params, tr.optimizer.params):
+                assert rel(p, rp) < 1e-6
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    tr._total_classes = C_
+    tr.online_after_task(0)
+    out = tr.online_evaluate([(x, y)])
+    assert set(out) == {"avg_loss", "avg_acc", "cls_acc", "task_acc", "confusion_matrix"}
+    assert 0.0 <= float(out["avg_acc"]) <= 1.0
+    assert int(np.sum(out["confusion_matrix"])) == n

@@ -147,3 +147,45 @@ def test_vitl14_oracle_matches_reference_golden(golden_dir):
     assert set(want) == set(out["grads"]) and len(want) == 96
     worst = max(_rel(out["grads"][k], v) for k, v in want.items())
     assert worst < 2e-3, worst      # fp16-packed fixture: 6e-4 rounding
+
+
+def adapter_case_inputs(name):
+    """Inputs of an ADAPTER_CASES golden (shared with the GPU parity test)."""
+    from tests.golden.make_golden import ADAPTER_CASES
+    cfg, tcfg, n, c, seed = ADAPTER_CASES[name]
+    wv, wt = vo.synth_weights(cfg, seed), vo.synth_text_weights(tcfg, seed + 1)
+    wa = vo.synth_adapter_weights(cfg.width, cfg.layers, "visual.transformer.resblocks.", seed + 2)
+    wta = vo.synth_adapter_weights(tcfg.width, tcfg.layers, "transformer.resblocks.", seed + 3)
+    images, labels = synth_inputs(cfg, n, c, seed + 100)
+    tokens = vo.synth_tokens(c, tcfg, seed + 300)
+    masks = vo.adapter_masks(seed + 400, cfg.layers, cfg.tokens, n)
+    tmasks = vo.adapter_masks(seed + 500, tcfg.layers, tcfg.context, c)
+    return cfg, tcfg, wv, wt, wa, wta, images, labels, tokens, masks, tmasks
+
+
+@pytest.mark.parametrize("name", ["adapter_tiny", "adapter_vitb16"])
+def test_adapter_oracle_matches_reference_golden(name, golden_dir):
+    """--method adapter-clip (N4): the oracle's adapter blocks (model.py:418-442, adapter.py:11-73
+    restated) in both towers against the reference's own classes, training mode with the same
+    injected dropout masks, and the eval-mode forward."""
+    from tests.golden.make_golden import load_grads
+    cfg, tcfg, wv, wt, wa, wta, images, labels, tokens, masks, tmasks = adapter_case_inputs(name)
+    gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    torch.set_num_threads(os.cpu_count() or 1)
+    dtype = torch.float64 if name == "adapter_tiny" else torch.float32
+    out = vo.adapter_step_oracle(
+        images, labels, wv, wa, None, cfg, logit_scale_exp=float(gold["logit_scale_exp"]),
+        dtype=dtype, masks=vo.masks_sample_major(masks), p=vo.ADAPTER_DROPOUT, tokens=tokens,
+        wt_np=wt, wta_np=wta, tcfg=tcfg, tmasks=vo.masks_sample_major(tmasks))
+    assert _rel(out["probs"], gold["probs"]) < 2e-5
+    assert abs(float(out["loss"]) - float(gold["loss"])) < 1e-5
+    np.testing.assert_array_equal(out["pred"], gold["pred"])
+    want = load_grads(gold)
+    assert set(want) <= set(out["grads"])
+    assert len(out["grads"]) == 4 * (cfg.layers + tcfg.layers)
+    worst = max(_rel(out["grads"][k], v) for k, v in want.items())
+    assert worst < 2e-3, worst      # fp16-packed fixture: 6e-4 rounding
+    ev = vo.adapter_step_oracle(images, labels, wv, wa, None, cfg,
+                                logit_scale_exp=float(gold["logit_scale_exp"]), dtype=dtype,
+                                tokens=tokens, wt_np=wt, wta_np=wta, tcfg=tcfg)
+    assert _rel(ev["probs"], gold["probs_eval"]) < 2e-5
