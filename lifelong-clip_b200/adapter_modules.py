@@ -63,6 +63,10 @@ class Adapter(nn.Module):
         self._ops_key = None
         self._calls = 0
         self._masks = []
+        # keep_bottleneck: retain the bf16 [T, 64] bottleneck(s) after ReLU and dropout of the
+        # latest call (one per application) - which gates were open (diagnostics / tests)
+        self.keep_bottleneck = False
+        self.last_bottleneck = ()
 
     # -- operands ------------------------------------------------------------------------------
     def params(self):
@@ -150,6 +154,7 @@ class _AdapterFn(torch.autograd.Function):
                                              out.data_ptr(), T, D, K.stream_ptr()),
                 "llc_adapter_forward")
         ctx.ad, ctx.yb, ctx.a, ctx.params, ctx.shape = ad, yb, a, params, x.shape
+        ad.last_bottleneck = (a,) if ad.keep_bottleneck else ()
         ctx.training = training
         ctx.res_is_x = add_residual and residual is None
         ctx.res_given = add_residual and residual is not None
@@ -220,6 +225,7 @@ class _AdapterBlockFn(torch.autograd.Function):
             C.byref(blk._cfg), C.byref(layer), C.byref(s), C.byref(b), C.byref(ab), N, L, 1, N,
             causal, int(training), K.stream_ptr()), "llc_adapter_block_forward")
         ctx.blk, ctx.bufs, ctx.abufs, ctx.shape, ctx.causal = blk, bufs, abufs, (L, N, D), causal
+        ad.last_bottleneck = (abufs["a1"], abufs["a2"]) if ad.keep_bottleneck else ()
         ctx.x_needs_grad, ctx.params, ctx.training, ctx.seed = x.requires_grad, params, training, seed
         return bufs["x_out"].view(L, N, D)
 

@@ -564,12 +564,21 @@ def synth_adapter_weights(width: int, layers: int, prefix: str = "visual.transfo
     return {k: v.astype(np.float32) for k, v in out.items()}
 
 
-def adapter_forward(y, w, prefix: str, mask=None, p: float = 0.0):
+def adapter_forward(y, w, prefix: str, mask=None, p: float = 0.0, gate=None):
     """Adapter.forward models/clip/adapter.py:53-73 with adapter_layernorm_option='none' and
     add_residual=True: y + scale * up(dropout(relu(down(y)))). mask: keep flags (same shape as
     the bottleneck) standing in for torch's dropout draw; the kept values are scaled by
-    1 / (1 - p) as nn.functional.dropout does."""
-    down = torch.relu(y @ w[prefix + "down_proj.weight"].T + w[prefix + "down_proj.bias"])
+    1 / (1 - p) as nn.functional.dropout does.
+    gate (kernel tests only): 0/1 flags replacing BOTH ReLU's own decision and the mask - the
+    pre-activation is multiplied by the gate. ReLU is discontinuous in its gradient at 0, so an
+    implementation that rounds the pre-activation (bf16) places a few gates differently from this
+    fp64 restatement; with the implementation's gates handed in, what is compared is arithmetic."""
+    down = y @ w[prefix + "down_proj.weight"].T + w[prefix + "down_proj.bias"]
+    if gate is not None:
+        down = down * gate.to(down.dtype) / (1.0 - p)
+        mask = None
+    else:
+        down = torch.relu(down)
     if mask is not None:
         down = down * mask.to(down.dtype) / (1.0 - p)
     up = down @ w[prefix + "up_proj.weight"].T + w[prefix + "up_proj.bias"]
@@ -577,21 +586,23 @@ def adapter_forward(y, w, prefix: str, mask=None, p: float = 0.0):
 
 
 def adapter_block_forward(x, w, prefix: str, cfg: VitCfg, causal: bool = False, masks=None,
-                          p: float = 0.0):
+                          p: float = 0.0, gates=None):
     """ResidualAttentionBlock_Adapter.forward models/clip/model.py:440-442 (vanilla attention and
-    MLP, one shared adaptmlp on both branches). masks: (mask1, mask2) or None."""
+    MLP, one shared adaptmlp on both branches). masks: (mask1, mask2) or None; gates: see
+    adapter_forward."""
     D = cfg.width
     m1, m2 = masks if masks is not None else (None, None)
+    g1, g2 = gates if gates is not None else (None, None)
     h = layer_norm(x, w[prefix + "ln_1.weight"], w[prefix + "ln_1.bias"])
     qkv = h @ w[prefix + "attn.in_proj_weight"].T + w[prefix + "attn.in_proj_bias"]
     q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
     o = attention_core(q, k, v, cfg.heads, causal)
     ya = o @ w[prefix + "attn.out_proj.weight"].T + w[prefix + "attn.out_proj.bias"]
-    x = x + adapter_forward(ya, w, prefix + "adaptmlp.", m1, p)
+    x = x + adapter_forward(ya, w, prefix + "adaptmlp.", m1, p, g1)
     h2 = layer_norm(x, w[prefix + "ln_2.weight"], w[prefix + "ln_2.bias"])
     z = h2 @ w[prefix + "mlp.c_fc.weight"].T + w[prefix + "mlp.c_fc.bias"]
     m = quick_gelu(z) @ w[prefix + "mlp.c_proj.weight"].T + w[prefix + "mlp.c_proj.bias"]
-    return x + adapter_forward(m, w, prefix + "adaptmlp.", m2, p)
+    return x + adapter_forward(m, w, prefix + "adaptmlp.", m2, p, g2)
 
 
 def adapter_step_oracle(images, labels_local, w_np, wa_np, text, cfg: VitCfg,
@@ -635,8 +646,9 @@ def adapter_step_oracle(images, labels_local, w_np, wa_np, text, cfg: VitCfg,
     loss.backward()
     out = {"feat": feat, "fnorm": f, "probs": probs, "logits": logits, "loss": loss,
            "pred": predict(probs), "tnorm": tn}
-    res = {k: v.detach().cpu().numpy() for k, v in out.items()}
-    res["grads"] = {k: v.grad.detach().cpu().numpy() for k, v in {**wa, **wta}.items()}
+    np_ = lambda v: (v.float() if v.dtype == torch.bfloat16 else v).detach().cpu().numpy()
+    res = {k: np_(v) for k, v in out.items()}
+    res["grads"] = {k: np_(v.grad) for k, v in {**wa, **wta}.items()}
     return res
 
 

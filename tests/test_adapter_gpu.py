@@ -42,6 +42,7 @@ def test_adapter_module_matches_oracle(D, T, training):
     mod = _load_adapter(Adapter(d_model=D, dropout=P, bottleneck=64, init_option="lora",
                                 adapter_scalar=0.1, adapter_layernorm_option="none"), w)
     mod.train(training)
+    mod.keep_bottleneck = True
     if training:
         mod.push_masks(torch.from_numpy(mask))
     xg = torch.from_numpy(x).cuda().requires_grad_(True)
@@ -49,10 +50,21 @@ def test_adapter_module_matches_oracle(D, T, training):
     out.backward(torch.from_numpy(dy).cuda())
     torch.cuda.synchronize()
 
+    # ReLU's gradient is discontinuous at 0: the kernel gates on the bf16-rounded pre-activation,
+    # so a handful of near-zero elements (6 of 19200 in the first case: a 3 % error of dx,
+    # reproduced exactly by emulating the roundings on the CPU) open differently than in fp64.
+    # The oracle takes the kernel's gates; the forward check below is against the plain oracle.
+    gate = (mod.last_bottleneck[0] > 0).cpu()
     wt = {("a." + k): torch.from_numpy(v).double().requires_grad_(True) for k, v in w.items()}
     xo = torch.from_numpy(x).double().requires_grad_(True)
-    want = vo.adapter_forward(xo, wt, "a.", torch.from_numpy(mask) if training else None,
-                              P if training else 0.0)
+    plain = vo.adapter_forward(xo.detach(), wt, "a.", torch.from_numpy(mask) if training else None,
+                               P if training else 0.0)
+    assert rel(out, plain) < 2e-3
+    z64 = (xo @ wt["a.down_proj.weight"].T + wt["a.down_proj.bias"]).detach()
+    open64 = (z64 > 0) & (torch.from_numpy(mask).bool() if training else torch.tensor(True))
+    flips = float((gate != open64).float().mean())
+    assert flips < 2e-3, flips
+    want = vo.adapter_forward(xo, wt, "a.", None, P if training else 0.0, gate=gate)
     want.backward(torch.from_numpy(dy).double())
     # the residual is carried in fp32: the output is exact up to the bf16 bottleneck branch
     assert rel(out, want) < 2e-3
@@ -79,10 +91,12 @@ def test_adapter_add_residual_false_and_explicit_residual():
     assert rel(mod(x, add_residual=False), base) < TOL
     assert rel(mod(x, residual=r) - r, base) < TOL
     xg, rg = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    mod.keep_bottleneck = True
     mod(xg, residual=rg).sum().backward()
     assert torch.equal(rg.grad, torch.ones_like(r))
     xo = x.double().cpu().requires_grad_(True)
-    (vo.adapter_forward(xo, wt, "a.") - xo).sum().backward()
+    gate = (mod.last_bottleneck[0] > 0).cpu()        # the kernel's ReLU gates (see above)
+    (vo.adapter_forward(xo, wt, "a.", gate=gate) - xo).sum().backward()
     assert rel(xg.grad, xo.grad) < TOL
 
 
@@ -132,19 +146,26 @@ def test_adapter_block_matches_oracle(causal):
     for k, p in blk.named_parameters():
         p.requires_grad = "adaptmlp" in k
     masks = vo.adapter_masks(77, 1, L, N)
+    blk.adaptmlp.keep_bottleneck = True
     blk.adaptmlp.push_masks(*[torch.from_numpy(m).reshape(L * N, -1) for m in masks[0]])
     x = rng.standard_normal((L, N, D)).astype(np.float32)
     dy = rng.standard_normal((L, N, D)).astype(np.float32)
+    wt = {k: torch.from_numpy(v).double() for k, v in w.items()}
+    wat = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in wa.items()}
+    xo = torch.from_numpy(x).double().permute(1, 0, 2).contiguous().requires_grad_(True)
     xg = torch.from_numpy(x).cuda().requires_grad_(True)
     out = blk(xg)
     out.backward(torch.from_numpy(dy).cuda())
     torch.cuda.synchronize()
 
-    wt = {k: torch.from_numpy(v).double() for k, v in w.items()}
-    wat = {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in wa.items()}
-    xo = torch.from_numpy(x).double().permute(1, 0, 2).contiguous().requires_grad_(True)
-    want = vo.adapter_block_forward(xo, {**wt, **wat}, pre, cfg, causal=causal,
-                                    masks=vo.masks_sample_major(masks)[0], p=P)
+    plain = vo.adapter_block_forward(xo.detach(), {**wt, **wat}, pre, cfg, causal=causal,
+                                     masks=vo.masks_sample_major(masks)[0], p=P)
+    assert rel(out.permute(1, 0, 2), plain.detach()) < TOL
+    # gradients: the oracle takes the kernel's ReLU/dropout gates (see the module test)
+    gates = [(a > 0).view(L, N, -1).permute(1, 0, 2).cpu() for a in blk.adaptmlp.last_bottleneck]
+    for g, mk in zip(gates, vo.masks_sample_major(masks)[0]):
+        assert float((g & (mk == 0)).sum()) == 0            # a dropped element is never open
+    want = vo.adapter_block_forward(xo, {**wt, **wat}, pre, cfg, causal=causal, p=P, gates=gates)
     want.backward(torch.from_numpy(dy).double().permute(1, 0, 2))
     assert rel(out.permute(1, 0, 2), want) < TOL
     assert rel(xg.grad.permute(1, 0, 2), xo.grad) < TOL
@@ -188,8 +209,23 @@ def _push_case_masks(m, masks, tmasks):
         blk.adaptmlp.push_masks(*[torch.from_numpy(x).reshape(-1, vo.ADAPTER_DIM) for x in pair])
 
 
-# bf16 operands in BOTH towers: the calibration of tests/test_round2_gpu.py (TOL_BOTH) applies
-TOL_ADAPTER = {"adapter_tiny": (3.5e-2, 6e-2), "adapter_vitb16": (2e-2, 5e-2)}
+# Gradient bounds (flat rel-L2, worst tensor) per tower. Besides bf16 operands in both towers (the
+# calibration of tests/test_round2_gpu.py), the bottleneck's ReLU makes the gradient
+# DISCONTINUOUS in the pre-activation: rounding it opens a few gates differently from fp32, each
+# flip an O(1) error of that element. Calibration (tools/parity_adapter_calib.py ->
+# profiles/r02_parity_adapter_vs_autocast.txt): PyTorch's OWN bf16 autocast of the same step, same
+# dropout masks, against the reference's fp32 output measures
+#   adapter_vitb16: image tower flat 2.2e-2 / worst 5.3e-2, text tower flat 7.4e-2 / worst 3.3e-1
+#   adapter_tiny:   image tower flat 6.4e-2 / worst 1.5e-1, text tower flat 5.6e-2 / worst 1.3e-1
+# (worst tensors: down_proj.bias of late blocks; the text tower's gradient enters through ONE row
+# per class and nearly cancels there). This path measures, on the same cases,
+#   adapter_vitb16: image 2.0e-2 / 5.4e-2 (median tensor 1.5e-2), text 7.8e-2 / 3.7e-1 (median
+#                   2.4e-2; the worst tensor is the SAME transformer.resblocks.10 down_proj.bias)
+#   adapter_tiny:   image 2.2e-2 / 4.3e-2, text 2.0e-2 / 2.3e-2.
+# Bounds (flat, worst tensor, median tensor): autocast's level, +20 % where this path sits on it.
+TOL_ADAPTER = {"adapter_tiny": {"visual.": (3.5e-2, 6e-2, 3e-2), "transformer.": (3.5e-2, 6e-2, 3e-2)},
+               "adapter_vitb16": {"visual.": (2.5e-2, 6.5e-2, 2e-2),
+                                  "transformer.": (9e-2, 4.5e-1, 3e-2)}}
 
 
 @pytest.mark.parametrize("name", ["adapter_tiny", "adapter_vitb16"])
@@ -216,7 +252,6 @@ def test_adapter_clip_matches_reference_golden(name, golden_dir):
     loss = torch.nn.CrossEntropyLoss()(probs, y)
     loss.backward()
     torch.cuda.synchronize()
-    tol_flat, tol_worst = TOL_ADAPTER[name]
     assert tuple(ft.shape) == (c, cfg.embed_dim)
     assert rel(probs, gold["probs"]) < TOL
     assert abs(loss.item() - float(gold["loss"])) < TOL * abs(float(gold["loss"]))
@@ -230,13 +265,17 @@ def test_adapter_clip_matches_reference_golden(name, golden_dir):
     assert len(got) == 4 * (cfg.layers + tcfg.layers) and all("adaptmlp" in k for k in got)
     assert set(want) <= set(got)
     for tower in ("visual.", "transformer."):
+        tol_flat, tol_worst, tol_median = TOL_ADAPTER[name][tower]
         keys = sorted(k for k in want if k.startswith(tower))
         fg = np.concatenate([got[k].ravel() for k in keys]).astype(np.float64)
         fw = np.concatenate([want[k].ravel() for k in keys]).astype(np.float64)
+        rels = [rel(got[k], want[k]) for k in keys]
+        print(f"{name} {tower} flat {rel(fg, fw):.2e} median {np.median(rels):.2e} worst "
+              f"{max(rels):.2e} ({keys[int(np.argmax(rels))]})")
         assert rel(fg, fw) < tol_flat, (tower, rel(fg, fw))
         assert cos(fg, fw) > 1.0 - tol_flat ** 2
-        rels = [rel(got[k], want[k]) for k in keys]
         assert max(rels) < tol_worst, (max(rels), keys[int(np.argmax(rels))])
+        assert float(np.median(rels)) < tol_median, float(np.median(rels))
     # the fused-loss path of the trainer gives the same gradients as CrossEntropyLoss(probs, y)
     m.zero_grad()
     _push_case_masks(m, masks, tmasks)
