@@ -446,6 +446,162 @@ def run_eval(args, model, names, dev, world, rank, local_rank):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_adapter(args, dev, world, rank, local_rank):
+    """--method adapter: the reference's second PEFT method on the same trainer
+    (scripts/adapter_clip.sh -> ResidualAttentionBlock_Adapter in the towers peft_encoder names,
+    models/clip/model.py:418-442). A step = block-by-block forward (dropout p = 0.1 on the
+    bottleneck) + loss + backward + all-reduce of the flat adapter gradient + fused AdamW."""
+    import torch
+    import torch.distributed as dist
+    from lifelong_clip_b200 import ops
+    from lifelong_clip_b200.adapter_clip import AdapterCLIP, SyntheticTokenizer
+    from lifelong_clip_b200.trainer import DevicePrefetcher, LoRAClipTrainer
+    from lifelong_clip_b200.transform import GpuTransform
+
+    S, p, D, layers, H, E = MODELS[args.model]
+    B, C = per_gpu_batch(args, world), args.classes
+    gB = global_batch(args, world)
+    torch.manual_seed(0)
+    model = AdapterCLIP(model_name=args.model, peft_method="adapter", peft_encoder=args.peft,
+                        vision_config=(S, p, D, layers, E)).to(dev)
+    # the reference's init leaves up_proj at zero (an identity adapter): randomise it so that the
+    # timed step differentiates a non-trivial function
+    with torch.no_grad():
+        for a in model.adapters():
+            a.up_proj.weight.normal_(0, 0.02)
+    names = [f"class {i}" for i in range(C)]
+    if args.peft == "both":
+        model.set_tokenizer(SyntheticTokenizer())
+    else:
+        model.set_text_features(names, torch.randn(C, E, generator=torch.Generator().manual_seed(1)))
+    trainer = LoRAClipTrainer(model, names, n_classes=C, n_tasks=5, lr=1e-3, online_iter=1,
+                              visible_classes="all", sharded_input=True)
+    trainer.online_before_task(0)
+    trainer.add_new_class(torch.arange(C))
+    model.set_token(trainer.exposed_classes_names)
+    lut = trainer._class_lut(trainer.exposed_classes)
+    gen = torch.Generator().manual_seed(100 + rank)
+    host_raw = [torch.randint(0, 256, (B, 3, 32, 32), generator=gen, dtype=torch.uint8).pin_memory()
+                for _ in range(3)]
+    host_y = [torch.randint(0, C, (B,), generator=gen).pin_memory() for _ in range(3)]
+    dev_x = [torch.randn(B, 3, S, S, device=dev,
+                         generator=torch.Generator(device=dev).manual_seed(7 + i + 10 * rank))
+             for i in range(2)]
+    dev_y = [ops.label_remap(y.to(dev), lut) for y in host_y[:2]]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(args.warmup):
+        trainer.block_step(dev_x[i % 2], dev_y[i % 2], gB, sync=False)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        trainer.block_step(dev_x[i % 2], dev_y[i % 2], gB, sync=False)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if sampler else None
+
+    mean, std = (0.5071, 0.4867, 0.4408), (0.2675, 0.2565, 0.2761)
+    trainer.train_transform = GpuTransform.train(S, mean, std)
+    idx = torch.arange(B)
+
+    def host_loader(n):
+        for i in range(n):
+            yield host_raw[i % 3], host_y[i % 3], idx
+
+    last = None
+    for i, (images, labels, ids) in enumerate(
+            DevicePrefetcher(host_loader(args.warmup + args.steps), dev)):
+        if i == args.warmup:
+            barrier()
+            e0.record()
+        last = trainer.online_step(images, labels, ids)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    trainer.train_transform = (lambda x: x)
+
+    ops.prof_enable(True)
+    for i in range(args.prof_steps):
+        trainer.block_step(dev_x[i % 2], dev_y[i % 2], gB, sync=False)
+    torch.cuda.synchronize()
+    recs = ops.prof_read()
+    ops.prof_enable(False)
+    agg = {}
+    for kind, m_, n_, k_, ms, fl, by in recs:
+        d = agg.setdefault((kind, m_, n_, k_), [0, 0.0, 0.0])
+        d[0] += 1; d[1] += ms; d[2] += by
+    by_shape = sorted(({"kind": kk[0], "m": kk[1], "n": kk[2], "k": kk[3],
+                        "launches_per_step": v[0] / args.prof_steps,
+                        "us_per_launch": 1e3 * v[1] / v[0],
+                        "gbs": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] else 0.0}
+                       for kk, v in agg.items()),
+                      key=lambda r: -r["us_per_launch"] * r["launches_per_step"])[:16]
+    by_kind = {}
+    for kind, m_, n_, k_, ms, fl, by in recs:
+        if kind == "gemm" and (n_ < 256 or k_ < 256):
+            kind = "gemm_skinny"        # adapter projections (N = 64 / K = 64), rank-r products
+        d = by_kind.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["launches"] += 1; d["ms"] += ms; d["flops"] += fl; d["bytes"] += by
+    peaks = load_peaks()
+    gemm = by_kind.get("gemm", {"launches": 0, "ms": 1e-9, "flops": 0.0})
+    total_ms = sum(d["ms"] for d in by_kind.values()) or 1.0
+    achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+    peak = peaks["bf16_sustained"] or peaks["bf16"]
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    cfg = workload_config(args, world)
+    cfg["workload"] = (f"CLIP {args.model} adapter-clip online step (bottleneck adapters, "
+                       f"ffn 64, dropout 0.1), stream+replay batch {args.batch}, bf16 operands")
+    cfg["method"] = "adapter-clip"
+    n_adapter = sum(p_.numel() for a in model.adapters() for p_ in a.parameters())
+    out = {
+        "metric": "train img/s, adapter-clip online step", "value": gB / (ms_dev * 1e-3),
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+        "clocks": clocks, "trainable_params": n_adapter,
+        "e2e": {"value": gB / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": (host_raw[0].numel() + host_y[0].numel() * 8) * world,
+                "d2h_bytes_per_step": 8 * world,
+                "api": "for images, labels, idx in DevicePrefetcher(pinned host loader): "
+                       "LoRAClipTrainer.online_step(images, labels, idx) -> (loss, acc)",
+                "last_loss_acc": list(last) if last else None},
+        "gpu_launches": launches * world,
+        "roofline": {"bound": "tensor", "kernel": "gemm2_kernel (tcgen05 cta_group::2 / TMEM): the "
+                     "frozen blocks' dense contractions", "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peaks["source"], "share_of_step": gemm["ms"] / total_ms},
+        "kernel_breakdown": {k: {"ms_per_step": d["ms"] / args.prof_steps,
+                                 "launches_per_step": d["launches"] / args.prof_steps,
+                                 "gbs": (d["bytes"] / (d["ms"] * 1e-3) / 1e9) if d["ms"] else 0.0}
+                             for k, d in sorted(by_kind.items())},
+        "top_launches": by_shape,
+        "cpu_baseline": None,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import numpy as np
     import torch
@@ -475,6 +631,10 @@ def run_ours(args):
     from lifelong_clip_b200.adapter_clip import SyntheticTokenizer
     from lifelong_clip_b200.transform import GpuTransform
 
+    if args.method == "adapter":
+        if args.mode != "train":
+            raise SystemExit("--method adapter measures the training step")
+        return run_adapter(args, dev, world, rank, local_rank)
     S, p, D, layers, H, E = MODELS[args.model]
     B, C = per_gpu_batch(args, world), args.classes
     gB = global_batch(args, world)
@@ -756,6 +916,9 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "eval"])
     ap.add_argument("--peft", default="image", choices=["image", "both"],
                     help="'both': LoRA text tower recomputed every step (scripts/lora_clip.sh)")
+    ap.add_argument("--method", default="lora", choices=["lora", "adapter"],
+                    help="'adapter': the adapter-clip method (scripts/adapter_clip.sh), a secondary "
+                         "line; the headline metric is the lora-clip step")
     ap.add_argument("--classes", type=int, default=None)
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--prof-steps", type=int, default=2)

@@ -296,7 +296,9 @@ typedef struct llc_vit_layer {
   void* f_in_B;    /* [16, 3D]: s * B_in^T     du_in = s dqkv . B_in         (backward) */
   void* f_out_B;   /* [16, D]:  s * B_o^T      du_o  = s dx_mid . B_o        (backward) */
   const float *bqkv, *bo, *bfc, *bproj, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-  /* live fp32 LoRA parameters and their gradient slots (views of the flat buffers) */
+  /* live fp32 LoRA parameters and their gradient slots (views of the flat buffers). All four
+   * slots NULL = frozen attention (vanilla block with zero factors): the backward skips the LoRA
+   * reductions; the pad columns of the dxb / dqkv scratch must then be zero on entry */
   const float *in_A, *in_B, *out_A, *out_B; /* [r,D] [3D,r] [r,D] [D,r] */
   float *g_in_A, *g_in_B, *g_out_A, *g_out_B;
 } llc_vit_layer;

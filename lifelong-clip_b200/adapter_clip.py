@@ -280,9 +280,12 @@ class _ProbsFn(torch.autograd.Function):
         ctx.eng, ctx.teng, ctx.head, ctx.thead = eng, teng, head, thead
         ctx.lora_v, ctx.lora_t, ctx.need_grad = lora_v, lora_t, need_grad
         ctx.scale = model.logit_scale_exp()
-        ctx.mark_non_differentiable(head.pred)
         tf = text if cls_idx is None else text.index_select(0, cls_idx)
-        return head.probs, head.fnorm, head.pred, tf.detach().clone()
+        # clones: outputs also reachable from ctx.head would form a cycle output -> grad_fn -> ctx
+        # -> output that is never collected
+        probs, fnorm, pred = head.probs.clone(), head.fnorm.clone(), head.pred.clone()
+        ctx.mark_non_differentiable(pred)
+        return probs, fnorm, pred, tf.detach().clone()
 
     @staticmethod
     def backward(ctx, d_probs, d_fnorm, _, d_text):

@@ -27,6 +27,12 @@ from .clip_modules import PAD, ResidualAttentionBlock, _bf16
 DIM = K.ADAPTER_DIM
 
 
+def _bf16e(rows, cols, device):
+    """Uninitialised bf16 buffer (every element is written before it is read); _bf16 zero-fills,
+    which the K-augmented buffers need for their pad columns."""
+    return torch.empty(rows, cols, dtype=torch.bfloat16, device=device)
+
+
 class Adapter(nn.Module):
     """models/clip/adapter.py:11-73 with adapter_layernorm_option='none' and a float scalar (what
     ResidualAttentionBlock_Adapter constructs, model.py:432-439)."""
@@ -202,11 +208,11 @@ class _AdapterBlockFn(torch.autograd.Function):
         bufs = dict(
             x_in=x2, h1=_bf16(T, D + PAD, dev), qkv=_bf16(T, 3 * D + PAD, dev),
             lse=torch.empty(N * blk.n_head * L, device=dev), o=_bf16(T, D + PAD, dev),
-            x_mid=torch.empty(T, D, device=dev), h2=_bf16(T, D, dev),
-            z=_bf16(T, M, dev) if need_grad else None, g=_bf16(T, M, dev),
+            x_mid=torch.empty(T, D, device=dev), h2=_bf16e(T, D, dev),
+            z=_bf16e(T, M, dev) if need_grad else None, g=_bf16e(T, M, dev),
             x_out=torch.empty(T, D, device=dev))
-        abufs = dict(ya=_bf16(T, D, dev), a1=_bf16(T, DIM, dev), m=_bf16(T, D, dev),
-                     a2=_bf16(T, DIM, dev),
+        abufs = dict(ya=_bf16e(T, D, dev), a1=_bf16e(T, DIM, dev), m=_bf16e(T, D, dev),
+                     a2=_bf16e(T, DIM, dev),
                      mask1=ad.pop_mask(T, dev) if training else None,
                      mask2=ad.pop_mask(T, dev) if training else None)
         b = K.BlockBufs()
@@ -224,10 +230,12 @@ class _AdapterBlockFn(torch.autograd.Function):
         K.check(K.load().llc_adapter_block_forward(
             C.byref(blk._cfg), C.byref(layer), C.byref(s), C.byref(b), C.byref(ab), N, L, 1, N,
             causal, int(training), K.stream_ptr()), "llc_adapter_block_forward")
+        out = bufs.pop("x_out")      # not needed by the backward; h2 / g are recomputed nowhere
+        bufs["h2"] = bufs["g"] = None   # ...and not read by it either: free them with the call
         ctx.blk, ctx.bufs, ctx.abufs, ctx.shape, ctx.causal = blk, bufs, abufs, (L, N, D), causal
         ad.last_bottleneck = (abufs["a1"], abufs["a2"]) if ad.keep_bottleneck else ()
         ctx.x_needs_grad, ctx.params, ctx.training, ctx.seed = x.requires_grad, params, training, seed
-        return bufs["x_out"].view(L, N, D)
+        return out.view(L, N, D)
 
     @staticmethod
     def backward(ctx, dy):
@@ -239,17 +247,17 @@ class _AdapterBlockFn(torch.autograd.Function):
         dx = dy.detach().float().contiguous().view(T, D).clone()
         grads = [torch.zeros_like(p, dtype=torch.float32) for p in ctx.params]
         lora = blk.lora_params()
-        lgrads = [torch.zeros_like(p, dtype=torch.float32) for p in lora]   # frozen: discarded
+        lgrads = [None] * 4       # frozen attention: no LoRA reductions (llc.h: llc_vit_layer)
         lib = K.load()
         scratch = dict(
-            dx=dx, dxb=_bf16(T, D + PAD, dev), dz=_bf16(T, M, dev), dh=_bf16(T, D, dev),
-            d_o=_bf16(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
+            dx=dx, dxb=_bf16(T, D + PAD, dev), dz=_bf16e(T, M, dev), dh=_bf16e(T, D, dev),
+            d_o=_bf16e(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
             partial=torch.empty(ops.lora_side_max_partials() * 3 * D * 8, device=dev),
             delta=torch.empty(N * blk.n_head * L, device=dev))
         s = K.BlockBwdBufs()
         for k, v in scratch.items():
             setattr(s, k, v.data_ptr())
-        extra = dict(da=_bf16(T, DIM, dev), d_branch=torch.empty(T, D, device=dev),
+        extra = dict(da=_bf16e(T, DIM, dev), d_branch=torch.empty(T, D, device=dev),
                      partial=torch.empty(lib.llc_adapter_partial_floats(D), device=dev))
         ab = K.AdapterBufs()
         for k, v in {**abufs, **extra}.items():

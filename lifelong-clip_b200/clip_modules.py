@@ -756,9 +756,13 @@ class _HeadProbsFn(torch.autograd.Function):
                         add_mask=add_mask, labels=labels, inv_batch=inv_batch,
                         double_softmax=double_softmax, want_dlogits=True).forward()
         ctx.head, ctx.shape, ctx.scale, ctx.fused = head, (L, N, D), float(scale), labels is not None
-        ctx.mark_non_differentiable(head.pred)
         loss = head.loss_rows.sum() if labels is not None else head.loss_rows.new_zeros(())
-        return head.probs, head.fnorm, head.pred, loss
+        # clones: an output that is also reachable from ctx (ctx.head) would close a reference
+        # cycle output -> grad_fn -> ctx -> output that Python's GC cannot see through, and the
+        # whole graph (every block's saved activations) would outlive the step
+        probs, fnorm, pred = head.probs.clone(), head.fnorm.clone(), head.pred.clone()
+        ctx.mark_non_differentiable(pred)
+        return probs, fnorm, pred, loss
 
     @staticmethod
     def backward(ctx, d_probs, d_fnorm, _, d_loss):

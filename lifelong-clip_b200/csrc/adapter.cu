@@ -408,16 +408,20 @@ extern "C" int llc_adapter_forward(const llc_adapter* ad, const void* y, int ld_
   RUN(llc_gemm_bf16_tn(y, ld_y, ad->wd, D, T, kDim, D, &e, stream));
   const float p = training ? ad->dropout : 0.f;
   const size_t n8 = (size_t)T * kDim / 8;
+  LLC_PROF_BEGIN(LLC_K_OTHER, T, kDim, 0, 0.0, 4.0 * T * kDim, st);
   adapter_act_kernel<<<grid_for(n8, 256), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(a), n8,
                                                        training ? mask : nullptr, ad->seed, use, p);
+  LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("adapter_act_kernel");
   e = llc_gemm_epi{};
   e.bias = ad->bu_s; e.resid = resid; e.ld_resid = D; e.out = out; e.ld_out = D; e.out_fp32 = 1;
   RUN(llc_gemm_bf16_tn(a, kDim, ad->wu, kDim, T, D, kDim, &e, stream));
   if (add_y) {
+    LLC_PROF_BEGIN(LLC_K_OTHER, T, D, 0, 0.0, 10.0 * T * D, st);
     add_bf16_rows_kernel<<<grid_for((size_t)T * D / 8, 256), 256, 0, st>>>(
         out, reinterpret_cast<const __nv_bfloat16*>(y), ld_y, T, D);
+    LLC_PROF_END(st);
     LLC_COUNT_LAUNCH();
     LLC_LAUNCH_CHECK("add_bf16_rows_kernel");
   }
@@ -445,8 +449,10 @@ extern "C" int llc_adapter_backward(const llc_adapter* ad, const void* y, int ld
   // dz = da o [a > 0] / (1 - p); d b_d = column sums
   float* part_b = partial + tok_region_floats();
   const int nb = act_bwd_blocks(T);
+  LLC_PROF_BEGIN(LLC_K_OTHER, T, kDim, 1, 0.0, 6.0 * T * kDim, st);
   adapter_act_bwd_kernel<<<nb, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(da),
                                             reinterpret_cast<const __nv_bfloat16*>(a), T, p, part_b);
+  LLC_PROF_END(st);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("adapter_act_bwd_kernel");
   adapter_bias_finish_kernel<<<1, kDim, 0, st>>>(part_b, nb, ad->g_down_b, accumulate);

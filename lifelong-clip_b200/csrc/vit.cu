@@ -292,9 +292,14 @@ static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   float* pr[4] = {s->partial, s->partial + preg, s->partial + 2 * preg, s->partial + 3 * preg};
   int np4[4] = {0, 0, 0, 0};
   cudaStream_t cst = (cudaStream_t)stream;
+  // frozen attention (no gradient slots: the vanilla block under the adapter-clip method, whose
+  // LoRA factors are zero buffers): nothing to reduce. The pad columns of dxb / dqkv are then
+  // never written; the caller provides them zeroed (they meet zero weight columns).
+  const bool frozen = !w->g_in_A && !w->g_in_B && !w->g_out_A && !w->g_out_B;
   // out-proj: du_o = s dx_mid B_o (-> dxb pad cols) and dB_o = s dx_mid^T u_o read the same
   // dx_mid: one fused pass when the shape allows, else a skinny GEMM plus a column-sum launch
-  if (llc_lora_fused_eligible(s->dxb, DA, T, D, r, o + D, DA, w->f_out_B, D, dxb + D, DA)) {
+  if (frozen) {
+  } else if (llc_lora_fused_eligible(s->dxb, DA, T, D, r, o + D, DA, w->f_out_B, D, dxb + D, DA)) {
     RUN(llc_lora_fused_tc(s->dxb, DA, T, D, r <= 4 ? 4 : 8, o + D, DA, w->f_out_B, D, dxb + D, DA, pr[0],
                           &np4[0], cst));
   } else {
@@ -310,7 +315,8 @@ static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   // dA_o = du_o^T o. The same pass over O also forms delta = rowsum(dO o O) for the attention
   // backward (from the O tiles it streams anyway and the L2-hot dO), when the shapes allow
   int delta_ready = 0;
-  if (s->delta && D == H * 64 && llc_attn_bwd_uses_delta(L) &&
+  if (frozen) {
+  } else if (s->delta && D == H * 64 && llc_attn_bwd_uses_delta(L) &&
       llc_colsum_tc_eligible(b->o, DA, T, D, dxb + D, DA)) {
     RUN(llc_colsum_tc_delta(b->o, DA, T, D, r <= 4 ? 4 : 8, dxb + D, DA, pr[1], &np4[1], s->d_o, D, s->delta, H,
                             cst));
@@ -321,8 +327,9 @@ static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   RUN(llc_attn_bwd_ws(b->qkv, QA, b->o, DA, s->d_o, D, b->lse, s->dqkv, QA, N, L, H, sn, sl, causal,
                       s->delta, delta_ready, stream));
   // in-proj: du = s dqkv B_in (-> dqkv pad cols), dB_in = s dqkv^T u, dA_in = du^T h1
-  if (llc_lora_fused_eligible(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D,
-                              QA)) {
+  if (frozen) {
+  } else if (llc_lora_fused_eligible(s->dqkv, QA, T, 3 * D, r, h1 + D, DA, w->f_in_B, 3 * D,
+                                     dqkv + 3 * D, QA)) {
     RUN(llc_lora_fused_tc(s->dqkv, QA, T, 3 * D, r <= 4 ? 4 : 8, h1 + D, DA, w->f_in_B, 3 * D, dqkv + 3 * D, QA,
                           pr[2], &np4[2], cst));
   } else {
@@ -332,9 +339,10 @@ static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
     RUN(llc_lora_side(s->dqkv, QA, T, 3 * D, r, nullptr, 0, 0, 0.f, h1 + D, DA, pr[2], &np4[2],
                       stream));
   }
-  RUN(llc_lora_side(b->h1, DA, T, D, r, nullptr, 0, 0, 0.f, dqkv + 3 * D, QA, pr[3], &np4[3],
-                    stream));
-  {
+  if (!frozen)
+    RUN(llc_lora_side(b->h1, DA, T, D, r, nullptr, 0, 0, 0.f, dqkv + 3 * D, QA, pr[3], &np4[3],
+                      stream));
+  if (!frozen) {
     llc_finish_job jobs[4] = {
         {pr[0], np4[0], D, sc, w->g_out_B, r, 1},
         {pr[1], np4[1], D, 1.0f, w->g_out_A, 1, D},
