@@ -145,6 +145,9 @@ class CLIP(nn.Module):
         from .engine import TextEngine
         if not self.has_text:
             raise RuntimeError("this CLIP was built without a text tower (text_config=None)")
+        if self.text_block_by_block:
+            raise RuntimeError("adapter blocks run block by block (_encode_text_blocks); the "
+                               "fused text engine only knows the LoRA / vanilla block")
         if self._text_engine is None:
             self._text_engine = TextEngine(self)
         return self._text_engine

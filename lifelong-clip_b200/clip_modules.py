@@ -639,6 +639,9 @@ class VisualTransformer(nn.Module):
 
     def engine(self):
         from .engine import VitEngine
+        if self.block_by_block:
+            raise RuntimeError("adapter blocks run block by block (forward_tokens); the fused "
+                               "tower engine only knows the LoRA / vanilla block")
         if self._engine is None:
             self._engine = VitEngine(self)
         return self._engine
@@ -676,10 +679,14 @@ class VisualTransformer(nn.Module):
 
     def get_patch_feature(self, x: torch.Tensor):
         """model.py:731-753: ln_post(CLS) without the projection, returned twice."""
-        eng = self.engine()
         with torch.no_grad():
-            eng.forward(x, training=False)
-            y = F.layer_norm(eng.cls_rows(), (self.width,), self.ln_post.weight.float(),
+            if self.block_by_block:
+                cls = self.forward_tokens(x)[0]
+            else:
+                eng = self.engine()
+                eng.forward(x, training=False)
+                cls = eng.cls_rows()
+            y = F.layer_norm(cls, (self.width,), self.ln_post.weight.float(),
                              self.ln_post.bias.float(), self.ln_post.eps)
         return y, y
 

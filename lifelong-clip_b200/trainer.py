@@ -269,6 +269,13 @@ class LoRAClipTrainer:
         `logit` are the class probabilities the reference's criterion is applied to, `loss` the
         mean loss; both stay on the device, no parameter is updated."""
         m = self.custom_clip
+        if self.block_mode:
+            with torch.no_grad():
+                y = y.to(self.device)
+                probs, _, _, loss, _ = m._forward_blocks(
+                    self.test_transform(x.to(self.device)), m.text_tokens, labels=y,
+                    inv_batch=1.0 / y.shape[0], double_softmax=self.double_softmax)
+            return probs, loss
         with torch.no_grad():
             eng = m.model.visual.engine()
             eng.forward(self.test_transform(x.to(self.device)), training=False)

@@ -338,3 +338,54 @@ def test_adapter_trainer_steps_and_evaluates():
     assert set(out) == {"avg_loss", "avg_acc", "cls_acc", "task_acc", "confusion_matrix"}
     assert 0.0 <= float(out["avg_acc"]) <= 1.0
     assert int(np.sum(out["confusion_matrix"])) == n
+
+
+@pytest.mark.parametrize("method", ["lora", "adapter"])
+def test_model_forward_and_patch_feature(method):
+    """The two secondary entry points other methods of the reference call on the same objects:
+    trainer.model_forward(x, y) -> (logit, loss) (methods/er_baseline.py:132-147 shape of the
+    call) and VisualTransformer.get_patch_feature (model.py:731-753: ln_post(CLS), no
+    projection), for both PEFT methods, against the fp64 oracle."""
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+    from tests.test_e2e_gpu import build_model
+    cfg = vo.VIT_TINY
+    C_, n, seed = 7, 5, 3
+    w = vo.synth_weights(cfg, seed)
+    rng = np.random.default_rng(seed)
+    images = rng.standard_normal((n, 3, cfg.image_size, cfg.image_size)).astype(np.float32)
+    labels = rng.integers(0, C_, n)
+    text = vo.synth_text_features(C_, cfg.embed_dim, seed + 1)
+    names = [f"c{i}" for i in range(C_)]
+    if method == "lora":
+        m = build_model(cfg, w)
+        want = vo.online_step_oracle(images, labels, w, text, cfg)
+        wt = vo.to_torch(w, torch.float64, lora_grad=False)
+        _, tokens_ = vo.vit_forward(torch.from_numpy(images).double(), wt, cfg, return_tokens=True)
+    else:
+        from lifelong_clip_b200.adapter_clip import AdapterCLIP
+        wa = vo.synth_adapter_weights(cfg.width, cfg.layers, "visual.transformer.resblocks.", 9)
+        m = AdapterCLIP(peft_method="adapter", peft_encoder="image",
+                        vision_config=(cfg.image_size, cfg.patch, cfg.width, cfg.layers,
+                                       cfg.embed_dim))
+        sd = {k: torch.from_numpy(v) for k, v in {**vo.strip_lora(w), **wa}.items()}
+        missing, unexpected = m.model.load_state_dict(sd, strict=False)
+        assert not unexpected and set(missing) <= {"logit_scale"}
+        m.cuda()
+        want = vo.adapter_step_oracle(images, labels, w, wa, text, cfg)     # eval mode: no masks
+        wt = {k: torch.from_numpy(v).double() for k, v in {**vo.strip_lora(w), **wa}.items()}
+        tokens_ = vo.patch_embed(torch.from_numpy(images).double(), wt, cfg)
+        for i in range(cfg.layers):
+            tokens_ = vo.adapter_block_forward(tokens_, wt, f"visual.transformer.resblocks.{i}.", cfg)
+    m.set_text_features(names, torch.from_numpy(text))
+    m.set_token(names)
+    m.eval()
+    tr = LoRAClipTrainer(m, names, n_classes=C_, visible_classes="all")
+    logit, loss = tr.model_forward(torch.from_numpy(images), torch.from_numpy(labels))
+    assert rel(logit, want["probs"]) < TOL
+    assert abs(float(loss) - float(want["loss"])) < TOL * abs(float(want["loss"]))
+    f1, f2 = m.model.visual.get_patch_feature(torch.from_numpy(images).cuda())
+    ln = vo.layer_norm(tokens_[:, 0, :], wt["visual.ln_post.weight"], wt["visual.ln_post.bias"])
+    assert f1 is f2 and rel(f1, ln) < TOL
+    if method == "adapter":
+        with pytest.raises(RuntimeError, match="block by block"):
+            m.model.visual.engine()
