@@ -393,6 +393,13 @@ typedef struct llc_adapter {
   float *g_down_w, *g_down_b, *g_up_w, *g_up_b; /* gradient slots (backward only) */
   void *wd, *wu, *wdT, *wuT;                    /* bf16 [64,D] [D,64] [D,64] [64,D] (wu, wuT scaled) */
   float* bu_s;                                  /* [D] scale * b_u */
+  /* block use only (NULL for a stand-alone module): the frozen block's transposed weights with 64
+   * spare K columns, which llc_adapter_refresh fills with the COMPOSED factors so that the
+   * bottleneck gradient rides in the pad columns of the backward's big GEMMs:
+   *   woT_ad    [D, D+64]   = the layer's woT_aug (W_o^T | pad): pad <- (W_d W_o)^T
+   *   wprojT_ad [mlp, D+64] = W_proj^T | (W_d W_proj)^T        (left part filled by the caller) */
+  void *woT_ad, *wprojT_ad;
+  int mlp_dim;
 } llc_adapter;
 int llc_adapter_refresh(const llc_adapter* ad, int D, void* stream);
 /* floats of the `partial` scratch of llc_adapter_backward */
@@ -422,7 +429,7 @@ typedef struct llc_adapter_bufs {
   void* a2;  /* [T, 64] bf16 (saved)                   */
   const unsigned char *mask1, *mask2; /* optional explicit dropout masks [T, 64] */
   void* da;        /* backward scratch [T, 64] bf16                        */
-  float* d_branch; /* backward scratch [T, D] fp32                         */
+  float* d_branch; /* unused (kept for layout stability)                   */
   float* partial;  /* backward scratch, llc_adapter_partial_floats(D)      */
 } llc_adapter_bufs;
 int llc_adapter_block_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_adapter* ad,

@@ -86,7 +86,8 @@ class BlockBwdBufs(C.Structure):
 class Adapter(C.Structure):
     _fields_ = [("scale", c_float), ("dropout", c_float), ("seed", C.c_ulonglong)] + \
         [(n, c_void) for n in ("down_w", "down_b", "up_w", "up_b", "g_down_w", "g_down_b",
-                               "g_up_w", "g_up_b", "wd", "wu", "wdT", "wuT", "bu_s")]
+                               "g_up_w", "g_up_b", "wd", "wu", "wdT", "wuT", "bu_s", "woT_ad",
+                               "wprojT_ad")] + [("mlp_dim", c_int)]
 
 
 class AdapterBufs(C.Structure):

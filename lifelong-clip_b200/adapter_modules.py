@@ -96,9 +96,11 @@ class Adapter(nn.Module):
         self._calls += 1
         return (torch.initial_seed() * 0x9E3779B1 + self._calls * 0x85EBCA77) & (2 ** 63 - 1)
 
-    def struct(self, params, grads=None, seed=0) -> K.Adapter:
+    def struct(self, params, grads=None, seed=0, block=None) -> K.Adapter:
         """llc_adapter for the given live tensors; the bf16 operands are re-derived whenever a
-        parameter changed (its version counter or storage)."""
+        parameter changed (its version counter or storage). block: the owning
+        ResidualAttentionBlock_Adapter - its transposed frozen weights then get the composed
+        columns (W_d W_o)^T / (W_d W_proj)^T the block's backward folds into its big GEMMs."""
         D = self.n_embd
         for p in params:
             if p.dtype != torch.float32 or not p.is_contiguous() or p.device.type != "cuda":
@@ -118,7 +120,18 @@ class Adapter(nn.Module):
         if grads is not None:
             for n, g in zip(("g_down_w", "g_down_b", "g_up_w", "g_up_b"), grads):
                 setattr(s, n, g.data_ptr())
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        packed = None
+        if block is not None:
+            packed = block.packed()
+            M = block.mlp.c_fc.out_features
+            if getattr(self, "_wprojT_src", None) is not packed:
+                self._wprojT_ad = _bf16(M, D + DIM, dev)
+                self._wprojT_ad[:, :D].copy_(packed.wprojT)
+                self._wprojT_src = packed
+            s.woT_ad = packed.woT_aug.data_ptr()        # [D, D + 64]: pad columns are free
+            s.wprojT_ad = self._wprojT_ad.data_ptr()
+            s.mlp_dim = M
+        key = tuple((p.data_ptr(), p._version) for p in params) + (id(packed),)
         if key != self._ops_key:
             K.check(K.load().llc_adapter_refresh(C.byref(s), D, K.stream_ptr()),
                     "llc_adapter_refresh")
@@ -127,6 +140,7 @@ class Adapter(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._ops = self._ops_key = None
+        self._wprojT_src = None
         return super()._apply(fn, *a, **k)
 
     def forward(self, x, add_residual=True, residual=None):
@@ -222,11 +236,12 @@ class _AdapterBlockFn(torch.autograd.Function):
         for k, v in abufs.items():
             setattr(ab, k, K.ptr(v))
         lora = blk.lora_params()
+        # (no LoRA refresh: the factors are zero buffers, and the pad columns of the packed
+        # transposed out-projection belong to the adapter's composed columns)
         layer = blk._layer_struct(lora, [None] * 4)
-        blk._refresh_lora(layer)
         causal = blk._causal_flag(L)
         seed = ad.next_seed()
-        s = ad.struct(params, seed=seed)
+        s = ad.struct(params, seed=seed, block=blk)
         K.check(K.load().llc_adapter_block_forward(
             C.byref(blk._cfg), C.byref(layer), C.byref(s), C.byref(b), C.byref(ab), N, L, 1, N,
             causal, int(training), K.stream_ptr()), "llc_adapter_block_forward")
@@ -257,7 +272,7 @@ class _AdapterBlockFn(torch.autograd.Function):
         s = K.BlockBwdBufs()
         for k, v in scratch.items():
             setattr(s, k, v.data_ptr())
-        extra = dict(da=_bf16e(T, DIM, dev), d_branch=torch.empty(T, D, device=dev),
+        extra = dict(da=_bf16e(T, DIM, dev), d_branch=None,
                      partial=torch.empty(lib.llc_adapter_partial_floats(D), device=dev))
         ab = K.AdapterBufs()
         for k, v in {**abufs, **extra}.items():
@@ -268,7 +283,7 @@ class _AdapterBlockFn(torch.autograd.Function):
         for k, v in bufs.items():
             setattr(b, k, K.ptr(v))
         layer = blk._layer_struct(lora, lgrads)
-        a = ad.struct(ctx.params, grads, seed=ctx.seed)
+        a = ad.struct(ctx.params, grads, seed=ctx.seed, block=blk)
         K.check(lib.llc_adapter_block_backward(
             C.byref(blk._cfg), C.byref(layer), C.byref(a), C.byref(b), C.byref(ab), C.byref(s), N,
             L, 1, N, ctx.causal, int(ctx.x_needs_grad), int(ctx.training), K.stream_ptr()),

@@ -297,6 +297,20 @@ adapter_refresh_kernel(const float* __restrict__ down_w, const float* __restrict
   }
 }
 
+// dst[t, col0 .. col0 + 64) = a[t, :]: the [T, 64] bottleneck gradient into the pad columns of a
+// K-augmented operand
+__global__ void __launch_bounds__(256)
+adapter_scatter_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ dst,
+                       int ld_dst, int col0, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i >> 3;
+    const int ch = (int)(i & 7);
+    *reinterpret_cast<uint4*>(dst + t * ld_dst + col0 + ch * 8) =
+        reinterpret_cast<const uint4*>(a)[i];
+  }
+}
+
 int grid_for(size_t items, int threads) {
   const size_t want = (items + threads - 1) / threads;
   const size_t cap = (size_t)llc_num_sms() * 8;
@@ -375,6 +389,20 @@ int check_adapter(const llc_adapter* ad, int T, int D, const char* who) {
 
 }  // namespace
 
+int llc_adapter_scatter(const void* a, void* dst, int ld_dst, int col0, int T, void* stream) {
+  LLC_REQUIRE(a && dst && ld_dst % 8 == 0 && col0 % 8 == 0 && T > 0, "llc_adapter_scatter: bad args");
+  const size_t n8 = (size_t)T * kDim / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  LLC_PROF_BEGIN(LLC_K_OTHER, T, kDim, 2, 0.0, 4.0 * T * kDim, st);
+  adapter_scatter_kernel<<<grid_for(n8, 256), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, col0,
+      n8);
+  LLC_PROF_END(st);
+  LLC_COUNT_LAUNCH();
+  LLC_LAUNCH_CHECK("adapter_scatter_kernel");
+  return 0;
+}
+
 extern "C" size_t llc_adapter_partial_floats(int D) {
   if (D <= 0 || D % 128 != 0) return 0;
   return tok_region_floats() + (size_t)llc_num_sms() * 4 * kDim;
@@ -391,6 +419,19 @@ extern "C" int llc_adapter_refresh(const llc_adapter* ad, int D, void* stream) {
       reinterpret_cast<__nv_bfloat16*>(ad->wuT), ad->bu_s);
   LLC_COUNT_LAUNCH();
   LLC_LAUNCH_CHECK("adapter_refresh_kernel");
+  // block use: the composed columns (W_d W_o)^T [D, 64] and (W_d W_proj)^T [mlp, 64] behind the
+  // transposed frozen weights, so that the backward's d_o / dz GEMMs take the bottleneck gradient
+  // as 64 more K columns (llc_adapter_block_backward)
+  if (ad->woT_ad != nullptr) {
+    LLC_REQUIRE(ad->wprojT_ad && ad->mlp_dim > 0, "llc_adapter_refresh: incomplete block operands");
+    const int KAD = D + kDim;
+    llc_gemm_epi e{};
+    e.out = reinterpret_cast<__nv_bfloat16*>(ad->woT_ad) + D; e.ld_out = D + LLC_LORA_LD;
+    RUN(llc_gemm_bf16_tn(ad->woT_ad, D + LLC_LORA_LD, ad->wd, D, D, kDim, D, &e, stream));
+    e = llc_gemm_epi{};
+    e.out = reinterpret_cast<__nv_bfloat16*>(ad->wprojT_ad) + D; e.ld_out = KAD;
+    RUN(llc_gemm_bf16_tn(ad->wprojT_ad, KAD, ad->wd, D, ad->mlp_dim, kDim, D, &e, stream));
+  }
   return 0;
 }
 

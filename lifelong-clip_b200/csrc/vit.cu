@@ -24,6 +24,7 @@ int llc_colsum_tc_delta(const void* X, int ld_x, int T, int C, int R, const void
                         float* partial, int* n_partials, const void* d_o, int ld_do, float* delta,
                         int delta_ld, cudaStream_t st);
 bool llc_attn_bwd_uses_delta(int L);
+int llc_adapter_scatter(const void* a, void* dst, int ld_dst, int col0, int T, void* stream);
 
 namespace {
 
@@ -274,9 +275,12 @@ extern "C" int llc_mha_forward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
 // attention half of the backward: from s->dxb = bf16 gradient of the out-projection's output
 // (pad columns free) to the LoRA gradients and, if need_dh1, s->dh = gradient of the attention
 // input h1 (bf16 [T, D])
+// k_do: K extent of the d_o GEMM when the caller has put more than the LoRA row product into the
+// pad columns of dxb / woT_aug (the adapter block: 64 columns, see llc_adapter_block_backward)
 static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
                               const llc_block_bufs* b, const llc_block_bwd_bufs* s, int N, int L,
-                              int sn, int sl, int causal, int need_dh1, void* stream) {
+                              int sn, int sl, int causal, int need_dh1, void* stream,
+                              int k_do = 0) {
   const int D = cfg->width, H = cfg->heads, r = cfg->lora_r;
   const float sc = cfg->lora_scale;
   const int T = N * L, DA = D + LLC_LORA_LD, QA = 3 * D + LLC_LORA_LD;  // row pitches
@@ -311,7 +315,7 @@ static int attn_half_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w,
   // d_o = dx_mid W_o + du_o A_o
   e = llc_gemm_epi{};
   e.out = s->d_o; e.ld_out = D;
-  RUN(GEMM(s->dxb, DA, w->woT_aug, DA, T, D, KA, &e, stream));
+  RUN(GEMM(s->dxb, DA, w->woT_aug, DA, T, D, k_do > 0 ? k_do : KA, &e, stream));
   // dA_o = du_o^T o. The same pass over O also forms delta = rowsum(dO o O) for the attention
   // backward (from the O tiles it streams anyway and the L2-hot dO), when the shapes allow
   int delta_ready = 0;
@@ -441,30 +445,34 @@ extern "C" int llc_adapter_block_backward(const llc_vit_cfg* cfg, const llc_vit_
                                           int N, int L, int sn, int sl, int causal, int need_dx_in,
                                           int training, void* stream) {
   RUN(check_cfg(cfg, "llc_adapter_block_backward"));
-  LLC_REQUIRE(w && ad && b && ab && s && ab->da && ab->d_branch && ab->partial && N > 0 && L > 0,
+  LLC_REQUIRE(w && ad && b && ab && s && ab->da && ab->partial && N > 0 && L > 0,
               "llc_adapter_block_backward: bad args");
   LLC_REQUIRE(b->z, "llc_adapter_block_backward: forward was not run in training mode");
+  LLC_REQUIRE(ad->wprojT_ad, "llc_adapter_block_backward: composed operands missing "
+                             "(llc_adapter_refresh with the block's weights)");
   const int D = cfg->width, M = cfg->mlp_dim;
-  const int T = N * L, DA = D + LLC_LORA_LD;
+  const int T = N * L, DA = D + LLC_LORA_LD, KAD = D + LLC_ADAPTER_DIM;
   llc_gemm_epi e;
-  // x_out = x_mid + m + s up(a2): adapter gradients, d_m = dx + dz2 W_d
-  RUN(llc_adapter_backward(ad, ab->m, D, ab->a2, s->dx, s->dxb, DA, ab->d_branch, 1, ab->da,
+  // x_out = x_mid + m + s up(a2): adapter gradients from dx; the gradient of the branch,
+  // d_m = dx + dz2 W_d, is never formed - it only feeds d_m W_proj = dx W_proj + dz2 (W_d W_proj):
+  // dz2 rides in the 64 pad columns of dxb against the composed columns of wprojT_ad
+  RUN(llc_adapter_backward(ad, ab->m, D, ab->a2, s->dx, s->dxb, DA, nullptr, 0, ab->da,
                            ab->partial, 0, training, T, D, stream));
-  RUN(llc_cast_bf16(ab->d_branch, s->dxb, T, D, DA, stream));
-  // dz = (d_m W_proj) o QuickGELU'(z); dh2 = dz W_fc; dx_mid = dx + LN2'(dh2)
+  RUN(llc_adapter_scatter(ab->da, s->dxb, DA, D, T, stream));
+  // dz = ([dx | dz2] [W_proj^T | (W_d W_proj)^T]^T) o QuickGELU'(z); dh2 = dz W_fc
   e = llc_gemm_epi{};
   e.act = 2; e.aux = b->z; e.ld_aux = M; e.out = s->dz; e.ld_out = M;
-  RUN(GEMM(s->dxb, DA, w->wprojT, D, T, M, D, &e, stream));
+  RUN(GEMM(s->dxb, DA, ad->wprojT_ad, KAD, T, M, KAD, &e, stream));
   e = llc_gemm_epi{};
   e.out = s->dh; e.ld_out = D;
   RUN(GEMM(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
   RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
                  stream));
-  // x_mid = x + ya + s up(a1)
-  RUN(llc_adapter_backward(ad, ab->ya, D, ab->a1, s->dx, s->dxb, DA, ab->d_branch, 1, ab->da,
+  // x_mid = x + ya + s up(a1): the same with d_o = dx W_o + dz1 (W_d W_o) (pad columns of woT_aug)
+  RUN(llc_adapter_backward(ad, ab->ya, D, ab->a1, s->dx, s->dxb, DA, nullptr, 0, ab->da,
                            ab->partial, 1, training, T, D, stream));
-  RUN(llc_cast_bf16(ab->d_branch, s->dxb, T, D, DA, stream));
-  RUN(attn_half_backward(cfg, w, b, s, N, L, sn, sl, causal, need_dx_in, stream));
+  RUN(llc_adapter_scatter(ab->da, s->dxb, DA, D, T, stream));
+  RUN(attn_half_backward(cfg, w, b, s, N, L, sn, sl, causal, need_dx_in, stream, KAD));
   if (need_dx_in)
     RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
                    stream));
