@@ -28,7 +28,7 @@ def _load_adapter(mod, w):
     return mod.cuda()
 
 
-@pytest.mark.parametrize("D,T", [(128, 300), (768, 1576), (512, 4100)])
+@pytest.mark.parametrize("D,T", [(128, 1), (128, 65), (128, 300), (768, 1576), (512, 4100)])
 @pytest.mark.parametrize("training", [True, False])
 def test_adapter_module_matches_oracle(D, T, training):
     """Adapter.forward(x) (add_residual=True) and its four parameter gradients + dx: the two
