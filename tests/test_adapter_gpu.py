@@ -391,3 +391,111 @@ def test_model_forward_and_patch_feature(method):
     if method == "adapter":
         with pytest.raises(RuntimeError, match="block by block"):
             m.model.visual.engine()
+
+
+def test_adapter_full_size_properties():
+    """BASELINE's token count (256 images x 197 tokens, D = 768): the adapter against the oracle
+    evaluated in fp64 on the same device (all 24 token slices x 6 column tiles of the
+    weight-gradient kernel), and size-independent properties: repeatable bit for bit, gradients
+    exactly linear in the incoming gradient, rows independent of their neighbours."""
+    from lifelong_clip_b200.adapter_modules import Adapter
+    D, T = 768, 197 * 256
+    w = _adapter_weights(D, 21)
+    mod = _load_adapter(Adapter(d_model=D, dropout=P, bottleneck=64, init_option="lora",
+                                adapter_scalar=0.1, adapter_layernorm_option="none"), w)
+    mod.train()
+    mod.keep_bottleneck = True
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(T, D, device="cuda", generator=g)
+    dy = torch.randn(T, D, device="cuda", generator=g)
+    mask = (torch.rand(T, vo.ADAPTER_DIM, device="cuda", generator=g) >= P).to(torch.uint8)
+
+    def run(xx, dd, mk):
+        mod.zero_grad()
+        mod.push_masks(mk)
+        xg = xx.clone().requires_grad_(True)
+        out = mod(xg)
+        out.backward(dd)
+        return out.detach(), xg.grad, [p.grad.clone() for p in mod.parameters()]
+
+    out, dx, grads = run(x, dy, mask)
+    gate = mod.last_bottleneck[0] > 0
+    wt = {("a." + k): torch.from_numpy(v).cuda().double().requires_grad_(True) for k, v in w.items()}
+    xo = x.double().requires_grad_(True)
+    want = vo.adapter_forward(xo, wt, "a.", None, P, gate=gate)
+    want.backward(dy.double())
+    assert rel(out - x, (want - xo).detach()) < TOL
+    assert rel(dx - dy, xo.grad - dy.double()) < TOL
+    for (name, _), gg in zip(mod.named_parameters(), grads):
+        gw = wt["a." + name].grad
+        assert rel(gg, gw) < TOL and cos(gg, gw) > 0.9999, (name, rel(gg, gw))
+    keep = float(gate.float().mean()) / float((mod.last_bottleneck[0] != 0).float().mean() + 1e-9)
+    assert abs(keep - 1.0) < 1e-6
+    # the same call again: bit-identical (fixed-order partial sums in every reduction)
+    out2, dx2, grads2 = run(x, dy, mask)
+    assert torch.equal(out, out2) and torch.equal(dx, dx2)
+    assert all(torch.equal(a, b) for a, b in zip(grads, grads2))
+    # twice the incoming gradient: exactly twice every gradient (power-of-two scaling commutes
+    # with every rounding on the way)
+    _, dx3, grads3 = run(x, 2 * dy, mask)
+    assert torch.equal(dx3, 2 * dx)
+    assert all(torch.equal(a, 2 * b) for a, b in zip(grads3, grads))
+    # rows are independent: the first half alone gives the same rows
+    h = T // 2
+    out4, dx4, grads4 = run(x[:h].contiguous(), dy[:h].contiguous(), mask[:h].contiguous())
+    assert torch.equal(out4, out[:h]) and torch.equal(dx4, dx[:h])
+    out5, dx5, grads5 = run(x[h:].contiguous(), dy[h:].contiguous(), mask[h:].contiguous())
+    for a, b, c in zip(grads, grads4, grads5):
+        assert rel(b + c, a) < 1e-5       # weight gradients add over token ranges (fp32 order)
+
+
+def test_adapter_block_full_size():
+    """One ViT-B/16 adapter block at the bench shape ([197, 256, 768]: the CTA-pair GEMMs with the
+    64 adapter columns in the K extension, the TMEM attention, 394 slabs of the weight-gradient
+    kernel) against the oracle in fp64 on the same device, plus repeatability and linearity."""
+    from lifelong_clip_b200.adapter_modules import ResidualAttentionBlock_Adapter
+    cfg = vo.VitCfg(layers=1)
+    L, N, D = cfg.tokens, 256, cfg.width
+    w = vo.strip_lora(vo.synth_weights(cfg, 3))
+    wa = vo.synth_adapter_weights(D, 1, "visual.transformer.resblocks.", 4)
+    pre = "visual.transformer.resblocks.0."
+    blk = ResidualAttentionBlock_Adapter(D, cfg.heads, None, {"ffn_num": 64})
+    blk.load_state_dict({k[len(pre):]: torch.from_numpy(v) for k, v in {**w, **wa}.items()
+                         if k.startswith(pre)})
+    blk.cuda().train()
+    for k, p in blk.named_parameters():
+        p.requires_grad = "adaptmlp" in k
+    blk.adaptmlp.keep_bottleneck = True
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(L, N, D, device="cuda", generator=g)
+    dy = torch.randn(L, N, D, device="cuda", generator=g)
+    masks = [(torch.rand(L * N, vo.ADAPTER_DIM, device="cuda", generator=g) >= P).to(torch.uint8)
+             for _ in range(2)]
+
+    def run(dd):
+        blk.zero_grad()
+        blk.adaptmlp.push_masks(*masks)
+        xg = x.clone().requires_grad_(True)
+        out = blk(xg)
+        out.backward(dd)
+        return out.detach(), xg.grad, {k: p.grad.clone() for k, p in blk.named_parameters()
+                                       if p.grad is not None}
+
+    out, dx, grads = run(dy)
+    gates = [(a > 0).view(L, N, -1).permute(1, 0, 2) for a in blk.adaptmlp.last_bottleneck]
+    wt = {k: torch.from_numpy(v).cuda().double() for k, v in w.items() if k.startswith(pre)}
+    wat = {k: torch.from_numpy(v).cuda().double().requires_grad_(True) for k, v in wa.items()}
+    xo = x.double().permute(1, 0, 2).contiguous().requires_grad_(True)
+    want = vo.adapter_block_forward(xo, {**wt, **wat}, pre, cfg, p=P, gates=gates)
+    want.backward(dy.double().permute(1, 0, 2))
+    assert rel(out.permute(1, 0, 2), want.detach()) < TOL
+    assert rel(dx.permute(1, 0, 2), xo.grad) < TOL
+    assert len(grads) == 4
+    for k, gg in grads.items():
+        gw = wat[pre + k].grad
+        assert rel(gg, gw) < TOL and cos(gg, gw) > 0.9999, (k, rel(gg, gw))
+    out2, dx2, grads2 = run(dy)
+    assert torch.equal(out, out2) and torch.equal(dx, dx2)
+    assert all(torch.equal(grads[k], grads2[k]) for k in grads)
+    _, dx3, grads3 = run(2 * dy)
+    assert torch.equal(dx3, 2 * dx) and all(torch.equal(grads3[k], 2 * grads[k]) for k in grads)
