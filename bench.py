@@ -338,7 +338,7 @@ def run_eval(args, model, names, dev, world, rank, local_rank):
 
     def step(i):
         eng.forward(dev_x[i % 2], training=False)
-        if args.peft == "both":
+        if args.peft in ("both", "text"):
             raise SystemExit("--mode eval measures the cached-text configuration (--peft image)")
         head = eng.eval_head(model._text_all, scale, cls_idx=model._cls_idx,
                              add_mask=model._add_mask, want_probs=True)
@@ -470,7 +470,7 @@ def run_adapter(args, dev, world, rank, local_rank):
         for a in model.adapters():
             a.up_proj.weight.normal_(0, 0.02)
     names = [f"class {i}" for i in range(C)]
-    if args.peft == "both":
+    if args.peft in ("both", "text"):
         model.set_tokenizer(SyntheticTokenizer())
     else:
         model.set_text_features(names, torch.randn(C, E, generator=torch.Generator().manual_seed(1)))
@@ -643,7 +643,7 @@ def run_ours(args):
                         vision_config=(S, p, D, layers, E)).to(dev)
     names = [f"class {i}" for i in range(C)]
     g = torch.Generator().manual_seed(1)
-    if args.peft == "both":
+    if args.peft in ("both", "text"):
         model.set_tokenizer(SyntheticTokenizer())
     else:
         model.set_text_features(names, torch.randn(C, E, generator=g))
@@ -914,8 +914,9 @@ def main():
                          "train / 4096 eval), per GPU under --scaling weak")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--mode", default="train", choices=["train", "eval"])
-    ap.add_argument("--peft", default="image", choices=["image", "both"],
-                    help="'both': LoRA text tower recomputed every step (scripts/lora_clip.sh)")
+    ap.add_argument("--peft", default="image", choices=["image", "both", "text"],
+                    help="'both': LoRA text tower recomputed every step (scripts/lora_clip.sh); "
+                         "'text': only the text tower trains, the image tower runs forward only")
     ap.add_argument("--method", default="lora", choices=["lora", "adapter"],
                     help="'adapter': the adapter-clip method (scripts/adapter_clip.sh), a secondary "
                          "line; the headline metric is the lora-clip step")

@@ -12,7 +12,11 @@ Text side, by `peft_encoder`:
            methods/adapter_clip.py:53-61,84 is a gather index into the cache;
   'both'   (what scripts/lora_clip.sh sets) the text tower carries LoRA and is recomputed every
            step for the visible classes (CLIP.encode_text, models/clip/model.py:941-956), with
-           gradients to its 48 LoRA tensors through the logit product.
+           gradients to its 48 LoRA tensors through the logit product;
+  'text'   only the text tower trains: the image tower is the frozen vanilla one, runs forward
+           without saved activations, and the head differentiates the class-token rows only to
+           reach the text features;
+  'none'   nothing trains (zero-shot evaluation).
 The BPE vocabulary file of OpenAI CLIP is not part of this repository: labels_tokenize() uses the
 tokenizer given to set_tokenizer() (any callable list[str] -> int64 [C, 77]); SyntheticTokenizer
 is the deterministic stand-in used by the synthetic benchmarks.
@@ -277,9 +281,15 @@ class _ProbsFn(torch.autograd.Function):
             thead = teng.forward(tokens, eot_rows(tokens),
                                  training=need_grad and _text_requires_grad(model, lora_t))
             text, cls_idx = thead.fnorm, None
-        eng.forward(images, training=need_grad)
-        head = eng.head(text, model.logit_scale_exp(), cls_idx=cls_idx, add_mask=add_mask,
-                        want_dlogits=teng is not None)
+        img_train = any(p.requires_grad for p in lora_v)
+        eng.forward(images, training=need_grad and img_train)
+        if img_train or not need_grad:
+            head = eng.head(text, model.logit_scale_exp(), cls_idx=cls_idx, add_mask=add_mask,
+                            want_dlogits=teng is not None)
+        else:   # frozen image tower: the head differentiates the compact class-token rows only
+            head = eng.head_compact(text, model.logit_scale_exp(), cls_idx=cls_idx,
+                                    add_mask=add_mask, want_dlogits=teng is not None)
+        ctx.img_train = img_train
         ctx.eng, ctx.teng, ctx.head, ctx.thead = eng, teng, head, thead
         ctx.lora_v, ctx.lora_t, ctx.need_grad = lora_v, lora_t, need_grad
         ctx.scale = model.logit_scale_exp()
@@ -304,7 +314,11 @@ class _ProbsFn(torch.autograd.Function):
             d_feat = ((d_fnorm - f * (f * d_fnorm).sum(-1, keepdim=True)) / nz).contiguous()
         dp = d_probs.detach().float().contiguous() if d_probs is not None else \
             torch.zeros_like(head.probs)
-        ctx.eng.backward_from_head(head, d_probs=dp, d_feat=d_feat)
+        if ctx.img_train:
+            ctx.eng.backward_from_head(head, d_probs=dp, d_feat=d_feat)
+        else:
+            head.args.skip_logit_grad = 0
+            head.backward(torch.zeros(head.N, head.D, device=dp.device), dp)   # -> head.dlogits
         g_v = tuple(g.clone() if p.requires_grad else None
                     for g, p in zip(ctx.eng.lora_grad_views, ctx.lora_v))
         g_t = (None,) * len(ctx.lora_t)
@@ -329,16 +343,17 @@ class AdapterCLIP(nn.Module):
             raise NotImplementedError("lifelong_clip_b200 implements the lora-clip and "
                                       "adapter-clip methods (scripts/lora_clip.sh, "
                                       "scripts/adapter_clip.sh)")
-        if peft_encoder not in ('image', 'both'):
-            raise NotImplementedError("peft_encoder must be 'image' (cached text features) or "
-                                      "'both' (text tower recomputed every step)")
+        if peft_encoder not in ('image', 'both', 'text', 'none'):   # configuration/config.py:15
+            raise ValueError("peft_encoder must be one of 'none', 'both', 'text', 'image'")
         self.device = device
         self.peft_method = peft_method
         self.peft_encoder = peft_encoder
+        self.text_trainable = peft_encoder in ('both', 'text')
+        self.image_trainable = peft_encoder in ('both', 'image')
         design_details = {'method': peft_method, 'peft_encoder': peft_encoder, 'ffn_num': 64,
                           'lora_alpha': 1, 'lora_r': 4}  # models/adapter_clip.py:24-30
         res, patch, width, layers, embed = vision_config or VISION_CONFIGS[model_name]
-        if text_config is None and peft_encoder == 'both':
+        if text_config is None and self.text_trainable:
             text_config = TEXT_CONFIGS[model_name]
         tc = text_config or (None,) * 5
         self.model = CLIP(embed, res, layers, width, patch, tc[0], tc[1], tc[2], tc[3], tc[4],
@@ -391,9 +406,9 @@ class AdapterCLIP(nn.Module):
     def set_text_features(self, class_names, features: torch.Tensor):
         """Cache one feature row per class name (model.py:941-956 output); rows are L2-normalised
         here as model.py:968-969 does every step. peft_encoder='image' only."""
-        if self.peft_encoder != 'image':
-            raise RuntimeError("peft_encoder='both' recomputes the text features every step; "
-                               "there is nothing to cache")
+        if self.text_trainable:
+            raise RuntimeError(f"peft_encoder={self.peft_encoder!r} recomputes the text features "
+                               "every step; there is nothing to cache")
         feats = features.detach().float()
         feats = feats / feats.norm(dim=-1, keepdim=True)
         dev = self.model.visual.proj.device
@@ -427,7 +442,7 @@ class AdapterCLIP(nn.Module):
         gather index into the cached text features (no per-step tokenisation); 'both': the token
         matrix of the visible classes (tokenised once per class name)."""
         key = tuple(classnames)
-        if self.peft_encoder == 'both':
+        if self.text_trainable:
             if self._tokens is None or key != self._cls_key:
                 self._tokens = self.labels_tokenize(list(classnames)).contiguous()
                 self._cls_key = key
@@ -478,7 +493,7 @@ class AdapterCLIP(nn.Module):
             probs, fnorm, _, _, tf = self._forward_blocks(image, text_tokens)
             return probs, fnorm, tf
         lv = vis.lora_params()
-        if self.peft_encoder == 'both':
+        if self.text_trainable:
             lt = self.model.text_lora_params()
             probs, fnorm, _, tf = _ProbsFn.apply(self.model, image, None, None, self._add_mask,
                                                  text_tokens, len(lv), *lv, *lt)
@@ -499,7 +514,7 @@ class AdapterCLIP(nn.Module):
 
     def text_features_blocks(self, text_tokens):
         """Normalised text features of the visible classes on the adapter path."""
-        if self.peft_encoder == 'both':
+        if self.text_trainable:
             return self.model._encode_text_blocks(text_tokens, normalise=True)
         return self._text_all.index_select(0, text_tokens)
 
@@ -512,7 +527,13 @@ class AdapterCLIP(nn.Module):
         m, vis = self.model, self.model.visual
         if t_hat is None:
             t_hat = self.text_features_blocks(text_tokens)
-        x = vis.forward_tokens(image.type(self.dtype))
+        if vis.block_by_block:
+            x = vis.forward_tokens(image.type(self.dtype))
+        else:   # frozen vanilla image tower (peft_encoder='text'): fused forward, no saved
+            with torch.no_grad():   # activations; the head sees the class-token rows [1, N, D]
+                eng = vis.engine()
+                eng.forward(image.type(self.dtype), training=False)
+                x = eng.cls_rows().contiguous().unsqueeze(0)
         f32 = lambda t: t.detach().float().contiguous()
         probs, fnorm, pred, loss = _HeadProbsFn.apply(
             x, t_hat, f32(vis.ln_post.weight), f32(vis.ln_post.bias), f32(vis.proj),

@@ -217,6 +217,15 @@ class VitEngine(_TowerEngine):
                         double_softmax=double_softmax, inv_batch=inv_batch,
                         want_dlogits=want_dlogits).forward()
 
+    def head_compact(self, text, logit_scale_exp, *, cls_idx=None, add_mask=None, labels=None,
+                     double_softmax=True, inv_batch=None, want_dlogits=False) -> ops.Head:
+        """The same head on a compact copy of the class-token rows [N, D] (frozen image tower:
+        its backward then writes an [N, D] gradient instead of a token-sized one)."""
+        return ops.Head(self.cls_rows().contiguous(), 1, self.ln_post[0], self.ln_post[1], self.proj,
+                        text, logit_scale_exp, self.N, cls_idx=cls_idx, add_mask=add_mask,
+                        labels=labels, double_softmax=double_softmax, inv_batch=inv_batch,
+                        want_dlogits=want_dlogits).forward()
+
     def features_only(self) -> ops.Head:
         self._feat_head = self.head(self._dummy_text, 1.0)
         return self._feat_head

@@ -79,7 +79,8 @@ class LoRAClipTrainer:
         gradient, so that they travel in the same all-reduce."""
         if self.block_mode:
             return self._block_scal
-        return self.custom_clip.model.visual.engine().scal
+        m = self.custom_clip.model
+        return (m.visual.engine() if self.image_trainable else m.text_engine()).scal
 
     @property
     def block_mode(self) -> bool:
@@ -89,7 +90,11 @@ class LoRAClipTrainer:
 
     @property
     def text_trainable(self) -> bool:
-        return self.custom_clip.peft_encoder == 'both'
+        return self.custom_clip.peft_encoder in ('both', 'text')
+
+    @property
+    def image_trainable(self) -> bool:
+        return self.custom_clip.peft_encoder in ('both', 'image')
 
     # ---- class bookkeeping (methods/_trainer.py:404-416, methods/adapter_clip.py:256-283) ------
     def add_new_class(self, class_name):
@@ -140,10 +145,18 @@ class LoRAClipTrainer:
 
     def _towers(self):
         m = self.custom_clip.model
-        return [m.visual] + ([m.text_side()] if self.text_trainable else [])
+        return ([m.visual] if self.image_trainable else []) + \
+            ([m.text_side()] if self.text_trainable else [])
 
     def reset_opt(self):
         """utils/train_utils.py:27-28: AdamW(lr, weight_decay=1e-5) over the trainable tensors."""
+        if not (self.image_trainable or self.text_trainable):
+            raise RuntimeError("peft_encoder='none': nothing is trainable (zero-shot evaluation "
+                               "only)")
+        if not self.image_trainable:
+            # the frozen image tower runs in its evaluation arena, whose address is not part of
+            # the graph key: launch eagerly (the step is dominated by the image forward anyway)
+            self.use_cuda_graph = False
         if self.block_mode:
             from .engine import ParamAdamW
             m = self.custom_clip
@@ -306,6 +319,25 @@ class LoRAClipTrainer:
             if getattr(self, "_eot_src", None) is not m._tokens:
                 self._eot, self._eot_src = eot_rows(m._tokens), m._tokens
             thead = teng.forward(m._tokens, self._eot, training=True, force_refresh=force_refresh)
+        if not self.image_trainable:
+            # peft_encoder='text': frozen image tower, forward only; the head's backward runs on
+            # the compact class-token rows and only its logit gradient is used
+            if tx is not None:
+                eng.forward(training=False, transform=tx, n=x.shape[0])
+            else:
+                eng.forward(x, training=False)
+            head = eng.head_compact(thead.fnorm, m.model.logit_scale_exp(), add_mask=m._add_mask,
+                                    labels=y_local, double_softmax=self.double_softmax,
+                                    inv_batch=1.0 / global_batch, want_dlogits=True)
+            head.args.skip_logit_grad = 0
+            dx_cls = torch.zeros(head.N, head.D, device=self.device)
+            head.keep = head.keep + (dx_cls,)
+            head.backward(dx_cls)
+            d_t = ops.head_dtext(head.dlogits, head.fnorm, m.model.logit_scale_exp())
+            head.keep = head.keep + (d_t,)
+            teng.backward(d_t)
+            ops.loss_acc(head.loss_rows, head.pred, y_local, self._scal)
+            return head
         if tx is not None:
             eng.forward(training=True, force_refresh=force_refresh, transform=tx, n=x.shape[0])
         else:

@@ -616,10 +616,16 @@ def adapter_step_oracle(images, labels_local, w_np, wa_np, text, cfg: VitCfg,
     keep flags [N, L, 64] (training-mode dropout), None = eval-mode. Returns probs, loss, pred and
     the gradients of every adaptmlp tensor."""
     wv = to_torch(strip_lora(w_np), dtype, lora_grad=False)
-    wa = {k: torch.from_numpy(v).to(dtype).requires_grad_(True) for k, v in wa_np.items()}
+    wa = {k: torch.from_numpy(v).to(dtype).requires_grad_(True) for k, v in (wa_np or {}).items()}
     w = {**wv, **wa}
     x = patch_embed(torch.from_numpy(images).to(dtype), w, cfg)
+    if not wa:   # peft_encoder='text': the image tower is the vanilla (frozen) one
+        w = {**w, **{k: torch.zeros(s, dtype=dtype) for k, s in param_shapes(cfg).items()
+                     if "lora" in k}}
     for i in range(cfg.layers):
+        if not wa:
+            x = block_forward(x, w, f"visual.transformer.resblocks.{i}.", cfg)
+            continue
         x = adapter_block_forward(x, w, f"visual.transformer.resblocks.{i}.", cfg,
                                   masks=None if masks is None else masks[i], p=p)
     feat = layer_norm(x[:, 0, :], w["visual.ln_post.weight"], w["visual.ln_post.bias"]) @ \

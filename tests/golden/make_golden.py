@@ -157,16 +157,20 @@ BIG_CASES = {
 }
 
 
-def run_reference_both(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes: int, seed: int):
+def run_reference_both(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes: int, seed: int,
+                       peft: str = "both"):
     """peft_encoder='both' (scripts/lora_clip.sh:10): the reference's CLIP with LoRA blocks in BOTH
-    towers; text features from its own encode_text (model.py:941-956), head model.py:966-973."""
+    towers; text features from its own encode_text (model.py:941-956), head model.py:966-973.
+    peft='text': LoRA blocks in the text tower only (the image tower is the vanilla one)."""
     ref_model = load_reference()
     torch.manual_seed(0)
     clip = ref_model.CLIP(cfg.embed_dim, cfg.image_size, cfg.layers, cfg.width, cfg.patch,
                           tcfg.context, tcfg.vocab, tcfg.width, tcfg.heads, tcfg.layers,
-                          {"method": "lora", "peft_encoder": "both",
+                          {"method": "lora", "peft_encoder": peft,
                            "lora_alpha": cfg.lora_alpha, "lora_r": cfg.lora_r}).float()
     wv, wt = vo.synth_weights(cfg, seed), vo.synth_text_weights(tcfg, seed + 1)
+    if peft == "text":
+        wv = vo.strip_lora(wv)
     sd = clip.state_dict()
     for k, v in {**wv, **wt}.items():
         assert k in sd and tuple(sd[k].shape) == v.shape, (k, v.shape)
@@ -204,7 +208,7 @@ def run_reference_both(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes: in
             assert "lora" in k
             out["grad:" + k] = p.grad.numpy()
             ng += 1
-    assert ng == 4 * (cfg.layers + tcfg.layers), ng
+    assert ng == 4 * ((cfg.layers if peft == "both" else 0) + tcfg.layers), ng
     return out
 
 
@@ -212,6 +216,13 @@ BOTH_CASES = {
     # name: (vision cfg, text cfg, batch, classes, seed)
     "both_tiny": (vo.VIT_TINY, vo.TEXT_TINY, 4, 6, 21),
     "both_vitb16": (vo.VIT_B16, vo.TEXT_B16, 8, 20, 23),
+}
+
+
+# peft_encoder='text' (scripts/*.sh list it next to 'both' and 'image'): name -> (..., method)
+TEXT_ONLY_CASES = {
+    "textonly_lora_tiny": (vo.VIT_TINY, vo.TEXT_TINY, 5, 6, 51, "lora"),
+    "textonly_adapter_tiny": (vo.VIT_TINY, vo.TEXT_TINY, 5, 6, 53, "adapter"),
 }
 
 
@@ -368,7 +379,8 @@ ADAPTER_CASES = {
 }
 
 
-def run_reference_adapter(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes: int, seed: int):
+def run_reference_adapter(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes: int, seed: int,
+                          peft: str = "both"):
     """--method adapter-clip (scripts/adapter_clip.sh): the reference's CLIP with
     ResidualAttentionBlock_Adapter in both towers (model.py:418-442, adapter.py:11-73). Dropout
     draws are replaced by oracle.adapter_masks (nn.functional.dropout is patched for the run: the
@@ -378,11 +390,13 @@ def run_reference_adapter(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes:
     torch.manual_seed(0)
     clip = ref_model.CLIP(cfg.embed_dim, cfg.image_size, cfg.layers, cfg.width, cfg.patch,
                           tcfg.context, tcfg.vocab, tcfg.width, tcfg.heads, tcfg.layers,
-                          {"method": "adapter", "peft_encoder": "both", "ffn_num": 64}).float()
+                          {"method": "adapter", "peft_encoder": peft, "ffn_num": 64}).float()
     wv = vo.strip_lora(vo.synth_weights(cfg, seed))
     wt = vo.strip_lora(vo.synth_text_weights(tcfg, seed + 1))
     wa = vo.synth_adapter_weights(cfg.width, cfg.layers, "visual.transformer.resblocks.", seed + 2)
     wta = vo.synth_adapter_weights(tcfg.width, tcfg.layers, "transformer.resblocks.", seed + 3)
+    if peft == "text":
+        wa = {}
     sd = clip.state_dict()
     for k, v in {**wv, **wt, **wa, **wta}.items():
         assert k in sd and tuple(sd[k].shape) == v.shape, (k, v.shape)
@@ -424,7 +438,7 @@ def run_reference_adapter(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes:
     torch.nn.functional.dropout = fake_dropout
     try:
         clip.train()
-        for pair in vo.adapter_masks(seed + 400, cfg.layers, cfg.tokens, n):
+        for pair in (vo.adapter_masks(seed + 400, cfg.layers, cfg.tokens, n) if wa else []):
             queue += [torch.from_numpy(m) for m in pair]
         for pair in vo.adapter_masks(seed + 500, tcfg.layers, tcfg.context, num_classes):
             queue += [torch.from_numpy(m) for m in pair]
@@ -458,7 +472,7 @@ def run_reference_adapter(cfg: vo.VitCfg, tcfg: vo.TextCfg, n: int, num_classes:
                 out["gscale:" + k] = np.float32(sc)
             else:
                 out["grad:" + k] = g
-    assert ng == 4 * (cfg.layers + tcfg.layers), ng
+    assert ng == 4 * ((cfg.layers if wa else 0) + tcfg.layers), ng
     return out
 
 
@@ -490,6 +504,14 @@ def main():
         if only and name not in only:
             continue
         out = run_reference_adapter(cfg, tcfg, n, c, seed)
+        path = os.path.join(HERE, f"ref_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(name, "loss", float(out["loss"]), "->", path, os.path.getsize(path), "bytes")
+    for name, (cfg, tcfg, n, c, seed, method) in TEXT_ONLY_CASES.items():
+        if only and name not in only:
+            continue
+        run = run_reference_both if method == "lora" else run_reference_adapter
+        out = run(cfg, tcfg, n, c, seed, peft="text")
         path = os.path.join(HERE, f"ref_{name}.npz")
         np.savez_compressed(path, **out)
         print(name, "loss", float(out["loss"]), "->", path, os.path.getsize(path), "bytes")

@@ -499,3 +499,100 @@ def test_adapter_block_full_size():
     assert all(torch.equal(grads[k], grads2[k]) for k in grads)
     _, dx3, grads3 = run(2 * dy)
     assert torch.equal(dx3, 2 * dx) and all(torch.equal(grads3[k], 2 * grads[k]) for k in grads)
+
+
+@pytest.mark.parametrize("name", ["textonly_lora_tiny", "textonly_adapter_tiny"])
+def test_peft_encoder_text_matches_reference_golden(name, golden_dir):
+    """peft_encoder='text' for both methods: the image tower is the frozen vanilla one (forward
+    without saved activations), gradients reach the text tower's PEFT tensors only - through
+    AdapterCLIP.forward + CrossEntropyLoss and through the trainer's step."""
+    from lifelong_clip_b200.adapter_clip import AdapterCLIP
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+    from tests.golden.make_golden import load_grads
+    from tests.test_oracle_golden import text_only_case_inputs
+    cfg, tcfg, method, wv, wt, wta, images, labels, tokens, tmasks = text_only_case_inputs(name)
+    gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    m = AdapterCLIP(peft_method=method, peft_encoder="text",
+                    vision_config=(cfg.image_size, cfg.patch, cfg.width, cfg.layers,
+                                   cfg.embed_dim),
+                    text_config=(tcfg.context, tcfg.vocab, tcfg.width, tcfg.heads, tcfg.layers))
+    sd = {**vo.strip_lora(wv), **(wt if method == "lora" else {**vo.strip_lora(wt), **wta})}
+    missing, unexpected = m.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()},
+                                                  strict=False)
+    assert not unexpected and set(missing) <= {"logit_scale"}, (missing, unexpected)
+    m.cuda()
+    for k, p in m.named_parameters():
+        if "adaptmlp" not in k and "lora" not in k:
+            p.requires_grad = False
+    trainable = [k for k, p in m.named_parameters() if p.requires_grad]
+    assert len(trainable) == 4 * tcfg.layers and all(".visual." not in k for k in trainable)
+    with torch.no_grad():
+        m.model.logit_scale.fill_(float(np.log(gold["logit_scale_exp"])))
+    c = tokens.shape[0]
+    names = [f"c{i}" for i in range(c)]
+    table = {m.prompt_template.format(nm): torch.from_numpy(tokens[i]) for i, nm in enumerate(names)}
+    m.set_tokenizer(lambda texts: torch.stack([table[t] for t in texts]))
+    m.set_token(names)
+    x, y = torch.from_numpy(images).cuda(), torch.from_numpy(labels).cuda()
+    m.train()
+
+    def push():
+        if method == "adapter":
+            for blk, pair in zip(m.model.transformer.resblocks, tmasks):
+                blk.adaptmlp.push_masks(*[torch.from_numpy(a).reshape(-1, vo.ADAPTER_DIM)
+                                          for a in pair])
+
+    push()
+    probs, fi, ft = m(x)
+    loss = torch.nn.CrossEntropyLoss()(probs, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    want = load_grads(gold)
+    got = {k[len("model."):]: p.grad.cpu().numpy() for k, p in m.named_parameters()
+           if p.grad is not None}
+    assert set(got) == set(want)
+    assert rel(probs, gold["probs"]) < TOL
+    assert abs(loss.item() - float(gold["loss"])) < TOL * abs(float(gold["loss"]))
+    keys = sorted(want)
+    fg = np.concatenate([got[k].ravel() for k in keys]).astype(np.float64)
+    fw = np.concatenate([want[k].ravel() for k in keys]).astype(np.float64)
+    # the calibration of the two-tower cases applies (tiny: autocast's own level 3e-2 .. 6e-2)
+    assert rel(fg, fw) < 7e-2 and cos(fg, fw) > 0.997, rel(fg, fw)
+    # the trainer's step: same gradients in its flat buffer, lr = 0 leaves the parameters alone
+    tr = LoRAClipTrainer(m, names, n_classes=c, lr=0.0, visible_classes="all")
+    tr.online_before_task(0)
+    tr.add_new_class(torch.arange(c))
+    m.set_token(names)
+    push()
+    if method == "lora":
+        loss_sum, n_correct = tr.fused_step(x, y, len(y))
+        eng = m.model.text_engine()
+        flat = {k: g.cpu().numpy() for k, g in zip([k for k in wt if "lora" in k],
+                                                   eng.lora_grad_views)}
+    else:
+        loss_sum, n_correct = tr.block_step(x, y, len(y))
+        flat = {k[len("model."):]: v.cpu().numpy() for (k, p), v in
+                zip([(k, p) for k, p in m.named_parameters() if p.requires_grad],
+                    tr.optimizer.views)}
+    assert abs(loss_sum - float(gold["loss"])) < TOL * abs(float(gold["loss"]))
+    f2 = np.concatenate([flat[k].ravel() for k in keys]).astype(np.float64)
+    assert rel(f2, fg) < TOL
+    assert n_correct == float((probs.argmax(-1) == y).sum())
+
+
+def test_peft_encoder_none_is_zero_shot_only():
+    from lifelong_clip_b200.adapter_clip import AdapterCLIP
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+    cfg = vo.VIT_TINY
+    m = AdapterCLIP(peft_encoder="none",
+                    vision_config=(cfg.image_size, cfg.patch, cfg.width, cfg.layers,
+                                   cfg.embed_dim)).cuda()
+    names = [f"c{i}" for i in range(4)]
+    m.set_text_features(names, torch.randn(4, cfg.embed_dim))
+    m.set_token(names)
+    assert not any("lora" in k or "adaptmlp" in k for k, _ in m.named_parameters())
+    probs, f, t = m(torch.randn(3, 3, cfg.image_size, cfg.image_size).cuda())
+    assert tuple(probs.shape) == (3, 4) and float((probs.sum(-1) - 1).abs().max()) < 1e-5
+    tr = LoRAClipTrainer(m, names, n_classes=4)
+    with pytest.raises(RuntimeError, match="nothing is trainable"):
+        tr.online_before_task(0)

@@ -189,3 +189,38 @@ def test_adapter_oracle_matches_reference_golden(name, golden_dir):
                                 logit_scale_exp=float(gold["logit_scale_exp"]), dtype=dtype,
                                 tokens=tokens, wt_np=wt, wta_np=wta, tcfg=tcfg)
     assert _rel(ev["probs"], gold["probs_eval"]) < 2e-5
+
+
+def text_only_case_inputs(name):
+    """Inputs of a TEXT_ONLY_CASES golden (peft_encoder='text'; shared with the GPU test)."""
+    from tests.golden.make_golden import TEXT_ONLY_CASES
+    cfg, tcfg, n, c, seed, method = TEXT_ONLY_CASES[name]
+    wv, wt = vo.synth_weights(cfg, seed), vo.synth_text_weights(tcfg, seed + 1)
+    wta = vo.synth_adapter_weights(tcfg.width, tcfg.layers, "transformer.resblocks.", seed + 3)
+    images, labels = synth_inputs(cfg, n, c, seed + 100)
+    tokens = vo.synth_tokens(c, tcfg, seed + 300)
+    tmasks = vo.adapter_masks(seed + 500, tcfg.layers, tcfg.context, c)
+    return cfg, tcfg, method, wv, wt, wta, images, labels, tokens, tmasks
+
+
+@pytest.mark.parametrize("name", ["textonly_lora_tiny", "textonly_adapter_tiny"])
+def test_text_only_oracle_matches_reference_golden(name, golden_dir):
+    """peft_encoder='text' (scripts/lora_clip.sh:10 / adapter_clip.sh:10 list it): PEFT blocks in
+    the text tower only, the image tower vanilla - against the reference's own CLIP."""
+    from tests.golden.make_golden import load_grads
+    cfg, tcfg, method, wv, wt, wta, images, labels, tokens, tmasks = text_only_case_inputs(name)
+    gold = np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+    ls = float(gold["logit_scale_exp"])
+    if method == "lora":
+        wv0 = {k: (np.zeros_like(v) if "lora" in k else v) for k, v in wv.items()}
+        out = vo.clip_step_oracle(images, labels, tokens, wv0, wt, cfg, tcfg, logit_scale_exp=ls)
+        out["grads"] = {k: v for k, v in out["grads"].items() if not k.startswith("visual.")}
+    else:
+        out = vo.adapter_step_oracle(images, labels, wv, None, None, cfg, logit_scale_exp=ls,
+                                     p=vo.ADAPTER_DROPOUT, tokens=tokens, wt_np=wt, wta_np=wta,
+                                     tcfg=tcfg, tmasks=vo.masks_sample_major(tmasks))
+    assert _rel(out["probs"], gold["probs"]) < 2e-5
+    assert abs(float(out["loss"]) - float(gold["loss"])) < 1e-5
+    want = load_grads(gold)
+    assert set(want) == set(out["grads"]) and len(want) == 4 * tcfg.layers
+    assert max(_rel(out["grads"][k], v) for k, v in want.items()) < 2e-3
