@@ -119,11 +119,37 @@ class LoRAClipTrainer:
             self.batch_exposed_classes = self.exposed_classes
             self.batch_exposed_classes_names = self.exposed_classes_names
         else:
-            for label in class_name.tolist():
-                if label not in self.batch_exposed_classes:
-                    self.batch_exposed_classes.append(label)
-            self.batch_exposed_classes_names = [self.all_classnames[i]
-                                                for i in self.batch_exposed_classes]
+            self.add_new_batch_class(class_name)
+
+    def add_new_batch_class(self, class_name):
+        """methods/adapter_clip.py:263-271: the classes of THIS batch join the batch-visible
+        list (emptied by add_new_class when there is no replay memory)."""
+        for label in class_name.tolist():
+            if label not in self.batch_exposed_classes:
+                self.batch_exposed_classes.append(label)
+        self.batch_exposed_classes_names = [self.all_classnames[i]
+                                            for i in self.batch_exposed_classes]
+
+    def update_schedule(self, reset=False):
+        """methods/adapter_clip.py:249-256 with the 'default' schedule of the scripts
+        (utils/train_utils.py:34-45: a constant learning rate): reset restores self.lr."""
+        if reset and self.optimizer is not None:
+            self.optimizer.lr = self.lr
+
+    def extract_vector(self, image):
+        """methods/adapter_clip.py:109-112: the model wrapper's (normalised) image features."""
+        with torch.no_grad():
+            return self.custom_clip.encode_image(image.to(self.device))
+
+    def report_training(self, epoch, sample_num, train_loss, train_acc):
+        """methods/adapter_clip.py:285-293 (the running-time / ETA fields belong to the driver
+        loop's clock and are left out)."""
+        import logging
+        lr = self.optimizer.lr if self.optimizer is not None else self.lr
+        logging.info(f"Train | epoch:{epoch}, Sample # {sample_num} | train_loss {train_loss:.4f} "
+                     f"| train_acc {train_acc:.4f} | lr {lr:.6f} | "
+                     f"Num_Classes {len(self.exposed_classes)} | "
+                     f"Num_Batch_Classes {len(self.batch_exposed_classes)}")
 
     def _class_lut(self, class_list):
         """Device LUT class id -> position in class_list; rebuilt only when the list changes."""
@@ -485,6 +511,45 @@ class LoRAClipTrainer:
                                      add_mask=m._add_mask, want_probs=False)
             ops.eval_accum(y, head.pred, self.n_tasks, Cn, cm, counts)
         return self._eval_dict(cm, counts)
+
+    @torch.no_grad()
+    def offline_evaluate(self, test_loader, classes_names):
+        """methods/adapter_clip.py:178-208: top-1 accuracy over an explicit class-name list (the
+        prediction index is the position in classes_names); the counters stay on the device and
+        are read once."""
+        m = self.custom_clip
+        m.eval()
+        prev = (m._cls_key, m.text_tokens)
+        m.set_token(list(classes_names))
+        total = torch.zeros(2, dtype=torch.int64, device=self.device)
+        t_hat = text = None
+        if self.block_mode:
+            t_hat = m.text_features_blocks(m.text_tokens)
+        elif self.text_trainable:
+            from .adapter_clip import eot_rows
+            text = m.model.text_engine().forward(m._tokens, eot_rows(m._tokens),
+                                                 training=False).fnorm
+        for batch in test_loader:
+            x = batch[0].to(self.device, non_blocking=True)
+            y = batch[1].to(self.device, non_blocking=True)
+            if self.block_mode:
+                pred = m._forward_blocks(self.test_transform(x), m.text_tokens, t_hat=t_hat)[2]
+            else:
+                eng = m.model.visual.engine()
+                eng.forward(self.test_transform(x), training=False)
+                if text is not None:
+                    pred = eng.eval_head(text, m.model.logit_scale_exp(), add_mask=m._add_mask,
+                                         want_probs=False).pred
+                else:
+                    pred = eng.eval_head(m._text_all, m.model.logit_scale_exp(),
+                                         cls_idx=m._cls_idx, add_mask=m._add_mask,
+                                         want_probs=False).pred
+            total[0] += (pred == y).sum()
+            total[1] += y.numel()
+        if prev[0] is not None:
+            m.set_token(list(prev[0]))
+        correct, n = total.tolist()
+        return correct / n
 
     def _block_evaluate(self, test_loader):
         m, Cn = self.custom_clip, self.n_classes

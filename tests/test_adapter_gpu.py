@@ -596,3 +596,41 @@ def test_peft_encoder_none_is_zero_shot_only():
     tr = LoRAClipTrainer(m, names, n_classes=4)
     with pytest.raises(RuntimeError, match="nothing is trainable"):
         tr.online_before_task(0)
+
+
+@pytest.mark.parametrize("method", ["lora", "adapter"])
+def test_offline_evaluate_extract_vector_update_schedule(method):
+    """methods/adapter_clip.py:109-112,178-208,249-256: the trainer's remaining entry points."""
+    from lifelong_clip_b200.adapter_clip import AdapterCLIP
+    from lifelong_clip_b200.trainer import LoRAClipTrainer
+    cfg = vo.VIT_TINY
+    C_, n = 6, 16
+    torch.manual_seed(3)
+    m = AdapterCLIP(peft_method=method, peft_encoder="image",
+                    vision_config=(cfg.image_size, cfg.patch, cfg.width, cfg.layers,
+                                   cfg.embed_dim)).cuda()
+    names = [f"c{i}" for i in range(C_)]
+    m.set_text_features(names, torch.randn(C_, cfg.embed_dim))
+    tr = LoRAClipTrainer(m, names, n_classes=C_, lr=2e-3, visible_classes="all")
+    tr.online_before_task(0)
+    x = torch.randn(n, 3, cfg.image_size, cfg.image_size)
+    y = torch.randint(0, C_, (n,))
+    tr.online_step(x, y, torch.arange(n))
+    order = [names[i] for i in (3, 0, 5, 1)]          # an explicit class list, its own index space
+    acc = tr.offline_evaluate([(x[:8], y[:8] % 4), (x[8:], y[8:] % 4)], order)
+    m.eval()
+    m.set_token(order)
+    with torch.no_grad():
+        probs, _, _ = m(x.cuda())
+    want = float((probs.argmax(-1).cpu() == y % 4).float().mean())
+    assert abs(acc - want) < 1e-6
+    f = tr.extract_vector(x)
+    with torch.no_grad():
+        assert torch.allclose(f, m.encode_image(x.cuda()), atol=1e-6)
+    assert float((f.norm(dim=-1) - 1).abs().max()) < 1e-4
+    tr.optimizer.lr = 0.5
+    tr.update_schedule(reset=True)
+    assert tr.optimizer.lr == 2e-3
+    tr.update_schedule()
+    assert tr.optimizer.lr == 2e-3                    # 'default' schedule: constant
+    tr.report_training(0, n, 1.0, 0.5)
