@@ -221,6 +221,37 @@ class CLIP(nn.Module):
 VisionCLIP = CLIP   # round-1 name
 
 
+def build_model(state_dict: dict, design_details: dict = None) -> CLIP:
+    """models/clip/model.py:1005-1066: a CLIP whose dimensions are read off an (OpenAI) checkpoint's
+    state_dict, with the PEFT blocks `design_details` asks for, the checkpoint loaded and every
+    parameter in fp32. ViT towers only (the ResNet towers of :16-191 are outside this package).
+    The PEFT tensors (lora_A / lora_B / adaptmlp.*) are not part of a checkpoint and keep their
+    reference initialisation; any OTHER missing or unexpected key raises."""
+    if "visual.proj" not in state_dict:
+        raise NotImplementedError("ResNet CLIP towers are not built by lifelong_clip_b200")
+    sd = {k: v for k, v in state_dict.items()
+          if k not in ("input_resolution", "context_length", "vocab_size")}
+    vision_width = sd["visual.conv1.weight"].shape[0]
+    vision_layers = len([k for k in sd if k.startswith("visual.")
+                         and k.endswith(".attn.in_proj_weight")])
+    patch = sd["visual.conv1.weight"].shape[-1]
+    grid = round((sd["visual.positional_embedding"].shape[0] - 1) ** 0.5)
+    embed_dim = sd["text_projection"].shape[1]
+    width = sd["ln_final.weight"].shape[0]
+    layers = len(set(k.split(".")[2] for k in sd if k.startswith("transformer.resblocks")))
+    model = CLIP(embed_dim, patch * grid, vision_layers, vision_width, patch,
+                 sd["positional_embedding"].shape[0], sd["token_embedding.weight"].shape[0],
+                 width, width // 64, layers, design_details or {})
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    bad = [k for k in missing if "lora" not in k and "adaptmlp" not in k]
+    if bad or unexpected:
+        raise RuntimeError(f"checkpoint does not match the model: missing {bad[:5]}, "
+                           f"unexpected {list(unexpected)[:5]}")
+    for p in model.parameters():
+        p.data = p.data.float()
+    return model.eval()
+
+
 def eot_rows(tokens: torch.Tensor) -> torch.Tensor:
     """Row of every prompt's EOT token in the flattened [C*ctx] token axis (model.py:953-954:
     x[arange, text.argmax(-1)])."""
@@ -339,6 +370,20 @@ class AdapterCLIP(nn.Module):
     def __init__(self, model_name="ViT-B/16", peft_method='lora', peft_encoder='image',
                  device=None, vision_config=None, text_config=None):
         super().__init__()
+        self._init_fields(peft_method, peft_encoder, device)
+        design_details = {'method': peft_method, 'peft_encoder': peft_encoder, 'ffn_num': 64,
+                          'lora_alpha': 1, 'lora_r': 4}  # models/adapter_clip.py:24-30
+        res, patch, width, layers, embed = vision_config or VISION_CONFIGS[model_name]
+        if text_config is None and self.text_trainable:
+            text_config = TEXT_CONFIGS[model_name]
+        tc = text_config or (None,) * 5
+        self.model = CLIP(embed, res, layers, width, patch, tc[0], tc[1], tc[2], tc[3], tc[4],
+                          design_details)
+        if device is not None:
+            self.model.to(device)
+        self.dtype = self.model.dtype
+
+    def _init_fields(self, peft_method, peft_encoder, device):
         if peft_method not in ('lora', 'adapter'):
             raise NotImplementedError("lifelong_clip_b200 implements the lora-clip and "
                                       "adapter-clip methods (scripts/lora_clip.sh, "
@@ -350,19 +395,8 @@ class AdapterCLIP(nn.Module):
         self.peft_encoder = peft_encoder
         self.text_trainable = peft_encoder in ('both', 'text')
         self.image_trainable = peft_encoder in ('both', 'image')
-        design_details = {'method': peft_method, 'peft_encoder': peft_encoder, 'ffn_num': 64,
-                          'lora_alpha': 1, 'lora_r': 4}  # models/adapter_clip.py:24-30
-        res, patch, width, layers, embed = vision_config or VISION_CONFIGS[model_name]
-        if text_config is None and self.text_trainable:
-            text_config = TEXT_CONFIGS[model_name]
-        tc = text_config or (None,) * 5
-        self.model = CLIP(embed, res, layers, width, patch, tc[0], tc[1], tc[2], tc[3], tc[4],
-                          design_details)
-        if device is not None:
-            self.model.to(device)
         self.text_tokens = None
         self.current_class_names = []
-        self.dtype = self.model.dtype
         self.prompt_template = "a bad photo of a {}."
         self._tokenizer = None
         self._text_names: list[str] = []
@@ -373,6 +407,21 @@ class AdapterCLIP(nn.Module):
         self._tok_cache = {}       # class name -> int64 [ctx] (host)
         self._tokens = None        # int64 [C, ctx] on the device ('both')
         self._add_mask = None
+
+    @classmethod
+    def from_state_dict(cls, state_dict, peft_method='lora', peft_encoder='image', device=None):
+        """What clip_loader.load(model_name, design_details=...) does once the checkpoint is in
+        memory (models/clip/clip_loader.py:83-139 -> build_model): the wrapper around a CLIP built
+        from an OpenAI state_dict."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        cls._init_fields(self, peft_method, peft_encoder, device)
+        self.model = build_model(state_dict, {'method': peft_method, 'peft_encoder': peft_encoder,
+                                              'ffn_num': 64, 'lora_alpha': 1, 'lora_r': 4})
+        if device is not None:
+            self.model.to(device)
+        self.dtype = self.model.dtype
+        return self
 
     # ---- text side ---------------------------------------------------------------------------
     def set_tokenizer(self, fn):

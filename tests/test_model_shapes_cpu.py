@@ -68,3 +68,36 @@ def test_adapter_init_is_the_references():
     w = a.down_proj.weight
     assert float(w.abs().max()) <= bound and float(w.abs().max()) > 0.95 * bound
     assert a.scale == 0.1 and a.dropout == 0.1 and a.down_proj.out_features == 64
+
+
+def test_build_model_reads_dimensions_off_a_checkpoint():
+    """models/clip/model.py:1005-1066 build_model: dimensions from an OpenAI-style state_dict,
+    PEFT blocks from design_details, checkpoint loaded (the PEFT tensors are not in it)."""
+    from lifelong_clip_b200.adapter_clip import AdapterCLIP, build_model
+    cfg = vo.VitCfg(image_size=48, patch=16, width=128, layers=3, heads=2, embed_dim=64)
+    tcfg = vo.TextCfg(context=12, vocab=50, width=128, heads=2, layers=2, embed_dim=64)
+    sd = {k: torch.from_numpy(v) for k, v in {**vo.strip_lora(vo.synth_weights(cfg, 1)),
+                                              **vo.strip_lora(vo.synth_text_weights(tcfg, 2))}.items()}
+    sd["logit_scale"] = torch.tensor(2.0)
+    for extra in ("input_resolution", "context_length", "vocab_size"):
+        sd[extra] = torch.tensor(0)
+    for method, key in (("lora", "lora"), ("adapter", "adaptmlp")):
+        clip = build_model(dict(sd), {"method": method, "peft_encoder": "both", "ffn_num": 64,
+                                      "lora_alpha": 1, "lora_r": 4})
+        v = clip.visual
+        assert (v.input_resolution, v.patch_size, v.width, v.layers) == (48, 16, 128, 3)
+        assert clip.context_length == 12 and clip.vocab_size == 50
+        assert len(clip.transformer.resblocks) == 2 and not clip.training
+        assert torch.equal(clip.visual.conv1.weight, sd["visual.conv1.weight"])
+        assert torch.equal(clip.token_embedding.weight, sd["token_embedding.weight"])
+        assert float(clip.logit_scale) == 2.0
+        peft = [k for k, _ in clip.named_parameters() if key in k]
+        assert len(peft) == 4 * (3 + 2)
+    m = AdapterCLIP.from_state_dict(dict(sd), peft_method="adapter", peft_encoder="text")
+    assert m.text_trainable and not m.image_trainable and m.model.context_length == 12
+    assert not any("adaptmlp" in k for k, _ in m.model.visual.named_parameters())
+    bad = dict(sd)
+    del bad["visual.ln_post.weight"]
+    import pytest
+    with pytest.raises(RuntimeError, match="does not match"):
+        build_model(bad, {"method": "lora", "peft_encoder": "image"})
