@@ -31,7 +31,8 @@ class LoRAClipTrainer:
                  online_iter=1, visible_classes='batch', memory=None, memory_provider=None,
                  memory_batchsize=0, memory_size=0, train_transform=None, test_transform=None,
                  use_amp=True, topk=1, double_softmax=True, device=None, rank=None,
-                 world_size=None, sharded_input=False, use_cuda_graph=True):
+                 world_size=None, sharded_input=False, use_cuda_graph=True, opt_name='adamw',
+                 sched_name='default'):
         self.custom_clip = model
         self.model = model
         self.device = device or model.model.visual.proj.device
@@ -39,6 +40,17 @@ class LoRAClipTrainer:
         self.n_classes = n_classes or len(class_names)
         self.n_tasks = n_tasks
         self.lr, self.online_iter, self.topk = lr, online_iter, topk
+        # utils/train_utils.py:16-59. 'adamw' (weight decay 1e-5, what every script sets) and
+        # 'adam' (the same update with weight decay 0) run on llc_adamw; the schedules the scripts
+        # use ('default', 'const') keep the learning rate constant
+        if opt_name not in ('adamw', 'adam'):
+            raise NotImplementedError(f"opt_name={opt_name!r}: the fused optimizer implements "
+                                      "adamw / adam (scripts/*.sh use adamw)")
+        if sched_name not in ('default', 'const'):
+            raise NotImplementedError(f"sched_name={sched_name!r}: only the constant schedules "
+                                      "('default', 'const') of the scripts are implemented")
+        self.opt_name, self.sched_name = opt_name, sched_name
+        self.weight_decay = 1e-5 if opt_name == 'adamw' else 0.0
         self.visible_classes = visible_classes
         self.memory, self.memory_provider = memory, memory_provider
         self.memory_batchsize, self.memory_size = memory_batchsize, memory_size
@@ -187,11 +199,12 @@ class LoRAClipTrainer:
             from .engine import ParamAdamW
             m = self.custom_clip
             self.optimizer = ParamAdamW([p for _, p in m.named_parameters()], lr=self.lr,
-                                        weight_decay=1e-5, on_step=m.invalidate_adapters)
+                                        weight_decay=self.weight_decay,
+                                        on_step=m.invalidate_adapters)
             m.invalidate_adapters()         # the parameters moved into the flat buffer
             self._block_scal = torch.zeros(2, device=self.device)
             return
-        self.optimizer = FlatAdamW(self._towers(), lr=self.lr, weight_decay=1e-5)
+        self.optimizer = FlatAdamW(self._towers(), lr=self.lr, weight_decay=self.weight_decay)
 
     def online_after_task(self, task_id):
         """methods/adapter_clip.py:129-130: set_token(self.all_classnames[:self._total_classes]),
