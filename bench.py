@@ -250,23 +250,129 @@ class CpuReference:
         return (time.perf_counter() - t0) / steps
 
 
+ADAPTER_METRIC = "train img/s, adapter-clip online step"
+
+
+def adapter_workload_config(args, world: int) -> dict:
+    cfg = workload_config(args, world)
+    cfg["workload"] = (f"CLIP {args.model} adapter-clip online step (bottleneck adapters, "
+                       f"ffn 64, dropout 0.1), stream+replay batch {args.batch}, bf16 operands")
+    cfg["method"] = "adapter-clip"
+    return cfg
+
+
+class CpuAdapterPort:
+    """CPU arm of `--method adapter`: the oracle's restatement of the adapter-clip step
+    (oracle/vit_oracle.py: adapter_block_forward in the towers `peft` names, dropout p = 0.1 from
+    torch's generator as the reference draws it, reference loss, backward, AdamW over adaptmlp.*)
+    in fp32 on all host threads. kind = "port"."""
+
+    kind = "port"
+
+    def __init__(self, model: str, classes: int, batch: int, peft: str, seed: int = 0):
+        import numpy as np
+        import torch
+        from oracle import vit_oracle as vo
+        self.torch, self.vo, self.peft = torch, vo, peft
+        S, p, D, layers, H, E = MODELS[model]
+        self.cfg = vo.VitCfg(image_size=S, patch=p, width=D, layers=layers, heads=H, embed_dim=E)
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        f32 = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+        self.w = f32(vo.strip_lora(vo.synth_weights(self.cfg, seed)))
+        self.w.update({k: torch.zeros(sh) for k, sh in vo.param_shapes(self.cfg).items()
+                       if "lora" in k})
+        self.train = {}
+        if peft in ("image", "both"):
+            self.train.update(f32(vo.synth_adapter_weights(
+                D, layers, "visual.transformer.resblocks.", seed + 3)))
+        self.text = torch.from_numpy(vo.synth_text_features(classes, E, seed + 1))
+        self.tcfg = None
+        if peft in ("both", "text"):
+            from lifelong_clip_b200.adapter_clip import TEXT_CONFIGS
+            ctx, vocab, tw, th, tl = TEXT_CONFIGS[model]
+            self.tcfg = vo.TextCfg(context=ctx, vocab=vocab, width=tw, heads=th, layers=tl,
+                                   embed_dim=E)
+            self.wt = f32(vo.strip_lora(vo.synth_text_weights(self.tcfg, seed + 4)))
+            self.train.update(f32(vo.synth_adapter_weights(tw, tl, "transformer.resblocks.",
+                                                           seed + 5)))
+            self.tokens = torch.from_numpy(vo.synth_tokens(classes, self.tcfg, seed + 6))
+        for t in self.train.values():
+            t.requires_grad_(True)
+        rng = np.random.default_rng(seed + 2)
+        self.x = torch.from_numpy(rng.standard_normal((batch, 3, S, S)).astype(np.float32))
+        self.y = torch.from_numpy(rng.integers(0, classes, size=(batch,)).astype(np.int64))
+        self.batch = batch
+        self.opt = torch.optim.AdamW(list(self.train.values()), lr=1e-3, weight_decay=1e-5)
+
+    def describe(self) -> str:
+        return f"fp32 oracle port of the reference's adapter-clip path (peft_encoder={self.peft})"
+
+    def _tower(self, x, w, prefix, cfg, layers, causal, adapters):
+        vo, torch = self.vo, self.torch
+        for i in range(layers):
+            pre = f"{prefix}{i}."
+            if adapters:
+                shape = x.shape[:-1] + (vo.ADAPTER_DIM,)
+                masks = tuple(torch.rand(shape) >= vo.ADAPTER_DROPOUT for _ in range(2))
+                x = vo.adapter_block_forward(x, w, pre, cfg, causal=causal, masks=masks,
+                                             p=vo.ADAPTER_DROPOUT)
+            else:
+                x = vo.block_forward(x, w, pre, cfg, causal=causal)
+        return x
+
+    def step(self) -> float:
+        vo, torch = self.vo, self.torch
+        self.opt.zero_grad(set_to_none=True)
+        w = {**self.w, **self.train}
+        x = vo.patch_embed(self.x, w, self.cfg)
+        x = self._tower(x, w, "visual.transformer.resblocks.", self.cfg, self.cfg.layers, False,
+                        self.peft in ("image", "both"))
+        feat = vo.layer_norm(x[:, 0, :], w["visual.ln_post.weight"],
+                             w["visual.ln_post.bias"]) @ w["visual.proj"]
+        if self.tcfg is not None:
+            wt = {**self.wt, **self.train}
+            wt.update({k: torch.zeros(sh) for k, sh in vo.text_param_shapes(self.tcfg).items()
+                       if "lora" in k and k not in wt})
+            t = wt["token_embedding.weight"][self.tokens] + wt["positional_embedding"]
+            bcfg = vo.VitCfg(width=self.tcfg.width, heads=self.tcfg.heads, layers=self.tcfg.layers)
+            t = self._tower(t, wt, "transformer.resblocks.", bcfg, self.tcfg.layers, True, True)
+            t = vo.layer_norm(t, wt["ln_final.weight"], wt["ln_final.bias"])
+            tf = t[torch.arange(t.shape[0]), self.tokens.argmax(dim=-1)] @ wt["text_projection"]
+            text = tf / tf.norm(dim=-1, keepdim=True)
+        else:
+            text = self.text
+        probs, logits, _ = vo.head_forward(feat, text, 1.0 / 0.07)
+        loss = vo.reference_loss(probs, self.y, logits, True)
+        loss.backward()
+        self.opt.step()
+        return float(loss.detach())
+
+    time_steps = CpuReference.time_steps
+
+
 def run_reference(args):
     """--impl reference: rank 0 alone times the CPU path; other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     b = args.cpu_batch
-    ref = CpuReference(args.model, args.classes, b)
+    if args.method == "adapter":
+        ref = CpuAdapterPort(args.model, args.classes, b, args.peft)
+    else:
+        ref = CpuReference(args.model, args.classes, b)
     sec = ref.time_steps(args.steps, args.warmup)
     v = b / sec
     sample = (f"{b}-image batch per step (of the {global_batch(args, args.gpus)}-image workload), "
               f"{ref.describe()}, fp32, fwd+loss+bwd+AdamW, {ref.cores} threads")
+    adapter = args.method == "adapter"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": ADAPTER_METRIC if adapter else METRIC, "value": v,
+        "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": (adapter_workload_config if adapter else workload_config)(args, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
                          "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -569,13 +675,17 @@ def run_adapter(args, dev, world, rank, local_rank):
         dist.destroy_process_group()
     if rank != 0:
         return
-    cfg = workload_config(args, world)
-    cfg["workload"] = (f"CLIP {args.model} adapter-clip online step (bottleneck adapters, "
-                       f"ffn 64, dropout 0.1), stream+replay batch {args.batch}, bf16 operands")
-    cfg["method"] = "adapter-clip"
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ref = CpuAdapterPort(args.model, C, args.cpu_batch, args.peft)
+        sec = ref.time_steps(1, 1)
+        cpu = {"value": args.cpu_batch / sec, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+               "sample": f"{args.cpu_batch}-image batch x 1 timed step (1 warm-up) of the same "
+                         f"model/classes: {ref.describe()}, fp32, fwd+loss+bwd+AdamW"}
+    cfg = adapter_workload_config(args, world)
     n_adapter = sum(p_.numel() for a in model.adapters() for p_ in a.parameters())
     out = {
-        "metric": "train img/s, adapter-clip online step", "value": gB / (ms_dev * 1e-3),
+        "metric": ADAPTER_METRIC, "value": gB / (ms_dev * 1e-3),
         "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
@@ -596,7 +706,7 @@ def run_adapter(args, dev, world, rank, local_rank):
                                  "gbs": (d["bytes"] / (d["ms"] * 1e-3) / 1e9) if d["ms"] else 0.0}
                              for k, d in sorted(by_kind.items())},
         "top_launches": by_shape,
-        "cpu_baseline": None,
+        "cpu_baseline": cpu,
     }
     print(json.dumps(out), flush=True)
 
