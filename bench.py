@@ -552,6 +552,143 @@ def run_eval(args, model, names, dev, world, rank, local_rank):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_maple(args, dev, world, rank, local_rank):
+    """--method maple (BASELINE.json configs[3]): MaPLe multi-modal deep prompts on frozen ViT-B/16
+    towers (models/maple.py:74-253): text encoder over the class prompts (C x 77 tokens, compound
+    prompts spliced at layers 1-2) + image encoder (197 + 3 prompt tokens) forward and backward
+    down to the prompt rows, cosine logits, CE on the logits (methods/maple.py:96), AdamW on
+    prompt_learner.* (torch's: ~1.2 M parameters in 9 tensors). Data parallel: images shard, every
+    rank runs the text side, the prompt gradients are all-reduced."""
+    import torch
+    import torch.distributed as dist
+    from lifelong_clip_b200 import ops
+    from lifelong_clip_b200.adapter_clip import SyntheticTokenizer
+    from lifelong_clip_b200.maple import MaPLe
+
+    S, p, D, layers, H, E = MODELS[args.model]
+    B, C = per_gpu_batch(args, world), args.classes
+    gB = global_batch(args, world)
+    torch.manual_seed(0)
+    m = MaPLe(model_name=args.model, vision_config=(S, p, D, layers, E)).to(dev)
+    m.set_tokenizer(SyntheticTokenizer())
+    for k, prm in m.named_parameters():          # methods/maple.py: only the prompt learner trains
+        prm.requires_grad = "prompt_learner" in k
+    m.update_class_names([f"class {i}" for i in range(C)])
+    params = [prm for prm in m.parameters() if prm.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-5)
+    gen = torch.Generator().manual_seed(100 + rank)
+    host_x = [torch.randn(B, 3, S, S, generator=gen).pin_memory() for _ in range(2)]
+    host_y = [torch.randint(0, C, (B,), generator=gen).pin_memory() for _ in range(2)]
+    dev_x = [x.to(dev) for x in host_x]
+    dev_y = [y.to(dev) for y in host_y]
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        logits = m(x)
+        loss = torch.nn.functional.cross_entropy(logits, y, reduction="sum") / gB
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([prm.grad.reshape(-1) for prm in params])
+            dist.all_reduce(flat)
+            off = 0
+            for prm in params:
+                prm.grad.copy_(flat[off:off + prm.numel()].view_as(prm))
+                off += prm.numel()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(args.warmup):
+        step(dev_x[i % 2], dev_y[i % 2])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(dev_x[i % 2], dev_y[i % 2])
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    # e2e: pinned host fp32 batches -> device -> step -> loss float on the host
+    last = None
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            barrier()
+            e0.record()
+        x = host_x[i % 2].to(dev, non_blocking=True)
+        y = host_y[i % 2].to(dev, non_blocking=True)
+        last = float(step(x, y))
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    ops.prof_enable(True)
+    for i in range(args.prof_steps):
+        step(dev_x[i % 2], dev_y[i % 2])
+    torch.cuda.synchronize()
+    recs = ops.prof_read()
+    ops.prof_enable(False)
+    by_kind = {}
+    for kind, m_, n_, k_, ms, fl, by in recs:
+        d = by_kind.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["launches"] += 1; d["ms"] += ms; d["flops"] += fl; d["bytes"] += by
+    peaks = load_peaks()
+    gemm = by_kind.get("gemm", {"launches": 0, "ms": 1e-9, "flops": 0.0})
+    total_ms = sum(d["ms"] for d in by_kind.values()) or 1.0
+    achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+    peak = peaks["bf16_sustained"] or peaks["bf16"]
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    cfg = workload_config(args, world)
+    cfg["workload"] = (f"MaPLe multi-modal prompt tuning on CLIP {args.model}: text + image encoder "
+                       f"forward / backward with deep prompts (n_ctx 3, depth 3), batch {args.batch}, "
+                       f"{C} classes (BASELINE.json configs[3])")
+    cfg["method"] = "maple"
+    cfg["tokens"] = (S // p) ** 2 + 1 + 3
+    cfg["loss"] = "CE on the logits (methods/maple.py:96)"
+    out = {
+        "metric": "train img/s, MaPLe prompt-tuning step", "value": gB / (ms_dev * 1e-3),
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+        "clocks": clocks, "trainable_params": sum(prm.numel() for prm in params),
+        "e2e": {"value": gB / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": (host_x[0].numel() * 4 + host_y[0].numel() * 8) * world,
+                "d2h_bytes_per_step": 4 * world,
+                "api": "logits = MaPLe(images); CE; backward; AdamW(prompt_learner) -> loss float",
+                "last_loss": last},
+        "gpu_launches": launches * world,
+        "roofline": {"bound": "tensor", "kernel": "gemm2_kernel (tcgen05 cta_group::2 / TMEM): the "
+                     "frozen blocks' dense contractions, forward and activation-gradient",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peaks["source"],
+                     "share_of_step": gemm["ms"] / total_ms},
+        "kernel_breakdown": {k: {"ms_per_step": d["ms"] / args.prof_steps,
+                                 "launches_per_step": d["launches"] / args.prof_steps}
+                             for k, d in sorted(by_kind.items())},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 def run_adapter(args, dev, world, rank, local_rank):
     """--method adapter: the reference's second PEFT method on the same trainer
     (scripts/adapter_clip.sh -> ResidualAttentionBlock_Adapter in the towers peft_encoder names,
@@ -741,10 +878,11 @@ def run_ours(args):
     from lifelong_clip_b200.adapter_clip import SyntheticTokenizer
     from lifelong_clip_b200.transform import GpuTransform
 
-    if args.method == "adapter":
+    if args.method in ("adapter", "maple"):
         if args.mode != "train":
-            raise SystemExit("--method adapter measures the training step")
-        return run_adapter(args, dev, world, rank, local_rank)
+            raise SystemExit(f"--method {args.method} measures the training step")
+        run = run_adapter if args.method == "adapter" else run_maple
+        return run(args, dev, world, rank, local_rank)
     S, p, D, layers, H, E = MODELS[args.model]
     B, C = per_gpu_batch(args, world), args.classes
     gB = global_batch(args, world)
@@ -1027,9 +1165,10 @@ def main():
     ap.add_argument("--peft", default="image", choices=["image", "both", "text"],
                     help="'both': LoRA text tower recomputed every step (scripts/lora_clip.sh); "
                          "'text': only the text tower trains, the image tower runs forward only")
-    ap.add_argument("--method", default="lora", choices=["lora", "adapter"],
-                    help="'adapter': the adapter-clip method (scripts/adapter_clip.sh), a secondary "
-                         "line; the headline metric is the lora-clip step")
+    ap.add_argument("--method", default="lora", choices=["lora", "adapter", "maple"],
+                    help="'adapter': the adapter-clip method (scripts/adapter_clip.sh); 'maple': "
+                         "MaPLe prompt tuning (BASELINE configs[3]) - secondary lines; the "
+                         "headline metric is the lora-clip step")
     ap.add_argument("--classes", type=int, default=None)
     ap.add_argument("--cpu-batch", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--prof-steps", type=int, default=2)

@@ -22,15 +22,9 @@ import torch.nn as nn
 
 from . import _capi as K
 from . import ops
-from .clip_modules import PAD, ResidualAttentionBlock, _bf16
+from .clip_modules import PAD, ResidualAttentionBlock, _bf16, _bf16e
 
 DIM = K.ADAPTER_DIM
-
-
-def _bf16e(rows, cols, device):
-    """Uninitialised bf16 buffer (every element is written before it is read); _bf16 zero-fills,
-    which the K-augmented buffers need for their pad columns."""
-    return torch.empty(rows, cols, dtype=torch.bfloat16, device=device)
 
 
 class Adapter(nn.Module):

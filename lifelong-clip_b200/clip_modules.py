@@ -175,7 +175,9 @@ class _MhaFn(torch.autograd.Function):
     def backward(ctx, dy):
         attn, bufs, (L, N, D) = ctx.attn, ctx.bufs, ctx.shape
         T, dev = L * N, dy.device
-        grads = [torch.zeros_like(p, dtype=torch.float32) for p in ctx.lora]
+        train_lora = any(p.requires_grad for p in ctx.lora)
+        grads = [torch.zeros_like(p, dtype=torch.float32) if train_lora else None
+                 for p in ctx.lora]
         scratch = dict(
             dx=dy.detach().float().contiguous().view(T, D), dxb=_bf16(T, D + PAD, dev),
             dh=_bf16(T, D, dev), d_o=_bf16(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
@@ -193,8 +195,9 @@ class _MhaFn(torch.autograd.Function):
                                           C.byref(s), N, L, 1, N, int(ctx.causal), int(need_dx),
                                           K.stream_ptr()), "llc_mha_backward")
         gx = scratch["dh"].float().view(L, N, D) if need_dx else None
-        return (None, gx, None) + tuple(g.to(p.dtype) if p.requires_grad else None
-                                        for g, p in zip(grads, ctx.lora))
+        return (None, gx, None) + tuple(
+            g.to(p.dtype) if (g is not None and p.requires_grad) else None
+            for g, p in zip(grads, ctx.lora))
 
 
 def _causal_flag(attn_mask, L: int) -> int:
@@ -296,7 +299,14 @@ LORA_NAMES = ("attn.in_proj_weight_lora_A", "attn.in_proj_weight_lora_B",
 
 
 def _bf16(rows, cols, device):
+    """Zero-filled bf16 buffer: the K-augmented operands (pad columns must hold zeros where no
+    kernel writes them)."""
     return torch.zeros(rows, cols, dtype=torch.bfloat16, device=device)
+
+
+def _bf16e(rows, cols, device):
+    """Uninitialised bf16 buffer (every element is written before it is read)."""
+    return torch.empty(rows, cols, dtype=torch.bfloat16, device=device)
 
 
 class PackedLayer:
@@ -366,8 +376,8 @@ class _BlockFn(torch.autograd.Function):
         bufs = dict(
             x_in=x2, h1=_bf16(T, D + PAD, dev), qkv=_bf16(T, 3 * D + PAD, dev),
             lse=torch.empty(N * blk.n_head * L, device=dev), o=_bf16(T, D + PAD, dev),
-            x_mid=torch.empty(T, D, device=dev), h2=_bf16(T, D, dev),
-            z=_bf16(T, M, dev) if need_grad else None, g=_bf16(T, M, dev),
+            x_mid=torch.empty(T, D, device=dev), h2=_bf16e(T, D, dev),
+            z=_bf16e(T, M, dev) if need_grad else None, g=_bf16e(T, M, dev),
             x_out=torch.empty(T, D, device=dev))
         b = K.BlockBufs()
         for k, v in bufs.items():
@@ -377,10 +387,12 @@ class _BlockFn(torch.autograd.Function):
         causal = blk._causal_flag(L)
         K.check(K.load().llc_block_forward(C.byref(blk._cfg), C.byref(layer), C.byref(b), N, L,
                                            1, N, causal, K.stream_ptr()), "llc_block_forward")
+        out = bufs.pop("x_out")
+        bufs["h2"] = bufs["g"] = None      # not read by the backward: freed with the call
         ctx.blk, ctx.bufs, ctx.shape, ctx.causal = blk, bufs, (L, N, D), causal
         ctx.x_needs_grad = x.requires_grad
         ctx.lora = lora
-        return bufs["x_out"].view(L, N, D)
+        return out.view(L, N, D)
 
     @staticmethod
     def backward(ctx, dy):
@@ -389,11 +401,15 @@ class _BlockFn(torch.autograd.Function):
         if bufs["z"] is None:
             raise RuntimeError("block forward ran without grad; cannot backpropagate")
         dx = dy.detach().float().contiguous().view(T, D).clone()
-        grads = [torch.zeros_like(p, dtype=torch.float32) for p in ctx.lora]
+        # vanilla (frozen) block: no gradient slots -> the backward skips the LoRA reductions
+        # (include/llc.h llc_vit_layer); the scratch below is zero-filled as that path requires
+        train_lora = any(p.requires_grad for p in ctx.lora)
+        grads = [torch.zeros_like(p, dtype=torch.float32) if train_lora else None
+                 for p in ctx.lora]
         s = K.BlockBwdBufs()
         scratch = dict(
-            dx=dx, dxb=_bf16(T, D + PAD, dev), dz=_bf16(T, M, dev), dh=_bf16(T, D, dev),
-            d_o=_bf16(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
+            dx=dx, dxb=_bf16(T, D + PAD, dev), dz=_bf16e(T, M, dev), dh=_bf16e(T, D, dev),
+            d_o=_bf16e(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
             partial=torch.empty(ops.lora_side_max_partials() * 3 * D * 8, device=dev),
             delta=torch.empty(N * blk.n_head * L, device=dev))
         for k, v in scratch.items():
@@ -409,7 +425,7 @@ class _BlockFn(torch.autograd.Function):
                                        N, L, 1, N, ctx.causal, int(ctx.x_needs_grad),
                                        K.stream_ptr()), "llc_block_backward")
         gx = dx.view(L, N, D) if ctx.x_needs_grad else None
-        return (None, gx) + tuple(g.to(p.dtype) if p.requires_grad else None
+        return (None, gx) + tuple(g.to(p.dtype) if (g is not None and p.requires_grad) else None
                                   for g, p in zip(grads, ctx.lora))
 
 
