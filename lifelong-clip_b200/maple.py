@@ -26,7 +26,6 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
 from .adapter_clip import CLIP, TEXT_CONFIGS, VISION_CONFIGS
 from .clip_modules import _CosineLogitFn, _RowFeatFn, embed_images
 
