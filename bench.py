@@ -582,11 +582,18 @@ def run_maple(args, dev, world, rank, local_rank):
     dev_x = [x.to(dev) for x in host_x]
     dev_y = [y.to(dev) for y in host_y]
 
+    graphed = None
+    if not args.no_graph:
+        from lifelong_clip_b200.maple import GraphedStep
+        graphed = GraphedStep(m, dev_x[0], dev_y[0], gB)
     def step(x, y):
-        opt.zero_grad(set_to_none=True)
-        logits = m(x)
-        loss = torch.nn.functional.cross_entropy(logits, y, reduction="sum") / gB
-        loss.backward()
+        if graphed is not None:
+            loss = graphed(x, y)
+        else:
+            opt.zero_grad(set_to_none=True)
+            logits = m(x)
+            loss = torch.nn.functional.cross_entropy(logits, y, reduction="sum") / gB
+            loss.backward()
         if world > 1:
             flat = torch.cat([prm.grad.reshape(-1) for prm in params])
             dist.all_reduce(flat)
@@ -625,6 +632,12 @@ def run_maple(args, dev, world, rank, local_rank):
     launches = ops.launch_count() - l0
     ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.stop() if sampler else None
+    if graphed is not None:     # libllc kernel nodes per replay = launches of one eager step
+        g_keep, graphed = graphed, None
+        n0 = ops.launch_count()
+        step(dev_x[0], dev_y[0])
+        launches = (ops.launch_count() - n0) * args.steps
+        graphed = g_keep
     # e2e: pinned host fp32 batches -> device -> step -> loss float on the host
     last = None
     for i in range(args.warmup + args.steps):
@@ -637,6 +650,7 @@ def run_maple(args, dev, world, rank, local_rank):
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    graphed = None              # per-launch events need eager launches
     ops.prof_enable(True)
     for i in range(args.prof_steps):
         step(dev_x[i % 2], dev_y[i % 2])
@@ -669,6 +683,7 @@ def run_maple(args, dev, world, rank, local_rank):
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
         "clocks": clocks, "trainable_params": sum(prm.numel() for prm in params),
+        "impl_details": {"cuda_graph": not args.no_graph},
         "e2e": {"value": gB / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": (host_x[0].numel() * 4 + host_y[0].numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world,

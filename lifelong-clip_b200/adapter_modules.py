@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from . import _capi as K
 from . import ops
-from .clip_modules import PAD, ResidualAttentionBlock, _bf16, _bf16e
+from .clip_modules import PAD, ResidualAttentionBlock, _bf16, _bf16e, _bf16p
 
 DIM = K.ADAPTER_DIM
 
@@ -214,8 +214,8 @@ class _AdapterBlockFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         training = blk.training and ad.dropout > 0
         bufs = dict(
-            x_in=x2, h1=_bf16(T, D + PAD, dev), qkv=_bf16(T, 3 * D + PAD, dev),
-            lse=torch.empty(N * blk.n_head * L, device=dev), o=_bf16(T, D + PAD, dev),
+            x_in=x2, h1=_bf16p(T, D, dev), qkv=_bf16p(T, 3 * D, dev),
+            lse=torch.empty(N * blk.n_head * L, device=dev), o=_bf16p(T, D, dev),
             x_mid=torch.empty(T, D, device=dev), h2=_bf16e(T, D, dev),
             z=_bf16e(T, M, dev) if need_grad else None, g=_bf16e(T, M, dev),
             x_out=torch.empty(T, D, device=dev))
@@ -259,8 +259,8 @@ class _AdapterBlockFn(torch.autograd.Function):
         lgrads = [None] * 4       # frozen attention: no LoRA reductions (llc.h: llc_vit_layer)
         lib = K.load()
         scratch = dict(
-            dx=dx, dxb=_bf16(T, D + PAD, dev), dz=_bf16e(T, M, dev), dh=_bf16e(T, D, dev),
-            d_o=_bf16e(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
+            dx=dx, dxb=_bf16p(T, D, dev), dz=_bf16e(T, M, dev), dh=_bf16e(T, D, dev),
+            d_o=_bf16e(T, D, dev), dqkv=_bf16p(T, 3 * D, dev),
             partial=torch.empty(ops.lora_side_max_partials() * 3 * D * 8, device=dev),
             delta=torch.empty(N * blk.n_head * L, device=dev))
         s = K.BlockBwdBufs()

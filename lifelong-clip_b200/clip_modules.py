@@ -157,9 +157,9 @@ class _MhaFn(torch.autograd.Function):
         if dev.type != "cuda":
             raise RuntimeError("lifelong_clip_b200 modules compute on CUDA (sm_100a) only; "
                                "move the module and its input to the GPU (no CPU fallback)")
-        bufs = dict(x_in=x.detach().float().contiguous().view(T, D), h1=_bf16(T, D + PAD, dev),
-                    qkv=_bf16(T, 3 * D + PAD, dev),
-                    lse=torch.empty(N * attn.num_heads * L, device=dev), o=_bf16(T, D + PAD, dev),
+        bufs = dict(x_in=x.detach().float().contiguous().view(T, D), h1=_bf16p(T, D, dev),
+                    qkv=_bf16p(T, 3 * D, dev),
+                    lse=torch.empty(N * attn.num_heads * L, device=dev), o=_bf16p(T, D, dev),
                     x_out=torch.empty(T, D, device=dev))
         b = K.BlockBufs()
         for k, v in bufs.items():
@@ -179,8 +179,8 @@ class _MhaFn(torch.autograd.Function):
         grads = [torch.zeros_like(p, dtype=torch.float32) if train_lora else None
                  for p in ctx.lora]
         scratch = dict(
-            dx=dy.detach().float().contiguous().view(T, D), dxb=_bf16(T, D + PAD, dev),
-            dh=_bf16(T, D, dev), d_o=_bf16(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
+            dx=dy.detach().float().contiguous().view(T, D), dxb=_bf16p(T, D, dev),
+            dh=_bf16(T, D, dev), d_o=_bf16(T, D, dev), dqkv=_bf16p(T, 3 * D, dev),
             partial=torch.empty(ops.lora_side_max_partials() * 3 * D * 8, device=dev),
             delta=torch.empty(N * attn.num_heads * L, device=dev))
         s = K.BlockBwdBufs()
@@ -200,17 +200,28 @@ class _MhaFn(torch.autograd.Function):
             for g, p in zip(grads, ctx.lora))
 
 
+_CAUSAL_CHECKED = {}
+
+
 def _causal_flag(attn_mask, L: int) -> int:
-    """None -> 0; the text tower's additive -inf upper triangle (model.py:926-932) -> 1."""
+    """None -> 0; the text tower's additive -inf upper triangle (model.py:926-932) -> 1. The
+    comparison (a device-to-host read when the mask lives on the GPU) runs once per mask object
+    and length, not once per block call."""
     if attn_mask is None:
         return 0
+    key = (id(attn_mask), attn_mask._version, attn_mask.data_ptr(), L)
+    if _CAUSAL_CHECKED.get(key):
+        return 1
     want = torch.full((L, L), float("-inf")).triu(1)
     m = attn_mask.detach().float().cpu()
-    if tuple(m.shape) == (L, L) and torch.equal(m, want):
-        return 1
-    if m.dim() == 2 and m.shape[0] >= L and torch.equal(m[:L, :L], want):
-        return 1   # a mask built for the full context, applied to a shorter sequence
-    raise NotImplementedError("only attn_mask=None or the causal mask is supported")
+    ok = (tuple(m.shape) == (L, L) and torch.equal(m, want)) or \
+        (m.dim() == 2 and m.shape[0] >= L and torch.equal(m[:L, :L], want))
+    if not ok:   # (second form: a mask built for the full context, applied to a shorter sequence)
+        raise NotImplementedError("only attn_mask=None or the causal mask is supported")
+    if len(_CAUSAL_CHECKED) > 256:
+        _CAUSAL_CHECKED.clear()
+    _CAUSAL_CHECKED[key] = True
+    return 1
 
 
 class MultiheadAttention(nn.Module):
@@ -304,6 +315,15 @@ def _bf16(rows, cols, device):
     return torch.zeros(rows, cols, dtype=torch.bfloat16, device=device)
 
 
+def _bf16p(rows, cols, device):
+    """bf16 [rows, cols + PAD] whose PAD columns are zero and whose first `cols` columns are
+    uninitialised: the activation-sized K-augmented buffers (h1, qkv, o, dxb, dqkv). Their body is
+    always written by a kernel; zero-filling all of it cost 0.7 GB of memset per block call."""
+    t = torch.empty(rows, cols + PAD, dtype=torch.bfloat16, device=device)
+    t[:, cols:].zero_()
+    return t
+
+
 def _bf16e(rows, cols, device):
     """Uninitialised bf16 buffer (every element is written before it is read)."""
     return torch.empty(rows, cols, dtype=torch.bfloat16, device=device)
@@ -374,8 +394,8 @@ class _BlockFn(torch.autograd.Function):
         # (grad mode is off inside Function.forward: ask autograd which inputs need gradients)
         need_grad = any(ctx.needs_input_grad)
         bufs = dict(
-            x_in=x2, h1=_bf16(T, D + PAD, dev), qkv=_bf16(T, 3 * D + PAD, dev),
-            lse=torch.empty(N * blk.n_head * L, device=dev), o=_bf16(T, D + PAD, dev),
+            x_in=x2, h1=_bf16p(T, D, dev), qkv=_bf16p(T, 3 * D, dev),
+            lse=torch.empty(N * blk.n_head * L, device=dev), o=_bf16p(T, D, dev),
             x_mid=torch.empty(T, D, device=dev), h2=_bf16e(T, D, dev),
             z=_bf16e(T, M, dev) if need_grad else None, g=_bf16e(T, M, dev),
             x_out=torch.empty(T, D, device=dev))
@@ -408,8 +428,8 @@ class _BlockFn(torch.autograd.Function):
                  for p in ctx.lora]
         s = K.BlockBwdBufs()
         scratch = dict(
-            dx=dx, dxb=_bf16(T, D + PAD, dev), dz=_bf16e(T, M, dev), dh=_bf16e(T, D, dev),
-            d_o=_bf16e(T, D, dev), dqkv=_bf16(T, 3 * D + PAD, dev),
+            dx=dx, dxb=_bf16p(T, D, dev), dz=_bf16e(T, M, dev), dh=_bf16e(T, D, dev),
+            d_o=_bf16e(T, D, dev), dqkv=_bf16p(T, 3 * D, dev),
             partial=torch.empty(ops.lora_side_max_partials() * 3 * D * 8, device=dev),
             delta=torch.empty(N * blk.n_head * L, device=dev))
         for k, v in scratch.items():
@@ -717,7 +737,7 @@ class _RowFeatFn(torch.autograd.Function):
         L, N, D = x.shape
         x2 = x.detach().float().contiguous().view(L * N, D)
         dummy = torch.zeros(1, proj.shape[1], device=x.device)
-        dummy[0, 0] = 1.0
+        dummy.narrow(1, 0, 1).fill_(1.0)       # (a device-side fill: CUDA-graph capturable)
         head = ops.Head(x2, 1, ln_g, ln_b, proj, dummy, 1.0, N, row_idx=rows).forward()
         ctx.head, ctx.shape, ctx.normalise = head, (L, N, D), normalise
         return (head.fnorm if normalise else head.feat).clone()

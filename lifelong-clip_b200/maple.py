@@ -168,4 +168,54 @@ class MaPLe(nn.Module):
             x = blk(x)
         f32 = lambda t: t.detach().float().contiguous()
         return _CosineLogitFn.apply(x, t_hat, f32(v.ln_post.weight), f32(v.ln_post.bias),
-                                    f32(v.proj), self.logit_scale.exp().item())
+                                    f32(v.proj), self.base_clip_model.logit_scale_exp())
+
+
+class GraphedStep:
+    """forward + CE + backward of a MaPLe model captured once in a CUDA graph and replayed (fixed
+    batch shape and class list): the 24 + 24 block calls, the prompt splicing and the prompt
+    learner's small torch ops become one launch, which removes the per-block host dispatch the
+    kernels do not hide (3.7 of 33.5 ms at the bench shape). Gradients land in the parameters'
+    .grad (memory of the graph's pool, stable across replays); the optimizer step and, under data
+    parallelism, the gradient all-reduce stay outside.
+
+        step = GraphedStep(model, x0, y0, global_batch)
+        loss = step(x, y); optimizer.step()
+    """
+
+    def __init__(self, model: MaPLe, x: torch.Tensor, y: torch.Tensor, global_batch: int = None):
+        self.m = model
+        self.x, self.y = x.detach().clone(), y.detach().clone()
+        self.gb = float(global_batch or x.shape[0])
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):      # warm-up: allocator pool, lazily packed operands
+            for _ in range(2):
+                self._zero()
+                self._fwd_bwd()
+        cur.wait_stream(side)
+        self._zero()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+        self.grads = [p.grad for p in self.params]      # tensors of the graph's memory pool
+
+    def _zero(self):
+        for p in self.params:
+            p.grad = None
+
+    def _fwd_bwd(self):
+        logits = self.m(self.x)
+        loss = F.cross_entropy(logits, self.y, reduction="sum") / self.gb
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        for p, g in zip(self.params, self.grads):       # (survives zero_grad(set_to_none=True))
+            p.grad = g
+        return self.loss

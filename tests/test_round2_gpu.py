@@ -733,3 +733,32 @@ def test_online_evaluate_with_gpu_test_transform():
     assert float(fused["avg_acc"]) == float(plain["avg_acc"])
     assert fused["confusion_matrix"] == plain["confusion_matrix"]
     assert fused["task_acc"] == plain["task_acc"]
+
+
+def test_maple_graphed_step_equals_eager():
+    """maple.GraphedStep: forward + CE + backward replayed from one CUDA graph gives the eager
+    gradients bit for bit, on new inputs too."""
+    from lifelong_clip_b200.adapter_clip import SyntheticTokenizer
+    from lifelong_clip_b200.maple import GraphedStep, MaPLe
+    cfg = vo.VitCfg(image_size=64, patch=16, width=256, layers=3, heads=4, embed_dim=128)
+    torch.manual_seed(1)
+    m = MaPLe(vision_config=(cfg.image_size, cfg.patch, cfg.width, cfg.layers, cfg.embed_dim),
+              text_config=(16, 300, 128, 2, 3)).cuda()
+    m.set_tokenizer(SyntheticTokenizer(16, 300))
+    for k, p in m.named_parameters():
+        p.requires_grad = "prompt_learner" in k
+    m.update_class_names([f"class{i}" for i in range(5)])
+    xs = [torch.randn(6, 3, 64, 64, device="cuda") for _ in range(2)]
+    ys = [torch.randint(0, 5, (6,), device="cuda") for _ in range(2)]
+    step = GraphedStep(m, xs[0], ys[0])
+    params = [p for p in m.parameters() if p.requires_grad]
+    for x, y in zip(xs[::-1], ys[::-1]):
+        loss_g = float(step(x, y))
+        got = [p.grad.clone() for p in params]
+        for p in params:
+            p.grad = None
+        loss = torch.nn.functional.cross_entropy(m(x), y)
+        loss.backward()
+        assert abs(loss_g - float(loss)) < 1e-6 * abs(float(loss))
+        for a, p in zip(got, params):
+            assert torch.equal(a, p.grad)
