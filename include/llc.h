@@ -364,6 +364,8 @@ typedef struct llc_block_bwd_bufs {
   void* dqkv;    /* [T, 3D+16] bf16 scratch                                        */
   float* partial;/* llc_lora_side partials: max_partials * 3D * r floats           */
   float* delta;  /* [N * heads * L] fp32 scratch: rowsum(dO o O) of the attention backward */
+  const float* dy; /* optional: the gradient of x_out in a buffer that must NOT be modified (an
+                      autograd input). dx is then output only; NULL = dx holds it on entry */
 } llc_block_bwd_bufs;
 int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w, const llc_block_bufs* b,
                        const llc_block_bwd_bufs* s, int N, int L, int tok_stride_n,

@@ -80,7 +80,7 @@ class BlockBufs(C.Structure):
 
 class BlockBwdBufs(C.Structure):
     _fields_ = [(n, c_void) for n in (
-        "dx", "dxb", "dz", "dh", "d_o", "dqkv", "partial", "delta")]
+        "dx", "dxb", "dz", "dh", "d_o", "dqkv", "partial", "delta", "dy")]
 
 
 class Adapter(C.Structure):

@@ -253,7 +253,10 @@ class _AdapterBlockFn(torch.autograd.Function):
         if bufs["z"] is None:
             raise RuntimeError("block forward ran without grad; cannot backpropagate")
         ad = blk.adaptmlp
-        dx = dy.detach().float().contiguous().view(T, D).clone()
+        # dy belongs to autograd and is only read (llc_block_bwd_bufs.dy); dx receives the
+        # gradient of the block's input
+        dyc = dy.detach().float().contiguous().view(T, D)
+        dx = torch.empty(T, D, device=dev)
         grads = [torch.zeros_like(p, dtype=torch.float32) for p in ctx.params]
         lora = blk.lora_params()
         lgrads = [None] * 4       # frozen attention: no LoRA reductions (llc.h: llc_vit_layer)
@@ -266,12 +269,13 @@ class _AdapterBlockFn(torch.autograd.Function):
         s = K.BlockBwdBufs()
         for k, v in scratch.items():
             setattr(s, k, v.data_ptr())
+        s.dy = dyc.data_ptr()
         extra = dict(da=_bf16e(T, DIM, dev), d_branch=None,
                      partial=torch.empty(lib.llc_adapter_partial_floats(D), device=dev))
         ab = K.AdapterBufs()
         for k, v in {**abufs, **extra}.items():
             setattr(ab, k, K.ptr(v))
-        K.check(lib.llc_cast_bf16(dx.data_ptr(), scratch["dxb"].data_ptr(), T, D, D + PAD,
+        K.check(lib.llc_cast_bf16(dyc.data_ptr(), scratch["dxb"].data_ptr(), T, D, D + PAD,
                                   K.stream_ptr()), "llc_cast_bf16")
         b = K.BlockBufs()
         for k, v in bufs.items():

@@ -420,7 +420,10 @@ class _BlockFn(torch.autograd.Function):
         T, M, dev = L * N, blk.mlp.c_fc.out_features, dy.device
         if bufs["z"] is None:
             raise RuntimeError("block forward ran without grad; cannot backpropagate")
-        dx = dy.detach().float().contiguous().view(T, D).clone()
+        # dy belongs to autograd and is only read (llc_block_bwd_bufs.dy); dx receives the
+        # gradient of the block's input
+        dyc = dy.detach().float().contiguous().view(T, D)
+        dx = torch.empty(T, D, device=dev)
         # vanilla (frozen) block: no gradient slots -> the backward skips the LoRA reductions
         # (include/llc.h llc_vit_layer); the scratch below is zero-filled as that path requires
         train_lora = any(p.requires_grad for p in ctx.lora)
@@ -434,8 +437,9 @@ class _BlockFn(torch.autograd.Function):
             delta=torch.empty(N * blk.n_head * L, device=dev))
         for k, v in scratch.items():
             setattr(s, k, v.data_ptr())
+        s.dy = dyc.data_ptr()
         lib = K.load()
-        K.check(lib.llc_cast_bf16(dx.data_ptr(), scratch["dxb"].data_ptr(), T, D, D + PAD,
+        K.check(lib.llc_cast_bf16(dyc.data_ptr(), scratch["dxb"].data_ptr(), T, D, D + PAD,
                                   K.stream_ptr()), "llc_cast_bf16")
         b = K.BlockBufs()
         for k, v in bufs.items():

@@ -385,8 +385,8 @@ extern "C" int llc_block_backward(const llc_vit_cfg* cfg, const llc_vit_layer* w
   // dx_mid = dx + LN2'(dh2); bf16 copy (the row product du_o = s dx_mid B_o runs on the tensor
   // cores inside attn_half_backward: fused into the LayerNorm kernel it cost 52 us per launch in
   // L1 traffic for the factor, profiles/)
-  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
-                 stream));
+  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dy ? s->dy : s->dx, s->dx, T, D, s->dxb, DA,
+                 nullptr, 0, 0.f, stream));
   RUN(attn_half_backward(cfg, w, b, s, N, L, sn, sl, causal, need_dx_in, stream));
   if (need_dx_in)   // dx_in = dx_mid + LN1'(dh1)
     RUN(llc_ln_bwd(b->x_in, D, w->ln1_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
@@ -466,8 +466,8 @@ extern "C" int llc_adapter_block_backward(const llc_vit_cfg* cfg, const llc_vit_
   e = llc_gemm_epi{};
   e.out = s->dh; e.ld_out = D;
   RUN(GEMM(s->dz, M, w->wfcT, M, T, D, M, &e, stream));
-  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dx, s->dx, T, D, s->dxb, DA, nullptr, 0, 0.f,
-                 stream));
+  RUN(llc_ln_bwd(b->x_mid, D, w->ln2_g, s->dh, D, s->dy ? s->dy : s->dx, s->dx, T, D, s->dxb, DA,
+                 nullptr, 0, 0.f, stream));
   // x_mid = x + ya + s up(a1): the same with d_o = dx W_o + dz1 (W_d W_o) (pad columns of woT_aug)
   RUN(llc_adapter_backward(ad, ab->ya, D, ab->a1, s->dx, s->dxb, DA, nullptr, 0, ab->da,
                            ab->partial, 1, training, T, D, stream));
@@ -732,7 +732,7 @@ static int vit_backward_impl(const llc_vit_cfg* cfg, const llc_vit_weights* w, i
   const Arena a = plan(d, 1);
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
   WsScope ws_scope(base + a.gemm_ws);
-  llc_block_bwd_bufs s;
+  llc_block_bwd_bufs s{};
   s.dx = dx_final;
   s.dxb = base + a.dxb;
   s.dz = base + a.dz;
@@ -842,7 +842,7 @@ extern "C" int llc_text_backward(const llc_vit_cfg* cfg, const llc_text_weights*
   const Arena a = plan(d, 1);
   uint8_t* base = reinterpret_cast<uint8_t*>(arena);
   WsScope ws_scope(base + a.gemm_ws);
-  llc_block_bwd_bufs s;
+  llc_block_bwd_bufs s{};
   s.dx = dx_final;
   s.dxb = base + a.dxb;
   s.dz = base + a.dz;
