@@ -1,5 +1,6 @@
 #!/bin/bash
-# rows-per-warp variants of the LayerNorm + rank-r row product kernel (llc_set_traversal bits 3-4)
+# rows-per-warp variants of the LayerNorm + rank-r row product kernel (were selected by bits 3-4 of
+# llc_set_traversal; measured, rejected and removed again - DESIGN.md section 8 has the numbers)
 cd /root/repo; mkdir -p gpurun_out
 for mode in 0 8 16 0 8; do
   LLC_TRAVERSAL=$mode timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
